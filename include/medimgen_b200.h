@@ -1,0 +1,181 @@
+/*
+ * medimgen_b200.h -- C ABI of the B200-native medimgen hot path (libmedimgen_b200.so).
+ *
+ * The reference (VKostoulas/Medical_Image_Generation, `medimgen`) has no FFI of its own: it is pure
+ * Python that dispatches to cuDNN/cuBLAS/ATen. Each entry point below replaces
+ * one of those library dispatch sites; the site is cited as `unet:N` =
+ * medimgen/diffusion_model_unet_with_strides.py:N, `ae:N` = medimgen/autoencoderkl_with_strides.py:N,
+ * `ldm:N` = medimgen/train_ldm.py:N, `aetrain:N` = medimgen/train_autoencoder.py:N.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; no torch types cross the ABI
+ *   - activations are channels-last: [N][D][H][W][C] (2-D problems use D = 1)
+ *   - conv filters are [Cout][kd][kh][kw][Cin] (== torch channels_last_3d of (Cout,Cin,kd,kh,kw))
+ *   - dtype codes: MIG_F32 = 0, MIG_BF16 = 1
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return value 0 = ok; otherwise mig_last_error() describes the failure (thread-local)
+ *   - no allocation, no hidden global state except a per-device attribute cache
+ */
+#ifndef MEDIMGEN_B200_H
+#define MEDIMGEN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIG_F32 0
+#define MIG_BF16 1
+
+#define MIG_ABI_VERSION 1
+
+/* Geometry of one N-d convolution (1 <= nd <= 3 handled by setting leading dims to 1). */
+typedef struct {
+  int32_t N;          /* batch */
+  int32_t in_dims[3]; /* D,H,W of the conv input  */
+  int32_t out_dims[3];/* D,H,W of the conv output */
+  int32_t Cin, Cout;
+  int32_t ksize[3], stride[3], pad[3];
+} mig_conv_geom;
+
+const char* mig_last_error(void);
+int mig_abi_version(void);
+/* 1 when the running device is sm_100 and the tcgen05 kernels are usable */
+int mig_has_tcgen05(void);
+
+/* ---- K1/K2/K3: Conv{2,3}d as implicit GEMM -------------------------------------------------------
+ * replaces nn.Conv{2,3}d inside monai Convolution: unet:510-518,557-565,630-659,664,1820,1935;
+ * ae:66-129,158-179,372-381,454-463,523-532,606-615,723-749.
+ * y[n,o,co] = sum_{tap,ci} x[n, o*stride - pad + tap, ci] * w[co,tap,ci] + bias[co]
+ *             (+ chan_bias[n,co]  -- the time-embedding add, unet:691-695)
+ *             (+ residual[n,o,co] -- the skip add, unet:701 / ae:204)
+ * `engine`: 0 = auto, 1 = SIMT fp32-accumulate CUDA-core path, 2 = tcgen05 tensor-core path (bf16 only). */
+int mig_conv_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+                 const float* chan_bias, const void* residual, void* y, int engine,
+                 void* workspace, int64_t workspace_bytes, void* stream);
+/* dx[n,i,ci] = sum_{tap,co} dy[n,(i+pad-tap)/stride,co] * w[co,tap,ci]   (conv backward-data) */
+int mig_conv_dgrad(const mig_conv_geom* g, int dtype, const void* dy, const void* w, void* dx, int engine,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* dw[co,tap,ci] += sum_{n,o} dy[n,o,co] * x[n,o*stride-pad+tap,ci]  (fp32, accumulates into dw);
+ * dbias[co] += sum dy[.,co] when dbias != NULL */
+int mig_conv_wgrad(const mig_conv_geom* g, int dtype, const void* x, const void* dy, float* dw, float* dbias,
+                   int engine, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mig_conv_workspace_bytes(const mig_conv_geom* g, int dtype, int which /*0 fwd,1 dgrad,2 wgrad*/, int engine);
+
+/* ---- generic strided batched GEMM (attention products unet:406-416, ae:271-281) -------------------
+ * C[b][m][n] = alpha * sum_k A[b][m][k] * B[b][k][n], element strides given; batch index b = bo*inner+bi
+ * with offsets bo*s?_outer + bi*s?_inner (heads live inside the channel dim). */
+typedef struct {
+  int32_t M, N, K, batch_outer, batch_inner;
+  int64_t a_m, a_k, a_outer, a_inner;
+  int64_t b_k, b_n, b_outer, b_inner;
+  int64_t c_m, c_n, c_outer, c_inner;
+  float alpha;
+  int32_t accumulate; /* C += ... (fp32 output only) */
+} mig_gemm_desc;
+int mig_gemm_strided(const mig_gemm_desc* d, int dtype_ab, int dtype_c, const void* A, const void* B, void* C,
+                     int engine, void* stream);
+
+/* ---- K4/K5: GroupNorm (+SiLU), nn.GroupNorm at unet:628,648,275,377,1932; ae:157,167,238,451,604 ----
+ * x,y: [N][S][C] channels-last, S = D*H*W. mean/rstd: [N][G] fp32 (saved for backward). */
+int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
+                      float* mean, float* rstd, int32_t N, int64_t S, int32_t C, int32_t G, float eps,
+                      int fuse_silu, void* workspace, int64_t workspace_bytes, void* stream);
+int mig_groupnorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* beta,
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                      int32_t N, int64_t S, int32_t C, int32_t G, int fuse_silu,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mig_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t G);
+
+/* LayerNorm over the last dim (BasicTransformerBlock norm1-3, unet:225-227) */
+int mig_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
+                      float* rstd, int64_t rows, int32_t C, float eps, void* stream);
+int mig_layernorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t C,
+                      void* stream);
+
+/* ---- elementwise family ------------------------------------------------------------------------- */
+int mig_silu_fwd(int dtype, const void* x, void* y, int64_t n, void* stream);            /* unet:677,1833 */
+int mig_silu_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t n, void* stream);
+int mig_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);   /* residual adds */
+int mig_scale(int dtype, const void* x, void* y, float s, int64_t n, void* stream);       /* ldm:157 */
+int mig_mul(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream);
+/* y = a + b*c : the reparameterisation z = mu + eps*sigma (ae:786-787) */
+int mig_addcmul(int dtype, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream);
+int mig_cast(int src_dtype, int dst_dtype, const void* x, void* y, int64_t n, void* stream);
+/* GEGLU: y[r][j] = x[r][j] * gelu(x[r][H+j]) (monai MLPBlock, unet:213) */
+int mig_geglu_fwd(int dtype, const void* x, void* y, int64_t rows, int32_t H, void* stream);
+int mig_geglu_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t rows, int32_t H, void* stream);
+/* torch.cat along channels (unet:1263,1377,1504) and its split backward */
+int mig_concat_channels(int dtype, const void* a, const void* b, void* y, int64_t rows, int32_t Ca, int32_t Cb,
+                        void* stream);
+int mig_split_channels(int dtype, const void* y, void* a, void* b, int64_t rows, int32_t Ca, int32_t Cb,
+                       void* stream);
+/* F.interpolate(mode="nearest", integer per-axis factors) unet:580, ae:99 and its sum-pool backward */
+int mig_upsample_nearest_fwd(int dtype, const void* x, void* y, int32_t N, const int32_t in_dims[3],
+                             const int32_t factors[3], int32_t C, void* stream);
+int mig_upsample_nearest_bwd(int dtype, const void* dy, void* dx, int32_t N, const int32_t in_dims[3],
+                             const int32_t factors[3], int32_t C, void* stream);
+/* NCDHW <-> NDHWC with optional dtype change (module boundary) */
+int mig_nchw_to_nhwc(int src_dtype, int dst_dtype, const void* x, void* y, int32_t N, int32_t C, int64_t S,
+                     void* stream);
+int mig_nhwc_to_nchw(int src_dtype, int dst_dtype, const void* x, void* y, int32_t N, int32_t C, int64_t S,
+                     void* stream);
+/* column sums of a [rows][C] matrix into fp32 out[C] (bias gradients); out += when accumulate */
+int mig_colsum(int dtype, const void* x, float* out, int64_t rows, int32_t C, int accumulate, void* stream);
+/* per-(n,c) broadcast add over S positions: y[n,s,c] = x[n,s,c] + b[n,c] and its reduction backward */
+int mig_chan_bias_bwd(int dtype, const void* dy, float* db, int32_t N, int64_t S, int32_t C, void* stream);
+
+/* row softmax over the last dim (fp32 math), attention_scores.softmax(dim=-1) unet:414 */
+int mig_softmax_fwd(int dtype_in, int dtype_out, const void* x, void* y, int64_t rows, int32_t cols, float scale,
+                    void* stream);
+int mig_softmax_bwd(int dtype_p, int dtype_d, const void* p, const void* dp, void* ds, int64_t rows, int32_t cols,
+                    float scale, void* stream);
+
+/* K7: sinusoidal timestep embedding, cos first (unet:461-485). t: fp32 [B] */
+int mig_timestep_embedding(const float* t, void* out, int out_dtype, int32_t B, int32_t dim, float max_period,
+                           void* stream);
+
+/* ---- K14/K15: DDPMScheduler (monai-generative, call sites ldm:160,165,362) ------------------------
+ * coefficient tables are fp32 [T] device arrays; timesteps int64 [B]; one sample = `per_sample` elements */
+int mig_ddpm_add_noise(int dtype, const void* x0, const void* noise, const int64_t* timesteps,
+                       const float* alphas_cumprod, void* out, int32_t B, int64_t per_sample, int32_t T,
+                       int velocity /*0: add_noise, 1: get_velocity*/, void* stream);
+/* one reverse step: prev = c0*clamp(x0_hat) + ct*x + sigma*z ; writes x0_hat when non-NULL.
+ * prediction: 0 epsilon, 1 sample, 2 v_prediction. `z` may be NULL when sigma == 0 (t == 0). */
+int mig_ddpm_step(int dtype, const void* model_out, const void* x, const void* z, void* prev, void* x0_hat,
+                  int64_t n, float sqrt_acp_t, float sqrt_one_minus_acp_t, float c0, float ct, float sigma,
+                  int prediction, int clip, void* stream);
+
+/* ---- K16/K17: losses --------------------------------------------------------------------------- */
+/* out[0] = mean((a-b)^2) (ldm:169) or mean(|a-b|) (aetrain:414); `partials` needs 2048 floats */
+int mig_mse_fwd(int dtype, const void* a, const void* b, float* out, float* partials, int64_t n, int l1,
+                void* stream);
+/* da = gscale[0] * d/da loss ; gscale is a device scalar (upstream grad) */
+int mig_mse_bwd(int dtype, const void* a, const void* b, const float* gscale, void* da, int64_t n, int l1,
+                void* stream);
+/* KL(N(mu,sigma)||N(0,1)) summed over non-batch dims, averaged over batch (aetrain:67-72) */
+int mig_kl_fwd(int dtype, const void* mu, const void* sigma, float* out, float* partials, int64_t n, int32_t B,
+               void* stream);
+int mig_kl_bwd(int dtype, const void* mu, const void* sigma, const float* gscale, void* dmu, void* dsigma,
+               int64_t n, int32_t B, void* stream);
+/* encode tail (ae:766-769): sigma = exp(clamp(logvar,-30,20)/2); z = mu + eps*sigma (ae:786-787) */
+int mig_vae_sample_fwd(int dtype, const void* mu, const void* logvar, const void* eps, void* sigma, void* z,
+                       int64_t n, void* stream);
+int mig_vae_sample_bwd(int dtype, const void* logvar, const void* eps, const void* sigma, const void* dz,
+                       const void* dsigma_ext, void* dmu, void* dlogvar, int64_t n, void* stream);
+
+/* ---- K18: optimizer on flat fp32 buffers (ldm:121,171-180) ---------------------------------------- */
+/* out[0] += sum(g^2) over n elements (call per segment, then sqrt on host/device) */
+int mig_sumsq(const float* g, float* out, int64_t n, void* stream);
+/* AdamW (decoupled weight decay, torch.optim.AdamW semantics); grad pre-scale = min(1, max_norm/(norm+1e-6))
+ * read from device scalar sumsq when max_norm > 0. bf16_shadow (optional) receives the updated params in bf16. */
+int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int32_t step, const float* sumsq, float max_norm,
+                   void* bf16_shadow, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEDIMGEN_B200_H */

@@ -1,0 +1,808 @@
+// Bandwidth-bound elementwise / layout / loss / scheduler / optimizer kernels.
+// All are HBM-roofline kernels: 128-bit coalesced accesses, grid = multiple of the SM count,
+// warp-shuffle reductions. Algorithmic bytes per element are listed in DESIGN.md.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace mig {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// generic unary / binary maps
+// ------------------------------------------------------------------------------------------------
+template <typename T, typename F, int NIN>
+__global__ void __launch_bounds__(256) map_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                  const T* __restrict__ c, T* __restrict__ y, int64_t n, int vec,
+                                                  F f) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nvec = vec ? n / V : 0;
+  for (int64_t i = tid; i < nvec; i += stride) {
+    Vec16<T> va = ld16(a + i * V), vb, vc, vy;
+    if (NIN > 1) vb = ld16(b + i * V);
+    if (NIN > 2) vc = ld16(c + i * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      vy.set(j, f(va.get(j), NIN > 1 ? vb.get(j) : 0.f, NIN > 2 ? vc.get(j) : 0.f));
+    st16(y + i * V, vy);
+  }
+  for (int64_t i = nvec * V + tid; i < n; i += stride)
+    y[i] = from_f<T>(f(to_f(a[i]), NIN > 1 ? to_f(b[i]) : 0.f, NIN > 2 ? to_f(c[i]) : 0.f));
+}
+
+template <typename T, int NIN, typename F>
+static int launch_map(const void* a, const void* b, const void* c, void* y, int64_t n, void* stream, F f,
+                      const char* what) {
+  if (n <= 0) return 0;
+  int vec = aligned16(a) && aligned16(y) && (NIN < 2 || aligned16(b)) && (NIN < 3 || aligned16(c));
+  int grid = bw_grid((n + Vec16<T>::N - 1) / Vec16<T>::N, 256);
+  map_kernel<T, F, NIN><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, (const T*)c, (T*)y, n, vec, f);
+  return check_launch(what);
+}
+
+struct SiluF { __device__ float operator()(float x, float, float) const { return silu_f(x); } };
+struct SiluBwdF { __device__ float operator()(float x, float dy, float) const { return dy * silu_grad_f(x); } };
+struct AddF { __device__ float operator()(float a, float b, float) const { return a + b; } };
+struct ScaleF { float s; __device__ float operator()(float a, float, float) const { return a * s; } };
+struct MulF { __device__ float operator()(float a, float b, float) const { return a * b; } };
+struct AddcmulF { __device__ float operator()(float a, float b, float c) const { return fmaf(b, c, a); } };
+
+}  // namespace mig
+
+using namespace mig;
+
+extern "C" int mig_silu_fwd(int dtype, const void* x, void* y, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, stream, SiluF{}, "silu_fwd")));
+}
+extern "C" int mig_silu_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 2>(x, dy, nullptr, dx, n, stream, SiluBwdF{}, "silu_bwd")));
+}
+extern "C" int mig_add(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 2>(a, b, nullptr, y, n, stream, AddF{}, "add")));
+}
+extern "C" int mig_mul(int dtype, const void* a, const void* b, void* y, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 2>(a, b, nullptr, y, n, stream, MulF{}, "mul")));
+}
+extern "C" int mig_addcmul(int dtype, const void* a, const void* b, const void* c, void* y, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 3>(a, b, c, y, n, stream, AddcmulF{}, "addcmul")));
+}
+extern "C" int mig_scale(int dtype, const void* x, void* y, float s, int64_t n, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, stream, ScaleF{s}, "scale")));
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ x, TD* __restrict__ y, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = to_f(x[i + j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) y[i + j] = from_f<TD>(v[j]);
+    } else {
+      for (int64_t j = i; j < n; ++j) y[j] = from_f<TD>(to_f(x[j]));
+    }
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_cast(int src_dtype, int dst_dtype, const void* x, void* y, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  int grid = bw_grid((n + 3) / 4, 256);
+  if (src_dtype == MIG_F32 && dst_dtype == MIG_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (__nv_bfloat16*)y, n);
+  else if (src_dtype == MIG_BF16 && dst_dtype == MIG_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (float*)y, n);
+  else if (src_dtype == MIG_F32 && dst_dtype == MIG_F32)
+    cast_kernel<float, float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n);
+  else if (src_dtype == MIG_BF16 && dst_dtype == MIG_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n);
+  else
+    MIG_REQUIRE(false, "mig_cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  return check_launch("cast");
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+template <typename T>
+__global__ void geglu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int H) {
+  const int64_t total = rows * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / H;
+    int j = (int)(i - r * H);
+    float a = to_f(x[r * 2 * H + j]), g = to_f(x[r * 2 * H + H + j]);
+    y[i] = from_f<T>(a * gelu_f(g));
+  }
+}
+template <typename T>
+__global__ void geglu_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx, int64_t rows,
+                                 int H) {
+  const int64_t total = rows * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / H;
+    int j = (int)(i - r * H);
+    float a = to_f(x[r * 2 * H + j]), g = to_f(x[r * 2 * H + H + j]), d = to_f(dy[i]);
+    dx[r * 2 * H + j] = from_f<T>(d * gelu_f(g));
+    dx[r * 2 * H + H + j] = from_f<T>(d * a * gelu_grad_f(g));
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_geglu_fwd(int dtype, const void* x, void* y, int64_t rows, int32_t H, void* stream) {
+  if (rows * H <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (geglu_fwd_kernel<T><<<bw_grid(rows * H, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (T*)y, rows, H)));
+  return check_launch("geglu_fwd");
+}
+extern "C" int mig_geglu_bwd(int dtype, const void* x, const void* dy, void* dx, int64_t rows, int32_t H,
+                             void* stream) {
+  if (rows * H <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (geglu_bwd_kernel<T><<<bw_grid(rows * H, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (const T*)dy, (T*)dx, rows, H)));
+  return check_launch("geglu_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel concat / split (rows = N*S voxels, channels-last so each row is contiguous)
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(256) concat_kernel(T* __restrict__ a, T* __restrict__ b, T* __restrict__ y,
+                                                     int64_t rows, int Ca, int Cb, int vec) {
+  constexpr int V = Vec16<T>::N;
+  const int C = Ca + Cb;
+  if (vec) {
+    const int cv = C / V, cav = Ca / V;
+    const int64_t total = rows * cv;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t r = i / cv;
+      int c = (int)(i - r * cv);
+      T* part = c < cav ? a + r * Ca + (int64_t)c * V : b + r * Cb + (int64_t)(c - cav) * V;
+      if (SPLIT) st16(part, ld16(y + i * V)); else st16(y + i * V, ld16(part));
+    }
+  } else {
+    const int64_t total = rows * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t r = i / C;
+      int c = (int)(i - r * C);
+      T* part = c < Ca ? a + r * Ca + c : b + r * Cb + (c - Ca);
+      if (SPLIT) *part = y[i]; else y[i] = *part;
+    }
+  }
+}
+template <typename T, bool SPLIT>
+static int launch_concat(const void* a, const void* b, const void* y, int64_t rows, int Ca, int Cb, void* stream) {
+  if (rows <= 0) return 0;
+  constexpr int V = Vec16<T>::N;
+  int vec = (Ca % V == 0) && (Cb % V == 0) && aligned16(a) && aligned16(b) && aligned16(y);
+  int64_t items = vec ? rows * ((Ca + Cb) / V) : rows * (Ca + Cb);
+  concat_kernel<T, SPLIT><<<bw_grid(items, 256), 256, 0, as_stream(stream)>>>((T*)a, (T*)b, (T*)y, rows, Ca, Cb, vec);
+  return check_launch(SPLIT ? "split_channels" : "concat_channels");
+}
+}  // namespace mig
+
+extern "C" int mig_concat_channels(int dtype, const void* a, const void* b, void* y, int64_t rows, int32_t Ca,
+                                   int32_t Cb, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_concat<T, false>(a, b, y, rows, Ca, Cb, stream)));
+}
+extern "C" int mig_split_channels(int dtype, const void* y, void* a, void* b, int64_t rows, int32_t Ca, int32_t Cb,
+                                  void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_concat<T, true>(a, b, y, rows, Ca, Cb, stream)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest upsample (integer factors) and its adjoint (sum over each fd*fh*fw cell)
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+struct UpGeom { int N, D, H, W, fd, fh, fw, C; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, UpGeom g,
+                                                           int cw /*elements per work item*/) {
+  const int OD = g.D * g.fd, OH = g.H * g.fh, OW = g.W * g.fw;
+  const int cpr = g.C / cw;
+  const int64_t total = (int64_t)g.N * OD * OH * OW * cpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cpr);
+    int64_t v = i / cpr;
+    int ow = (int)(v % OW); v /= OW;
+    int oh = (int)(v % OH); v /= OH;
+    int od = (int)(v % OD);
+    int n = (int)(v / OD);
+    int64_t src = ((((int64_t)n * g.D + od / g.fd) * g.H + oh / g.fh) * g.W + ow / g.fw) * g.C + (int64_t)c * cw;
+    int64_t dst = (i / cpr) * g.C + (int64_t)c * cw;
+    if (cw > 1) st16(y + dst, ld16(x + src)); else y[dst] = x[src];
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, UpGeom g,
+                                                           int cw) {
+  const int OH = g.H * g.fh, OW = g.W * g.fw;
+  const int cpr = g.C / cw;
+  const int64_t total = (int64_t)g.N * g.D * g.H * g.W * cpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cpr);
+    int64_t v = i / cpr;
+    int w = (int)(v % g.W); v /= g.W;
+    int h = (int)(v % g.H); v /= g.H;
+    int d = (int)(v % g.D);
+    int n = (int)(v / g.D);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < g.fd; ++a)
+      for (int b = 0; b < g.fh; ++b)
+        for (int e = 0; e < g.fw; ++e) {
+          int64_t src = ((((int64_t)n * g.D * g.fd + d * g.fd + a) * OH + h * g.fh + b) * OW + w * g.fw + e) * g.C +
+                        (int64_t)c * cw;
+          if (cw > 1) {
+            Vec16<T> t = ld16(dy + src);
+#pragma unroll
+            for (int j = 0; j < Vec16<T>::N; ++j) acc[j] += t.get(j);
+          } else {
+            acc[0] += to_f(dy[src]);
+          }
+        }
+    int64_t dst = (i / cpr) * g.C + (int64_t)c * cw;
+    if (cw > 1) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < Vec16<T>::N; ++j) o.set(j, acc[j]);
+      st16(dx + dst, o);
+    } else {
+      dx[dst] = from_f<T>(acc[0]);
+    }
+  }
+}
+template <typename T, bool BWD>
+static int launch_upsample(const void* src, void* dst, int N, const int32_t* in_dims, const int32_t* f, int C,
+                           void* stream) {
+  UpGeom g{N, in_dims[0], in_dims[1], in_dims[2], f[0], f[1], f[2], C};
+  MIG_REQUIRE(f[0] >= 1 && f[1] >= 1 && f[2] >= 1, "upsample: factors must be >= 1");
+  constexpr int V = Vec16<T>::N;
+  int cw = (C % V == 0 && aligned16(src) && aligned16(dst)) ? V : 1;
+  int64_t vox = (int64_t)N * g.D * g.H * g.W * (BWD ? 1 : (int64_t)f[0] * f[1] * f[2]);
+  if (vox == 0) return 0;
+  int grid = bw_grid(vox * (C / cw), 256);
+  if (BWD) upsample_bwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)src, (T*)dst, g, cw);
+  else upsample_fwd_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)src, (T*)dst, g, cw);
+  return check_launch(BWD ? "upsample_bwd" : "upsample_fwd");
+}
+}  // namespace mig
+
+extern "C" int mig_upsample_nearest_fwd(int dtype, const void* x, void* y, int32_t N, const int32_t in_dims[3],
+                                        const int32_t factors[3], int32_t C, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_upsample<T, false>(x, y, N, in_dims, factors, C, stream)));
+}
+extern "C" int mig_upsample_nearest_bwd(int dtype, const void* dy, void* dx, int32_t N, const int32_t in_dims[3],
+                                        const int32_t factors[3], int32_t C, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_upsample<T, true>(dy, dx, N, in_dims, factors, C, stream)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCDHW <-> NDHWC transposes through a padded smem tile (coalesced on both sides)
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+// src viewed as [B][R][Ccols] row-major -> dst [B][Ccols][R]
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_kernel(const TS* __restrict__ x, TD* __restrict__ y, int64_t R,
+                                                        int64_t Ccols) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z;
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const TS* xs = x + b * R * Ccols;
+  TD* yd = y + b * R * Ccols;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int64_t r = r0 + i, c = c0 + threadIdx.x;
+    if (r < R && c < Ccols) tile[i][threadIdx.x] = to_f(xs[r * Ccols + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Ccols) yd[c * R + r] = from_f<TD>(tile[threadIdx.x][i]);
+  }
+}
+template <typename TS, typename TD>
+static int launch_transpose(const void* x, void* y, int B, int64_t R, int64_t Ccols, void* stream) {
+  if (B * R * Ccols == 0) return 0;
+  MIG_REQUIRE((R + 31) / 32 < 65536, "transpose: too many row tiles");
+  dim3 grid((unsigned)((Ccols + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)B), block(32, 8);
+  transpose_kernel<TS, TD><<<grid, block, 0, as_stream(stream)>>>((const TS*)x, (TD*)y, R, Ccols);
+  return check_launch("transpose");
+}
+static int transpose_dispatch(int sd, int dd, const void* x, void* y, int B, int64_t R, int64_t Cc, void* stream) {
+  if (sd == MIG_F32 && dd == MIG_F32) return launch_transpose<float, float>(x, y, B, R, Cc, stream);
+  if (sd == MIG_F32 && dd == MIG_BF16) return launch_transpose<float, __nv_bfloat16>(x, y, B, R, Cc, stream);
+  if (sd == MIG_BF16 && dd == MIG_F32) return launch_transpose<__nv_bfloat16, float>(x, y, B, R, Cc, stream);
+  if (sd == MIG_BF16 && dd == MIG_BF16) return launch_transpose<__nv_bfloat16, __nv_bfloat16>(x, y, B, R, Cc, stream);
+  set_error("transpose: bad dtypes");
+  return 1;
+}
+}  // namespace mig
+
+extern "C" int mig_nchw_to_nhwc(int src_dtype, int dst_dtype, const void* x, void* y, int32_t N, int32_t C, int64_t S,
+                                void* stream) {
+  // y is only 65535-limited in grid.y = C tiles; put the long axis (S) on grid.x
+  return transpose_dispatch(src_dtype, dst_dtype, x, y, N, C, S, stream);
+}
+extern "C" int mig_nhwc_to_nchw(int src_dtype, int dst_dtype, const void* x, void* y, int32_t N, int32_t C, int64_t S,
+                                void* stream) {
+  // [N][S][C] -> [N][C][S]; rows = S may exceed 65535*32 only for > 2M voxels per sample
+  if ((S + 31) / 32 >= 65536) {
+    set_error("nhwc_to_nchw: sample too large for the transposing grid (S=%lld)", (long long)S);
+    return 1;
+  }
+  return transpose_dispatch(src_dtype, dst_dtype, x, y, N, S, C, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients) and per-(n,c) sums (time-embedding gradient)
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+// out[b][c] (+)= sum_{r in [0,R)} x[b][r][c]; grid (ceil(C/32), chunks, B); block (32, 8)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t R,
+                                                     int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int64_t b = blockIdx.z;
+  const T* xs = x + b * R * C;
+  float acc = 0.f;
+  if (c < C)
+    for (int64_t r = (int64_t)blockIdx.y * 8 + threadIdx.y; r < R; r += (int64_t)gridDim.y * 8) acc += to_f(xs[r * C + c]);
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + b * C + c, t);
+  }
+}
+template <typename T>
+static int launch_colsum(const void* x, float* out, int B, int64_t R, int C, int accumulate, void* stream) {
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C, as_stream(stream));
+  if (B * R * C == 0) return 0;
+  int ctiles = (C + 31) / 32;
+  int64_t want = (int64_t)device_info().sm_count * 4 / (ctiles * (int64_t)B) + 1;
+  int64_t maxchunks = (R + 7) / 8;
+  int chunks = (int)(want < maxchunks ? want : maxchunks);
+  if (chunks < 1) chunks = 1;
+  if (chunks > 65535) chunks = 65535;
+  dim3 grid(ctiles, chunks, B), block(32, 8);
+  colsum_kernel<T><<<grid, block, 0, as_stream(stream)>>>((const T*)x, out, R, C);
+  return check_launch("colsum");
+}
+}  // namespace mig
+
+extern "C" int mig_colsum(int dtype, const void* x, float* out, int64_t rows, int32_t C, int accumulate, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_colsum<T>(x, out, 1, rows, C, accumulate, stream)));
+}
+extern "C" int mig_chan_bias_bwd(int dtype, const void* dy, float* db, int32_t N, int64_t S, int32_t C, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_colsum<T>(dy, db, N, S, C, 0, stream)));
+}
+
+// ------------------------------------------------------------------------------------------------
+// row softmax (fp32 math) forward / backward. One CTA per row; rows up to a few thousand columns.
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, int cols,
+                                                          float scale) {
+  __shared__ float red[33];
+  const TI* xr = x + (int64_t)blockIdx.x * cols;
+  TO* yr = y + (int64_t)blockIdx.x * cols;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) mx = fmaxf(mx, to_f(xr[c]) * scale);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) sum += __expf(to_f(xr[c]) * scale - mx);
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) yr[c] = from_f<TO>(__expf(to_f(xr[c]) * scale - mx) * inv);
+}
+// ds = scale * p * (dp - sum(dp*p))
+template <typename TP, typename TD>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const TP* __restrict__ p, const TD* __restrict__ dp,
+                                                          TD* __restrict__ ds, int cols, float scale) {
+  __shared__ float red[33];
+  const TP* pr = p + (int64_t)blockIdx.x * cols;
+  const TD* dr = dp + (int64_t)blockIdx.x * cols;
+  TD* sr = ds + (int64_t)blockIdx.x * cols;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) dot += to_f(pr[c]) * to_f(dr[c]);
+  dot = block_sum(dot, red);
+  for (int c = threadIdx.x; c < cols; c += blockDim.x)
+    sr[c] = from_f<TD>(scale * to_f(pr[c]) * (to_f(dr[c]) - dot));
+}
+}  // namespace mig
+
+extern "C" int mig_softmax_fwd(int dtype_in, int dtype_out, const void* x, void* y, int64_t rows, int32_t cols,
+                               float scale, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  MIG_REQUIRE(rows < (1ll << 31), "softmax: too many rows");
+  cudaStream_t s = as_stream(stream);
+  if (dtype_in == MIG_F32 && dtype_out == MIG_F32)
+    softmax_fwd_kernel<float, float><<<(unsigned)rows, 256, 0, s>>>((const float*)x, (float*)y, cols, scale);
+  else if (dtype_in == MIG_F32 && dtype_out == MIG_BF16)
+    softmax_fwd_kernel<float, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)y, cols, scale);
+  else if (dtype_in == MIG_BF16 && dtype_out == MIG_BF16)
+    softmax_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, cols, scale);
+  else
+    MIG_REQUIRE(false, "softmax_fwd: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
+  return check_launch("softmax_fwd");
+}
+extern "C" int mig_softmax_bwd(int dtype_p, int dtype_d, const void* p, const void* dp, void* ds, int64_t rows,
+                               int32_t cols, float scale, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  cudaStream_t s = as_stream(stream);
+  if (dtype_p == MIG_F32 && dtype_d == MIG_F32)
+    softmax_bwd_kernel<float, float><<<(unsigned)rows, 256, 0, s>>>((const float*)p, (const float*)dp, (float*)ds, cols, scale);
+  else if (dtype_p == MIG_BF16 && dtype_d == MIG_F32)
+    softmax_bwd_kernel<__nv_bfloat16, float><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)p, (const float*)dp, (float*)ds, cols, scale);
+  else if (dtype_p == MIG_BF16 && dtype_d == MIG_BF16)
+    softmax_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, cols, scale);
+  else
+    MIG_REQUIRE(false, "softmax_bwd: unsupported dtype pair %d / %d", dtype_p, dtype_d);
+  return check_launch("softmax_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// timestep embedding: out[b][j] = cos(t*f_j) for j < half, sin(t*f_{j-half}) for half <= j < 2*half, 0 pad
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+template <typename T>
+__global__ void temb_kernel(const float* __restrict__ t, T* __restrict__ out, int B, int dim, float log_period) {
+  const int half = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * dim; i += gridDim.x * blockDim.x) {
+    int b = i / dim, j = i - b * dim;
+    float v = 0.f;
+    if (j < 2 * half) {
+      int k = j < half ? j : j - half;
+      // same op order as the reference: exp(-log(P) * k / half), then t * f  (unet:479-481)
+      float f = expf((-log_period * (float)k) / (float)half);
+      float a = t[b] * f;
+      v = j < half ? cosf(a) : sinf(a);
+    }
+    out[i] = from_f<T>(v);
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_timestep_embedding(const float* t, void* out, int out_dtype, int32_t B, int32_t dim,
+                                      float max_period, void* stream) {
+  if (B * dim <= 0) return 0;
+  float lp = logf(max_period);
+  MIG_DISPATCH_DTYPE(out_dtype, T, (temb_kernel<T><<<bw_grid((int64_t)B * dim, 256), 256, 0, as_stream(stream)>>>(
+                                       t, (T*)out, B, dim, lp)));
+  return check_launch("timestep_embedding");
+}
+
+// ------------------------------------------------------------------------------------------------
+// DDPM scheduler kernels
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+// grid.y = sample index; coefficients gathered once per CTA (bit-exact indexing: acp[t[b]])
+template <typename T>
+__global__ void __launch_bounds__(256) add_noise_kernel(const T* __restrict__ x0, const T* __restrict__ noise,
+                                                        const int64_t* __restrict__ ts,
+                                                        const float* __restrict__ acp, T* __restrict__ out,
+                                                        int64_t per, int Tn, int velocity, int vec) {
+  constexpr int V = Vec16<T>::N;
+  const int b = blockIdx.y;
+  int64_t t = ts[b];
+  t = t < 0 ? 0 : (t >= Tn ? Tn - 1 : t);
+  // the reference casts the table to the sample dtype before the sqrt (scheduler.add_noise)
+  const float a_tab = to_f(from_f<T>(acp[t]));
+  const float ca = to_f(from_f<T>(sqrtf(a_tab)));
+  const float cb = to_f(from_f<T>(sqrtf(to_f(from_f<T>(1.f - a_tab)))));
+  const T* xs = x0 + (int64_t)b * per;
+  const T* ns = noise + (int64_t)b * per;
+  T* os = out + (int64_t)b * per;
+  const int64_t nvec = vec ? per / V : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> vx = ld16_stream(xs + i * V), vn = ld16_stream(ns + i * V), vo;
+#pragma unroll
+    for (int j = 0; j < V; ++j)
+      vo.set(j, velocity ? ca * vn.get(j) - cb * vx.get(j) : ca * vx.get(j) + cb * vn.get(j));
+    st16(os + i * V, vo);
+  }
+  for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float x = to_f(xs[i]), n = to_f(ns[i]);
+    os[i] = from_f<T>(velocity ? ca * n - cb * x : ca * x + cb * n);
+  }
+}
+
+struct StepCoef { float sa, sb, c0, ct, sigma; int prediction, clip; };
+template <typename T>
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const T* __restrict__ eps, const T* __restrict__ x,
+                                                        const T* __restrict__ z, T* __restrict__ prev,
+                                                        T* __restrict__ x0_out, int64_t n, StepCoef k, int vec) {
+  constexpr int V = Vec16<T>::N;
+  const int64_t nvec = vec ? n / V : 0;
+  auto f = [&](float e, float xv, float zv, float& x0) {
+    if (k.prediction == 0) x0 = (xv - k.sb * e) / k.sa;
+    else if (k.prediction == 1) x0 = e;
+    else x0 = k.sa * xv - k.sb * e;
+    if (k.clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    return k.c0 * x0 + k.ct * xv + k.sigma * zv;
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> ve = ld16_stream(eps + i * V), vx = ld16_stream(x + i * V), vz, vp, v0;
+    if (z) vz = ld16_stream(z + i * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float x0;
+      vp.set(j, f(ve.get(j), vx.get(j), z ? vz.get(j) : 0.f, x0));
+      v0.set(j, x0);
+    }
+    st16(prev + i * V, vp);
+    if (x0_out) st16(x0_out + i * V, v0);
+  }
+  for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float x0;
+    prev[i] = from_f<T>(f(to_f(eps[i]), to_f(x[i]), z ? to_f(z[i]) : 0.f, x0));
+    if (x0_out) x0_out[i] = from_f<T>(x0);
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_ddpm_add_noise(int dtype, const void* x0, const void* noise, const int64_t* timesteps,
+                                  const float* alphas_cumprod, void* out, int32_t B, int64_t per_sample, int32_t T,
+                                  int velocity, void* stream) {
+  if (B <= 0 || per_sample <= 0) return 0;
+  MIG_REQUIRE(B < 65536, "add_noise: batch too large");
+  MIG_DISPATCH_DTYPE(dtype, TT, {
+    constexpr int V = Vec16<TT>::N;
+    int vec = aligned16(x0) && aligned16(noise) && aligned16(out) && (per_sample % V == 0);
+    int gx = bw_grid((per_sample + V - 1) / V, 256, 8) / B + 1;
+    dim3 grid(gx, B);
+    add_noise_kernel<TT><<<grid, 256, 0, as_stream(stream)>>>((const TT*)x0, (const TT*)noise, timesteps, alphas_cumprod,
+                                                            (TT*)out, per_sample, T, velocity, vec);
+  });
+  return check_launch("ddpm_add_noise");
+}
+
+extern "C" int mig_ddpm_step(int dtype, const void* model_out, const void* x, const void* z, void* prev, void* x0_hat,
+                             int64_t n, float sqrt_acp_t, float sqrt_one_minus_acp_t, float c0, float ct, float sigma,
+                             int prediction, int clip, void* stream) {
+  if (n <= 0) return 0;
+  MIG_REQUIRE(z != nullptr || sigma == 0.f, "ddpm_step: noise buffer required when sigma != 0");
+  StepCoef k{sqrt_acp_t, sqrt_one_minus_acp_t, c0, ct, sigma, prediction, clip};
+  MIG_DISPATCH_DTYPE(dtype, TT, {
+    constexpr int V = Vec16<TT>::N;
+    int vec = aligned16(model_out) && aligned16(x) && aligned16(prev) && (!z || aligned16(z)) &&
+              (!x0_hat || aligned16(x0_hat));
+    ddpm_step_kernel<TT><<<bw_grid((n + V - 1) / V, 256), 256, 0, as_stream(stream)>>>(
+        (const TT*)model_out, (const TT*)x, (const TT*)z, (TT*)prev, (TT*)x0_hat, n, k, vec);
+  });
+  return check_launch("ddpm_step");
+}
+
+// ------------------------------------------------------------------------------------------------
+// losses
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+constexpr int kLossBlocks = 1024;
+
+template <typename T, int MODE>  // MODE 0: (a-b)^2, 1: |a-b|, 2: KL term of (mu=a, sigma=b)
+__global__ void __launch_bounds__(256) loss_partial_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                           float* __restrict__ partials, int64_t n, int vec) {
+  __shared__ float red[33];
+  constexpr int V = Vec16<T>::N;
+  const int64_t nvec = vec ? n / V : 0;
+  float acc = 0.f;
+  auto term = [](float x, float y) {
+    if (MODE == 0) { float d = x - y; return d * d; }
+    if (MODE == 1) return fabsf(x - y);
+    float s2 = y * y;
+    return 0.5f * (x * x + s2 - logf(s2) - 1.f);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    Vec16<T> va = ld16_stream(a + i * V), vb = ld16_stream(b + i * V);
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc += term(va.get(j), vb.get(j));
+  }
+  for (int64_t i = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc += term(to_f(a[i]), to_f(b[i]));
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+// deterministic second stage: one CTA sums the partials in double
+__global__ void loss_final_kernel(const float* __restrict__ partials, int nparts, float* __restrict__ out,
+                                  double inv_count) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += (double)partials[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = (float)(red[0] * inv_count);
+}
+template <typename T, int MODE>
+static int launch_loss(const void* a, const void* b, float* out, float* partials, int64_t n, double inv_count,
+                       void* stream) {
+  MIG_REQUIRE(n > 0, "loss: empty input");
+  constexpr int V = Vec16<T>::N;
+  int vec = aligned16(a) && aligned16(b);
+  int grid = bw_grid((n + V - 1) / V, 256, 4);
+  if (grid > kLossBlocks) grid = kLossBlocks;
+  loss_partial_kernel<T, MODE><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, partials, n, vec);
+  loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, out, inv_count);
+  return check_launch("loss_fwd");
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) loss_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b,
+                                                       const float* __restrict__ gscale, T* __restrict__ da,
+                                                       T* __restrict__ db, int64_t n, float k) {
+  const float g = gscale[0] * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float x = to_f(a[i]), y = to_f(b[i]);
+    if (MODE == 0) {
+      da[i] = from_f<T>(2.f * (x - y) * g);
+    } else if (MODE == 1) {
+      float d = x - y;
+      da[i] = from_f<T>((d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * g);
+    } else {  // KL: d/dmu = mu ; d/dsigma = sigma - 1/sigma
+      da[i] = from_f<T>(x * g);
+      db[i] = from_f<T>((y - 1.f / y) * g);
+    }
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_mse_fwd(int dtype, const void* a, const void* b, float* out, float* partials, int64_t n, int l1,
+                           void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, {
+    if (l1) return (launch_loss<T, 1>(a, b, out, partials, n, 1.0 / (double)n, stream));
+    return (launch_loss<T, 0>(a, b, out, partials, n, 1.0 / (double)n, stream));
+  });
+}
+extern "C" int mig_mse_bwd(int dtype, const void* a, const void* b, const float* gscale, void* da, int64_t n, int l1,
+                           void* stream) {
+  if (n <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, {
+    int grid = bw_grid(n, 256);
+    if (l1) loss_bwd_kernel<T, 1><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, gscale, (T*)da, nullptr, n, 1.f / (float)n);
+    else loss_bwd_kernel<T, 0><<<grid, 256, 0, as_stream(stream)>>>((const T*)a, (const T*)b, gscale, (T*)da, nullptr, n, 1.f / (float)n);
+  });
+  return check_launch("mse_bwd");
+}
+extern "C" int mig_kl_fwd(int dtype, const void* mu, const void* sigma, float* out, float* partials, int64_t n,
+                          int32_t B, void* stream) {
+  MIG_REQUIRE(B > 0, "kl: batch must be positive");
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_loss<T, 2>(mu, sigma, out, partials, n, 1.0 / (double)B, stream)));
+}
+extern "C" int mig_kl_bwd(int dtype, const void* mu, const void* sigma, const float* gscale, void* dmu, void* dsigma,
+                          int64_t n, int32_t B, void* stream) {
+  if (n <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (loss_bwd_kernel<T, 2><<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)mu, (const T*)sigma, gscale, (T*)dmu, (T*)dsigma, n, 1.f / (float)B)));
+  return check_launch("kl_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// VAE reparameterisation tail
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+template <typename T>
+__global__ void vae_sample_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ logvar,
+                                      const T* __restrict__ eps, T* __restrict__ sigma, T* __restrict__ z, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float lv = fminf(fmaxf(to_f(logvar[i]), -30.f), 20.f);
+    float s = expf(0.5f * lv);
+    sigma[i] = from_f<T>(s);
+    if (z) z[i] = from_f<T>(to_f(mu[i]) + to_f(eps[i]) * s);
+  }
+}
+// dmu = dz ; dsigma_total = dz*eps + dsigma_ext ; dlogvar = dsigma_total * sigma/2 inside the clamp, else 0
+template <typename T>
+__global__ void vae_sample_bwd_kernel(const T* __restrict__ logvar, const T* __restrict__ eps,
+                                      const T* __restrict__ sigma, const T* __restrict__ dz,
+                                      const T* __restrict__ dsig_ext, T* __restrict__ dmu, T* __restrict__ dlogvar,
+                                      int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float g = dz ? to_f(dz[i]) : 0.f;
+    float ds = (dz ? g * to_f(eps[i]) : 0.f) + (dsig_ext ? to_f(dsig_ext[i]) : 0.f);
+    float lv = to_f(logvar[i]);
+    bool inside = lv >= -30.f && lv <= 20.f;
+    if (dmu) dmu[i] = from_f<T>(g);
+    dlogvar[i] = from_f<T>(inside ? ds * 0.5f * to_f(sigma[i]) : 0.f);
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_vae_sample_fwd(int dtype, const void* mu, const void* logvar, const void* eps, void* sigma, void* z,
+                                  int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (vae_sample_fwd_kernel<T><<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)mu, (const T*)logvar, (const T*)eps, (T*)sigma, (T*)z, n)));
+  return check_launch("vae_sample_fwd");
+}
+extern "C" int mig_vae_sample_bwd(int dtype, const void* logvar, const void* eps, const void* sigma, const void* dz,
+                                  const void* dsigma_ext, void* dmu, void* dlogvar, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (vae_sample_bwd_kernel<T><<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)logvar, (const T*)eps, (const T*)sigma, (const T*)dz,
+                                   (const T*)dsigma_ext, (T*)dmu, (T*)dlogvar, n)));
+  return check_launch("vae_sample_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer: sum of squares + fused clip/AdamW over flat fp32 buffers
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n,
+                                                    int vec) {
+  __shared__ float red[33];
+  float acc = 0.f;
+  const int64_t nvec = vec ? n / 4 : 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(g)[i];
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    acc += g[i] * g[i];
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt, max_norm; };
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                    AdamArgs a, const float* __restrict__ sumsq,
+                                                    __nv_bfloat16* __restrict__ shadow) {
+  float clip = 1.f;
+  if (a.max_norm > 0.f && sumsq) {
+    // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
+    float c = a.max_norm / (sqrtf(sumsq[0]) + 1e-6f);
+    clip = c < 1.f ? c : 1.f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * clip;
+    float pi = p[i] * (1.f - a.lr * a.wd);
+    float mi = a.b1 * m[i] + (1.f - a.b1) * gi;
+    float vi = a.b2 * v[i] + (1.f - a.b2) * gi * gi;
+    float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+    pi -= (a.lr / a.bc1) * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_sumsq(const float* g, float* out, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  sumsq_kernel<<<bw_grid((n + 3) / 4, 256, 4), 256, 0, as_stream(stream)>>>(g, out, n, aligned16(g));
+  return check_launch("sumsq");
+}
+extern "C" int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
+                              float max_norm, void* bf16_shadow, void* stream) {
+  if (n <= 0) return 0;
+  MIG_REQUIRE(step >= 1, "adamw: step counts from 1");
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, (float)(1.0 - pow((double)beta1, (double)step)),
+             (float)sqrt(1.0 - pow((double)beta2, (double)step)), max_norm};
+  adamw_kernel<<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, sumsq, (__nv_bfloat16*)bf16_shadow);
+  return check_launch("adamw");
+}

@@ -1,0 +1,70 @@
+"""DiffusionInferer / LatentDiffusionInferer with monai-generative's interface (the external dependency used at
+train_ddpm.py:191,243 and train_ldm.py:112,157,362), driving the B200 modules and the fused scheduler kernels."""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class DiffusionInferer:
+    def __init__(self, scheduler) -> None:
+        self.scheduler = scheduler
+
+    def __call__(self, inputs, diffusion_model, noise, timesteps, condition=None, mode: str = "crossattn"):
+        if mode not in ("crossattn", "concat"):
+            raise NotImplementedError(f"{mode} condition is not supported")
+        noisy = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
+        if mode == "concat":
+            noisy = torch.cat([noisy, condition], dim=1)
+            condition = None
+        return diffusion_model(x=noisy, timesteps=timesteps, context=condition)
+
+    @torch.no_grad()
+    def sample(self, input_noise, diffusion_model, scheduler=None, save_intermediates: bool = False,
+               intermediate_steps: int = 100, conditioning=None, mode: str = "crossattn", verbose: bool = True,
+               step_noises=None):
+        """Reverse process over `scheduler.timesteps`; the model is called with `torch.Tensor((t,))` like upstream.
+        `step_noises` (optional list) injects the per-step z for parity tests."""
+        if mode not in ("crossattn", "concat"):
+            raise NotImplementedError(f"{mode} condition is not supported")
+        scheduler = scheduler or self.scheduler
+        image = input_noise
+        intermediates = []
+        for i, t in enumerate(scheduler.timesteps):
+            tt = torch.Tensor((t,)).to(input_noise.device)
+            if mode == "concat":
+                out = diffusion_model(torch.cat([image, conditioning], dim=1), timesteps=tt, context=None)
+            else:
+                out = diffusion_model(image, timesteps=tt, context=conditioning)
+            z = None if step_noises is None else step_noises[i]
+            image, _ = scheduler.step(out, t, image, noise=z)
+            if save_intermediates and t % intermediate_steps == 0:
+                intermediates.append(image)
+        return (image, intermediates) if save_intermediates else image
+
+
+class LatentDiffusionInferer(DiffusionInferer):
+    def __init__(self, scheduler, scale_factor: float = 1.0) -> None:
+        super().__init__(scheduler=scheduler)
+        self.scale_factor = scale_factor
+
+    def __call__(self, inputs, autoencoder_model, diffusion_model, noise, timesteps, condition=None,
+                 mode: str = "crossattn"):
+        with torch.no_grad():
+            latent = ops.scale(autoencoder_model.encode_stage_2_inputs(inputs), float(self.scale_factor))
+        return super().__call__(inputs=latent, diffusion_model=diffusion_model, noise=noise, timesteps=timesteps,
+                                condition=condition, mode=mode)
+
+    @torch.no_grad()
+    def sample(self, input_noise, autoencoder_model, diffusion_model, scheduler=None, save_intermediates: bool = False,
+               intermediate_steps: int = 100, conditioning=None, mode: str = "crossattn", verbose: bool = True,
+               step_noises=None):
+        out = super().sample(input_noise, diffusion_model, scheduler, save_intermediates, intermediate_steps,
+                             conditioning, mode, verbose, step_noises)
+        latent, inter = out if save_intermediates else (out, None)
+        image = autoencoder_model.decode_stage_2_outputs(ops.scale(latent, 1.0 / float(self.scale_factor)))
+        if save_intermediates:
+            return image, [autoencoder_model.decode_stage_2_outputs(ops.scale(l, 1.0 / float(self.scale_factor)))
+                           for l in inter]
+        return image

@@ -1,0 +1,798 @@
+"""Autograd-aware operators over the C ABI (libmedimgen_b200.so).
+
+Every function here launches hand-written sm_100a kernels through `_lib.call`; torch supplies only
+device memory, the current CUDA stream and the autograd tape. Activations are logical
+(N, C, *spatial) tensors in channels-last memory (NDHWC / NHWC), conv filters are logical
+(Cout, Cin, *k) tensors in channels-last memory ([Cout][taps][Cin]) -- exactly the layouts the
+kernels consume, so no repacking happens on the hot path.
+
+Reference call sites are cited per operator (unet:N = medimgen/diffusion_model_unet_with_strides.py:N,
+ae:N = medimgen/autoencoderkl_with_strides.py:N).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import BF16, F32, call
+
+_ENGINE = _lib.ENGINE_AUTO
+
+
+def set_engine(engine: int) -> None:
+    """0 = auto (tcgen05 where eligible), 1 = force the SIMT family, 2 = require tcgen05."""
+    global _ENGINE
+    _ENGINE = engine
+
+
+def get_engine() -> int:
+    return _ENGINE
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}: the B200 path computes in float32 or bfloat16")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: tensor is on {t.device}; medical_image_generation_b200 runs on CUDA (sm_100a) "
+                           "only and has no CPU path")
+
+
+_workspaces: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream): kernels on one stream are serialised, so reuse is safe."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _mf(ndim: int):
+    return {4: torch.channels_last, 5: torch.channels_last_3d}.get(ndim, torch.contiguous_format)
+
+
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.is_contiguous(memory_format=_mf(t.ndim)) if t.ndim in (4, 5) else t.is_contiguous()
+
+
+def empty_cl(shape, dtype, device) -> torch.Tensor:
+    return torch.empty(tuple(shape), dtype=dtype, device=device, memory_format=_mf(len(shape)))
+
+
+def _sp3(spatial: Sequence[int]) -> tuple:
+    s = tuple(int(v) for v in spatial)
+    return (1,) * (3 - len(s)) + s
+
+
+# ----------------------------------------------------------------------------------------------
+# layout / dtype at the module boundary
+# ----------------------------------------------------------------------------------------------
+def _relayout(x: torch.Tensor, dtype: torch.dtype, to_cl: bool) -> torch.Tensor:
+    N, Cc = x.shape[0], x.shape[1]
+    S = x.numel() // max(N * Cc, 1)
+    if to_cl:
+        y = empty_cl(x.shape, dtype, x.device)
+        call("mig_nchw_to_nhwc", _dt(x), _dt(y), _ptr(x), _ptr(y), N, Cc, S, _stream())
+    else:
+        y = torch.empty(x.shape, dtype=dtype, device=x.device)
+        call("mig_nhwc_to_nchw", _dt(x), _dt(y), _ptr(x), _ptr(y), N, Cc, S, _stream())
+    return y
+
+
+class _ToChannelsLast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        ctx.was_cl = _is_cl(x)
+        if ctx.was_cl:
+            if x.dtype == dtype:
+                return x.view_as(x)
+            y = empty_cl(x.shape, dtype, x.device)
+            call("mig_cast", _dt(x), _dt(y), _ptr(x), _ptr(y), x.numel(), _stream())
+            return y
+        return _relayout(x.contiguous(), dtype, True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = as_cl(dy)
+        if ctx.was_cl:
+            if dy.dtype == ctx.src_dtype:
+                return dy, None
+            dx = empty_cl(dy.shape, ctx.src_dtype, dy.device)
+            call("mig_cast", _dt(dy), _dt(dx), _ptr(dy), _ptr(dx), dy.numel(), _stream())
+            return dx, None
+        return _relayout(dy, ctx.src_dtype, False), None
+
+
+class _FromChannelsLast(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        return _relayout(as_cl(x), dtype, False)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _relayout(dy.contiguous(), ctx.src_dtype, True), None
+
+
+def as_cl(x: torch.Tensor) -> torch.Tensor:
+    """Non-differentiable: make sure the memory is channels-last (used on incoming gradients)."""
+    if _is_cl(x):
+        return x
+    return _relayout(x.contiguous(), x.dtype, True)
+
+
+def to_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """(N,C,*sp) any layout/dtype -> channels-last memory in the compute dtype (differentiable)."""
+    _require_cuda(x, "to_channels_last")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    if _is_cl(x) and x.dtype == dtype:
+        return x
+    return _ToChannelsLast.apply(x, dtype)
+
+
+def from_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """channels-last compute tensor -> standard contiguous (N,C,*sp) tensor of `dtype` (differentiable)."""
+    return _FromChannelsLast.apply(x, dtype)
+
+
+# ----------------------------------------------------------------------------------------------
+# filter cache: compute-dtype copy of an fp32 master filter, refreshed when the parameter changes
+# ----------------------------------------------------------------------------------------------
+_filter_cache: dict = {}
+
+
+def _filter_for(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    w = weight.detach()
+    if not _is_cl(w):
+        w = w.contiguous(memory_format=_mf(w.ndim))
+    if w.dtype == dtype:
+        return w
+    key = (weight.data_ptr(), dtype)
+    hit = _filter_cache.get(key)
+    if hit is not None and hit[0] == weight._version and hit[1].shape == w.shape:
+        return hit[1]
+    wk = torch.empty_like(w, dtype=dtype)  # preserves the channels-last strides
+    call("mig_cast", _dt(w), _dt(wk), _ptr(w), _ptr(wk), w.numel(), _stream())
+    _filter_cache[key] = (weight._version, wk)
+    return wk
+
+
+def clear_caches() -> None:
+    _filter_cache.clear()
+    _workspaces.clear()
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution (K1/K2/K3) and linear (1x1x1 conv over rows)
+# ----------------------------------------------------------------------------------------------
+def _geom(N, in_sp, Cin, Cout, ksize, stride, pad):
+    in3, k3, s3 = _sp3(in_sp), _sp3(ksize), _sp3(stride)
+    p3 = (0,) * (3 - len(pad)) + tuple(int(v) for v in pad)
+    out3 = tuple((in3[i] + 2 * p3[i] - k3[i]) // s3[i] + 1 for i in range(3))
+    if min(out3) < 1:
+        raise RuntimeError(f"conv: kernel {k3} with padding {p3} does not fit input {in3}")
+    return _lib.conv_geom(N, in3, out3, Cin, Cout, k3, s3, p3), out3
+
+
+class _ConvFn(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, chan_bias, residual, stride, padding):
+        N, Cin = x.shape[0], x.shape[1]
+        nd = x.ndim - 2
+        Cout = weight.shape[0]
+        if weight.shape[1] != Cin:
+            raise RuntimeError(f"conv: input has {Cin} channels but the filter expects {weight.shape[1]}")
+        geom, out3 = _geom(N, x.shape[2:], Cin, Cout, weight.shape[2:], stride, padding)
+        wk = _filter_for(weight, x.dtype)
+        y = empty_cl((N, Cout, *out3[3 - nd:]), x.dtype, x.device)
+        if residual is not None and residual.shape != y.shape:
+            raise RuntimeError(f"Sizes of tensors must match: residual {tuple(residual.shape)} vs conv output "
+                               f"{tuple(y.shape)}")
+        dt = _dt(x)
+        need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+        ws = _workspace(need, x.device)
+        call("mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias), _ptr(residual),
+             _ptr(y), _ENGINE, _ptr(ws), ws.numel(), _stream())
+        ctx.geom = geom
+        ctx.has = (bias is not None, chan_bias is not None, residual is not None)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        geom = ctx.geom
+        dy = as_cl(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dt = _dt(x)
+        lib = _lib.load()
+        dx = dw = db = dcb = dres = None
+        if ctx.needs_input_grad[0]:
+            wk = _filter_for(weight, x.dtype)
+            dx = torch.empty_like(x)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 1, _ENGINE)
+            ws = _workspace(need, x.device)
+            call("mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
+                 _stream())
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has[0] and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            if want_w:
+                dw = empty_cl(weight.shape, torch.float32, x.device).zero_()
+            if want_b:
+                db = torch.zeros(weight.shape[0], dtype=torch.float32, device=x.device)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
+            ws = _workspace(need, x.device)
+            call("mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ENGINE, _ptr(ws),
+                 ws.numel(), _stream())
+        if ctx.has[1] and ctx.needs_input_grad[3]:
+            N, Cout = dy.shape[0], dy.shape[1]
+            dcb = torch.empty((N, Cout), dtype=torch.float32, device=dy.device)
+            call("mig_chan_bias_bwd", dt, _ptr(dy), _ptr(dcb), N, dy.numel() // (N * Cout), Cout, _stream())
+        if ctx.has[2] and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dw, db, dcb, dres, None, None
+
+
+def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=None):
+    """Conv{2,3}d with fused epilogue: + bias[c] + chan_bias[n,c] (time embedding, unet:691-695)
+    + residual (skip add, unet:701 / ae:204). x, residual: channels-last compute dtype."""
+    _require_cuda(x, "conv_nd")
+    nd = x.ndim - 2
+    s = tuple(stride) if isinstance(stride, (list, tuple)) else (stride,) * nd
+    p = tuple(padding) if isinstance(padding, (list, tuple)) else (padding,) * nd
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    if chan_bias is not None:
+        chan_bias = chan_bias.float().contiguous()
+    if residual is not None and (not _is_cl(residual) or residual.dtype != x.dtype):
+        residual = to_channels_last(residual, x.dtype)
+    return _ConvFn.apply(x, weight, bias, chan_bias, residual, s, p)
+
+
+class _LinearFn(Function):
+    """y[r, o] = sum_i x[r, i] w[o, i] + b[o]  -- a 1x1x1 conv over `rows` voxels (unet:436-438,1832-1834)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        rows, K = x.shape
+        O = weight.shape[0]
+        geom, _ = _geom(1, (1, 1, rows), K, O, (1, 1, 1), (1, 1, 1), (0, 0, 0))
+        wk = weight.detach()
+        if wk.dtype != x.dtype:
+            wk = _filter_for(weight, x.dtype)
+        wk = wk.contiguous()
+        y = torch.empty((rows, O), dtype=x.dtype, device=x.device)
+        dt = _dt(x)
+        need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+        ws = _workspace(need, x.device)
+        call("mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), None, None, _ptr(y), _ENGINE, _ptr(ws),
+             ws.numel(), _stream())
+        ctx.geom = geom
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        geom = ctx.geom
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dt = _dt(x)
+        lib = _lib.load()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wk = weight.detach()
+            if wk.dtype != x.dtype:
+                wk = _filter_for(weight, x.dtype)
+            wk = wk.contiguous()
+            dx = torch.empty_like(x)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 1, _ENGINE)
+            ws = _workspace(need, x.device)
+            call("mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
+                 _stream())
+        want_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or want_b:
+            if ctx.needs_input_grad[1]:
+                dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
+            if want_b:
+                db = torch.zeros(weight.shape[0], dtype=torch.float32, device=x.device)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
+            ws = _workspace(need, x.device)
+            call("mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ENGINE, _ptr(ws),
+                 ws.numel(), _stream())
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear over the last dim; x (..., in) contiguous."""
+    _require_cuda(x, "linear")
+    shp = x.shape
+    y = _LinearFn.apply(x.reshape(-1, shp[-1]).contiguous(), weight, bias)
+    return y.reshape(*shp[:-1], weight.shape[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU), LayerNorm, SiLU
+# ----------------------------------------------------------------------------------------------
+class _GroupNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        N, Cc = x.shape[0], x.shape[1]
+        S = x.numel() // (N * Cc)
+        y = torch.empty_like(x)
+        mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
+        ws = _workspace(need, x.device)
+        call("mig_groupnorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), N, S, Cc,
+             groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.cfg = (groups, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        groups, silu = ctx.cfg
+        dy = as_cl(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        N, Cc = x.shape[0], x.shape[1]
+        S = x.numel() // (N * Cc)
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(beta)
+        need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
+        ws = _workspace(need, x.device)
+        call("mig_groupnorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx),
+             _ptr(dgamma), _ptr(dbeta), N, S, Cc, groups, int(silu), _ptr(ws), ws.numel(), _stream())
+        return dx, dgamma, dbeta, None, None, None
+
+
+def group_norm(x, gamma, beta, groups: int, eps: float, silu: bool = False):
+    """nn.GroupNorm (fp32 statistics) with optional fused SiLU (unet:628-629,648,1932-1933; ae:157,194)."""
+    _require_cuda(x, "group_norm")
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    return _GroupNormFn.apply(x, gamma, beta, int(groups), float(eps), bool(silu))
+
+
+class _LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        rows, Cc = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty_like(mean)
+        call("mig_layernorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, Cc,
+             float(eps), _stream())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dy = dy.contiguous()
+        rows, Cc = x.shape
+        dx = torch.empty_like(x)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        call("mig_layernorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
+             _ptr(dgamma), _ptr(dbeta), rows, Cc, _stream())
+        return dx, dgamma, dbeta, None
+
+
+def layer_norm(x, gamma, beta, eps: float = 1e-5):
+    shp = x.shape
+    return _LayerNormFn.apply(x.reshape(-1, shp[-1]).contiguous(), gamma, beta, float(eps)).reshape(shp)
+
+
+class _SiluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.empty_like(x)
+        call("mig_silu_fwd", _dt(x), _ptr(x), _ptr(y), x.numel(), _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = dy.contiguous() if x.is_contiguous() else as_cl(dy)
+        dx = torch.empty_like(x)
+        call("mig_silu_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(dx), x.numel(), _stream())
+        return dx
+
+
+def silu(x):
+    _require_cuda(x, "silu")
+    if not (x.is_contiguous() or _is_cl(x)):
+        x = x.contiguous()
+    return _SiluFn.apply(x)
+
+
+class _AddFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        y = torch.empty_like(a)
+        call("mig_add", _dt(a), _ptr(a), _ptr(b), _ptr(y), a.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    """Elementwise add of two tensors with identical shape, dtype and memory layout."""
+    if a.shape != b.shape:
+        raise RuntimeError(f"Sizes of tensors must match: {tuple(a.shape)} vs {tuple(b.shape)}")
+    if b.dtype != a.dtype:
+        b = b.to(a.dtype)
+    if a.stride() != b.stride():
+        b = as_cl(b) if _is_cl(a) else b.contiguous()
+        if a.stride() != b.stride():
+            a = a.contiguous()
+            b = b.contiguous()
+    return _AddFn.apply(a, b)
+
+
+class _ScaleFn(Function):
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        y = torch.empty_like(x)
+        call("mig_scale", _dt(x), _ptr(x), _ptr(y), float(s), x.numel(), _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous() if not _is_cl(dy) else dy
+        dx = torch.empty_like(dy)
+        call("mig_scale", _dt(dy), _ptr(dy), _ptr(dx), float(ctx.s), dy.numel(), _stream())
+        return dx, None
+
+
+def scale(x, s: float):
+    if not (x.is_contiguous() or _is_cl(x)):
+        x = x.contiguous()
+    return _ScaleFn.apply(x, float(s))
+
+
+class _GegluFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        rows, H2 = x.shape
+        y = torch.empty((rows, H2 // 2), dtype=x.dtype, device=x.device)
+        call("mig_geglu_fwd", _dt(x), _ptr(x), _ptr(y), rows, H2 // 2, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("mig_geglu_bwd", _dt(x), _ptr(x), _ptr(dy.contiguous()), _ptr(dx), x.shape[0], x.shape[1] // 2, _stream())
+        return dx
+
+
+def geglu(x):
+    """x[..., :H] * gelu(x[..., H:]) (monai MLPBlock act="GEGLU", unet:213)."""
+    shp = x.shape
+    return _GegluFn.apply(x.reshape(-1, shp[-1]).contiguous()).reshape(*shp[:-1], shp[-1] // 2)
+
+
+# ----------------------------------------------------------------------------------------------
+# concat / upsample
+# ----------------------------------------------------------------------------------------------
+class _CatFn(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        N, Ca, Cb = a.shape[0], a.shape[1], b.shape[1]
+        y = empty_cl((N, Ca + Cb, *a.shape[2:]), a.dtype, a.device)
+        rows = a.numel() // Ca
+        call("mig_concat_channels", _dt(a), _ptr(a), _ptr(b), _ptr(y), rows, Ca, Cb, _stream())
+        ctx.split = (Ca, Cb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Ca, Cb = ctx.split
+        dy = as_cl(dy)
+        N = dy.shape[0]
+        da = empty_cl((N, Ca, *dy.shape[2:]), dy.dtype, dy.device)
+        db = empty_cl((N, Cb, *dy.shape[2:]), dy.dtype, dy.device)
+        call("mig_split_channels", _dt(dy), _ptr(dy), _ptr(da), _ptr(db), dy.numel() // (Ca + Cb), Ca, Cb, _stream())
+        return da, db
+
+
+def cat_channels(a, b):
+    """torch.cat([a, b], dim=1) on channels-last tensors (unet:1263,1377,1504)."""
+    if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {tuple(a.shape)} but got "
+                           f"size {tuple(b.shape)}")
+    if b.dtype != a.dtype:
+        b = b.to(a.dtype)
+    return _CatFn.apply(to_channels_last(a, a.dtype), to_channels_last(b, b.dtype))
+
+
+class _UpsampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, factors):
+        N, Cc = x.shape[0], x.shape[1]
+        nd = x.ndim - 2
+        in3, f3 = _sp3(x.shape[2:]), (1,) * (3 - nd) + tuple(factors)
+        out_sp = tuple(x.shape[2 + i] * factors[i] for i in range(nd))
+        y = empty_cl((N, Cc, *out_sp), x.dtype, x.device)
+        I3 = C.c_int32 * 3
+        call("mig_upsample_nearest_fwd", _dt(x), _ptr(x), _ptr(y), N, I3(*in3), I3(*f3), Cc, _stream())
+        ctx.cfg = (in3, f3, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        in3, f3, shape = ctx.cfg
+        dy = as_cl(dy)
+        dx = empty_cl(shape, dy.dtype, dy.device)
+        I3 = C.c_int32 * 3
+        call("mig_upsample_nearest_bwd", _dt(dy), _ptr(dy), _ptr(dx), shape[0], I3(*in3), I3(*f3), shape[1], _stream())
+        return dx, None
+
+
+def upsample_nearest(x, factors):
+    """F.interpolate(x, scale_factor=factors, mode='nearest') for integer per-axis factors (unet:580, ae:99)."""
+    nd = x.ndim - 2
+    f = tuple(factors) if isinstance(factors, (list, tuple)) else (factors,) * nd
+    fi = tuple(int(v) for v in f)
+    if any(float(a) != float(b) for a, b in zip(f, fi)) or min(fi) < 1:
+        raise RuntimeError(f"upsample_nearest: only positive integer scale factors are supported, got {f}")
+    if all(v == 1 for v in fi):
+        return x
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    return _UpsampleFn.apply(x, fi)
+
+
+# ----------------------------------------------------------------------------------------------
+# attention core: softmax(scale * Q K^T) V with heads inside the channel dim (unet:406-416)
+# ----------------------------------------------------------------------------------------------
+def _gemm(A, B, Cm, M, N, K, bo, bi, a, b, c, alpha=1.0, accumulate=False):
+    d = _lib.GemmDesc()
+    d.M, d.N, d.K, d.batch_outer, d.batch_inner = M, N, K, bo, bi
+    d.a_m, d.a_k, d.a_outer, d.a_inner = a
+    d.b_k, d.b_n, d.b_outer, d.b_inner = b
+    d.c_m, d.c_n, d.c_outer, d.c_inner = c
+    d.alpha, d.accumulate = float(alpha), int(accumulate)
+    call("mig_gemm_strided", C.byref(d), _dt(A), _dt(Cm), _ptr(A), _ptr(B), _ptr(Cm), _ENGINE, _stream())
+
+
+class _SdpaFn(Function):
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale_):
+        B, Lq, Cc = q.shape
+        Lk = k.shape[1]
+        dh = Cc // heads
+        dev = q.device
+        # scores in fp32 (softmax statistics in fp32 as under autocast), probabilities in the compute dtype
+        S = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
+        _gemm(q, k, S, Lq, Lk, dh, B, heads, (Cc, 1, Lq * Cc, dh), (1, Cc, Lk * Cc, dh),
+              (Lk, 1, heads * Lq * Lk, Lq * Lk))
+        P = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
+        call("mig_softmax_fwd", F32, _dt(P), _ptr(S), _ptr(P), B * heads * Lq, Lk, float(scale_), _stream())
+        del S
+        O = torch.empty((B, Lq, Cc), dtype=q.dtype, device=dev)
+        _gemm(P, v, O, Lq, dh, Lk, B, heads, (Lk, 1, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lk * Cc, dh),
+              (Cc, 1, Lq * Cc, dh))
+        ctx.save_for_backward(q, k, v, P)
+        ctx.cfg = (heads, scale_)
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        q, k, v, P = ctx.saved_tensors
+        heads, scale_ = ctx.cfg
+        B, Lq, Cc = q.shape
+        Lk = k.shape[1]
+        dh = Cc // heads
+        dev = q.device
+        dO = dO.contiguous()
+        if dO.dtype != q.dtype:
+            dO = dO.to(q.dtype)
+        sP = (Lk, 1, heads * Lq * Lk, Lq * Lk)
+        # dV[key, d] = sum_q P[q, key] dO[q, d]
+        dV = torch.empty_like(v)
+        _gemm(P, dO, dV, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lq * Cc, dh),
+              (Cc, 1, Lk * Cc, dh))
+        # dP[q, key] = sum_d dO[q, d] V[key, d]
+        dP = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
+        _gemm(dO, v, dP, Lq, Lk, dh, B, heads, (Cc, 1, Lq * Cc, dh), (1, Cc, Lk * Cc, dh), sP)
+        # dS = scale * P * (dP - rowsum(dP * P))   (gradient w.r.t. the UNscaled scores)
+        dS = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
+        if q.dtype == torch.float32:
+            call("mig_softmax_bwd", F32, F32, _ptr(P), _ptr(dP), _ptr(dS), B * heads * Lq, Lk, float(scale_), _stream())
+        else:
+            dS32 = dP  # in place on the fp32 buffer, then narrowed
+            call("mig_softmax_bwd", BF16, F32, _ptr(P), _ptr(dP), _ptr(dS32), B * heads * Lq, Lk, float(scale_),
+                 _stream())
+            call("mig_cast", F32, BF16, _ptr(dS32), _ptr(dS), dS.numel(), _stream())
+        del dP
+        # dQ[q, d] = sum_key dS[q, key] K[key, d] ; dK[key, d] = sum_q dS[q, key] Q[q, d]
+        dQ = torch.empty_like(q)
+        _gemm(dS, k, dQ, Lq, dh, Lk, B, heads, sP, (Cc, 1, Lk * Cc, dh), (Cc, 1, Lq * Cc, dh))
+        dK = torch.empty_like(k)
+        _gemm(dS, q, dK, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lq * Cc, dh),
+              (Cc, 1, Lk * Cc, dh))
+        return dQ, dK, dV, None, None
+
+
+def sdpa(q, k, v, heads: int, scale_: float):
+    """softmax(scale * q k^T) v per head; q (B,Lq,C), k/v (B,Lk,C), heads split the channel dim."""
+    _require_cuda(q, "sdpa")
+    return _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), int(heads), float(scale_))
+
+
+# ----------------------------------------------------------------------------------------------
+# timestep embedding, scheduler, losses
+# ----------------------------------------------------------------------------------------------
+def timestep_embedding(timesteps, dim: int, dtype=torch.float32, max_period: int = 10000):
+    """unet:461-485 (cos first, then sin; odd dims zero-padded). No gradient flows to timesteps."""
+    if timesteps.ndim != 1:
+        raise ValueError("Timesteps should be a 1d-array")
+    _require_cuda(timesteps, "timestep_embedding")
+    t = timesteps.detach().float().contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=dtype, device=t.device)
+    call("mig_timestep_embedding", _ptr(t), _ptr(out), _dt(out), t.shape[0], dim, float(max_period), _stream())
+    return out
+
+
+class _MseFn(Function):
+    @staticmethod
+    def forward(ctx, a, b, l1):
+        out = torch.empty((), dtype=torch.float32, device=a.device)
+        partials = torch.empty(2048, dtype=torch.float32, device=a.device)
+        call("mig_mse_fwd", _dt(a), _ptr(a), _ptr(b), _ptr(out), _ptr(partials), a.numel(), int(l1), _stream())
+        ctx.save_for_backward(a, b)
+        ctx.l1 = l1
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.float().contiguous()
+        da = torch.empty_like(a)
+        call("mig_mse_bwd", _dt(a), _ptr(a), _ptr(b), _ptr(g), _ptr(da), a.numel(), int(ctx.l1), _stream())
+        return da, None, None
+
+
+def _pair(a, b):
+    if a.shape != b.shape:
+        raise RuntimeError(f"loss: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+    if a.dtype not in (torch.float32, torch.bfloat16):
+        a = a.float()
+    b = b.to(a.dtype)
+    if a.stride() != b.stride() or not (a.is_contiguous() or _is_cl(a)):
+        a, b = a.contiguous(), b.contiguous()
+    return a, b
+
+
+def mse_loss(pred, target):
+    """F.mse_loss(pred.float(), target.float()) (ldm:169): mean reduction, fp32 scalar. Grad flows to pred."""
+    a, b = _pair(pred, target.detach())
+    return _MseFn.apply(a, b, False)
+
+
+def l1_loss(pred, target):
+    """L1Loss()(pred.float(), target.float()) (aetrain:414)."""
+    a, b = _pair(pred, target.detach())
+    return _MseFn.apply(a, b, True)
+
+
+class _KlFn(Function):
+    @staticmethod
+    def forward(ctx, mu, sigma):
+        out = torch.empty((), dtype=torch.float32, device=mu.device)
+        partials = torch.empty(2048, dtype=torch.float32, device=mu.device)
+        call("mig_kl_fwd", _dt(mu), _ptr(mu), _ptr(sigma), _ptr(out), _ptr(partials), mu.numel(), mu.shape[0], _stream())
+        ctx.save_for_backward(mu, sigma)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        mu, sigma = ctx.saved_tensors
+        g = g.float().contiguous()
+        dmu, dsig = torch.empty_like(mu), torch.empty_like(sigma)
+        call("mig_kl_bwd", _dt(mu), _ptr(mu), _ptr(sigma), _ptr(g), _ptr(dmu), _ptr(dsig), mu.numel(), mu.shape[0],
+             _stream())
+        return dmu, dsig
+
+
+def kl_loss(z_mu, z_sigma):
+    """0.5*sum(mu^2 + sigma^2 - log(sigma^2) - 1) over non-batch dims, mean over batch (aetrain:67-72)."""
+    a, b = _pair(z_mu, z_sigma)
+    if not b.requires_grad and z_sigma.requires_grad:
+        b = z_sigma.contiguous()
+    return _KlFn.apply(a, b)
+
+
+class _VaeSigmaFn(Function):
+    """sigma = exp(clamp(logvar, -30, 20) / 2)  (ae:766-769); gradient is zero outside the clamp."""
+
+    @staticmethod
+    def forward(ctx, logvar):
+        sigma = torch.empty_like(logvar)
+        call("mig_vae_sample_fwd", _dt(logvar), None, _ptr(logvar), None, _ptr(sigma), None, logvar.numel(), _stream())
+        ctx.save_for_backward(logvar, sigma)
+        return sigma
+
+    @staticmethod
+    def backward(ctx, dsigma):
+        logvar, sigma = ctx.saved_tensors
+        if dsigma.stride() != sigma.stride():
+            dsigma = as_cl(dsigma) if _is_cl(sigma) else dsigma.contiguous()
+        if dsigma.dtype != sigma.dtype:
+            dsigma = dsigma.to(sigma.dtype)
+        dlv = torch.empty_like(sigma)
+        call("mig_vae_sample_bwd", _dt(sigma), _ptr(logvar), None, _ptr(sigma), None, _ptr(dsigma), None, _ptr(dlv),
+             sigma.numel(), _stream())
+        return dlv
+
+
+def vae_sigma(logvar):
+    if not (logvar.is_contiguous() or _is_cl(logvar)):
+        logvar = logvar.contiguous()
+    return _VaeSigmaFn.apply(logvar)
+
+
+class _ReparamFn(Function):
+    """z = mu + eps * sigma (ae:786-787)."""
+
+    @staticmethod
+    def forward(ctx, mu, sigma, eps):
+        z = torch.empty_like(mu)
+        call("mig_addcmul", _dt(mu), _ptr(mu), _ptr(eps), _ptr(sigma), _ptr(z), mu.numel(), _stream())
+        ctx.save_for_backward(eps)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        (eps,) = ctx.saved_tensors
+        if dz.stride() != eps.stride():
+            dz = as_cl(dz) if _is_cl(eps) else dz.contiguous()
+        if dz.dtype != eps.dtype:
+            dz = dz.to(eps.dtype)
+        dsigma = torch.empty_like(eps)
+        call("mig_mul", _dt(eps), _ptr(dz), _ptr(eps), _ptr(dsigma), eps.numel(), _stream())
+        return dz, dsigma, None
+
+
+def vae_reparam(mu, sigma, eps):
+    eps = eps.to(mu.dtype)
+    if not (mu.stride() == sigma.stride() == eps.stride()) or not (mu.is_contiguous() or _is_cl(mu)):
+        mu, sigma, eps = mu.contiguous(), sigma.contiguous(), eps.contiguous()
+    return _ReparamFn.apply(mu, sigma, eps)

@@ -1,0 +1,464 @@
+"""B200-native drop-in for medimgen's strided `DiffusionModelUNet`.
+
+Same constructor, `forward(x, timesteps, context, class_labels, ...)` signature, error behaviour and
+`state_dict` layout as medimgen/diffusion_model_unet_with_strides.py (`unet:N` below), so reference
+checkpoints (`ckpt['network_state_dict']`) and the training scripts drop in unchanged. The compute is
+entirely different: activations live in channels-last bf16 (or fp32) memory and every operator is a
+hand-written sm_100a kernel behind the C ABI (see ops.py); GroupNorm+SiLU, the time-embedding add and
+the residual add are fused around the implicit-GEMM convolutions.
+
+Reference quirks kept on purpose: `proj_attn` exists but is never applied; zero-
+initialised conv2 / proj_out / out conv; the middle block always has attention with
+`num_head_channels[-1]`; Upsample uses a fixed 3^n kernel with the LEVEL's padding.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+from torch import nn
+
+from . import ops
+from .layers import (ConvBlock, GroupNorm, LayerNorm, Linear, SelfAttentionBlock, SiLU, _tup, zero_module)
+
+__all__ = ["DiffusionModelUNet"]
+
+_COMPUTE = (torch.float32, torch.bfloat16)
+
+
+def _entry(x):
+    return ops.to_channels_last(x, x.dtype if x.dtype in _COMPUTE else torch.float32)
+
+
+class CrossAttention(nn.Module):
+    """unet:72-175: q/k/v without bias, output projection with bias (+dropout, identity at p=0 / eval)."""
+
+    def __init__(self, query_dim, cross_attention_dim=None, num_attention_heads=8, num_head_channels=64, dropout=0.0,
+                 upcast_attention=False, use_flash_attention=False):
+        super().__init__()
+        inner = num_head_channels * num_attention_heads
+        cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.scale = 1 / (num_head_channels ** 0.5)
+        self.num_heads = num_attention_heads
+        self.upcast_attention = upcast_attention  # scores are always accumulated and soft-maxed in fp32 here
+        self.use_flash_attention = use_flash_attention
+        self.to_q = Linear(query_dim, inner, bias=False)
+        self.to_k = Linear(cross_attention_dim, inner, bias=False)
+        self.to_v = Linear(cross_attention_dim, inner, bias=False)
+        self.to_out = nn.Sequential(Linear(inner, query_dim), nn.Dropout(dropout))
+
+    def forward(self, x, context=None):
+        ctx = x if context is None else context.to(x.dtype)
+        o = ops.sdpa(self.to_q(x), self.to_k(ctx), self.to_v(ctx), self.num_heads, self.scale)
+        return self.to_out(o)
+
+
+class _GegluMLP(nn.Module):
+    """monai MLPBlock(act="GEGLU") (unet:213): linear1 -> x*gelu(gate) -> linear2."""
+
+    def __init__(self, hidden, mlp_dim, dropout):
+        super().__init__()
+        self.linear1 = Linear(hidden, mlp_dim * 2)
+        self.linear2 = Linear(mlp_dim, hidden)
+        self.drop1 = nn.Dropout(dropout)
+        self.drop2 = nn.Dropout(dropout)
+
+    def forward(self, x):
+        return self.drop2(self.linear2(self.drop1(ops.geglu(self.linear1(x)))))
+
+
+class BasicTransformerBlock(nn.Module):
+    """unet:178-234."""
+
+    def __init__(self, num_channels, num_attention_heads, num_head_channels, dropout=0.0, cross_attention_dim=None,
+                 upcast_attention=False, use_flash_attention=False):
+        super().__init__()
+        kw = dict(num_attention_heads=num_attention_heads, num_head_channels=num_head_channels, dropout=dropout,
+                  upcast_attention=upcast_attention, use_flash_attention=use_flash_attention)
+        self.attn1 = CrossAttention(query_dim=num_channels, **kw)
+        self.ff = _GegluMLP(num_channels, num_channels * 4, dropout)
+        self.attn2 = CrossAttention(query_dim=num_channels, cross_attention_dim=cross_attention_dim, **kw)
+        self.norm1 = LayerNorm(num_channels)
+        self.norm2 = LayerNorm(num_channels)
+        self.norm3 = LayerNorm(num_channels)
+
+    def forward(self, x, context=None):
+        x = ops.add(self.attn1(self.norm1(x)), x)
+        x = ops.add(self.attn2(self.norm2(x), context=context), x)
+        return ops.add(self.ff(self.norm3(x)), x)
+
+
+class SpatialTransformer(nn.Module):
+    """unet:237-342: GN -> 1x1 conv -> transformer blocks over (B, L, C) tokens -> zero-init 1x1 conv + residual."""
+
+    def __init__(self, spatial_dims, in_channels, num_attention_heads, num_head_channels, num_layers=1, dropout=0.0,
+                 norm_num_groups=32, norm_eps=1e-6, cross_attention_dim=None, upcast_attention=False,
+                 use_flash_attention=False):
+        super().__init__()
+        self.spatial_dims, self.in_channels = spatial_dims, in_channels
+        inner = num_attention_heads * num_head_channels
+        self.norm = GroupNorm(norm_num_groups, in_channels, norm_eps)
+        self.proj_in = ConvBlock(spatial_dims, in_channels, inner, strides=1, kernel_size=1, padding=0)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner, num_attention_heads, num_head_channels, dropout, cross_attention_dim,
+                                  upcast_attention, use_flash_attention) for _ in range(num_layers)])
+        self.proj_out = zero_module(ConvBlock(spatial_dims, inner, in_channels, strides=1, kernel_size=1, padding=0))
+
+    def forward(self, x, context=None):
+        x = _entry(x)
+        B = x.shape[0]
+        h = self.proj_in(self.norm(x))
+        inner = h.shape[1]
+        tokens = h.permute(0, *range(2, h.ndim), 1).reshape(B, -1, inner)
+        for blk in self.transformer_blocks:
+            tokens = blk(tokens, context=context)
+        h = tokens.reshape(B, *x.shape[2:], inner).permute(0, x.ndim - 1, *range(1, x.ndim - 1))
+        return self.proj_out(h, residual=x)
+
+
+def get_timestep_embedding(timesteps, embedding_dim: int, max_period: int = 10000):
+    """unet:461-485."""
+    return ops.timestep_embedding(timesteps, embedding_dim, torch.float32, max_period)
+
+
+class Downsample(nn.Module):
+    """unet:488-531: strided conv (use_conv=True) -- the AvgPool variant only exists inside resblock_updown."""
+
+    def __init__(self, spatial_dims, num_channels, use_conv, out_channels=None, stride=2, kernel_size=4, padding=1):
+        super().__init__()
+        self.num_channels = num_channels
+        self.out_channels = out_channels or num_channels
+        self.use_conv = use_conv
+        if use_conv:
+            self.op = ConvBlock(spatial_dims, num_channels, self.out_channels, strides=stride, kernel_size=kernel_size,
+                                padding=padding)
+        else:
+            if self.num_channels != self.out_channels:
+                raise ValueError("num_channels and out_channels must be equal when use_conv=False")
+            raise NotImplementedError("AvgPool down-sampling (resblock_updown=True) is not on the B200 hot path yet")
+
+    def forward(self, x, emb=None):
+        del emb
+        if x.shape[1] != self.num_channels:
+            raise ValueError(f"Input number of channels ({x.shape[1]}) is not equal to expected number of channels "
+                             f"({self.num_channels})")
+        return self.op(_entry(x))
+
+
+class Upsample(nn.Module):
+    """unet:534-588: nearest x stride, then a 3^n conv whose padding is the LEVEL padding (reference defect kept)."""
+
+    def __init__(self, spatial_dims, num_channels, use_conv, out_channels=None, stride=2, padding=1):
+        super().__init__()
+        self.num_channels = num_channels
+        self.out_channels = out_channels or num_channels
+        self.use_conv = use_conv
+        self.stride = stride
+        self.conv = ConvBlock(spatial_dims, num_channels, self.out_channels, strides=1, kernel_size=3,
+                              padding=padding) if use_conv else None
+
+    def forward(self, x, emb=None):
+        del emb
+        if x.shape[1] != self.num_channels:
+            raise ValueError("Input channels should be equal to num_channels")
+        x = ops.upsample_nearest(_entry(x), _tup(self.stride, x.ndim - 2))
+        return self.conv(x) if self.use_conv else x
+
+
+class ResnetBlock(nn.Module):
+    """unet:591-701. GN1+SiLU (one kernel) -> conv1 (+time-embedding add in the epilogue) -> GN2+SiLU ->
+    conv2 (+skip add in the epilogue; the skip is x or a 1x1 conv of x)."""
+
+    def __init__(self, spatial_dims, in_channels, temb_channels, out_channels=None, up=False, down=False,
+                 norm_num_groups=32, norm_eps=1e-6, kernel_size=2, stride=4, padding=1):
+        super().__init__()
+        self.spatial_dims = spatial_dims
+        self.channels = in_channels
+        self.emb_channels = temb_channels
+        self.out_channels = out_channels or in_channels
+        self.up, self.down = up, down
+        if up or down:
+            raise NotImplementedError("resblock_updown=True is not on the B200 hot path yet (SURVEY.md K12)")
+        self.norm1 = GroupNorm(norm_num_groups, in_channels, norm_eps)
+        self.nonlinearity = SiLU()
+        self.conv1 = ConvBlock(spatial_dims, in_channels, self.out_channels, strides=1, kernel_size=3, padding=1)
+        self.upsample = self.downsample = None
+        self.time_emb_proj = Linear(temb_channels, self.out_channels)
+        self.norm2 = GroupNorm(norm_num_groups, self.out_channels, norm_eps)
+        self.conv2 = zero_module(ConvBlock(spatial_dims, self.out_channels, self.out_channels, strides=1,
+                                           kernel_size=3, padding=1))
+        if self.out_channels == in_channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = ConvBlock(spatial_dims, in_channels, self.out_channels, strides=1, kernel_size=1,
+                                             padding=0)
+
+    def forward(self, x, emb):
+        x = _entry(x)
+        h = self.norm1(x, silu=True)
+        # the (B, 4*C0) embedding path stays in fp32: it is tiny and feeds the conv epilogue as an fp32 bias
+        temb = self.time_emb_proj(self.nonlinearity(emb if emb.dtype == torch.float32 else emb.float()))
+        h = self.conv1(h, chan_bias=temb)
+        h = self.norm2(h, silu=True)
+        skip = x if isinstance(self.skip_connection, nn.Identity) else self.skip_connection(x)
+        return self.conv2(h, residual=skip)
+
+
+class _LevelBlock(nn.Module):
+    """Shared body of the eight Down/Up block classes of the reference (unet:704-1513): `resnets`,
+    optional `attentions`, optional `downsampler` / `upsampler`; module names follow the reference."""
+
+    def _make_attention(self, kind, spatial_dims, channels, nhc, G, eps, tl, cad, upcast, flash, drop):
+        if kind == "self":
+            return SelfAttentionBlock(spatial_dims, channels, nhc, G, eps, flash)
+        return SpatialTransformer(spatial_dims, channels, channels // nhc, nhc, tl, drop, G, eps, cad, upcast, flash)
+
+
+class DownBlock(_LevelBlock):
+    def __init__(self, spatial_dims, in_channels, out_channels, temb_channels, num_res_blocks=1, norm_num_groups=32,
+                 norm_eps=1e-6, add_downsample=True, resblock_updown=False, attention=None, num_head_channels=1,
+                 transformer_num_layers=1, cross_attention_dim=None, upcast_attention=False,
+                 use_flash_attention=False, dropout_cattn=0.0, stride=2, kernel_size=4, padding=1):
+        super().__init__()
+        self.resblock_updown = resblock_updown
+        resnets, attentions = [], []
+        for i in range(num_res_blocks):
+            resnets.append(ResnetBlock(spatial_dims, in_channels if i == 0 else out_channels, temb_channels,
+                                       out_channels, norm_num_groups=norm_num_groups, norm_eps=norm_eps))
+            if attention:
+                attentions.append(self._make_attention(attention, spatial_dims, out_channels, num_head_channels,
+                                                       norm_num_groups, norm_eps, transformer_num_layers,
+                                                       cross_attention_dim, upcast_attention, use_flash_attention,
+                                                       dropout_cattn))
+        if attention:
+            self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+        self._cross = attention == "cross"
+        if add_downsample:
+            if resblock_updown:
+                self.downsampler = ResnetBlock(spatial_dims, out_channels, temb_channels, out_channels, down=True,
+                                               norm_num_groups=norm_num_groups, norm_eps=norm_eps, stride=stride,
+                                               kernel_size=kernel_size, padding=padding)
+            else:
+                self.downsampler = Downsample(spatial_dims, out_channels, True, out_channels, stride, kernel_size,
+                                              padding)
+        else:
+            self.downsampler = None
+
+    def forward(self, hidden_states, temb, context=None):
+        outs = []
+        attns = getattr(self, "attentions", None)
+        for i, resnet in enumerate(self.resnets):
+            hidden_states = resnet(hidden_states, temb)
+            if attns is not None:
+                hidden_states = attns[i](hidden_states, context=context) if self._cross else attns[i](hidden_states)
+            outs.append(hidden_states)
+        if self.downsampler is not None:
+            hidden_states = self.downsampler(hidden_states, temb)
+            outs.append(hidden_states)
+        return hidden_states, outs
+
+
+class MidBlock(_LevelBlock):
+    """AttnMidBlock / CrossAttnMidBlock (unet:1038-1173): resnet_1 -> attention -> resnet_2."""
+
+    def __init__(self, spatial_dims, in_channels, temb_channels, norm_num_groups=32, norm_eps=1e-6, attention="self",
+                 num_head_channels=1, transformer_num_layers=1, cross_attention_dim=None, upcast_attention=False,
+                 use_flash_attention=False, dropout_cattn=0.0):
+        super().__init__()
+        self.resnet_1 = ResnetBlock(spatial_dims, in_channels, temb_channels, in_channels,
+                                    norm_num_groups=norm_num_groups, norm_eps=norm_eps)
+        self.attention = self._make_attention(attention, spatial_dims, in_channels, num_head_channels,
+                                              norm_num_groups, norm_eps, transformer_num_layers, cross_attention_dim,
+                                              upcast_attention, use_flash_attention, dropout_cattn)
+        self.resnet_2 = ResnetBlock(spatial_dims, in_channels, temb_channels, in_channels,
+                                    norm_num_groups=norm_num_groups, norm_eps=norm_eps)
+        self._cross = attention == "cross"
+
+    def forward(self, hidden_states, temb, context=None):
+        hidden_states = self.resnet_1(hidden_states, temb)
+        hidden_states = self.attention(hidden_states, context=context) if self._cross else self.attention(hidden_states)
+        return self.resnet_2(hidden_states, temb)
+
+
+class UpBlock(_LevelBlock):
+    def __init__(self, spatial_dims, in_channels, prev_output_channel, out_channels, temb_channels, num_res_blocks=1,
+                 norm_num_groups=32, norm_eps=1e-6, add_upsample=True, resblock_updown=False, attention=None,
+                 num_head_channels=1, transformer_num_layers=1, cross_attention_dim=None, upcast_attention=False,
+                 use_flash_attention=False, dropout_cattn=0.0, stride=2, kernel_size=4, padding=1):
+        super().__init__()
+        self.resblock_updown = resblock_updown
+        resnets, attentions = [], []
+        for i in range(num_res_blocks):
+            skip_ch = in_channels if i == num_res_blocks - 1 else out_channels
+            res_in = prev_output_channel if i == 0 else out_channels
+            resnets.append(ResnetBlock(spatial_dims, res_in + skip_ch, temb_channels, out_channels,
+                                       norm_num_groups=norm_num_groups, norm_eps=norm_eps))
+            if attention:
+                attentions.append(self._make_attention(attention, spatial_dims, out_channels, num_head_channels,
+                                                       norm_num_groups, norm_eps, transformer_num_layers,
+                                                       cross_attention_dim, upcast_attention, use_flash_attention,
+                                                       dropout_cattn))
+        # registration order decides parameter order (optimizer_state_dict indices of reference checkpoints):
+        # AttnUpBlock registers resnets first (unet:1349-1350), CrossAttnUpBlock attentions first (unet:1477-1478)
+        if attention == "cross":
+            self.attentions = nn.ModuleList(attentions)
+        self.resnets = nn.ModuleList(resnets)
+        if attention == "self":
+            self.attentions = nn.ModuleList(attentions)
+        self._cross = attention == "cross"
+        if add_upsample:
+            if resblock_updown:
+                self.upsampler = ResnetBlock(spatial_dims, out_channels, temb_channels, out_channels, up=True,
+                                             norm_num_groups=norm_num_groups, norm_eps=norm_eps, stride=stride,
+                                             kernel_size=kernel_size, padding=padding)
+            else:
+                self.upsampler = Upsample(spatial_dims, out_channels, True, out_channels, stride, padding)
+        else:
+            self.upsampler = None
+
+    def forward(self, hidden_states, res_hidden_states_list, temb, context=None):
+        attns = getattr(self, "attentions", None)
+        res = list(res_hidden_states_list)
+        for i, resnet in enumerate(self.resnets):
+            hidden_states = ops.cat_channels(hidden_states, res.pop())  # unet:1260-1263
+            hidden_states = resnet(hidden_states, temb)
+            if attns is not None:
+                hidden_states = attns[i](hidden_states, context=context) if self._cross else attns[i](hidden_states)
+        if self.upsampler is not None:
+            hidden_states = self.upsampler(hidden_states, temb)
+        return hidden_states
+
+
+class DiffusionModelUNet(nn.Module):
+    """Drop-in for unet:1713-2021. Extra (optional) keyword: `compute_dtype` (torch.bfloat16 default; torch.float32
+    selects the fp32 CUDA-core path used for the 1e-4 parity bar)."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int,
+                 num_res_blocks: Sequence[int] | int = (2, 2, 2, 2), num_channels: Sequence[int] = (32, 64, 64, 64),
+                 attention_levels: Sequence[bool] = (False, False, True, True), norm_num_groups: int = 32,
+                 norm_eps: float = 1e-6, resblock_updown: bool = False, num_head_channels: int | Sequence[int] = 8,
+                 with_conditioning: bool = False, transformer_num_layers: int = 1,
+                 cross_attention_dim: int | None = None, num_class_embeds: int | None = None,
+                 upcast_attention: bool = False, use_flash_attention: bool = False, dropout_cattn: float = 0.0,
+                 strides=((2, 2, 2), (2, 2, 2), (2, 2, 2)), kernel_sizes=((4, 4, 4), (4, 4, 4), (4, 4, 4)),
+                 paddings=(1, 1, 1), compute_dtype: torch.dtype = torch.bfloat16) -> None:
+        super().__init__()
+        # argument validation in the reference's order and wording (unet:1766-1809)
+        if with_conditioning is True and cross_attention_dim is None:
+            raise ValueError("DiffusionModelUNet expects dimension of the cross-attention conditioning "
+                             "(cross_attention_dim) when using with_conditioning.")
+        if cross_attention_dim is not None and with_conditioning is False:
+            raise ValueError("DiffusionModelUNet expects with_conditioning=True when specifying the "
+                             "cross_attention_dim.")
+        if dropout_cattn > 1.0 or dropout_cattn < 0.0:
+            raise ValueError("Dropout cannot be negative or >1.0!")
+        if any((c % norm_num_groups) != 0 for c in num_channels):
+            raise ValueError("DiffusionModelUNet expects all num_channels being multiple of norm_num_groups")
+        if len(num_channels) != len(attention_levels):
+            raise ValueError("DiffusionModelUNet expects num_channels being same size of attention_levels")
+        if isinstance(num_head_channels, int):
+            num_head_channels = (num_head_channels,) * len(attention_levels)
+        if len(num_head_channels) != len(attention_levels):
+            raise ValueError("num_head_channels should have the same length as attention_levels. For the i levels "
+                             "without attention, i.e. `attention_level[i]=False`, the num_head_channels[i] will be "
+                             "ignored.")
+        if isinstance(num_res_blocks, int):
+            num_res_blocks = (num_res_blocks,) * len(num_channels)
+        if len(num_res_blocks) != len(num_channels):
+            raise ValueError("`num_res_blocks` should be a single integer or a tuple of integers with the same length "
+                             "as `num_channels`.")
+        # use_flash_attention: the reference needs xformers + CUDA (unet:1803-1809); here the flag is accepted and
+        # the native attention kernels are always used.
+        self.in_channels = in_channels
+        self.block_out_channels = num_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_levels = attention_levels
+        self.num_head_channels = num_head_channels
+        self.with_conditioning = with_conditioning
+        self.compute_dtype = compute_dtype
+        L = len(num_channels)
+        akind = "cross" if with_conditioning else "self"
+        common = dict(norm_num_groups=norm_num_groups, norm_eps=norm_eps, resblock_updown=resblock_updown,
+                      transformer_num_layers=transformer_num_layers, cross_attention_dim=cross_attention_dim,
+                      upcast_attention=upcast_attention, use_flash_attention=use_flash_attention,
+                      dropout_cattn=dropout_cattn)
+
+        # NB: like the reference, indexing strides[i+1] raises IndexError for too-short defaults (unet:1867)
+        self.conv_in = ConvBlock(spatial_dims, in_channels, num_channels[0], strides=strides[0],
+                                 kernel_size=kernel_sizes[0], padding=paddings[0])
+        time_embed_dim = num_channels[0] * 4
+        self.time_embed = nn.Sequential(Linear(num_channels[0], time_embed_dim), SiLU(),
+                                        Linear(time_embed_dim, time_embed_dim))
+        self.num_class_embeds = num_class_embeds
+        if num_class_embeds is not None:
+            self.class_embedding = nn.Embedding(num_class_embeds, time_embed_dim)
+
+        self.down_blocks = nn.ModuleList([])
+        output_channel = num_channels[0]
+        for i in range(L):
+            input_channel, output_channel = output_channel, num_channels[i]
+            final = i == L - 1
+            self.down_blocks.append(DownBlock(
+                spatial_dims, input_channel, output_channel, time_embed_dim, num_res_blocks=num_res_blocks[i],
+                add_downsample=not final, attention=akind if attention_levels[i] else None,
+                num_head_channels=num_head_channels[i],
+                stride=strides[i + 1] if not final else None, kernel_size=kernel_sizes[i + 1] if not final else None,
+                padding=paddings[i + 1] if not final else None, **common))
+
+        mid_kw = {k: v for k, v in common.items() if k != "resblock_updown"}
+        self.middle_block = MidBlock(spatial_dims, num_channels[-1], time_embed_dim, attention=akind,
+                                     num_head_channels=num_head_channels[-1], **mid_kw)
+
+        self.up_blocks = nn.ModuleList([])
+        rch, rres = list(reversed(num_channels)), list(reversed(num_res_blocks))
+        rattn, rnhc = list(reversed(attention_levels)), list(reversed(num_head_channels))
+        rs, rk, rp = list(reversed(strides)), list(reversed(kernel_sizes)), list(reversed(paddings))
+        output_channel = rch[0]
+        for i in range(L):
+            prev_output_channel, output_channel = output_channel, rch[i]
+            input_channel = rch[min(i + 1, L - 1)]
+            final = i == L - 1
+            self.up_blocks.append(UpBlock(
+                spatial_dims, input_channel, prev_output_channel, output_channel, time_embed_dim,
+                num_res_blocks=rres[i] + 1, add_upsample=not final, attention=akind if rattn[i] else None,
+                num_head_channels=rnhc[i], stride=rs[i] if not final else None,
+                kernel_size=rk[i] if not final else None, padding=rp[i] if not final else None, **common))
+
+        self.out = nn.Sequential(
+            GroupNorm(norm_num_groups, num_channels[0], norm_eps), SiLU(),
+            zero_module(ConvBlock(spatial_dims, num_channels[0], out_channels, strides=1, kernel_size=3, padding=1)))
+
+    def forward(self, x, timesteps, context=None, class_labels=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None):
+        out_dtype = x.dtype if x.dtype.is_floating_point else torch.float32
+        cdt = self.compute_dtype
+        # time embedding path in fp32 (unet:1966-1972 computes the table in fp32, then casts)
+        t_emb = get_timestep_embedding(timesteps, self.block_out_channels[0])
+        emb = self.time_embed[2](self.time_embed[1](self.time_embed[0](t_emb)))
+        if self.num_class_embeds is not None:
+            if class_labels is None:
+                raise ValueError("class_labels should be provided when num_class_embeds > 0")
+            emb = ops.add(emb, self.class_embedding(class_labels).to(emb.dtype))
+        if context is not None and self.with_conditioning is False:
+            raise ValueError("model should have with_conditioning = True if context is provided")
+        if context is not None:
+            context = context.to(cdt).contiguous()
+
+        h = self.conv_in(ops.to_channels_last(x, cdt))
+        skips = [h]
+        for blk in self.down_blocks:
+            h, res = blk(hidden_states=h, temb=emb, context=context)
+            skips.extend(res)
+        if down_block_additional_residuals is not None:
+            skips = [ops.add(s, ops.to_channels_last(r, cdt)) for s, r in zip(skips, down_block_additional_residuals)]
+        h = self.middle_block(hidden_states=h, temb=emb, context=context)
+        if mid_block_additional_residual is not None:
+            h = ops.add(h, ops.to_channels_last(mid_block_additional_residual, cdt))
+        for blk in self.up_blocks:
+            n = len(blk.resnets)
+            res, skips = skips[-n:], skips[:-n]
+            h = blk(hidden_states=h, res_hidden_states_list=res, temb=emb, context=context)
+        h = self.out[2](self.out[0](h, silu=True))
+        return ops.from_channels_last(h, out_dtype)

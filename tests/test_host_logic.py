@@ -1,0 +1,180 @@
+"""CPU-only: C-ABI library loads and exports every declared symbol; module constructors, state_dict layout and
+error behaviour mirror the reference; scheduler integer logic is bit-exact against the oracle restatement."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import medical_image_generation_b200 as mig
+from medical_image_generation_b200 import _lib
+from oracle import ddpm_oracle, torch_oracle as O
+from oracle.golden_util import CASES, golden_params
+
+
+def test_library_exports_every_declared_symbol():
+    assert os.path.exists(_lib.LIB_PATH), "build the extension first: python -m medical_image_generation_b200.build"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/medimgen_b200.h but not exported"
+    assert set(declared) == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.load().mig_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.ConvGeom) == 4 * (1 + 3 + 3 + 2 + 9)
+    assert ctypes.sizeof(_lib.GemmDesc) == 4 * 5 + 4 + 8 * 12 + 8  # 5 ints (+pad), 12 int64, float+int
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_state_dict_layout_matches_reference(golden, name):
+    g = golden(name)
+    cls = mig.DiffusionModelUNet if g["kind"] == "unet" else mig.AutoencoderKL
+    m = cls(**g["cfg"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(g["shapes"].keys())          # same keys, same order
+    for k, shape in g["shapes"].items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    # parameter registration order == reference (optimizer_state_dict indices of reference checkpoints)
+    assert [n for n, _ in m.named_parameters()] == list(g["shapes"].keys())
+    # loading reference-layout tensors (plain contiguous) keeps values and the kernel-friendly filter layout
+    params = golden_params(g["shapes"], g["seed"])
+    m.load_state_dict(params)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, params[k]), k
+    for p in m.parameters():
+        if p.ndim in (4, 5):
+            fmt = torch.channels_last if p.ndim == 4 else torch.channels_last_3d
+            assert p.is_contiguous(memory_format=fmt)
+    # save / load round trip through torch.save like train_ldm.py:472-477
+    import io
+    buf = io.BytesIO()
+    torch.save({"network_state_dict": m.state_dict()}, buf)
+    buf.seek(0)
+    m2 = cls(**g["cfg"])
+    m2.load_state_dict(torch.load(buf)["network_state_dict"])
+    for k, v in m2.state_dict().items():
+        assert torch.equal(v, params[k])
+
+
+def test_zero_init_and_unused_proj_attn():
+    m = mig.DiffusionModelUNet(**CASES["unet3d_small"]["cfg"])
+    sd = m.state_dict()
+    assert float(sd["out.2.conv.weight"].abs().max()) == 0.0
+    assert float(sd["down_blocks.0.resnets.0.conv2.conv.weight"].abs().max()) == 0.0
+    assert float(sd["down_blocks.0.resnets.0.conv1.conv.weight"].abs().max()) > 0.0
+    assert "middle_block.attention.proj_attn.weight" in sd
+
+
+def test_constructor_errors_mirror_reference():
+    U, A = mig.DiffusionModelUNet, mig.AutoencoderKL
+    ok = CASES["unet3d_small"]["cfg"]
+    with pytest.raises(IndexError):   # 3 default strides for 4 default levels (unet:1745-1763 with :1867)
+        U(spatial_dims=3, in_channels=1, out_channels=1)
+    with pytest.raises(IndexError):   # ae:664-667 with ae:413
+        A(spatial_dims=3)
+    with pytest.raises(ValueError, match="cross_attention_dim"):
+        U(**{**ok, "with_conditioning": True})
+    with pytest.raises(ValueError, match="with_conditioning=True"):
+        U(**{**ok, "cross_attention_dim": 8})
+    with pytest.raises(ValueError, match="Dropout"):
+        U(**{**ok, "dropout_cattn": 1.5})
+    with pytest.raises(ValueError, match="multiple of norm_num_groups"):
+        U(**{**ok, "num_channels": [30, 64, 96]})
+    with pytest.raises(ValueError, match="same size of attention_levels"):
+        U(**{**ok, "attention_levels": [False, True]})
+    with pytest.raises(ValueError, match="num_head_channels"):
+        U(**{**ok, "num_head_channels": [0, 64]})
+    with pytest.raises(ValueError, match="num_res_blocks"):
+        U(**{**ok, "num_res_blocks": [2, 2]})
+    with pytest.raises(ZeroDivisionError):  # middle block always uses num_head_channels[-1] (unet:1875-1888)
+        U(**{**ok, "attention_levels": [False, False, False], "num_head_channels": [0, 0, 0]})
+    aok = CASES["ae3d_small"]["cfg"]
+    with pytest.raises(ValueError, match="multiple of norm_num_groups"):
+        A(**{**aok, "num_channels": [16, 30, 64]})
+    with pytest.raises(ValueError, match="same size of attention_levels"):
+        A(**{**aok, "attention_levels": [False]})
+
+
+def test_no_cpu_fallback():
+    m = mig.DiffusionModelUNet(**CASES["unet2d_small"]["cfg"])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.randn(1, 1, 16, 16), torch.tensor([3]))
+    s = mig.DDPMScheduler()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        s.add_noise(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4), torch.tensor([1]))
+
+
+SCHEDS = [dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205),
+          dict(num_train_timesteps=1000, schedule="linear_beta", beta_start=0.0005, beta_end=0.0195),
+          dict(num_train_timesteps=250, schedule="sigmoid_beta"),
+          dict(num_train_timesteps=1000, schedule="linear_beta", variance_type="fixed_large",
+               prediction_type="v_prediction")]
+
+
+@pytest.mark.parametrize("kw", SCHEDS)
+def test_scheduler_tables_and_timesteps_bit_exact_vs_oracle(kw):
+    s, o = mig.DDPMScheduler(**kw), ddpm_oracle.OracleDDPMScheduler(**kw)
+    assert torch.equal(s.betas, o.betas) and torch.equal(s.alphas_cumprod, o.alphas_cumprod)
+    assert torch.equal(s.timesteps, o.timesteps)
+    T = kw["num_train_timesteps"]
+    for n in (T, T // 2, 50, 7, 3, 1):
+        s.set_timesteps(n)
+        o.set_timesteps(n)
+        assert s.timesteps.dtype == torch.int64 and torch.equal(s.timesteps, o.timesteps)
+        assert int(s.timesteps[-1]) == 0 and len(s.timesteps) == n
+    with pytest.raises(ValueError):
+        s.set_timesteps(T + 1)
+
+
+@pytest.mark.parametrize("kw", SCHEDS[:2])
+def test_step_coefficients_match_oracle_posterior(kw):
+    """host-side fp32 scalars == what the oracle's step() uses (checked through a scalar 'tensor')."""
+    s, o = mig.DDPMScheduler(**kw), ddpm_oracle.OracleDDPMScheduler(**kw)
+    for t in (0, 1, 2, 499, 998, 999):
+        k = s.step_coefficients(t)
+        x, e, z = torch.tensor([0.3]), torch.tensor([-0.7]), torch.tensor([1.3])
+        prev, x0 = o.step(e, t, x, noise=z)
+        x0_mine = torch.clamp((x - k["sqrt_one_minus_acp"] * e) / k["sqrt_acp"], -1, 1)
+        mine = k["c0"] * x0_mine + k["ct"] * x + k["sigma"] * z
+        assert abs(float(mine - prev)) <= 2e-6 * max(1.0, abs(float(prev))), t
+        assert k["t_prev"] == t - 1
+        if t == 0:
+            assert k["sigma"] == 0.0
+
+
+def test_oracle_scheduler_closed_form_identities():
+    """The oracle is unpinned by the reference (third-party, absent): check it against DDPM identities."""
+    o = ddpm_oracle.OracleDDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015,
+                                        beta_end=0.0205, clip_sample=False)
+    acp = o.alphas_cumprod
+    assert torch.all(acp[1:] < acp[:-1]) and 0 < float(acp[-1]) < float(acp[0]) < 1
+    g = torch.Generator().manual_seed(0)
+    x0, eps = torch.rand(2, 3, 4, 4, 4, generator=g) * 2 - 1, torch.randn(2, 3, 4, 4, 4, generator=g)
+    for t in (0, 10, 500, 999):
+        ts = torch.tensor([t, t])
+        xt = o.add_noise(x0, eps, ts)
+        prev, x0_hat = o.step(eps, t, xt, noise=torch.zeros_like(xt))
+        assert torch.allclose(x0_hat, x0, atol=2e-3 if t > 900 else 1e-4)       # true eps recovers x0
+        v = o.get_velocity(x0, eps, ts)
+        a, b = acp[t] ** 0.5, (1 - acp[t]) ** 0.5
+        assert torch.allclose(a * xt - b * v, x0, atol=1e-5)                     # v-parameterisation identity
+        if t == 0:
+            assert torch.allclose(prev, x0, atol=1e-4)                            # posterior mean at t=0 is x0
+        else:  # posterior mean of q(x_{t-1}|x_t,x_0) equals sqrt(acp_prev) x0 + sqrt(1-acp_prev-var) * eps direction
+            want_mean = (acp[t - 1] ** 0.5 * o.betas[t] / (1 - acp[t])) * x0 + \
+                        (o.alphas[t] ** 0.5 * (1 - acp[t - 1]) / (1 - acp[t])) * xt
+            assert torch.allclose(prev, want_mean, atol=1e-5)
+
+
+def test_planner_shapes_for_baseline_configs():
+    """The benchmark shapes come from the reference's planner (configuration.py:751-902)."""
+    p = O.compute_downsample_parameters([96, 96, 96], 3)
+    assert [q[0] for q in p] == [[1, 1, 1], [2, 2, 2], [2, 2, 2]] and O.compute_output_size([96, 96, 96], p) == [24] * 3
+    p = O.compute_downsample_parameters([160, 160, 128], 3)
+    assert O.compute_output_size([160, 160, 128], p) == [40, 40, 32]
+    p = O.compute_downsample_parameters([32, 32, 16], 3)   # thin axis: kernel 1 / pad 0 (the Upsample defect case)
+    assert p[0][1] == [3, 3, 1] and p[0][2] == [1, 1, 0]

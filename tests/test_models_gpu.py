@@ -1,0 +1,195 @@
+"""GPU: whole-model and per-block parity of the B200 modules against (a) the committed golden vectors produced
+by the UNMODIFIED reference and (b) the CPU oracle run live on the same seeded inputs.
+fp32 path: 1e-4 relative; bf16 path: 2e-2 relative (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from util import BF16_TOL, FP32_TOL, rel_err, tol_for
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _build(g, dtype):
+    import medical_image_generation_b200 as mig
+    from oracle.golden_util import golden_params
+    cls = mig.DiffusionModelUNet if g["kind"] == "unet" else mig.AutoencoderKL
+    m = cls(**g["cfg"], compute_dtype=dtype)
+    params = golden_params(g["shapes"], g["seed"])
+    m.load_state_dict(params)
+    return m.to(DEV).train(), params
+
+
+UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond"]
+AES = ["ae3d_small", "ae3d_attn_aniso", "ae2d_small"]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", UNETS)
+def test_unet_matches_reference_golden(golden, name, dtype):
+    from oracle.golden_util import sketch
+    g = golden(name)
+    m, _ = _build(g, dtype)
+    inp = g["inputs"]
+    x = inp["x"].to(DEV).requires_grad_(True)
+    kw = {}
+    if "context" in inp:
+        kw = dict(context=inp["context"].to(DEV), class_labels=inp["class_labels"].to(DEV))
+    taps = {}
+    hooks = [m.conv_in.register_forward_hook(lambda _m, _i, o: taps.__setitem__("conv_in", o)),
+             m.middle_block.register_forward_hook(lambda _m, _i, o: taps.__setitem__("mid", o)),
+             m.down_blocks[0].resnets[0].register_forward_hook(lambda _m, _i, o: taps.__setitem__("down0_res0", o)),
+             m.up_blocks[0].register_forward_hook(lambda _m, _i, o: taps.__setitem__("up0", o))]
+    y = m(x, inp["timesteps"].to(DEV), **kw)
+    for h in hooks:
+        h.remove()
+    tol = tol_for(dtype)
+    assert y.shape == g["out"].shape and y.dtype == torch.float32
+    for k in ("conv_in", "down0_res0", "mid", "up0"):                    # per-block outputs
+        assert rel_err(taps[k], g["taps"][k]) < tol, k
+    assert rel_err(y, g["out"]) < tol
+    (y * inp["probe"].to(DEV)).sum().backward()
+    gtol = tol * (1 if dtype == torch.float32 else 2.5)   # bf16 activation grads pass through ~40 rounding layers
+    assert rel_err(x.grad, g["grad_x"]) < gtol
+    named = dict(m.named_parameters())
+    for k in g["no_grad_params"]:
+        assert named[k].grad is None, k
+    worst = 0.0
+    for k, sk in g["grad_sketch"].items():
+        assert named[k].grad is not None, k
+        worst = max(worst, rel_err(sketch(named[k].grad), sk, floor=0.1))
+    assert worst < (1e-3 if dtype == torch.float32 else 6e-2), worst
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", AES)
+def test_autoencoder_matches_reference_golden(golden, name, dtype):
+    from medical_image_generation_b200 import ops
+    from oracle.golden_util import sketch
+    g = golden(name)
+    m, _ = _build(g, dtype)
+    inp = g["inputs"]
+    x = inp["x"].to(DEV).requires_grad_(True)
+    z_mu, z_sigma = m.encode(x)
+    z = ops.vae_reparam(z_mu, z_sigma, inp["eps"].to(DEV))   # sampling() with the golden's noise injected (ae:786)
+    recon = m.decode(z)
+    tol = tol_for(dtype)
+    assert rel_err(z_mu, g["z_mu"]) < tol and rel_err(z_sigma, g["z_sigma"]) < tol
+    assert rel_err(recon, g["out"]) < tol
+    kl = ops.kl_loss(z_mu, z_sigma)
+    loss = ops.l1_loss(recon, x.detach()) + 1e-7 * kl          # train_autoencoder.py:412-414
+    assert rel_err(kl, g["kl"]) < tol and rel_err(loss, g["loss"]) < tol
+    loss.backward()
+    gtol = 1e-3 if dtype == torch.float32 else 0.25           # L1's sign() gradient flips on rounding noise
+    assert rel_err(x.grad, g["grad_x"]) < gtol
+    named = dict(m.named_parameters())
+    worst = max(rel_err(sketch(named[k].grad), sk, floor=0.1) for k, sk in g["grad_sketch"].items())
+    assert worst < (2e-3 if dtype == torch.float32 else 0.25), worst
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_per_block_parity_vs_oracle(dtype):
+    """ResnetBlock / AttentionBlock / Downsample / Upsample called directly with NCDHW tensors, like a user of the
+    reference would, against the oracle's block functions."""
+    from medical_image_generation_b200 import unet as U, layers
+    from oracle import torch_oracle as O
+    g = torch.Generator().manual_seed(21)
+    tol = tol_for(dtype)
+
+    def randomise(mod):
+        with torch.no_grad():
+            for p in mod.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * (0.2 if p.ndim > 1 else 0.3) + (1.0 if p.ndim == 1 and p.shape[0] > 0 and False else 0.0))
+        return mod
+
+    x = torch.randn(2, 32, 6, 6, 6, generator=g)
+    emb = torch.randn(2, 64, generator=g)
+    rb = randomise(U.ResnetBlock(3, 32, 64, 48, norm_num_groups=16)).to(DEV)
+    sd = {"blk." + k: v.detach().cpu().contiguous() for k, v in rb.state_dict().items()}
+    want = O.unet_resnet_block(sd, "blk", x, emb, 16, 1e-6)
+    got = rb(x.to(DEV).to(dtype), emb.to(DEV))
+    assert got.shape == want.shape and rel_err(got, want) < tol
+
+    ab = randomise(layers.SelfAttentionBlock(3, 32, 16, norm_num_groups=16)).to(DEV)
+    sd = {"blk." + k: v.detach().cpu().contiguous() for k, v in ab.state_dict().items()}
+    want = O.self_attention_block(sd, "blk", x, 16, 1e-6, 16)
+    assert rel_err(ab(x.to(DEV).to(dtype)), want) < tol
+
+    ds = randomise(U.Downsample(3, 32, True, 32, stride=[2, 2, 1], kernel_size=[3, 3, 3], padding=[1, 1, 1])).to(DEV)
+    sd = {"blk." + k: v.detach().cpu().contiguous() for k, v in ds.state_dict().items()}
+    want = O._conv(sd, "blk.op", x, [2, 2, 1], [1, 1, 1])
+    assert rel_err(ds(x.to(DEV).to(dtype)), want) < tol
+
+    up = randomise(U.Upsample(3, 32, True, 32, stride=[2, 2, 1], padding=[1, 1, 1])).to(DEV)
+    sd = {"blk." + k: v.detach().cpu().contiguous() for k, v in up.state_dict().items()}
+    want = O._conv(sd, "blk.conv", O._nearest_up(x, [2, 2, 1]), 1, [1, 1, 1])
+    got = up(x.to(DEV).to(dtype))
+    assert got.shape == want.shape and rel_err(got, want) < tol
+
+
+def test_upsample_defect_raises_like_reference():
+    """Planner output for a thin axis (kernel 1 / pad 0) breaks the reference U-Net's skip concat with a RuntimeError
+    (SURVEY.md section 0.6); the drop-in must fail the same way, not silently 'fix' it."""
+    import medical_image_generation_b200 as mig
+    from oracle import torch_oracle as O
+    p = O.compute_downsample_parameters([32, 32, 16], 3)
+    m = mig.DiffusionModelUNet(spatial_dims=3, in_channels=2, out_channels=2, num_res_blocks=1,
+                               num_channels=[16, 32, 32], attention_levels=[False, False, True],
+                               num_head_channels=[0, 0, 32], norm_num_groups=16, strides=[q[0] for q in p],
+                               kernel_sizes=[q[1] for q in p], paddings=[q[2] for q in p]).to(DEV)
+    with pytest.raises(RuntimeError, match="[Ss]izes of tensors must match"):
+        m(torch.randn(1, 2, 32, 32, 16, device=DEV), torch.tensor([5], device=DEV))
+
+
+def test_inferer_sampling_loop_matches_oracle(golden):
+    """DiffusionInferer.sample over 8 steps with injected per-step noise == oracle loop over the oracle U-Net."""
+    import medical_image_generation_b200 as mig
+    from oracle import torch_oracle as O
+    from oracle.ddpm_oracle import OracleDDPMScheduler, OracleDiffusionInferer
+    g = golden("unet3d_aniso")
+    m, params = _build(g, torch.float32)
+    m.eval()
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    s, o = mig.DDPMScheduler(**kw), OracleDDPMScheduler(**kw)
+    s.set_timesteps(8); o.set_timesteps(8)
+    assert torch.equal(s.timesteps.cpu(), o.timesteps)
+    gen = torch.Generator().manual_seed(77)
+    x = torch.randn(1, 1, 12, 12, 6, generator=gen)
+    zs = [torch.randn(x.shape, generator=gen) for _ in range(8)]
+    want = OracleDiffusionInferer(o).sample(
+        x, lambda img, timesteps, context=None: O.unet_forward(params, g["cfg"], img, timesteps), o, step_noises=zs)
+    got = mig.DiffusionInferer(s).sample(x.to(DEV), m, s, verbose=False, step_noises=[z.to(DEV) for z in zs])
+    assert rel_err(got, want) < 5e-4
+
+
+def test_train_step_loss_curve_tracks_oracle(golden):
+    """20 AdamW steps of epsilon-prediction training (train_ldm.py:143-183 semantics) on the small 3-D U-Net:
+    fp32 CUDA path vs the oracle driven by torch.optim.AdamW on CPU, same data/noise/timesteps."""
+    import medical_image_generation_b200 as mig
+    from oracle import torch_oracle as O
+    from oracle.ddpm_oracle import OracleDDPMScheduler
+    from oracle.golden_util import golden_params
+    g = golden("unet3d_aniso")
+    m, _ = _build(g, torch.float32)
+    ref_params = {k: v.clone().requires_grad_(True) for k, v in golden_params(g["shapes"], g["seed"]).items()}
+    used = [k for k in ref_params if "proj_attn" not in k]
+    opt_ref = torch.optim.AdamW([ref_params[k] for k in used], lr=1e-4)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    s, o = mig.DDPMScheduler(**kw), OracleDDPMScheduler(**kw)
+    gen = torch.Generator().manual_seed(5)
+    curve, curve_ref = [], []
+    for step in range(20):
+        x0 = torch.randn(2, 1, 12, 12, 6, generator=gen)
+        noise = torch.randn(x0.shape, generator=gen)
+        t = torch.randint(0, 1000, (2,), generator=gen)
+        loss_ref = torch.nn.functional.mse_loss(O.unet_forward(ref_params, g["cfg"], o.add_noise(x0, noise, t), t), noise)
+        opt_ref.zero_grad(); loss_ref.backward()
+        torch.nn.utils.clip_grad_norm_([ref_params[k] for k in used], 1.0); opt_ref.step()
+        pred = m(s.add_noise(x0.to(DEV), noise.to(DEV), t.to(DEV)), t.to(DEV))
+        loss = mig.ops.mse_loss(pred, noise.to(DEV))
+        opt.zero_grad(set_to_none=True); loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0); opt.step()
+        curve.append(float(loss)); curve_ref.append(float(loss_ref))
+    assert max(abs(a - b) / abs(b) for a, b in zip(curve, curve_ref)) < 2e-3, (curve, curve_ref)
+    assert curve[-1] < curve[0]

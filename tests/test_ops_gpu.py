@@ -1,0 +1,346 @@
+"""GPU: every C-ABI operator against a plain PyTorch fp32 CPU reference of the same op.
+fp32 path within 1e-4 relative error, bf16 path within 2e-2 (tolerances from BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import BF16_TOL, FP32_TOL, bf16_round, rel_err, tol_for
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from medical_image_generation_b200 import ops
+    return ops
+
+
+def _cl(t):
+    return t.contiguous(memory_format=torch.channels_last_3d if t.ndim == 5 else torch.channels_last)
+
+
+# (N, Cin, Cout, spatial, kernel, stride, pad)
+CONV_CASES = [
+    (2, 16, 32, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (1, 64, 64, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 32, 32, (9, 8, 7), (3, 3, 3), (2, 2, 2), (1, 1, 1)),      # strided Downsample, odd sizes
+    (1, 16, 24, (12, 12, 6), (3, 3, 1), (2, 2, 1), (1, 1, 0)),    # anisotropic kernel/stride/pad
+    (2, 3, 32, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # conv_in: 3 channels (SIMT only)
+    (2, 32, 3, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # out conv: 3 output channels
+    (2, 48, 96, (5, 5, 5), (1, 1, 1), (1, 1, 1), (0, 0, 0)),      # 1x1x1 skip conv
+    (1, 128, 256, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # wide: BN=256 tile, K=3456
+    (3, 8, 8, (10, 10), (3, 3), (1, 1), (1, 1)),                  # 2-D
+    (1, 1, 16, (16, 16), (3, 3), (1, 1), (1, 1)),                 # 2-D, single input channel
+    (1, 24, 40, (7, 7, 7), (3, 3, 3), (1, 1, 1), (0, 1, 1)),      # Upsample defect geometry: pad 0 with kernel 3
+]
+
+
+def _conv_ref(x, w, b, s, p):
+    return (F.conv3d if x.ndim == 5 else F.conv2d)(x, w, b, stride=s, padding=p)
+
+
+@pytest.mark.parametrize("dtype,engine", [(torch.float32, 1), (torch.bfloat16, 1), (torch.bfloat16, 0)])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_bwd(case, dtype, engine):
+    ops = _ops()
+    N, Cin, Cout, sp, k, s, p = case
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = torch.randn((N, Cin, *sp), generator=g)
+    w = torch.randn((Cout, Cin, *k), generator=g) / math.sqrt(Cin * math.prod(k))
+    b = torch.randn(Cout, generator=g) * 0.1
+    cb = torch.randn((N, Cout), generator=g) * 0.1
+    if dtype == torch.bfloat16:  # the reference sees the same rounded operands
+        x, w = bf16_round(x), bf16_round(w)
+    xr, wr, br, cbr = (t.clone().requires_grad_(True) for t in (x, w, b, cb))
+    y_ref = _conv_ref(xr, wr, br, s, p)
+    res = torch.randn(y_ref.shape, generator=g)
+    if dtype == torch.bfloat16:
+        res = bf16_round(res)
+    resr = res.clone().requires_grad_(True)
+    y_ref = y_ref + cbr.reshape(N, Cout, *([1] * len(sp))) + resr
+    probe = torch.randn(y_ref.shape, generator=g)
+    (y_ref * probe).sum().backward()
+
+    ops.set_engine(engine)
+    try:
+        xd = _cl(x.to(DEV).to(dtype)).requires_grad_(True)
+        wd = _cl(w.to(DEV)).requires_grad_(True)
+        bd = b.to(DEV).requires_grad_(True)
+        cbd = cb.to(DEV).requires_grad_(True)
+        resd = _cl(res.to(DEV).to(dtype)).requires_grad_(True)
+        y = ops.conv_nd(xd, wd, bd, s, p, chan_bias=cbd, residual=resd)
+        assert y.shape == y_ref.shape and y.dtype == dtype
+        (y.float() * probe.to(DEV)).sum().backward()
+    finally:
+        ops.set_engine(0)
+    tol = tol_for(dtype)
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(xd.grad, xr.grad) < tol
+    assert rel_err(wd.grad, wr.grad) < tol
+    assert rel_err(bd.grad, br.grad) < tol
+    assert rel_err(cbd.grad, cbr.grad) < tol
+    assert rel_err(resd.grad, resr.grad) < tol
+    assert wd.grad.dtype == torch.float32
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,K,O,bias", [(5, 32, 48, True), (300, 64, 64, True), (7, 24, 16, False),
+                                            (1000, 256, 512, True), (2, 1024, 768, True)])
+def test_linear(rows, K, O, bias, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows)
+    x, w = torch.randn(rows, K, generator=g), torch.randn(O, K, generator=g) / math.sqrt(K)
+    b = torch.randn(O, generator=g) * 0.1 if bias else None
+    if dtype == torch.bfloat16:
+        x, w = bf16_round(x), bf16_round(w)
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if bias else None
+    y_ref = F.linear(xr, wr, br)
+    probe = torch.randn(y_ref.shape, generator=g)
+    (y_ref * probe).sum().backward()
+    xd, wd = x.to(DEV).to(dtype).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True) if bias else None
+    y = ops.linear(xd, wd, bd)
+    (y.float() * probe.to(DEV)).sum().backward()
+    tol = tol_for(dtype)
+    assert rel_err(y, y_ref) < tol and rel_err(xd.grad, xr.grad) < tol and rel_err(wd.grad, wr.grad) < tol
+    if bias:
+        assert rel_err(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("silu", [False, True])
+@pytest.mark.parametrize("N,C,G,sp", [(2, 32, 16, (6, 6, 6)), (1, 256, 32, (5, 4, 3)), (2, 16, 16, (9, 9)),
+                                      (1, 1536, 32, (3, 3, 3)), (2, 64, 8, (17, 5, 3)), (1, 32, 32, (24, 24, 24))])
+def test_group_norm(N, C, G, sp, silu, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + G)
+    x = torch.randn((N, C, *sp), generator=g) * 2 + 0.5
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    xr, gr, br = (t.clone().requires_grad_(True) for t in (x, gamma, beta))
+    y_ref = F.group_norm(xr, G, gr, br, 1e-6)
+    if silu:
+        y_ref = F.silu(y_ref)
+    probe = torch.randn(y_ref.shape, generator=g)
+    (y_ref * probe).sum().backward()
+    xd = _cl(x.to(DEV).to(dtype)).requires_grad_(True)
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    y = ops.group_norm(xd, gd, bd, G, 1e-6, silu=silu)
+    pd = _cl(probe.to(DEV).to(dtype)) if dtype == torch.bfloat16 else probe.to(DEV)
+    if dtype == torch.bfloat16:  # reference backward must see the same rounded upstream gradient
+        xr.grad = None; gr.grad = None; br.grad = None
+        y2 = F.group_norm(xr, G, gr, br, 1e-6)
+        y2 = F.silu(y2) if silu else y2
+        (y2 * bf16_round(probe)).sum().backward()
+    y.backward(pd.to(dtype))
+    tol = tol_for(dtype)
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(xd.grad, xr.grad) < tol
+    assert rel_err(gd.grad, gr.grad) < tol and rel_err(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Lq,Lk,C,heads", [(2, 64, 64, 32, 1), (1, 216, 216, 96, 1), (2, 27, 27, 64, 4),
+                                              (2, 30, 3, 32, 2), (1, 130, 130, 256, 1)])
+def test_sdpa(B, Lq, Lk, C, heads, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(Lq + C)
+    q, k, v = (torch.randn(B, L, C, generator=g) for L in (Lq, Lk, Lk))
+    if dtype == torch.bfloat16:
+        q, k, v = bf16_round(q), bf16_round(k), bf16_round(v)
+    scale = 1 / math.sqrt(C / heads)
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+
+    def split(t):
+        return t.reshape(B, -1, heads, C // heads).permute(0, 2, 1, 3)
+
+    p = torch.softmax(split(qr) @ split(kr).transpose(-1, -2) * scale, dim=-1)
+    o_ref = (p @ split(vr)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    probe = torch.randn(o_ref.shape, generator=g)
+    (o_ref * probe).sum().backward()
+    qd, kd, vd = (t.to(DEV).to(dtype).requires_grad_(True) for t in (q, k, v))
+    o = ops.sdpa(qd, kd, vd, heads, scale)
+    (o.float() * probe.to(DEV)).sum().backward()
+    tol = tol_for(dtype)
+    assert rel_err(o, o_ref) < tol
+    assert rel_err(qd.grad, qr.grad) < tol * 1.5 and rel_err(kd.grad, kr.grad) < tol * 1.5
+    assert rel_err(vd.grad, vr.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_elementwise_family(dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    tol = tol_for(dtype)
+    x = torch.randn(2, 24, 5, 6, 7, generator=g)
+    x = bf16_round(x) if dtype == torch.bfloat16 else x
+    xd = _cl(x.to(DEV).to(dtype)).requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    # silu
+    y = ops.silu(xd); y.float().sum().backward()
+    F.silu(xr).sum().backward()
+    assert rel_err(y, F.silu(x)) < tol and rel_err(xd.grad, xr.grad) < tol
+    # concat / split
+    a, b = torch.randn(2, 8, 4, 4, 4, generator=g), torch.randn(2, 24, 4, 4, 4, generator=g)
+    ad, bd = _cl(a.to(DEV).to(dtype)).requires_grad_(True), _cl(b.to(DEV).to(dtype)).requires_grad_(True)
+    c = ops.cat_channels(ad, bd)
+    pr = torch.randn(c.shape, generator=g)
+    (c.float() * pr.to(DEV)).sum().backward()
+    assert rel_err(c, torch.cat([a, b], 1)) < tol
+    assert rel_err(ad.grad, pr[:, :8]) < tol and rel_err(bd.grad, pr[:, 8:]) < tol
+    # odd channel counts (scalar path)
+    a3, b5 = torch.randn(1, 3, 4, 4, generator=g), torch.randn(1, 5, 4, 4, generator=g)
+    c2 = ops.cat_channels(_cl(a3.to(DEV).to(dtype)), _cl(b5.to(DEV).to(dtype)))
+    assert rel_err(c2, torch.cat([a3, b5], 1)) < tol
+    # nearest upsample + adjoint
+    for f in [(2, 2, 2), (2, 2, 1), (1, 3, 2)]:
+        u = torch.randn(2, 16, 3, 4, 5, generator=g)
+        ud = _cl(u.to(DEV).to(dtype)).requires_grad_(True)
+        ur = u.clone().requires_grad_(True)
+        yu = ops.upsample_nearest(ud, f)
+        yr = F.interpolate(ur, scale_factor=tuple(float(v) for v in f), mode="nearest")
+        pu = torch.randn(yr.shape, generator=g)
+        (yu.float() * pu.to(DEV)).sum().backward(); (yr * pu).sum().backward()
+        assert yu.shape == yr.shape and rel_err(yu, yr) < tol and rel_err(ud.grad, ur.grad) < tol
+    # layout round trip
+    z = torch.randn(2, 5, 3, 4, 6, generator=g)
+    zc = ops.to_channels_last(z.to(DEV), dtype)
+    assert zc.is_contiguous(memory_format=torch.channels_last_3d) and rel_err(zc, z) < tol
+    back = ops.from_channels_last(zc, torch.float32)
+    assert back.is_contiguous() and rel_err(back, z) < tol
+    # geglu
+    h = torch.randn(7, 2 * 24, generator=g)
+    hd, hr = h.to(DEV).to(dtype).requires_grad_(True), (bf16_round(h) if dtype == torch.bfloat16 else h).clone().requires_grad_(True)
+    yg = ops.geglu(hd); yg.float().sum().backward()
+    a_, g_ = hr.chunk(2, -1); (a_ * F.gelu(g_)).sum().backward()
+    assert rel_err(yg, a_ * F.gelu(g_)) < tol and rel_err(hd.grad, hr.grad) < tol
+    # layer norm
+    ln_x = torch.randn(11, 48, generator=g)
+    gam, bet = 1 + 0.1 * torch.randn(48, generator=g), 0.1 * torch.randn(48, generator=g)
+    lx = (bf16_round(ln_x) if dtype == torch.bfloat16 else ln_x)
+    lr, gr_, br_ = lx.clone().requires_grad_(True), gam.clone().requires_grad_(True), bet.clone().requires_grad_(True)
+    ld, gd_, bd_ = lx.to(DEV).to(dtype).requires_grad_(True), gam.to(DEV).requires_grad_(True), bet.to(DEV).requires_grad_(True)
+    pl = torch.randn(11, 48, generator=g)
+    yl = ops.layer_norm(ld, gd_, bd_, 1e-5); (yl.float() * pl.to(DEV)).sum().backward()
+    yl_ref = F.layer_norm(lr, (48,), gr_, br_, 1e-5); (yl_ref * pl).sum().backward()
+    assert rel_err(yl, yl_ref) < tol and rel_err(ld.grad, lr.grad) < tol * 2
+    assert rel_err(gd_.grad, gr_.grad) < tol * 2 and rel_err(bd_.grad, br_.grad) < tol * 2
+
+
+def test_timestep_embedding_matches_reference_formula():
+    ops = _ops()
+    from oracle import torch_oracle as O
+    for dim in (32, 256, 7):
+        t = torch.tensor([0, 1, 17, 500, 999])
+        got = ops.timestep_embedding(t.to(DEV), dim)
+        assert got.shape == (5, dim)
+        assert float((got.cpu() - O.timestep_embedding(t, dim)).abs().max()) < 2e-4  # sin/cos of args up to 999 rad
+    with pytest.raises(ValueError):
+        ops.timestep_embedding(torch.zeros(2, 2, device=DEV), 8)
+
+
+def test_losses_and_vae_tail():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    for shape in [(2, 3, 7, 5, 3), (1, 1, 33)]:
+        a, b = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+        for l1 in (False, True):
+            ar = a.clone().requires_grad_(True)
+            ref = F.l1_loss(ar, b) if l1 else F.mse_loss(ar, b)
+            (ref * 3.0).backward()
+            ad = a.to(DEV).requires_grad_(True)
+            got = (ops.l1_loss if l1 else ops.mse_loss)(ad, b.to(DEV))
+            (got * 3.0).backward()
+            assert got.dtype == torch.float32 and rel_err(got, ref) < 1e-6 and rel_err(ad.grad, ar.grad) < 1e-6
+    mu, lv = torch.randn(2, 3, 4, 4, 4, generator=g), torch.randn(2, 3, 4, 4, 4, generator=g) * 8
+    lv[0, 0, 0, 0, 0], lv[0, 0, 0, 0, 1] = -40.0, 30.0   # exercise both clamp sides
+    eps = torch.randn(mu.shape, generator=g)
+    mr, lr = mu.clone().requires_grad_(True), lv.clone().requires_grad_(True)
+    sig_r = torch.exp(torch.clamp(lr, -30.0, 20.0) / 2)
+    z_r = mr + eps * sig_r
+    kl_r = 0.5 * torch.sum(mr.pow(2) + sig_r.pow(2) - torch.log(sig_r.pow(2)) - 1, dim=[1, 2, 3, 4])
+    kl_r = torch.sum(kl_r) / kl_r.shape[0]
+    (z_r.sum() + 1e-3 * kl_r).backward()
+    md, ld = mu.to(DEV).requires_grad_(True), lv.to(DEV).requires_grad_(True)
+    sig = ops.vae_sigma(ld)
+    z = ops.vae_reparam(md, sig, eps.to(DEV))
+    kl = ops.kl_loss(md, sig)
+    (z.sum() + 1e-3 * kl).backward()
+    assert rel_err(sig, sig_r) < 1e-6 and rel_err(z, z_r) < 1e-6 and rel_err(kl, kl_r) < 1e-5
+    assert rel_err(md.grad, mr.grad) < 1e-5 and rel_err(ld.grad, lr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_scheduler_kernels_vs_oracle(dtype):
+    import medical_image_generation_b200 as mig
+    from oracle.ddpm_oracle import OracleDDPMScheduler
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    g = torch.Generator().manual_seed(9)
+    for pred in ("epsilon", "v_prediction", "sample"):
+        s, o = mig.DDPMScheduler(prediction_type=pred, **kw), OracleDDPMScheduler(prediction_type=pred, **kw)
+        x0, n = torch.randn(4, 3, 6, 5, 4, generator=g), torch.randn(4, 3, 6, 5, 4, generator=g)
+        ts = torch.tensor([0, 1, 500, 999])
+        if dtype == torch.bfloat16:
+            x0, n = bf16_round(x0), bf16_round(n)
+        got = s.add_noise(x0.to(DEV).to(dtype), n.to(DEV).to(dtype), ts.to(DEV))
+        want = o.add_noise(x0.to(dtype), n.to(dtype), ts)          # oracle in the same dtype, like upstream
+        tol = 1e-6 if dtype == torch.float32 else 8e-3
+        assert rel_err(got, want) < tol
+        assert rel_err(s.get_velocity(x0.to(DEV).to(dtype), n.to(DEV).to(dtype), ts.to(DEV)),
+                       o.get_velocity(x0.to(dtype), n.to(dtype), ts)) < tol
+        for t in (999, 500, 1, 0):
+            e, x, z = (torch.randn(2, 3, 5, 5, 5, generator=g) for _ in range(3))
+            if dtype == torch.bfloat16:
+                e, x, z = bf16_round(e), bf16_round(x), bf16_round(z)
+            prev, x0h = s.step(e.to(DEV).to(dtype), t, x.to(DEV).to(dtype), noise=z.to(DEV).to(dtype))
+            wprev, wx0 = o.step(e, t, x, noise=z)
+            tol2 = 2e-6 if dtype == torch.float32 else 8e-3
+            assert rel_err(prev, wprev) < tol2 and rel_err(x0h, wx0) < tol2, (pred, t)
+    # t == 0 adds no noise; empty batch edge
+    prev, _ = s.step(torch.zeros(1, 1, 4, 4, device=DEV), 0, torch.ones(1, 1, 4, 4, device=DEV))
+    assert torch.isfinite(prev).all()
+
+
+def test_adamw_and_clip_match_torch():
+    import ctypes as C
+    from medical_image_generation_b200 import _lib
+    g = torch.Generator().manual_seed(11)
+    n = 10007
+    p0, grads = torch.randn(n, generator=g), [torch.randn(n, generator=g) * (3.0 if i == 0 else 0.01) for i in range(4)]
+    pr = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([pr], lr=2e-5)
+    p = p0.clone().to(DEV); m = torch.zeros(n, device=DEV); v = torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for step, gr in enumerate(grads, 1):
+        pr.grad = gr.clone()
+        torch.nn.utils.clip_grad_norm_([pr], max_norm=1.0)
+        opt.step()
+        gd = gr.to(DEV)
+        ss = torch.zeros(1, device=DEV)
+        _lib.call("mig_sumsq", C.c_void_p(gd.data_ptr()), C.c_void_p(ss.data_ptr()), n, st)
+        assert rel_err(ss.sqrt(), gr.norm()) < 1e-5
+        _lib.call("mig_adamw_step", C.c_void_p(p.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(m.data_ptr()),
+                  C.c_void_p(v.data_ptr()), n, 2e-5, 0.9, 0.999, 1e-8, 0.01, step, C.c_void_p(ss.data_ptr()), 1.0,
+                  C.c_void_p(shadow.data_ptr()), st)
+        assert rel_err(p, pr.detach()) < 1e-6
+    assert rel_err(shadow, p) < 4e-3
+
+
+def test_errors_are_loud():
+    ops = _ops()
+    x = torch.randn(1, 8, 4, 4, 4, device=DEV)
+    w = torch.randn(4, 6, 3, 3, 3, device=DEV)
+    with pytest.raises(RuntimeError, match="channels"):
+        ops.conv_nd(x, w, None, 1, 1)
+    with pytest.raises(RuntimeError, match="match"):
+        ops.cat_channels(x, torch.randn(1, 8, 4, 4, 3, device=DEV))
+    with pytest.raises(RuntimeError, match="does not fit"):
+        ops.conv_nd(torch.randn(1, 8, 1, 1, 1, device=DEV), torch.randn(4, 8, 3, 3, 3, device=DEV), None, 1, 0)
+    with pytest.raises(TypeError):
+        ops.silu(torch.zeros(4, device=DEV, dtype=torch.float16))
