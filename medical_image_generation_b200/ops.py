@@ -170,18 +170,20 @@ def _filter_for(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
         w = w.contiguous(memory_format=_mf(w.ndim))
     if w.dtype == dtype:
         return w
-    key = (weight.data_ptr(), dtype)
-    hit = _filter_cache.get(key)
-    if hit is not None and hit[0] == weight._version and hit[1].shape == w.shape:
+    # The cache lives ON the parameter object (never keyed by address: freed storage is reused by other
+    # tensors). An entry is valid only for the same storage address AND the same in-place version counter.
+    cache = weight.__dict__.setdefault("_mig_filter_cache", {})
+    stamp = (weight.data_ptr(), weight._version)
+    hit = cache.get(dtype)
+    if hit is not None and hit[0] == stamp and hit[1].shape == w.shape:
         return hit[1]
     wk = torch.empty_like(w, dtype=dtype)  # preserves the channels-last strides
     call("mig_cast", _dt(w), _dt(wk), _ptr(w), _ptr(wk), w.numel(), _stream())
-    _filter_cache[key] = (weight._version, wk)
+    cache[dtype] = (stamp, wk)
     return wk
 
 
 def clear_caches() -> None:
-    _filter_cache.clear()
     _workspaces.clear()
 
 
