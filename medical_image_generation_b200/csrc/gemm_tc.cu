@@ -20,12 +20,14 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tc_host.cuh"
 
 namespace mig {
 
 using namespace tc;
 
 int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream);
+bool tc_wgrad_eligible(const mig_conv_geom* g);  // gemm_tc2.cu
 
 constexpr int TBM = 128;        // UMMA M
 constexpr int TBK = 64;         // K per stage (one 128-byte swizzle row of bf16)
@@ -275,39 +277,6 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 // ---------------------------------------------------------------------------------------------------
 // host: tensor maps
 // ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// up to 4-d bf16 map; dims[0] is the contiguous one; strides in BYTES for dims 1..rank-1
-static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
-  EncodeTiledFn enc = get_encode();
-  MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
-  cuuint64_t gd[5];
-  cuuint64_t gs[4];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
-  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
-  return 0;
-}
-
 static int pick_bn(int cdst) { return cdst > 128 ? 256 : (cdst > 64 ? 128 : (cdst > 32 ? 64 : 32)); }
 
 template <int BN>
@@ -330,7 +299,7 @@ bool tc_conv_eligible(const mig_conv_geom* g, int dtype, int which) {
   if (dtype != MIG_BF16) return false;
   if (which == 0) return g->Cin % 8 == 0;
   if (which == 1) return g->Cout % 8 == 0;
-  return false;  // wgrad: see tc_conv_wgrad (enabled once validated)
+  return tc_wgrad_eligible(g);
 }
 
 static int split_plan(const Gather& q, int bn, int* splits, int* kb_per) {
@@ -420,17 +389,6 @@ int tc_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* d
   MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(tc): workspace too small");
   if (filter_transpose(MIG_BF16, w, ws, g->Cout, T, g->Cin, stream)) return 2;
   return run_conv_tc(q, dy, ws, nullptr, nullptr, nullptr, dx, (uint8_t*)ws + wt_bytes, ws_bytes - wt_bytes, stream);
-}
-
-int tc_conv_wgrad(const mig_conv_geom*, const void*, const void*, float*, void*, int64_t, void*) {
-  set_error("conv_wgrad(tc): not enabled in this build");
-  return 1;
-}
-
-bool tc_gemm_eligible(const mig_gemm_desc*, int, int) { return false; }
-int tc_gemm_strided(const mig_gemm_desc*, int, const void*, const void*, void*, void*) {
-  set_error("gemm(tc): not enabled in this build");
-  return 1;
 }
 
 }  // namespace mig

@@ -1,0 +1,174 @@
+"""Data-parallel training engine for the LDM / DDPM step (train_ldm.py:143-183, train_ddpm.py:183-201 semantics).
+
+B200-first layout of the optimiser state: ONE flat fp32 buffer each for master parameters, gradients, Adam m and v
+and ONE flat bf16 "shadow" of the parameters. Every nn.Parameter becomes a strided view into the master buffer
+(filters keep their channels-last [Cout][taps][Cin] strides), so:
+  * the weight-gradient kernels accumulate straight into the flat gradient buffer (no per-parameter zero/accumulate),
+  * gradient clipping is one sum-of-squares launch, AdamW is one fused launch that also refreshes the bf16 shadow the
+    tensor-core kernels read (no per-step fp32->bf16 filter casts),
+  * gradient buckets for the NCCL all-reduce are contiguous slices -- launched from the backward pass as soon as every
+    gradient of a bucket has been produced, on torch.distributed's communication stream (overlap with backward).
+Parameters that never receive a gradient (`proj_attn`) are placed at the tail of the buffers and are
+skipped by the optimiser exactly like torch.optim.AdamW skips `grad is None`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from ._lib import call
+
+
+def _dist_on() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+class FlatAdamW:
+    """AdamW + global-norm clipping over flat buffers; numerics follow torch.optim.AdamW / clip_grad_norm_."""
+
+    def __init__(self, module: torch.nn.Module, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, max_grad_norm: Optional[float] = 1.0, bucket_mb: float = 64.0,
+                 unused: Iterable[str] = ("proj_attn",)):
+        named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not named:
+            raise ValueError("module has no trainable parameters")
+        dev = named[0][1].device
+        if dev.type != "cuda":
+            raise RuntimeError("FlatAdamW needs the module on a CUDA device")
+        is_unused = lambda n: any(tag in n for tag in unused)  # noqa: E731
+        # backward produces gradients roughly in reverse registration order: lay the buffer out in that order so a
+        # bucket (contiguous slice) completes early and can be reduced while the rest of backward still runs
+        used = [(n, p) for n, p in reversed(named) if not is_unused(n)]
+        tail = [(n, p) for n, p in named if is_unused(n)]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+        self.used_numel = sum(p.numel() for _, p in used)
+        total = self.used_numel + sum(p.numel() for _, p in tail)
+        self.master = torch.empty(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
+        self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.params = []
+        off = 0
+        for n, p in used + tail:
+            k = p.numel()
+            with torch.no_grad():
+                view = self.master[off:off + k].as_strided(p.shape, p.stride())
+                view.copy_(p)
+                p.data = view
+            p.main_grad = self.grad[off:off + k].as_strided(p.shape, p.stride())
+            p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
+            p._mig_slot = (off, k)
+            self.params.append((n, p))
+            off += k
+        call("mig_cast", 0, 1, ops._ptr(self.master), ops._ptr(self.shadow), total, ops._stream())
+        # ---- gradient buckets (contiguous slices of the used region) ----
+        self.buckets = []
+        self._bucket_of = {}
+        if _dist_on():
+            cap = int(bucket_mb * (1 << 20) / 4)
+            start, count, members = 0, 0, []
+            for n, p in used:
+                members.append(p)
+                count += p.numel()
+                if count >= cap:
+                    self.buckets.append(dict(lo=start, hi=start + count, pending=len(members), n=len(members), work=None))
+                    for q in members:
+                        self._bucket_of[id(q)] = len(self.buckets) - 1
+                    start, count, members = start + count, 0, []
+            if members:
+                self.buckets.append(dict(lo=start, hi=start + count, pending=len(members), n=len(members), work=None))
+                for q in members:
+                    self._bucket_of[id(q)] = len(self.buckets) - 1
+            ops.set_grad_ready_hook(self._grad_ready)
+        self._seen = set()
+
+    # called from the backward kernels' wrappers once a parameter's gradient is complete in `main_grad`
+    def _grad_ready(self, p) -> None:
+        b = self._bucket_of.get(id(p))
+        if b is None or id(p) in self._seen:
+            return
+        self._seen.add(id(p))
+        bk = self.buckets[b]
+        bk["pending"] -= 1
+        if bk["pending"] == 0:
+            bk["work"] = dist.all_reduce(self.grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.AVG, async_op=True)
+
+    def zero_grad(self) -> None:
+        self.grad.zero_()
+        self._seen.clear()
+        for bk in self.buckets:
+            bk["pending"], bk["work"] = bk["n"], None
+
+    def finish_grad_sync(self) -> None:
+        """Reduce whatever bucket did not fire during backward (e.g. a parameter unused this step), then wait."""
+        for bk in self.buckets:
+            if bk["work"] is None:
+                bk["work"] = dist.all_reduce(self.grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.AVG, async_op=True)
+        for bk in self.buckets:
+            bk["work"].wait()
+
+    def step(self) -> None:
+        if self.buckets:
+            self.finish_grad_sync()
+        self.step_count += 1
+        st = ops._stream()
+        sumsq_ptr = None
+        max_norm = 0.0
+        if self.max_grad_norm:
+            self.sumsq.zero_()
+            call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), self.used_numel, st)
+            sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
+        call("mig_adamw_step", ops._ptr(self.master), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
+             self.used_numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+             float(self.weight_decay), int(self.step_count), sumsq_ptr, max_norm, ops._ptr(self.shadow), st)
+
+    def grad_norm(self) -> torch.Tensor:
+        """Global gradient norm of the last step() (device scalar; no sync)."""
+        return self.sumsq.sqrt()
+
+    def state_dict(self) -> dict:
+        return dict(step=self.step_count, m=self.m, v=self.v, lr=self.lr)
+
+    def close(self) -> None:
+        ops.set_grad_ready_hook(None)
+
+
+class LDMTrainer:
+    """One optimiser micro-step of train_ldm.LDM.train_one_epoch (train_ldm.py:143-183) on latents already encoded
+    and scaled (the frozen autoencoder's `encode_stage_2_inputs(images) * scale_factor` is run by the caller, under
+    no_grad, exactly as the reference does), data-parallel across the process group when one is initialised."""
+
+    def __init__(self, unet, scheduler, lr: float = 2e-5, grad_clip_max_norm: Optional[float] = 1.0,
+                 weight_decay: float = 1e-2, bucket_mb: float = 64.0):
+        self.unet, self.scheduler = unet, scheduler
+        self.opt = FlatAdamW(unet, lr=lr, weight_decay=weight_decay, max_grad_norm=grad_clip_max_norm,
+                             bucket_mb=bucket_mb)
+        if _dist_on():  # identical replicas: broadcast rank 0's parameters (flat: one collective)
+            dist.broadcast(self.opt.master, src=0)
+            call("mig_cast", 0, 1, ops._ptr(self.opt.master), ops._ptr(self.opt.shadow), self.opt.master.numel(),
+                 ops._stream())
+
+    def step(self, latents_scaled: torch.Tensor, noise: Optional[torch.Tensor] = None,
+             timesteps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        s = self.scheduler
+        x0 = latents_scaled
+        if timesteps is None:  # train_ldm.py:145
+            timesteps = torch.randint(0, s.num_train_timesteps, (x0.shape[0],), device=x0.device).long()
+        if noise is None:      # train_ldm.py:159
+            noise = torch.randn_like(x0)
+        self.opt.zero_grad()
+        noisy = s.add_noise(original_samples=x0, noise=noise, timesteps=timesteps)
+        pred = self.unet(x=noisy, timesteps=timesteps)
+        target = s.get_velocity(x0, noise, timesteps) if s.prediction_type == "v_prediction" else noise
+        loss = ops.mse_loss(pred, target)
+        loss.backward()
+        self.opt.step()
+        return loss
