@@ -47,9 +47,12 @@ class FlatAdamW:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
-        self.used_numel = sum(p.numel() for _, p in used)
-        total = self.used_numel + sum(p.numel() for _, p in tail)
-        self.master = torch.empty(total, dtype=torch.float32, device=dev)
+        # every parameter starts on a 64-element boundary (256 B fp32 / 128 B bf16): TMA and the 16-byte vector paths
+        # need aligned bases. Padding elements stay exactly zero (zero grad, zero master) through AdamW.
+        pad = lambda k: (k + 63) // 64 * 64  # noqa: E731
+        self.used_numel = sum(pad(p.numel()) for _, p in used)
+        total = self.used_numel + sum(pad(p.numel()) for _, p in tail)
+        self.master = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.m = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
         self.v = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
@@ -67,7 +70,7 @@ class FlatAdamW:
             p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
             p._mig_slot = (off, k)
             self.params.append((n, p))
-            off += k
+            off += pad(k)
         call("mig_cast", 0, 1, ops._ptr(self.master), ops._ptr(self.shadow), total, ops._stream())
         # ---- gradient buckets (contiguous slices of the used region) ----
         self.buckets = []
@@ -77,7 +80,7 @@ class FlatAdamW:
             start, count, members = 0, 0, []
             for n, p in used:
                 members.append(p)
-                count += p.numel()
+                count += pad(p.numel())
                 if count >= cap:
                     self.buckets.append(dict(lo=start, hi=start + count, pending=len(members), n=len(members), work=None))
                     for q in members:
@@ -116,6 +119,11 @@ class FlatAdamW:
             bk["work"].wait()
 
     def step(self) -> None:
+        # gradients that arrived through plain autograd (.grad) -- e.g. nn.Embedding -- join the flat buffer here
+        for _, p in self.params:
+            if p.grad is not None:
+                p.main_grad.add_(p.grad)
+                p.grad = None
         if self.buckets:
             self.finish_grad_sync()
         self.step_count += 1

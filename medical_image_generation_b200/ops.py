@@ -161,10 +161,63 @@ def from_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------
 # filter cache: compute-dtype copy of an fp32 master filter, refreshed when the parameter changes
 # ----------------------------------------------------------------------------------------------
-_filter_cache: dict = {}
+_PROFILE = None  # list of (kind, algorithmic flops, (Cin, Cout, out_dims, ksize), start_event, end_event) or None
+
+
+def profile_start() -> None:
+    """bench.py: record CUDA events (on the launching stream) around every conv implicit-GEMM launch."""
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop() -> list:
+    global _PROFILE
+    out, _PROFILE = _PROFILE or [], None
+    return out
+
+
+def _conv_call(kind, geom, name, *args):
+    if _PROFILE is None:
+        return call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call(name, *args)
+    e1.record()
+    od, ks = tuple(geom.out_dims), tuple(geom.ksize)
+    flops = 2.0 * geom.N * od[0] * od[1] * od[2] * geom.Cout * geom.Cin * ks[0] * ks[1] * ks[2]
+    _PROFILE.append((kind, flops, (geom.Cin, geom.Cout, od, ks), e0, e1))
+
+
+_grad_ready_hook = None
+
+
+def set_grad_ready_hook(fn) -> None:
+    """engine.FlatAdamW registers a callback fired when a parameter's gradient is complete in `param.main_grad`."""
+    global _grad_ready_hook
+    _grad_ready_hook = fn
+
+
+def _deliver(param, grad):
+    """Route a parameter gradient: into `param.main_grad` (flat-buffer view owned by engine.FlatAdamW) when present --
+    returning None to autograd -- else hand it to autograd unchanged. `grad=None` means the kernel already accumulated
+    into main_grad."""
+    if param is None:
+        return grad
+    mg = getattr(param, "main_grad", None)
+    if mg is None:
+        return grad
+    if grad is not None:
+        mg.add_(grad)
+    if _grad_ready_hook is not None:
+        _grad_ready_hook(param)
+    return None
 
 
 def _filter_for(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    if dtype == torch.bfloat16:
+        shadow = getattr(weight, "_mig_shadow", None)  # bf16 copy kept current by the fused AdamW kernel
+        if shadow is not None:
+            return shadow
     w = weight.detach()
     if not _is_cl(w):
         w = w.contiguous(memory_format=_mf(w.ndim))
@@ -216,16 +269,18 @@ class _ConvFn(Function):
         dt = _dt(x)
         need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
         ws = _workspace(need, x.device)
-        call("mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias), _ptr(residual),
+        _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias), _ptr(residual),
              _ptr(y), _ENGINE, _ptr(ws), ws.numel(), _stream())
         ctx.geom = geom
         ctx.has = (bias is not None, chan_bias is not None, residual is not None)
+        ctx.bias_ref, ctx.weight_ref = bias, weight  # the Parameter objects (carry main_grad / shadow attributes)
         ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, _ = ctx.saved_tensors
+        weight = ctx.weight_ref
         geom = ctx.geom
         dy = as_cl(dy)
         if dy.dtype != x.dtype:
@@ -238,18 +293,29 @@ class _ConvFn(Function):
             dx = torch.empty_like(x)
             need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 1, _ENGINE)
             ws = _workspace(need, x.device)
-            call("mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
+            _conv_call("dgrad", geom, "mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
                  _stream())
         want_w, want_b = ctx.needs_input_grad[1], ctx.has[0] and ctx.needs_input_grad[2]
         if want_w or want_b:
+            bias = ctx.bias_ref
+            weight = ctx.weight_ref
+            w_main = getattr(weight, "main_grad", None) if want_w else None
+            b_main = getattr(bias, "main_grad", None) if want_b else None
+            dw_buf = db_buf = None
             if want_w:
-                dw = empty_cl(weight.shape, torch.float32, x.device).zero_()
+                dw_buf = w_main if w_main is not None else empty_cl(weight.shape, torch.float32, x.device).zero_()
             if want_b:
-                db = torch.zeros(weight.shape[0], dtype=torch.float32, device=x.device)
+                db_buf = b_main if b_main is not None else torch.zeros(weight.shape[0], dtype=torch.float32,
+                                                                     device=x.device)
             need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
             ws = _workspace(need, x.device)
-            call("mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ENGINE, _ptr(ws),
+            # the kernels ACCUMULATE: straight into the flat gradient buffer when the engine owns the parameter
+            _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw_buf), _ptr(db_buf), _ENGINE, _ptr(ws),
                  ws.numel(), _stream())
+            if want_w:
+                dw = _deliver(weight, None) if w_main is not None else dw_buf
+            if want_b:
+                db = _deliver(bias, None) if b_main is not None else db_buf
         if ctx.has[1] and ctx.needs_input_grad[3]:
             N, Cout = dy.shape[0], dy.shape[1]
             dcb = torch.empty((N, Cout), dtype=torch.float32, device=dy.device)
@@ -291,16 +357,18 @@ class _LinearFn(Function):
         dt = _dt(x)
         need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
         ws = _workspace(need, x.device)
-        call("mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), None, None, _ptr(y), _ENGINE, _ptr(ws),
+        _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), None, None, _ptr(y), _ENGINE, _ptr(ws),
              ws.numel(), _stream())
         ctx.geom = geom
         ctx.has_bias = bias is not None
+        ctx.bias_ref, ctx.weight_ref = bias, weight
         ctx.save_for_backward(x, weight)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
+        x, _ = ctx.saved_tensors
+        weight = ctx.weight_ref
         geom = ctx.geom
         dy = dy.contiguous()
         if dy.dtype != x.dtype:
@@ -316,18 +384,28 @@ class _LinearFn(Function):
             dx = torch.empty_like(x)
             need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 1, _ENGINE)
             ws = _workspace(need, x.device)
-            call("mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
+            _conv_call("dgrad", geom, "mig_conv_dgrad", C.byref(geom), dt, _ptr(dy), _ptr(wk), _ptr(dx), _ENGINE, _ptr(ws), ws.numel(),
                  _stream())
-        want_b = ctx.has_bias and ctx.needs_input_grad[2]
-        if ctx.needs_input_grad[1] or want_b:
-            if ctx.needs_input_grad[1]:
-                dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            bias = ctx.bias_ref
+            w_main = getattr(weight, "main_grad", None) if want_w else None
+            b_main = getattr(bias, "main_grad", None) if want_b else None
+            dw_buf = db_buf = None
+            if want_w:
+                dw_buf = w_main if w_main is not None else torch.zeros(weight.shape, dtype=torch.float32,
+                                                                     device=x.device)
             if want_b:
-                db = torch.zeros(weight.shape[0], dtype=torch.float32, device=x.device)
+                db_buf = b_main if b_main is not None else torch.zeros(weight.shape[0], dtype=torch.float32,
+                                                                     device=x.device)
             need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
             ws = _workspace(need, x.device)
-            call("mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw), _ptr(db), _ENGINE, _ptr(ws),
+            _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw_buf), _ptr(db_buf), _ENGINE, _ptr(ws),
                  ws.numel(), _stream())
+            if want_w:
+                dw = _deliver(weight, None) if w_main is not None else dw_buf
+            if want_b:
+                db = _deliver(bias, None) if b_main is not None else db_buf
         return dx, dw, db
 
 
@@ -356,6 +434,7 @@ class _GroupNormFn(Function):
              groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.cfg = (groups, silu)
+        ctx.refs = (gamma, beta)
         return y
 
     @staticmethod
@@ -374,7 +453,7 @@ class _GroupNormFn(Function):
         ws = _workspace(need, x.device)
         call("mig_groupnorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx),
              _ptr(dgamma), _ptr(dbeta), N, S, Cc, groups, int(silu), _ptr(ws), ws.numel(), _stream())
-        return dx, dgamma, dbeta, None, None, None
+        return dx, _deliver(ctx.refs[0], dgamma), _deliver(ctx.refs[1], dbeta), None, None, None
 
 
 def group_norm(x, gamma, beta, groups: int, eps: float, silu: bool = False):
@@ -395,6 +474,7 @@ class _LayerNormFn(Function):
         call("mig_layernorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), rows, Cc,
              float(eps), _stream())
         ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.refs = (gamma, beta)
         return y
 
     @staticmethod
@@ -407,7 +487,7 @@ class _LayerNormFn(Function):
         dbeta = torch.empty_like(gamma)
         call("mig_layernorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx),
              _ptr(dgamma), _ptr(dbeta), rows, Cc, _stream())
-        return dx, dgamma, dbeta, None
+        return dx, _deliver(ctx.refs[0], dgamma), _deliver(ctx.refs[1], dbeta), None
 
 
 def layer_norm(x, gamma, beta, eps: float = 1e-5):
