@@ -1,0 +1,542 @@
+// tcgen05 engine, part 3: all-TMA implicit-GEMM convolution (stride 1, channel counts that are multiples of 64).
+//
+// The im2col matrix is never gathered by threads. The NDHWC activation tensor is described to the TMA unit as a
+// 5-d tensor (C, W, H, D, N); a GEMM row tile is a BOX of voxels (bw x bh x bd = 64 voxels, two boxes per 128-row
+// UMMA tile) and the K loop walks (filter tap, 64-channel chunk). For tap (tz,ty,tx) the A tile is simply the same
+// box shifted by the tap offset; coordinates that fall outside the tensor are filled with zeros by the TMA unit,
+// which IS the convolution's zero padding (the halo). One elected thread issues 2 (A) + 1 (B, filters) TMA loads
+// per stage, one thread issues the UMMAs, four warps only run the epilogue -- there is no address arithmetic and
+// no load instruction in the main loop at all, and up to STAGES-1 whole stages (~150 KB) are in flight per SM.
+//
+//   conv_tma_kernel   fwd and dgrad (dgrad = same kernel on dY with mirrored taps and the transposed filter)
+//   wgrad_tma_kernel  dW[Cout][tap*Cin] += dY^T * im2col(X): both operands MN-major, voxel reduction walks boxes,
+//                     split across CTAs, fp32 red.global.add into the gradient.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace mig {
+
+using namespace tc;
+
+int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream);
+
+constexpr int TBM = 128, TBK = 64, kThreads = 192, PANEL = 64 * 128;
+__host__ __device__ constexpr int tma_stages(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+struct BoxGeom {
+  int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad) == source extent
+  int bd, bh, bw;        // box (bd*bh*bw == 64)
+  int nbd, nbh, nbw;     // boxes per axis
+  int64_t num_boxes;     // N*nbd*nbh*nbw
+  int ks[3];             // kernel
+  int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: sign +1, off -pad; dgrad: sign -1, off +pad)
+  int sign;
+  int Csrc, Cdst, K;     // K = taps*Csrc
+  int cchunks;           // Csrc / 64
+};
+
+__device__ __forceinline__ void box_origin(const BoxGeom& g, int64_t box, int& n, int& d0, int& h0, int& w0) {
+  int64_t r = box;
+  w0 = (int)(r % g.nbw) * g.bw; r /= g.nbw;
+  h0 = (int)(r % g.nbh) * g.bh; r /= g.nbh;
+  d0 = (int)(r % g.nbd) * g.bd;
+  n = (int)(r / g.nbd);
+}
+
+struct ConvTmaParams {
+  BoxGeom g;
+  const float* bias;
+  const float* chan_bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+  float* partial;
+  int num_kb, kb_per_split;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                               const __grid_constant__ CUtensorMap wmap,
+                                                               ConvTmaParams p) {
+  constexpr int STAGES = tma_stages(BN);
+  constexpr int A_BYTES = TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BoxGeom& g = p.g;
+  const int64_t box0 = (int64_t)blockIdx.x * 2;
+  const int n0 = blockIdx.y * BN;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<(BN < 32 ? 32 : BN)>(smem_u32(&tmem_slot));
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&xmap); tma_prefetch_desc(&wmap); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = tmem_slot;
+
+  if (warp < 4) {
+    // ===================== epilogue =====================
+    const int row = warp * 32 + lane;
+    const int64_t box = box0 + (row >> 6);
+    const int r = row & 63;
+    const bool mok = box < g.num_boxes;
+    int n = 0, d0 = 0, h0 = 0, w0 = 0;
+    if (mok) box_origin(g, box, n, d0, h0, w0);
+    const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
+    const int64_t m = (((int64_t)n * g.D + d0 + ld) * g.H + h0 + lh) * g.W + w0 + lw;
+    mbar_wait(accbar, 0);
+    tcgen05_fence_after();
+    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= g.Cdst) break;
+      float v[16];
+      tmem_ld16(trow + c0, v);
+      if (!mok) continue;
+      const int col0 = n0 + c0;
+      if (p.partial) {
+        float* dst = p.partial + m * g.Cdst + col0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (col0 + e < g.Cdst) atomicAdd(dst + e, v[e]);
+        continue;
+      }
+      const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += p.bias[col0 + e];
+      }
+      if (p.chan_bias) {
+        const float* cb = p.chan_bias + (int64_t)n * g.Cdst + col0;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += cb[e];
+      }
+      __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
+      if (full16) {
+        if (p.residual) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
+          uint4 r0 = rp[0], r1 = rp[1];
+          const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+          const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+        }
+        reinterpret_cast<uint4*>(dst)[0] = o0;
+        reinterpret_cast<uint4*>(dst)[1] = o1;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (col0 + e < g.Cdst) {
+            float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
+            dst[e] = __float2bfloat16_rn(v[e] + rr);
+          }
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(TBM, BN, 0, 0);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(full0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TBK / 16; ++kk)
+          umma_bf16(tmem_acc, make_smem_desc(a_smem + kk * 32, 16, 1024), make_smem_desc(b_smem + kk * 32, 16, 1024),
+                    idesc, (it | kk) ? 1u : 0u);
+        umma_commit(empty0 + 8 * s);
+        if (it == nkb - 1) umma_commit(accbar);
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    // ===================== TMA issuer =====================
+    int bn_[2], bd_[2], bh_[2], bw_[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (box0 + h < g.num_boxes) box_origin(g, box0 + h, bn_[h], bd_[h], bh_[h], bw_[h]);
+      else { bn_[h] = g.N; bd_[h] = bh_[h] = bw_[h] = 0; }   // fully out of bounds -> zero rows
+    }
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+      const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
+      const int kb = kb_begin + it;
+      int tap = kb / g.cchunks;
+      const int c0 = (kb - tap * g.cchunks) * 64;
+      const int t2 = tap % g.ks[2]; tap /= g.ks[2];
+      const int t1 = tap % g.ks[1];
+      const int t0 = tap / g.ks[1];
+      const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
+      mbar_arrive_expect_tx(bar, STAGE_BYTES);
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        tma_load_5d(a_smem + h * PANEL, &xmap, bar, c0, bw_[h] + dx, bh_[h] + dy, bd_[h] + dz, bn_[h]);
+      tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
+  }
+}
+
+// split-K finish (same as gemm_tc.cu's, rows here are plain voxel indices because `partial` is indexed by m)
+__global__ void __launch_bounds__(256) tma_splitk_finish(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                         const float* __restrict__ chan_bias,
+                                                         const __nv_bfloat16* __restrict__ residual,
+                                                         __nv_bfloat16* __restrict__ out, int64_t M, int C, int64_t Mo) {
+  const int64_t total = M * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / C;
+    const int c = (int)(i - m * C);
+    float v = partial[i];
+    if (bias) v += bias[c];
+    if (chan_bias) v += chan_bias[(m / Mo) * C + c];
+    if (residual) v += __bfloat162float(residual[i]);
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wgrad
+// ---------------------------------------------------------------------------------------------------
+struct WgradTmaParams {
+  BoxGeom g;        // rows = conv OUTPUT voxels (dY); source = X; sign +1, off = -pad; Csrc = Cin, Cdst = Cout
+  float* dw;
+  int64_t boxes_per_split;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap dymap,
+                                                                const __grid_constant__ CUtensorMap xmap,
+                                                                WgradTmaParams p) {
+  constexpr int STAGES = tma_stages(BN);
+  constexpr int NPAN = BN / 64;
+  constexpr int A_BYTES = 2 * PANEL, B_BYTES = NPAN * PANEL, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const BoxGeom& g = p.g;
+  const int co0 = blockIdx.x * TBM;
+  const int n0 = blockIdx.y * BN;     // column offset in K = tap*Cin + ci
+  const int64_t bb = (int64_t)blockIdx.z * p.boxes_per_split;
+  const int nst = (int)(min(g.num_boxes, bb + p.boxes_per_split) - bb);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<BN>(smem_u32(&tmem_slot));
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&dymap); tma_prefetch_desc(&xmap); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_acc = tmem_slot;
+
+  if (warp < 4) {
+    mbar_wait(accbar, 0);
+    tcgen05_fence_after();
+    const int co = co0 + warp * 32 + lane;
+    const bool cok = co < g.Cdst && nst > 0;
+    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= g.K) break;
+      float v[16];
+      tmem_ld16(trow + c0, v);
+      if (!cok) continue;
+      float* dst = p.dw + (int64_t)co * g.K + n0 + c0;
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        if (n0 + c0 + e < g.K) atomicAdd(dst + e, v[e]);
+    }
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc(TBM, BN, 1, 1);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(full0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TBK / 16; ++kk)
+          umma_bf16(tmem_acc, make_smem_desc(a_smem + kk * 2048, PANEL, 1024),
+                    make_smem_desc(b_smem + kk * 2048, PANEL, 1024), idesc, (it | kk) ? 1u : 0u);
+        umma_commit(empty0 + 8 * s);
+        if (it == nst - 1) umma_commit(accbar);
+      }
+      __syncwarp();
+    }
+    if (nst <= 0 && lane == 0) mbar_arrive(accbar);
+  } else if (lane == 0) {
+    // per-panel (tap, channel chunk) of the B operand: fixed for the whole kernel
+    int dz[NPAN], dy[NPAN], dx[NPAN], cc[NPAN];
+#pragma unroll
+    for (int q = 0; q < NPAN; ++q) {
+      const int k = n0 + q * 64;
+      int tap = k / g.Csrc;
+      cc[q] = k < g.K ? k - tap * g.Csrc : -1;
+      const int t2 = tap % g.ks[2]; tap /= g.ks[2];
+      const int t1 = tap % g.ks[1];
+      const int t0 = tap / g.ks[1];
+      dz[q] = t0 + g.off[0]; dy[q] = t1 + g.off[1]; dx[q] = t2 + g.off[2];
+    }
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % STAGES;
+      mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+      const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
+      int n, d0, h0, w0;
+      box_origin(g, bb + it, n, d0, h0, w0);
+      mbar_arrive_expect_tx(bar, STAGE_BYTES);
+      tma_load_5d(a_smem, &dymap, bar, co0, w0, h0, d0, n);
+      tma_load_5d(a_smem + PANEL, &dymap, bar, co0 + 64, w0, h0, d0, n);
+#pragma unroll
+      for (int q = 0; q < NPAN; ++q) {
+        // a panel past the end of K is loaded fully out of bounds (n = N) -> zeros, keeps the byte count fixed
+        if (cc[q] >= 0) tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc[q], w0 + dx[q], h0 + dy[q], d0 + dz[q], n);
+        else tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<BN>(tmem_acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------
+static bool pick_box(int D, int H, int W, int* bd, int* bh, int* bw) {
+  // 64 voxels per box, every factor a power of two dividing the extent; prefer wide W (contiguous rows in memory)
+  static const int cand[][3] = {{1, 8, 8}, {2, 4, 8}, {4, 2, 8}, {8, 1, 8}, {1, 4, 16}, {2, 2, 16}, {4, 1, 16},
+                                {4, 4, 4}, {2, 8, 4}, {8, 2, 4}, {1, 16, 4}, {16, 1, 4}, {1, 2, 32}, {2, 1, 32},
+                                {1, 1, 64}, {8, 4, 2}, {4, 8, 2}, {16, 2, 2}, {2, 16, 2}, {8, 8, 1}, {16, 4, 1},
+                                {4, 16, 1}};
+  for (auto& c : cand)
+    if (D % c[0] == 0 && H % c[1] == 0 && W % c[2] == 0) {
+      *bd = c[0]; *bh = c[1]; *bw = c[2];
+      return true;
+    }
+  return false;
+}
+
+// which: 0 fwd, 1 dgrad, 2 wgrad
+bool tma_conv_eligible(const mig_conv_geom* g, int which) {
+  for (int i = 0; i < 3; ++i)
+    if (g->stride[i] != 1) return false;
+  const int csrc = which == 1 ? g->Cout : g->Cin;
+  if (csrc % 64 != 0) return false;
+  if (which == 2 && g->Cout % 8 != 0) return false;
+  if (which != 2 && (which == 0 ? g->Cout : g->Cin) < 8) return false;
+  // rows: fwd -> output extent, dgrad -> input extent, wgrad -> output extent
+  const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
+  int bd, bh, bw;
+  return pick_box(dims[0], dims[1], dims[2], &bd, &bh, &bw);
+}
+
+static int make_act_map(CUtensorMap* m, const void* base, int N, const int32_t dims[3], int C, int bd, int bh, int bw) {
+  // 5-d (C, W, H, D, N) with a 64-channel x box window
+  EncodeTiledFn enc = get_encode();
+  MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gd[5] = {(cuuint64_t)C, (cuuint64_t)dims[2], (cuuint64_t)dims[1], (cuuint64_t)dims[0], (cuuint64_t)N};
+  cuuint64_t gs[4] = {(cuuint64_t)C * 2, (cuuint64_t)dims[2] * C * 2, (cuuint64_t)dims[1] * dims[2] * C * 2,
+                      (cuuint64_t)dims[0] * dims[1] * dims[2] * C * 2};
+  cuuint32_t bx[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(5d activation map) failed with %d", (int)r);
+  return 0;
+}
+
+static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
+  BoxGeom b{};
+  const int32_t* rows = which == 1 ? g->in_dims : g->out_dims;
+  b.N = g->N; b.D = rows[0]; b.H = rows[1]; b.W = rows[2];
+  pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
+  b.nbd = b.D / b.bd; b.nbh = b.H / b.bh; b.nbw = b.W / b.bw;
+  b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
+  int taps = 1;
+  for (int i = 0; i < 3; ++i) {
+    b.ks[i] = g->ksize[i];
+    b.off[i] = which == 1 ? g->pad[i] : -g->pad[i];
+    taps *= g->ksize[i];
+  }
+  b.sign = which == 1 ? -1 : 1;
+  b.Csrc = which == 1 ? g->Cout : g->Cin;
+  b.Cdst = which == 1 ? g->Cin : g->Cout;
+  b.K = taps * b.Csrc;
+  b.cchunks = b.Csrc / 64;
+  return b;
+}
+
+template <int BN>
+static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const ConvTmaParams& p, dim3 grid,
+                           cudaStream_t st) {
+  constexpr int smem = tma_stages(BN) * (TBM * 128 + BN * 128) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MIG_REQUIRE(e == cudaSuccess, "conv_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  conv_tma_kernel<BN><<<grid, kThreads, smem, st>>>(xm, wm, p);
+  return check_launch("conv_tma_kernel");
+}
+
+// src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc]
+static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
+                        const float* chan_bias, const void* residual, void* out, void* ws, int64_t ws_bytes,
+                        void* stream) {
+  BoxGeom b = make_box_geom(g, which);
+  cudaStream_t st = as_stream(stream);
+  const int32_t* sdims = which == 1 ? g->out_dims : g->in_dims;   // extent of the SOURCE tensor (same as rows: stride 1)
+  CUtensorMap xm, wm;
+  if (make_act_map(&xm, src, g->N, sdims, b.Csrc, b.bd, b.bh, b.bw)) return 1;
+  const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
+  uint64_t dims[2] = {(uint64_t)b.K, (uint64_t)b.Cdst};
+  uint64_t strides[1] = {(uint64_t)b.K * 2};
+  uint32_t box[2] = {TBK, (uint32_t)bn};
+  if (make_map(&wm, wk, 2, dims, strides, box)) return 1;
+  ConvTmaParams p{};
+  p.g = b;
+  p.bias = bias; p.chan_bias = chan_bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = (__nv_bfloat16*)out;
+  p.num_kb = b.K / TBK;
+  const int64_t mtiles = (b.num_boxes + 1) / 2, ntiles = (b.Cdst + bn - 1) / bn;
+  const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
+  int splits = 1;
+  const int sms = device_info().sm_count;
+  if (mtiles * ntiles * 2 <= sms) {
+    splits = (int)(sms / (mtiles * ntiles));
+    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1 && (ws == nullptr || ws_bytes < M * b.Cdst * 4)) splits = 1;
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  if (splits > 1) {
+    p.partial = (float*)ws;
+    cudaMemsetAsync(ws, 0, (size_t)(M * b.Cdst * 4), st);
+  }
+  dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
+  int rc;
+  switch (bn) {
+    case 256: rc = launch_conv_tma<256>(xm, wm, p, grid, st); break;
+    case 128: rc = launch_conv_tma<128>(xm, wm, p, grid, st); break;
+    case 64: rc = launch_conv_tma<64>(xm, wm, p, grid, st); break;
+    default: rc = launch_conv_tma<32>(xm, wm, p, grid, st); break;
+  }
+  if (rc) return rc;
+  if (splits > 1) {
+    tma_splitk_finish<<<bw_grid(M * b.Cdst, 256), 256, 0, st>>>((const float*)ws, bias, chan_bias,
+                                                                (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M,
+                                                                b.Cdst, (int64_t)b.D * b.H * b.W);
+    return check_launch("tma_splitk_finish");
+  }
+  return 0;
+}
+
+int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
+                 const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream) {
+  return run_conv_tma(g, 0, x, w, bias, chan_bias, residual, y, ws, ws_bytes, stream);
+}
+
+int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                   void* stream) {
+  const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
+  int64_t wt_bytes = ((int64_t)g->Cin * T * g->Cout * 2 + 255) / 256 * 256;
+  MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(tma): workspace too small");
+  if (filter_transpose(MIG_BF16, w, ws, g->Cout, T, g->Cin, stream)) return 2;
+  return run_conv_tma(g, 1, dy, ws, nullptr, nullptr, nullptr, dx, (uint8_t*)ws + wt_bytes, ws_bytes - wt_bytes, stream);
+}
+
+template <int BN>
+static int launch_wgrad_tma(const CUtensorMap& dym, const CUtensorMap& xm, const WgradTmaParams& p, dim3 grid,
+                            cudaStream_t st) {
+  constexpr int smem = tma_stages(BN) * (2 * PANEL + (BN / 64) * PANEL) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MIG_REQUIRE(e == cudaSuccess, "wgrad_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  wgrad_tma_kernel<BN><<<grid, kThreads, smem, st>>>(dym, xm, p);
+  return check_launch("wgrad_tma_kernel");
+}
+
+int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream) {
+  BoxGeom b = make_box_geom(g, 2);
+  cudaStream_t st = as_stream(stream);
+  CUtensorMap dym, xm;
+  if (make_act_map(&dym, dy, g->N, g->out_dims, g->Cout, b.bd, b.bh, b.bw)) return 1;
+  if (make_act_map(&xm, x, g->N, g->in_dims, g->Cin, b.bd, b.bh, b.bw)) return 1;
+  const int bn = b.K > 128 ? 256 : (b.K > 64 ? 128 : 64);
+  WgradTmaParams p{};
+  p.g = b;
+  p.dw = dw;
+  const int64_t tiles = (int64_t)((g->Cout + TBM - 1) / TBM) * ((b.K + bn - 1) / bn);
+  int64_t splits = ((int64_t)device_info().sm_count * 3 + tiles - 1) / tiles;
+  if (splits > b.num_boxes / 4) splits = b.num_boxes / 4;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  p.boxes_per_split = (b.num_boxes + splits - 1) / splits;
+  splits = (b.num_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
+  dim3 grid((unsigned)((g->Cout + TBM - 1) / TBM), (unsigned)((b.K + bn - 1) / bn), (unsigned)splits);
+  MIG_REQUIRE(grid.y < 65536, "conv_wgrad(tma): filter too large");
+  switch (bn) {
+    case 256: return launch_wgrad_tma<256>(dym, xm, p, grid, st);
+    case 128: return launch_wgrad_tma<128>(dym, xm, p, grid, st);
+    default: return launch_wgrad_tma<64>(dym, xm, p, grid, st);
+  }
+}
+
+}  // namespace mig

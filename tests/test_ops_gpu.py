@@ -35,6 +35,14 @@ CONV_CASES = [
     (3, 8, 8, (10, 10), (3, 3), (1, 1), (1, 1)),                  # 2-D
     (1, 1, 16, (16, 16), (3, 3), (1, 1), (1, 1)),                 # 2-D, single input channel
     (1, 24, 40, (7, 7, 7), (3, 3, 3), (1, 1, 1), (0, 1, 1)),      # Upsample defect geometry: pad 0 with kernel 3
+    # all-TMA kernels (stride 1, Cin/Cout multiples of 64, box-tileable extents)
+    (2, 64, 128, (4, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),     # box 1x8x8
+    (1, 128, 64, (8, 4, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # box 4x4x4, two channel chunks
+    (1, 64, 64, (10, 12, 12), (3, 3, 3), (1, 1, 1), (0, 1, 1)),   # pad 0 on one axis: output smaller than input
+    (3, 64, 64, (8, 8, 8), (1, 1, 1), (1, 1, 1), (0, 0, 0)),      # 1x1x1, odd number of boxes (tile tail)
+    (2, 64, 64, (16, 16), (3, 3), (1, 1), (1, 1)),                # 2-D
+    (1, 192, 320, (4, 4, 8), (3, 3, 1), (1, 1, 1), (1, 1, 0)),    # anisotropic kernel, N tile tail (320 = 256 + 64)
+    (1, 64, 24, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),      # narrow output (BN = 32), dgrad falls back (Cout % 64)
 ]
 
 
