@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     const int row = warp * 32 + lane;
     const int64_t box = box0 + (row >> 6);
     const int r = row & 63;
-    const bool mok = box < g.num_boxes;
+    bool mok = box < g.num_boxes;
     int n = 0, d0 = 0, h0 = 0, w0 = 0;
     if (mok) box_origin(g, box, n, d0, h0, w0);
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
+    mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
     const int64_t m = (((int64_t)n * g.D + d0 + ld) * g.H + h0 + lh) * g.W + w0 + lw;
     mbar_wait(accbar, 0);
     tcgen05_fence_after();
@@ -183,30 +184,30 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       }
       __syncwarp();
     }
-  } else if (lane == 0) {
-    // ===================== TMA issuer =====================
-    int bn_[2], bd_[2], bh_[2], bw_[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (box0 + h < g.num_boxes) box_origin(g, box0 + h, bn_[h], bd_[h], bh_[h], bw_[h]);
-      else { bn_[h] = g.N; bd_[h] = bh_[h] = bw_[h] = 0; }   // fully out of bounds -> zero rows
-    }
+  } else {
+    // ===================== TMA issuers: lanes 0,1 -> the two A boxes, lane 2 -> the filter box =====================
+    int bn_ = g.N, bd_ = 0, bh_ = 0, bw_ = 0;   // default: fully out of bounds -> zero rows (odd tile tail)
+    if (lane < 2 && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
     for (int it = 0; it < nkb; ++it) {
       const int s = it % STAGES;
-      mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
       const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
       const int kb = kb_begin + it;
-      int tap = kb / g.cchunks;
-      const int c0 = (kb - tap * g.cchunks) * 64;
-      const int t2 = tap % g.ks[2]; tap /= g.ks[2];
-      const int t1 = tap % g.ks[1];
-      const int t0 = tap / g.ks[1];
-      const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
-      mbar_arrive_expect_tx(bar, STAGE_BYTES);
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-        tma_load_5d(a_smem + h * PANEL, &xmap, bar, c0, bw_[h] + dx, bh_[h] + dy, bd_[h] + dz, bn_[h]);
-      tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
+      if (lane == 0) {  // one lane polls the barrier; the others park at the warp barrier
+        mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+      }
+      __syncwarp();
+      if (lane < 2) {
+        int tap = kb / g.cchunks;
+        const int c0 = (kb - tap * g.cchunks) * 64;
+        const int t2 = tap % g.ks[2]; tap /= g.ks[2];
+        const int t1 = tap % g.ks[1];
+        const int t0 = tap / g.ks[1];
+        const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
+        tma_load_5d(a_smem + lane * PANEL, &xmap, bar, c0, bw_ + dx, bh_ + dy, bd_ + dz, bn_);
+      } else if (lane == 2) {
+        tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
+      }
     }
   }
   __syncthreads();
@@ -312,33 +313,39 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
       __syncwarp();
     }
     if (nst <= 0 && lane == 0) mbar_arrive(accbar);
-  } else if (lane == 0) {
-    // per-panel (tap, channel chunk) of the B operand: fixed for the whole kernel
-    int dz[NPAN], dy[NPAN], dx[NPAN], cc[NPAN];
-#pragma unroll
-    for (int q = 0; q < NPAN; ++q) {
+  } else {
+    // TMA issuers, one lane per box: lanes 0,1 -> the two dY panels; lanes 2..2+NPAN-1 -> the im2col(X) panels.
+    // Each X panel is one fixed (tap, 64-channel chunk) for the whole kernel.
+    const int q = lane - 2;
+    int dz = 0, dy = 0, dx = 0, cc = -1;
+    if (q >= 0 && q < NPAN) {
       const int k = n0 + q * 64;
       int tap = k / g.Csrc;
-      cc[q] = k < g.K ? k - tap * g.Csrc : -1;
+      cc = k < g.K ? k - tap * g.Csrc : -1;
       const int t2 = tap % g.ks[2]; tap /= g.ks[2];
       const int t1 = tap % g.ks[1];
       const int t0 = tap / g.ks[1];
-      dz[q] = t0 + g.off[0]; dy[q] = t1 + g.off[1]; dx[q] = t2 + g.off[2];
+      dz = t0 + g.off[0]; dy = t1 + g.off[1]; dx = t2 + g.off[2];
     }
     for (int it = 0; it < nst; ++it) {
       const int s = it % STAGES;
-      mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
       const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
-      int n, d0, h0, w0;
-      box_origin(g, bb + it, n, d0, h0, w0);
-      mbar_arrive_expect_tx(bar, STAGE_BYTES);
-      tma_load_5d(a_smem, &dymap, bar, co0, w0, h0, d0, n);
-      tma_load_5d(a_smem + PANEL, &dymap, bar, co0 + 64, w0, h0, d0, n);
-#pragma unroll
-      for (int q = 0; q < NPAN; ++q) {
-        // a panel past the end of K is loaded fully out of bounds (n = N) -> zeros, keeps the byte count fixed
-        if (cc[q] >= 0) tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc[q], w0 + dx[q], h0 + dy[q], d0 + dz[q], n);
-        else tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
+      if (lane == 0) {
+        mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+      }
+      __syncwarp();
+      if (lane < 2 + NPAN) {
+        int n, d0, h0, w0;
+        box_origin(g, bb + it, n, d0, h0, w0);
+        if (lane < 2) {
+          tma_load_5d(a_smem + lane * PANEL, &dymap, bar, co0 + lane * 64, w0, h0, d0, n);
+        } else if (cc >= 0) {
+          tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc, w0 + dx, h0 + dy, d0 + dz, n);
+        } else {
+          // a panel past the end of K is loaded fully out of bounds (n = N) -> zeros, keeps the byte count fixed
+          tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
+        }
       }
     }
   }
@@ -358,12 +365,19 @@ static bool pick_box(int D, int H, int W, int* bd, int* bh, int* bw) {
                                 {4, 4, 4}, {2, 8, 4}, {8, 2, 4}, {1, 16, 4}, {16, 1, 4}, {1, 2, 32}, {2, 1, 32},
                                 {1, 1, 64}, {8, 4, 2}, {4, 8, 2}, {16, 2, 2}, {2, 16, 2}, {8, 8, 1}, {16, 4, 1},
                                 {4, 16, 1}};
-  for (auto& c : cand)
-    if (D % c[0] == 0 && H % c[1] == 0 && W % c[2] == 0) {
+  // Boxes may overhang the tensor (TMA zero-fills out-of-bounds voxels, the epilogue masks them): pick the shape
+  // that wastes the fewest rows; exact tilings (efficiency 1) win, e.g. 24^3 -> 1x8x8, 12^3 -> 4x4x4, 6^3 -> 2x4x8.
+  double best = 0.0;
+  for (auto& c : cand) {
+    const double cover = (double)((D + c[0] - 1) / c[0] * c[0]) * ((H + c[1] - 1) / c[1] * c[1]) *
+                         ((W + c[2] - 1) / c[2] * c[2]);
+    const double eff = (double)D * H * W / cover;
+    if (eff > best + 1e-9) {
+      best = eff;
       *bd = c[0]; *bh = c[1]; *bw = c[2];
-      return true;
     }
-  return false;
+  }
+  return best >= 0.5;   // below that the cp.async gather kernels are the better choice
 }
 
 // which: 0 fwd, 1 dgrad, 2 wgrad
@@ -401,7 +415,7 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   const int32_t* rows = which == 1 ? g->in_dims : g->out_dims;
   b.N = g->N; b.D = rows[0]; b.H = rows[1]; b.W = rows[2];
   pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
-  b.nbd = b.D / b.bd; b.nbh = b.H / b.bh; b.nbw = b.W / b.bw;
+  b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
   b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
   int taps = 1;
   for (int i = 0; i < 3; ++i) {

@@ -1,0 +1,131 @@
+// Helpers that keep odd shapes off the slow paths:
+//   * skinny linear kernels for <= 32 rows (the (B, 4*C0) time-embedding path: 17 time_emb_proj layers + the
+//     time_embed MLP, unet:691-695,1832-1834). They are bandwidth-bound on the weight matrix, which is read once.
+//   * channel padding so that 1/3-channel end convolutions (conv_in, out) can use the tcgen05 kernels.
+#include "common.cuh"
+
+namespace mig {
+
+// ---- skinny linear: y[r][o] = sum_k x[r][k] w[o][k] + b[o], rows <= 32 --------------------------------
+template <typename T, int R>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+                                                         const float* __restrict__ bias, T* __restrict__ y, int rows,
+                                                         int K, int O) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= O) return;
+  for (int r0 = 0; r0 < rows; r0 += R) {
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = to_f(w[(int64_t)o * K + k]);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (r0 + i < rows) acc[i] = fmaf(to_f(x[(int64_t)(r0 + i) * K + k]), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float s = warp_sum(acc[i]);
+      if (lane == 0 && r0 + i < rows) y[(int64_t)(r0 + i) * O + o] = from_f<T>(s + (bias ? bias[o] : 0.f));
+    }
+  }
+}
+// dx[r][k] = sum_o dy[r][o] w[o][k]   (thread per k: w rows are read coalesced, once)
+template <typename T, int R>
+__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w,
+                                                           T* __restrict__ dx, int rows, int K, int O) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  for (int r0 = 0; r0 < rows; r0 += R) {
+    float acc[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) acc[i] = 0.f;
+    for (int o = 0; o < O; ++o) {
+      const float wv = to_f(w[(int64_t)o * K + k]);
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (r0 + i < rows) acc[i] = fmaf(to_f(dy[(int64_t)(r0 + i) * O + o]), wv, acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      if (r0 + i < rows) dx[(int64_t)(r0 + i) * K + k] = from_f<T>(acc[i]);
+  }
+}
+// dw[o][k] += sum_r dy[r][o] x[r][k]
+template <typename T>
+__global__ void __launch_bounds__(256) skinny_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                           float* __restrict__ dw, int rows, int K, int O) {
+  const int64_t total = (int64_t)O * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i / K), k = (int)(i - (int64_t)o * K);
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc = fmaf(to_f(dy[(int64_t)r * O + o]), to_f(x[(int64_t)r * K + k]), acc);
+    dw[i] += acc;
+  }
+}
+
+bool skinny_eligible(const mig_conv_geom* g) {
+  const int64_t rows = (int64_t)g->N * g->in_dims[0] * g->in_dims[1] * g->in_dims[2];
+  return rows <= 32 && g->ksize[0] == 1 && g->ksize[1] == 1 && g->ksize[2] == 1 && g->stride[0] == 1 &&
+         g->stride[1] == 1 && g->stride[2] == 1 && g->pad[0] == 0 && g->pad[1] == 0 && g->pad[2] == 0;
+}
+static int rows_of(const mig_conv_geom* g) { return g->N * g->in_dims[0] * g->in_dims[1] * g->in_dims[2]; }
+
+int skinny_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+               const float* chan_bias, const void* residual, void* y, void* stream) {
+  MIG_REQUIRE(!chan_bias && !residual, "skinny linear: fused epilogue inputs are not supported");
+  const int rows = rows_of(g), K = g->Cin, O = g->Cout;
+  MIG_DISPATCH_DTYPE(dtype, T, (skinny_fwd_kernel<T, 8><<<(O + 7) / 8, 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (const T*)w, bias, (T*)y, rows, K, O)));
+  return check_launch("skinny_fwd");
+}
+int skinny_dgrad(const mig_conv_geom* g, int dtype, const void* dy, const void* w, void* dx, void* stream) {
+  const int rows = rows_of(g), K = g->Cin, O = g->Cout;
+  MIG_DISPATCH_DTYPE(dtype, T, (skinny_dgrad_kernel<T, 8><<<(K + 255) / 256, 256, 0, as_stream(stream)>>>(
+                                   (const T*)dy, (const T*)w, (T*)dx, rows, K, O)));
+  return check_launch("skinny_dgrad");
+}
+int skinny_wgrad(const mig_conv_geom* g, int dtype, const void* x, const void* dy, float* dw, void* stream) {
+  const int rows = rows_of(g), K = g->Cin, O = g->Cout;
+  MIG_DISPATCH_DTYPE(dtype, T, (skinny_wgrad_kernel<T><<<bw_grid((int64_t)O * K, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)x, (const T*)dy, dw, rows, K, O)));
+  return check_launch("skinny_wgrad");
+}
+
+// ---- channel padding ------------------------------------------------------------------------------------
+// dst[r][0..Cp) = src[r][0..C) followed by zeros
+template <typename T>
+__global__ void __launch_bounds__(256) pad_channels_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                           int64_t rows, int C, int Cp) {
+  const int64_t total = rows * Cp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Cp;
+    const int c = (int)(i - r * Cp);
+    dst[i] = c < C ? src[r * C + c] : from_f<T>(0.f);
+  }
+}
+// dst[r][c] += src[r][c] for c < C, rows < rows_dst  (fp32 gradient un-padding; src is [rows_src][Cp])
+__global__ void __launch_bounds__(256) unpad_add_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int64_t rows, int C, int Cp) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C;
+    const int c = (int)(i - r * C);
+    dst[i] += src[r * Cp + c];
+  }
+}
+
+int pad_channels(int dtype, const void* src, void* dst, int64_t rows, int C, int Cp, void* stream) {
+  if (rows * Cp <= 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (pad_channels_kernel<T><<<bw_grid(rows * Cp, 256), 256, 0, as_stream(stream)>>>(
+                                   (const T*)src, (T*)dst, rows, C, Cp)));
+  return check_launch("pad_channels");
+}
+int unpad_add(const float* src, float* dst, int64_t rows, int C, int Cp, void* stream) {
+  if (rows * C <= 0) return 0;
+  unpad_add_kernel<<<bw_grid(rows * C, 256), 256, 0, as_stream(stream)>>>(src, dst, rows, C, Cp);
+  return check_launch("unpad_add");
+}
+
+}  // namespace mig
