@@ -4,9 +4,13 @@
 // 5-d tensor (C, W, H, D, N); a GEMM row tile is a BOX of voxels (bw x bh x bd = 64 voxels, two boxes per 128-row
 // UMMA tile) and the K loop walks (filter tap, 64-channel chunk). For tap (tz,ty,tx) the A tile is simply the same
 // box shifted by the tap offset; coordinates that fall outside the tensor are filled with zeros by the TMA unit,
-// which IS the convolution's zero padding (the halo). One elected thread issues 2 (A) + 1 (B, filters) TMA loads
-// per stage, one thread issues the UMMAs, four warps only run the epilogue -- there is no address arithmetic and
-// no load instruction in the main loop at all, and up to STAGES-1 whole stages (~150 KB) are in flight per SM.
+// which IS the convolution's zero padding (the halo). A few elected lanes issue the TMA loads, one thread issues
+// the UMMAs, four warps only run the epilogue -- there is no address arithmetic and no load instruction in the
+// main loop at all, and up to STAGES-1 whole stages (~130 KB) are in flight per SM.
+//
+// Measured (profiles/): the limiter of these kernels is the TMA unit's row rate (each 128-byte box row costs a few
+// cycles), not L2 or HBM bandwidth, so the CTA tile is made as large as TMEM allows: MT = 2 stacks two 128-row
+// UMMA accumulators (2 x 256 TMEM columns = all 512) that share every B stage, i.e. a 256 x 256 tile per CTA.
 //
 //   conv_tma_kernel   fwd and dgrad (dgrad = same kernel on dY with mirrored taps and the transposed filter)
 //   wgrad_tma_kernel  dW[Cout][tap*Cin] += dY^T * im2col(X): both operands MN-major, voxel reduction walks boxes,
@@ -24,7 +28,11 @@ using namespace tc;
 int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream);
 
 constexpr int TBM = 128, TBK = 64, kThreads = 192, PANEL = 64 * 128;
-__host__ __device__ constexpr int tma_stages(int bn) { return bn >= 256 ? 4 : (bn >= 128 ? 6 : 8); }
+constexpr int kSmemBudget = 200 * 1024;
+__host__ __device__ constexpr int stages_of(int stage_bytes) {
+  return kSmemBudget / stage_bytes > 8 ? 8 : kSmemBudget / stage_bytes;
+}
+__host__ __device__ constexpr int tmem_cols(int c) { return c <= 32 ? 32 : (c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512))); }
 
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -36,12 +44,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
 }
 
 struct BoxGeom {
-  int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad) == source extent
-  int bd, bh, bw;        // box (bd*bh*bw == 64)
-  int nbd, nbh, nbw;     // boxes per axis
+  int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad)
+  int bd, bh, bw;        // box (bd*bh*bw == 64); boxes may overhang the tensor
+  int nbd, nbh, nbw;     // boxes per axis (ceil)
   int64_t num_boxes;     // N*nbd*nbh*nbw
   int ks[3];             // kernel
-  int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: sign +1, off -pad; dgrad: sign -1, off +pad)
+  int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: +1, -pad; dgrad: -1, +pad)
   int sign;
   int Csrc, Cdst, K;     // K = taps*Csrc
   int cchunks;           // Csrc / 64
@@ -65,12 +73,14 @@ struct ConvTmaParams {
   int num_kb, kb_per_split;
 };
 
-template <int BN>
+// BN: output-channel tile; MT: number of stacked 128-row accumulators (CTA tile = MT*128 voxels x BN channels)
+template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                const __grid_constant__ CUtensorMap wmap,
                                                                ConvTmaParams p) {
-  constexpr int STAGES = tma_stages(BN);
-  constexpr int A_BYTES = TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int A_BYTES = MT * TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = stages_of(STAGE_BYTES);
+  constexpr int TCOLS = tmem_cols(MT * BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -78,7 +88,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BoxGeom& g = p.g;
-  const int64_t box0 = (int64_t)blockIdx.x * 2;
+  const int64_t box0 = (int64_t)blockIdx.x * (2 * MT);
   const int n0 = blockIdx.y * BN;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
@@ -91,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     mbar_init(accbar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<(BN < 32 ? 32 : BN)>(smem_u32(&tmem_slot));
+  if (warp == 4) tmem_alloc<TCOLS>(smem_u32(&tmem_slot));
   if (warp == 5 && lane == 0) { tma_prefetch_desc(&xmap); tma_prefetch_desc(&wmap); }
   tcgen05_fence_before();
   __syncthreads();
@@ -101,68 +111,71 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   if (warp < 4) {
     // ===================== epilogue =====================
     const int row = warp * 32 + lane;
-    const int64_t box = box0 + (row >> 6);
     const int r = row & 63;
-    bool mok = box < g.num_boxes;
-    int n = 0, d0 = 0, h0 = 0, w0 = 0;
-    if (mok) box_origin(g, box, n, d0, h0, w0);
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
-    mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
-    const int64_t m = (((int64_t)n * g.D + d0 + ld) * g.H + h0 + lh) * g.W + w0 + lw;
     mbar_wait(accbar, 0);
     tcgen05_fence_after();
-    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= g.Cdst) break;
-      float v[16];
-      tmem_ld16(trow + c0, v);
-      if (!mok) continue;
-      const int col0 = n0 + c0;
-      if (p.partial) {
-        float* dst = p.partial + m * g.Cdst + col0;
+    for (int mt = 0; mt < MT; ++mt) {
+      const int64_t box = box0 + mt * 2 + (row >> 6);
+      bool mok = box < g.num_boxes;
+      int n = 0, d0 = 0, h0 = 0, w0 = 0;
+      if (mok) box_origin(g, box, n, d0, h0, w0);
+      mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
+      const int64_t m = (((int64_t)n * g.D + d0 + ld) * g.H + h0 + lh) * g.W + w0 + lw;
+      const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= g.Cdst) break;
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        if (!mok) continue;
+        const int col0 = n0 + c0;
+        if (p.partial) {
+          float* dst = p.partial + m * g.Cdst + col0;
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (col0 + e < g.Cdst) atomicAdd(dst + e, v[e]);
-        continue;
-      }
-      const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
-      if (p.bias) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += p.bias[col0 + e];
-      }
-      if (p.chan_bias) {
-        const float* cb = p.chan_bias + (int64_t)n * g.Cdst + col0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += cb[e];
-      }
-      __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
-      if (full16) {
-        if (p.residual) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
-          uint4 r0 = rp[0], r1 = rp[1];
-          const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
-          const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < g.Cdst) atomicAdd(dst + e, v[e]);
+          continue;
         }
-        uint4 o0, o1;
-        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+        const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
+        if (p.bias) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+          for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += p.bias[col0 + e];
         }
-        reinterpret_cast<uint4*>(dst)[0] = o0;
-        reinterpret_cast<uint4*>(dst)[1] = o1;
-      } else {
+        if (p.chan_bias) {
+          const float* cb = p.chan_bias + (int64_t)n * g.Cdst + col0;
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (col0 + e < g.Cdst) {
-            float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
-            dst[e] = __float2bfloat16_rn(v[e] + rr);
+          for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += cb[e];
+        }
+        __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
+        if (full16) {
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+            const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
           }
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+          }
+          reinterpret_cast<uint4*>(dst)[0] = o0;
+          reinterpret_cast<uint4*>(dst)[1] = o1;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < g.Cdst) {
+              float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
+              dst[e] = __float2bfloat16_rn(v[e] + rr);
+            }
+        }
       }
     }
     tcgen05_fence_before();
@@ -176,18 +189,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       if (lane == 0) {
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TBK / 16; ++kk)
-          umma_bf16(tmem_acc, make_smem_desc(a_smem + kk * 32, 16, 1024), make_smem_desc(b_smem + kk * 32, 16, 1024),
-                    idesc, (it | kk) ? 1u : 0u);
+        for (int kk = 0; kk < TBK / 16; ++kk) {
+          const uint64_t bd = make_smem_desc(b_smem + kk * 32, 16, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            umma_bf16(tmem_acc + mt * BN, make_smem_desc(a_smem + mt * (TBM * 128) + kk * 32, 16, 1024), bd, idesc,
+                      (it | kk) ? 1u : 0u);
+        }
         umma_commit(empty0 + 8 * s);
         if (it == nkb - 1) umma_commit(accbar);
       }
       __syncwarp();
     }
   } else {
-    // ===================== TMA issuers: lanes 0,1 -> the two A boxes, lane 2 -> the filter box =====================
-    int bn_ = g.N, bd_ = 0, bh_ = 0, bw_ = 0;   // default: fully out of bounds -> zero rows (odd tile tail)
-    if (lane < 2 && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
+    // ============ TMA issuers: lanes 0..2MT-1 -> the A boxes, lane 2MT -> the filter box ============
+    int bn_ = g.N, bd_ = 0, bh_ = 0, bw_ = 0;   // default: fully out of bounds -> zero rows (tile tail)
+    if (lane < 2 * MT && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
     for (int it = 0; it < nkb; ++it) {
       const int s = it % STAGES;
       const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
@@ -197,7 +214,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         mbar_arrive_expect_tx(bar, STAGE_BYTES);
       }
       __syncwarp();
-      if (lane < 2) {
+      if (lane < 2 * MT) {
         int tap = kb / g.cchunks;
         const int c0 = (kb - tap * g.cchunks) * 64;
         const int t2 = tap % g.ks[2]; tap /= g.ks[2];
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         const int t0 = tap / g.ks[1];
         const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
         tma_load_5d(a_smem + lane * PANEL, &xmap, bar, c0, bw_ + dx, bh_ + dy, bd_ + dz, bn_);
-      } else if (lane == 2) {
+      } else if (lane == 2 * MT) {
         tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
       }
     }
@@ -213,11 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
-    tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_acc);
+    tmem_dealloc<TCOLS>(tmem_acc);
   }
 }
 
-// split-K finish (same as gemm_tc.cu's, rows here are plain voxel indices because `partial` is indexed by m)
+// split-K finish: out = bf16(partial + bias + chan_bias + residual); `partial` is indexed by plain voxel index
 __global__ void __launch_bounds__(256) tma_splitk_finish(const float* __restrict__ partial, const float* __restrict__ bias,
                                                          const float* __restrict__ chan_bias,
                                                          const __nv_bfloat16* __restrict__ residual,
@@ -243,13 +260,15 @@ struct WgradTmaParams {
   int64_t boxes_per_split;
 };
 
-template <int BN>
+// CTA tile: MT*128 output channels x BN filter columns; reduction over voxel boxes
+template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap dymap,
                                                                 const __grid_constant__ CUtensorMap xmap,
                                                                 WgradTmaParams p) {
-  constexpr int STAGES = tma_stages(BN);
-  constexpr int NPAN = BN / 64;
-  constexpr int A_BYTES = 2 * PANEL, B_BYTES = NPAN * PANEL, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int NPAN = BN / 64, APAN = 2 * MT;
+  constexpr int A_BYTES = APAN * PANEL, B_BYTES = NPAN * PANEL, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = stages_of(STAGE_BYTES);
+  constexpr int TCOLS = tmem_cols(MT * BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
@@ -257,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BoxGeom& g = p.g;
-  const int co0 = blockIdx.x * TBM;
+  const int co0 = blockIdx.x * (TBM * MT);
   const int n0 = blockIdx.y * BN;     // column offset in K = tap*Cin + ci
   const int64_t bb = (int64_t)blockIdx.z * p.boxes_per_split;
   const int nst = (int)(min(g.num_boxes, bb + p.boxes_per_split) - bb);
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
     mbar_init(accbar, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<BN>(smem_u32(&tmem_slot));
+  if (warp == 4) tmem_alloc<TCOLS>(smem_u32(&tmem_slot));
   if (warp == 5 && lane == 0) { tma_prefetch_desc(&dymap); tma_prefetch_desc(&xmap); }
   tcgen05_fence_before();
   __syncthreads();
@@ -280,19 +299,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
   if (warp < 4) {
     mbar_wait(accbar, 0);
     tcgen05_fence_after();
-    const int co = co0 + warp * 32 + lane;
-    const bool cok = co < g.Cdst && nst > 0;
-    const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= g.K) break;
-      float v[16];
-      tmem_ld16(trow + c0, v);
-      if (!cok) continue;
-      float* dst = p.dw + (int64_t)co * g.K + n0 + c0;
+    for (int mt = 0; mt < MT; ++mt) {
+      const int co = co0 + mt * TBM + warp * 32 + lane;
+      const bool cok = co < g.Cdst && nst > 0;
+      const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= g.K) break;
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        if (!cok) continue;
+        float* dst = p.dw + (int64_t)co * g.K + n0 + c0;
 #pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (n0 + c0 + e < g.K) atomicAdd(dst + e, v[e]);
+        for (int e = 0; e < 16; ++e)
+          if (n0 + c0 + e < g.K) atomicAdd(dst + e, v[e]);
+      }
     }
     tcgen05_fence_before();
   } else if (warp == 4) {
@@ -304,9 +326,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
       if (lane == 0) {
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TBK / 16; ++kk)
-          umma_bf16(tmem_acc, make_smem_desc(a_smem + kk * 2048, PANEL, 1024),
-                    make_smem_desc(b_smem + kk * 2048, PANEL, 1024), idesc, (it | kk) ? 1u : 0u);
+        for (int kk = 0; kk < TBK / 16; ++kk) {
+          const uint64_t bd = make_smem_desc(b_smem + kk * 2048, PANEL, 1024);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            umma_bf16(tmem_acc + mt * BN, make_smem_desc(a_smem + mt * 2 * PANEL + kk * 2048, PANEL, 1024), bd, idesc,
+                      (it | kk) ? 1u : 0u);
+        }
         umma_commit(empty0 + 8 * s);
         if (it == nst - 1) umma_commit(accbar);
       }
@@ -314,9 +340,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
     }
     if (nst <= 0 && lane == 0) mbar_arrive(accbar);
   } else {
-    // TMA issuers, one lane per box: lanes 0,1 -> the two dY panels; lanes 2..2+NPAN-1 -> the im2col(X) panels.
-    // Each X panel is one fixed (tap, 64-channel chunk) for the whole kernel.
-    const int q = lane - 2;
+    // TMA issuers, one lane per box: lanes 0..APAN-1 -> the dY panels; lanes APAN..APAN+NPAN-1 -> the im2col(X)
+    // panels. Each X panel is one fixed (tap, 64-channel chunk) for the whole kernel.
+    const int q = lane - APAN;
     int dz = 0, dy = 0, dx = 0, cc = -1;
     if (q >= 0 && q < NPAN) {
       const int k = n0 + q * 64;
@@ -335,10 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
         mbar_arrive_expect_tx(bar, STAGE_BYTES);
       }
       __syncwarp();
-      if (lane < 2 + NPAN) {
+      if (lane < APAN + NPAN) {
         int n, d0, h0, w0;
         box_origin(g, bb + it, n, d0, h0, w0);
-        if (lane < 2) {
+        if (lane < APAN) {
           tma_load_5d(a_smem + lane * PANEL, &dymap, bar, co0 + lane * 64, w0, h0, d0, n);
         } else if (cc >= 0) {
           tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc, w0 + dx, h0 + dy, d0 + dz, n);
@@ -352,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
-    tmem_dealloc<BN>(tmem_acc);
+    tmem_dealloc<TCOLS>(tmem_acc);
   }
 }
 
@@ -360,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
 // host
 // ---------------------------------------------------------------------------------------------------
 static bool pick_box(int D, int H, int W, int* bd, int* bh, int* bw) {
-  // 64 voxels per box, every factor a power of two dividing the extent; prefer wide W (contiguous rows in memory)
+  // 64 voxels per box, power-of-two factors; prefer wide W (contiguous rows in memory)
   static const int cand[][3] = {{1, 8, 8}, {2, 4, 8}, {4, 2, 8}, {8, 1, 8}, {1, 4, 16}, {2, 2, 16}, {4, 1, 16},
                                 {4, 4, 4}, {2, 8, 4}, {8, 2, 4}, {1, 16, 4}, {16, 1, 4}, {1, 2, 32}, {2, 1, 32},
                                 {1, 1, 64}, {8, 4, 2}, {4, 8, 2}, {16, 2, 2}, {2, 16, 2}, {8, 8, 1}, {16, 4, 1},
@@ -388,7 +414,6 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   if (csrc % 64 != 0) return false;
   if (which == 2 && g->Cout % 8 != 0) return false;
   if (which != 2 && (which == 0 ? g->Cout : g->Cin) < 8) return false;
-  // rows: fwd -> output extent, dgrad -> input extent, wgrad -> output extent
   const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
   int bd, bh, bw;
   return pick_box(dims[0], dims[1], dims[2], &bd, &bh, &bw);
@@ -431,17 +456,18 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   return b;
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const ConvTmaParams& p, dim3 grid,
                            cudaStream_t st) {
-  constexpr int smem = tma_stages(BN) * (TBM * 128 + BN * 128) + 1024;
+  constexpr int stage = MT * TBM * 128 + BN * 128;
+  constexpr int smem = stages_of(stage) * stage + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     MIG_REQUIRE(e == cudaSuccess, "conv_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tma_kernel<BN><<<grid, kThreads, smem, st>>>(xm, wm, p);
+  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, p);
   return check_launch("conv_tma_kernel");
 }
 
@@ -451,7 +477,7 @@ static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, cons
                         void* stream) {
   BoxGeom b = make_box_geom(g, which);
   cudaStream_t st = as_stream(stream);
-  const int32_t* sdims = which == 1 ? g->out_dims : g->in_dims;   // extent of the SOURCE tensor (same as rows: stride 1)
+  const int32_t* sdims = which == 1 ? g->out_dims : g->in_dims;   // extent of the SOURCE tensor
   CUtensorMap xm, wm;
   if (make_act_map(&xm, src, g->N, sdims, b.Csrc, b.bd, b.bh, b.bw)) return 1;
   const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
@@ -465,10 +491,14 @@ static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, cons
   p.residual = (const __nv_bfloat16*)residual;
   p.out = (__nv_bfloat16*)out;
   p.num_kb = b.K / TBK;
-  const int64_t mtiles = (b.num_boxes + 1) / 2, ntiles = (b.Cdst + bn - 1) / bn;
+  const int sms = device_info().sm_count;
+  const int64_t ntiles = (b.Cdst + bn - 1) / bn;
+  // 256-row tiles when they still fill the chip about twice; otherwise 128-row tiles (+ split-K when very small)
+  int mt = 1;
+  if (bn == 256 && ((b.num_boxes + 3) / 4) * ntiles >= (int64_t)sms * 2) mt = 2;
+  const int64_t mtiles = (b.num_boxes + 2 * mt - 1) / (2 * mt);
   const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
   int splits = 1;
-  const int sms = device_info().sm_count;
   if (mtiles * ntiles * 2 <= sms) {
     splits = (int)(sms / (mtiles * ntiles));
     if (splits > p.num_kb / 8) splits = p.num_kb / 8;
@@ -483,12 +513,11 @@ static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, cons
   }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
   int rc;
-  switch (bn) {
-    case 256: rc = launch_conv_tma<256>(xm, wm, p, grid, st); break;
-    case 128: rc = launch_conv_tma<128>(xm, wm, p, grid, st); break;
-    case 64: rc = launch_conv_tma<64>(xm, wm, p, grid, st); break;
-    default: rc = launch_conv_tma<32>(xm, wm, p, grid, st); break;
-  }
+  if (mt == 2) rc = launch_conv_tma<256, 2>(xm, wm, p, grid, st);
+  else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, p, grid, st);
+  else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, p, grid, st);
+  else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, p, grid, st);
+  else rc = launch_conv_tma<32, 1>(xm, wm, p, grid, st);
   if (rc) return rc;
   if (splits > 1) {
     tma_splitk_finish<<<bw_grid(M * b.Cdst, 256), 256, 0, st>>>((const float*)ws, bias, chan_bias,
@@ -513,17 +542,18 @@ int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* 
   return run_conv_tma(g, 1, dy, ws, nullptr, nullptr, nullptr, dx, (uint8_t*)ws + wt_bytes, ws_bytes - wt_bytes, stream);
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_wgrad_tma(const CUtensorMap& dym, const CUtensorMap& xm, const WgradTmaParams& p, dim3 grid,
                             cudaStream_t st) {
-  constexpr int smem = tma_stages(BN) * (2 * PANEL + (BN / 64) * PANEL) + 1024;
+  constexpr int stage = (2 * MT + BN / 64) * PANEL;
+  constexpr int smem = stages_of(stage) * stage + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     MIG_REQUIRE(e == cudaSuccess, "wgrad_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  wgrad_tma_kernel<BN><<<grid, kThreads, smem, st>>>(dym, xm, p);
+  wgrad_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(dym, xm, p);
   return check_launch("wgrad_tma_kernel");
 }
 
@@ -534,23 +564,24 @@ int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float*
   if (make_act_map(&dym, dy, g->N, g->out_dims, g->Cout, b.bd, b.bh, b.bw)) return 1;
   if (make_act_map(&xm, x, g->N, g->in_dims, g->Cin, b.bd, b.bh, b.bw)) return 1;
   const int bn = b.K > 128 ? 256 : (b.K > 64 ? 128 : 64);
+  const int mt = (bn == 256 && g->Cout >= 256) ? 2 : 1;
   WgradTmaParams p{};
   p.g = b;
   p.dw = dw;
-  const int64_t tiles = (int64_t)((g->Cout + TBM - 1) / TBM) * ((b.K + bn - 1) / bn);
+  const int mrows = TBM * mt;
+  const int64_t tiles = (int64_t)((g->Cout + mrows - 1) / mrows) * ((b.K + bn - 1) / bn);
   int64_t splits = ((int64_t)device_info().sm_count * 3 + tiles - 1) / tiles;
   if (splits > b.num_boxes / 4) splits = b.num_boxes / 4;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   p.boxes_per_split = (b.num_boxes + splits - 1) / splits;
   splits = (b.num_boxes + p.boxes_per_split - 1) / p.boxes_per_split;
-  dim3 grid((unsigned)((g->Cout + TBM - 1) / TBM), (unsigned)((b.K + bn - 1) / bn), (unsigned)splits);
+  dim3 grid((unsigned)((g->Cout + mrows - 1) / mrows), (unsigned)((b.K + bn - 1) / bn), (unsigned)splits);
   MIG_REQUIRE(grid.y < 65536, "conv_wgrad(tma): filter too large");
-  switch (bn) {
-    case 256: return launch_wgrad_tma<256>(dym, xm, p, grid, st);
-    case 128: return launch_wgrad_tma<128>(dym, xm, p, grid, st);
-    default: return launch_wgrad_tma<64>(dym, xm, p, grid, st);
-  }
+  if (mt == 2) return launch_wgrad_tma<256, 2>(dym, xm, p, grid, st);
+  if (bn == 256) return launch_wgrad_tma<256, 1>(dym, xm, p, grid, st);
+  if (bn == 128) return launch_wgrad_tma<128, 1>(dym, xm, p, grid, st);
+  return launch_wgrad_tma<64, 1>(dym, xm, p, grid, st);
 }
 
 }  // namespace mig

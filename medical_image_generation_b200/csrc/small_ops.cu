@@ -31,25 +31,39 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ x
     }
   }
 }
-// dx[r][k] = sum_o dy[r][o] w[o][k]   (thread per k: w rows are read coalesced, once)
+// dx[r][k] = sum_o dy[r][o] w[o][k]. CTA = 32 consecutive k (one 128-byte run of every filter row) x 32 slices of
+// the o range; each warp walks its o slice with coalesced row reads, partial sums are reduced through shared
+// memory. Grid = K/32 CTAs, so the filter is read exactly once with ~1000 threads per CTA in flight.
 template <typename T, int R>
-__global__ void __launch_bounds__(256) skinny_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w,
-                                                           T* __restrict__ dx, int rows, int K, int O) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+__global__ void __launch_bounds__(1024) skinny_dgrad_kernel(const T* __restrict__ dy, const T* __restrict__ w,
+                                                            T* __restrict__ dx, int rows, int K, int O) {
+  __shared__ float red[32][R][33];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;   // grp = o slice
+  const int k = blockIdx.x * 32 + lane;
   for (int r0 = 0; r0 < rows; r0 += R) {
     float acc[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) acc[i] = 0.f;
-    for (int o = 0; o < O; ++o) {
-      const float wv = to_f(w[(int64_t)o * K + k]);
+    if (k < K) {
+#pragma unroll 4
+      for (int o = grp; o < O; o += 32) {
+        const float wv = to_f(w[(int64_t)o * K + k]);
 #pragma unroll
-      for (int i = 0; i < R; ++i)
-        if (r0 + i < rows) acc[i] = fmaf(to_f(dy[(int64_t)(r0 + i) * O + o]), wv, acc[i]);
+        for (int i = 0; i < R; ++i)
+          if (r0 + i < rows) acc[i] = fmaf(to_f(dy[(int64_t)(r0 + i) * O + o]), wv, acc[i]);
+      }
     }
 #pragma unroll
-    for (int i = 0; i < R; ++i)
-      if (r0 + i < rows) dx[(int64_t)(r0 + i) * K + k] = from_f<T>(acc[i]);
+    for (int i = 0; i < R; ++i) red[grp][i][lane] = acc[i];
+    __syncthreads();
+    // warp `grp` finishes row r0+grp (for grp < R): sum over the 32 o slices
+    if (grp < R && r0 + grp < rows && k < K) {
+      float s = 0.f;
+#pragma unroll 8
+      for (int g2 = 0; g2 < 32; ++g2) s += red[g2][grp][lane];
+      dx[(int64_t)(r0 + grp) * K + k] = from_f<T>(s);
+    }
+    __syncthreads();
   }
 }
 // dw[o][k] += sum_r dy[r][o] x[r][k]
@@ -82,7 +96,7 @@ int skinny_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, 
 }
 int skinny_dgrad(const mig_conv_geom* g, int dtype, const void* dy, const void* w, void* dx, void* stream) {
   const int rows = rows_of(g), K = g->Cin, O = g->Cout;
-  MIG_DISPATCH_DTYPE(dtype, T, (skinny_dgrad_kernel<T, 8><<<(K + 255) / 256, 256, 0, as_stream(stream)>>>(
+  MIG_DISPATCH_DTYPE(dtype, T, (skinny_dgrad_kernel<T, 8><<<(K + 31) / 32, 1024, 0, as_stream(stream)>>>(
                                    (const T*)dy, (const T*)w, (T*)dx, rows, K, O)));
   return check_launch("skinny_dgrad");
 }

@@ -43,6 +43,9 @@ CONV_CASES = [
     (2, 64, 64, (16, 16), (3, 3), (1, 1), (1, 1)),                # 2-D
     (1, 192, 320, (4, 4, 8), (3, 3, 1), (1, 1, 1), (1, 1, 0)),    # anisotropic kernel, N tile tail (320 = 256 + 64)
     (1, 64, 24, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),      # narrow output (BN = 32), dgrad falls back (Cout % 64)
+    (8, 64, 256, (24, 24, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),  # BASELINE-size level 0: fwd uses the 256x256 CTA tile
+    (8, 256, 64, (24, 24, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),  # ... and dgrad / wgrad use it here
+    (2, 128, 256, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # 6^3: overhanging 2x4x8 boxes, split-K
 ]
 
 
