@@ -132,10 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         if (!mok) continue;
         const int col0 = n0 + c0;
         if (p.partial) {
-          float* dst = p.partial + m * g.Cdst + col0;
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (col0 + e < g.Cdst) atomicAdd(dst + e, v[e]);
+          red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
           continue;
         }
         const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
@@ -310,10 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
         float v[16];
         tmem_ld16(trow + c0, v);
         if (!cok) continue;
-        float* dst = p.dw + (int64_t)co * g.K + n0 + c0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (n0 + c0 + e < g.K) atomicAdd(dst + e, v[e]);
+        red_add_16(p.dw + (int64_t)co * g.K + n0 + c0, v, g.K - n0 - c0);
       }
     }
     tcgen05_fence_before();
@@ -493,18 +487,31 @@ static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, cons
   p.num_kb = b.K / TBK;
   const int sms = device_info().sm_count;
   const int64_t ntiles = (b.Cdst + bn - 1) / bn;
-  // 256-row tiles when they still fill the chip about twice; otherwise 128-row tiles (+ split-K when very small)
-  int mt = 1;
-  if (bn == 256 && ((b.num_boxes + 3) / 4) * ntiles >= (int64_t)sms * 2) mt = 2;
-  const int64_t mtiles = (b.num_boxes + 2 * mt - 1) / (2 * mt);
   const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
-  int splits = 1;
-  if (mtiles * ntiles * 2 <= sms) {
-    splits = (int)(sms / (mtiles * ntiles));
-    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
-    if (splits < 1) splits = 1;
+  // Tile / split-K plan from a small cost model (cycles): a stage costs the larger of its UMMA time and its TMA
+  // row-issue time (measured: ~3.5 cycles per 5-d box row, ~1.5 per 2-d filter row); a CTA adds prologue and
+  // epilogue; the grid runs in ceil(CTAs / SMs) waves. 256-row tiles amortise the filter stage, split-K fills
+  // the chip on the small deep levels.
+  int mt = 1, splits = 1;
+  {
+    const bool ws_ok = ws != nullptr && ws_bytes >= M * b.Cdst * 4;
+    double best = 1e30;
+    static const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
+    for (int m_ = 1; m_ <= (bn == 256 ? 2 : 1); ++m_) {
+      const int64_t mtiles_ = (b.num_boxes + 2 * m_ - 1) / (2 * m_);
+      const double t_stage = fmax(512.0 * m_ * bn / 256.0, 128.0 * m_ * 3.5 + bn * 1.5);
+      for (int s_ : cand_s) {
+        if (s_ > 1 && (!ws_ok || p.num_kb / s_ < 4)) continue;
+        const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
+        const double kb = (double)((p.num_kb + s_ - 1) / s_);
+        const double t_epi = 2500.0 + m_ * (bn / 16) * (s_ > 1 ? 160.0 : 110.0);
+        double t = waves * (kb * t_stage + t_epi + 2500.0);
+        if (s_ > 1) t += (double)M * b.Cdst * 14.0 / 3000.0 + 8000.0;   // memset + fp32 reductions + finish pass
+        if (t < best) { best = t; mt = m_; splits = s_; }
+      }
+    }
   }
-  if (splits > 1 && (ws == nullptr || ws_bytes < M * b.Cdst * 4)) splits = 1;
+  const int64_t mtiles = (b.num_boxes + 2 * mt - 1) / (2 * mt);
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (splits > 1) {
@@ -563,16 +570,33 @@ int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float*
   CUtensorMap dym, xm;
   if (make_act_map(&dym, dy, g->N, g->out_dims, g->Cout, b.bd, b.bh, b.bw)) return 1;
   if (make_act_map(&xm, x, g->N, g->in_dims, g->Cin, b.bd, b.bh, b.bw)) return 1;
-  const int bn = b.K > 128 ? 256 : (b.K > 64 ? 128 : 64);
-  const int mt = (bn == 256 && g->Cout >= 256) ? 2 : 1;
+  // Tile / split plan from the same kind of cost model as the forward kernel: stage = max(UMMA, TMA row issue),
+  // CTA = stages + prologue + fp32 reduction epilogue (16-byte red ops), grid = ceil(CTAs / SMs) waves.
+  int bn = 64, mt = 1;
+  int64_t splits = 1;
+  {
+    const int sms = device_info().sm_count;
+    static const int cand_t[][2] = {{256, 2}, {256, 1}, {128, 1}, {64, 1}};
+    double best = 1e30;
+    for (auto& c : cand_t) {
+      const int bn_ = c[0], mt_ = c[1];
+      if (bn_ > 64 && b.K <= bn_ / 2) continue;
+      if (mt_ == 2 && g->Cout <= 128) continue;
+      const int64_t tiles = (int64_t)((g->Cout + TBM * mt_ - 1) / (TBM * mt_)) * ((b.K + bn_ - 1) / bn_);
+      const double t_stage = fmax(512.0 * mt_ * bn_ / 256.0, 64.0 * 3.5 * (2 * mt_ + bn_ / 64));
+      const double t_epi = 2500.0 + mt_ * 128.0 * bn_ / 5.0;
+      for (int64_t s_ = 1; s_ <= b.num_boxes && s_ <= 4096; s_ = s_ < 8 ? s_ + 1 : s_ + s_ / 4) {
+        const double waves = (double)((tiles * s_ + sms - 1) / sms);
+        const double st = (double)((b.num_boxes + s_ - 1) / s_);
+        const double t = waves * (st * t_stage + t_epi + 2500.0);
+        if (t < best) { best = t; bn = bn_; mt = mt_; splits = s_; }
+      }
+    }
+  }
   WgradTmaParams p{};
   p.g = b;
   p.dw = dw;
   const int mrows = TBM * mt;
-  const int64_t tiles = (int64_t)((g->Cout + mrows - 1) / mrows) * ((b.K + bn - 1) / bn);
-  int64_t splits = ((int64_t)device_info().sm_count * 3 + tiles - 1) / tiles;
-  if (splits > b.num_boxes / 4) splits = b.num_boxes / 4;
-  if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   p.boxes_per_split = (b.num_boxes + splits - 1) / splits;
   splits = (b.num_boxes + p.boxes_per_split - 1) / p.boxes_per_split;

@@ -167,10 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (!mok) continue;
       const int col0 = n0 + c0;
       if (p.partial) {
-        float* dst = p.partial + m * g.Cdst + col0;
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (col0 + e < g.Cdst) atomicAdd(dst + e, v[e]);
+        red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
         continue;
       }
       const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);

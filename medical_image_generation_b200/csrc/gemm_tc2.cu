@@ -143,10 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
       float v[16];
       tmem_ld16(trow + c0, v);
       if (!cok) continue;
-      float* dst = p.dw + (int64_t)co * g.K + n0 + c0;
-#pragma unroll
-      for (int e = 0; e < 16; ++e)
-        if (n0 + c0 + e < g.K) atomicAdd(dst + e, v[e]);
+      red_add_16(p.dw + (int64_t)co * g.K + n0 + c0, v, g.K - n0 - c0);
     }
     tcgen05_fence_before();
   } else if (warp == 4) {

@@ -117,6 +117,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16-byte vector reduction into global memory (sm_90+): one L2 operation carries four fp32 addends.
+// `p` must be 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// 16 consecutive fp32 columns; falls back to scalar atomics for tails / unaligned rows
+__device__ __forceinline__ void red_add_16(float* dst, const float v[16], int valid) {
+  if (valid >= 16 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) red_add_v4(dst + e, v[e], v[e + 1], v[e + 2], v[e + 3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e)
+      if (e < valid) atomicAdd(dst + e, v[e]);
+  }
+}
+
 // ---- descriptors ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout type 2), descriptor version 1 (sm_100).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4
