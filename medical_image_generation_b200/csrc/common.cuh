@@ -129,11 +129,12 @@ __device__ __forceinline__ float block_max(float v, float* smem) {
   return smem[32];
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// MUFU-based forms (ex2 + rcp, ~2 ulp): the normalisation kernels are otherwise bound by this math, not by HBM
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 // d/dx [x*sigmoid(x)] = s*(1 + x*(1-s))
 __device__ __forceinline__ float silu_grad_f(float x) {
-  float s = 1.f / (1.f + __expf(-x));
-  return s * (1.f + x * (1.f - s));
+  float s = __fdividef(1.f, 1.f + __expf(-x));
+  return s * fmaf(x, 1.f - s, 1.f);
 }
 
 // grid sizing for bandwidth kernels: enough CTAs to fill 148 SMs a few times over, capped.

@@ -36,6 +36,9 @@ int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const flo
 int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
                    void* stream);
 int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
+bool tma_dgrad_strided_eligible(const mig_conv_geom* g);
+int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                           void* stream);
 // small_ops.cu
 bool skinny_eligible(const mig_conv_geom* g);
 int skinny_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
@@ -85,8 +88,10 @@ static int run_fwd(const mig_conv_geom* g, const void* x, const void* w, const f
 }
 static int run_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t wsb,
                      void* stream) {
-  if (tma_enabled() && tma_conv_eligible(g, 1) && aligned16(dy) && aligned16(w) && aligned16(dx))
-    return tma_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
+  if (tma_enabled() && aligned16(dy) && aligned16(w) && aligned16(dx)) {
+    if (tma_conv_eligible(g, 1)) return tma_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
+    if (tma_dgrad_strided_eligible(g)) return tma_conv_dgrad_strided(g, dy, w, dx, ws, wsb, stream);
+  }
   return tc_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
 }
 static int run_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* ws, int64_t wsb,

@@ -53,6 +53,9 @@ struct BoxGeom {
   int sign;
   int Csrc, Cdst, K;     // K = taps*Csrc
   int cchunks;           // Csrc / 64
+  // where a row lands in the output tensor: coordinate = row*os + oo inside an (OD,OH,OW) volume. Identity except
+  // for strided dgrad, where each stride-residue class of input voxels is its own dense stride-1 problem.
+  int os[3], oo[3], OD, OH, OW;
 };
 
 __device__ __forceinline__ void box_origin(const BoxGeom& g, int64_t box, int& n, int& d0, int& h0, int& w0) {
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       int n = 0, d0 = 0, h0 = 0, w0 = 0;
       if (mok) box_origin(g, box, n, d0, h0, w0);
       mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
-      const int64_t m = (((int64_t)n * g.D + d0 + ld) * g.H + h0 + lh) * g.W + w0 + lw;
+      const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
+                            g.OW + (w0 + lw) * g.os[2] + g.oo[2];
       const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -447,6 +451,8 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   b.Cdst = which == 1 ? g->Cin : g->Cout;
   b.K = taps * b.Csrc;
   b.cchunks = b.Csrc / 64;
+  for (int i = 0; i < 3; ++i) { b.os[i] = 1; b.oo[i] = 0; }
+  b.OD = b.D; b.OH = b.H; b.OW = b.W;
   return b;
 }
 
@@ -465,15 +471,26 @@ static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const C
   return check_launch("conv_tma_kernel");
 }
 
+static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const void* src, const void* wk,
+                           const float* bias, const float* chan_bias, const void* residual, void* out, void* ws,
+                           int64_t ws_bytes, void* stream);
+
 // src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc]
 static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
                         const float* chan_bias, const void* residual, void* out, void* ws, int64_t ws_bytes,
                         void* stream) {
   BoxGeom b = make_box_geom(g, which);
-  cudaStream_t st = as_stream(stream);
   const int32_t* sdims = which == 1 ? g->out_dims : g->in_dims;   // extent of the SOURCE tensor
+  return launch_box_conv(b, g->N, sdims, src, wk, bias, chan_bias, residual, out, ws, ws_bytes, stream);
+}
+
+// Launch the kernel for a prepared geometry. Split-K (needs `ws`) is only legal when rows map 1:1 to the output.
+static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const void* src, const void* wk,
+                           const float* bias, const float* chan_bias, const void* residual, void* out, void* ws,
+                           int64_t ws_bytes, void* stream) {
+  cudaStream_t st = as_stream(stream);
   CUtensorMap xm, wm;
-  if (make_act_map(&xm, src, g->N, sdims, b.Csrc, b.bd, b.bh, b.bw)) return 1;
+  if (make_act_map(&xm, src, N, sdims, b.Csrc, b.bd, b.bh, b.bw)) return 1;
   const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
   uint64_t dims[2] = {(uint64_t)b.K, (uint64_t)b.Cdst};
   uint64_t strides[1] = {(uint64_t)b.K * 2};
@@ -547,6 +564,107 @@ int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* 
   MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(tma): workspace too small");
   if (filter_transpose(MIG_BF16, w, ws, g->Cout, T, g->Cin, stream)) return 2;
   return run_conv_tma(g, 1, dy, ws, nullptr, nullptr, nullptr, dx, (uint8_t*)ws + wt_bytes, ws_bytes - wt_bytes, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// strided dgrad by stride-residue classes
+// ---------------------------------------------------------------------------------------------------
+// dx[i] = sum_t dy[(i + p - t)/s] w[t] over the taps with (i + p - t) % s == 0. Input voxels with the same residue
+// rho = (i + p) mod s (per axis) see the same tap subset {rho, rho+s, ...}; writing i = s*j + o and t = rho + s*u
+// gives dx_class[j] = sum_u dy[j - u + base] w[rho + s*u]: a dense stride-1 problem per class (2^d classes for
+// stride 2), whose rows scatter back to dx with stride s. Total work = the useful work (no zero taps).
+int filter_transpose_taps(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, int ntaps, const int* taps,
+                          void* stream);
+
+struct AxisClass { int o, ext, nu, base, rho; };
+static AxisClass axis_class(int in, int k, int s, int p, int rho) {
+  AxisClass a;
+  a.rho = rho;
+  a.o = ((rho - p) % s + s) % s;
+  a.ext = in > a.o ? (in - a.o + s - 1) / s : 0;
+  a.nu = rho < k ? (k - rho + s - 1) / s : 0;
+  a.base = (a.o + p - rho) / s;
+  return a;
+}
+
+bool tma_dgrad_strided_eligible(const mig_conv_geom* g) {
+  bool any = false;
+  for (int i = 0; i < 3; ++i) {
+    if (g->stride[i] < 1 || g->stride[i] > 2) return false;
+    any = any || g->stride[i] == 2;
+  }
+  if (!any || g->Cout % 64 != 0 || g->Cin < 8) return false;
+  for (int r0 = 0; r0 < g->stride[0]; ++r0)
+    for (int r1 = 0; r1 < g->stride[1]; ++r1)
+      for (int r2 = 0; r2 < g->stride[2]; ++r2) {
+        AxisClass a[3] = {axis_class(g->in_dims[0], g->ksize[0], g->stride[0], g->pad[0], r0),
+                          axis_class(g->in_dims[1], g->ksize[1], g->stride[1], g->pad[1], r1),
+                          axis_class(g->in_dims[2], g->ksize[2], g->stride[2], g->pad[2], r2)};
+        if (a[0].ext == 0 || a[1].ext == 0 || a[2].ext == 0) continue;
+        if (a[0].nu * a[1].nu * a[2].nu > 32) return false;
+        int bd, bh, bw;
+        if (!pick_box(a[0].ext, a[1].ext, a[2].ext, &bd, &bh, &bw)) return false;
+      }
+  return true;
+}
+
+int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                           void* stream) {
+  const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
+  const int64_t wt_bytes = ((int64_t)g->Cin * T * g->Cout * 2 + 255) / 256 * 256 + 27 * 256;
+  MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(tma, strided): workspace too small");
+  cudaStream_t st = as_stream(stream);
+  bool need_zero = false;
+  uint8_t* wp = (uint8_t*)ws;
+  for (int r0 = 0; r0 < g->stride[0]; ++r0)
+    for (int r1 = 0; r1 < g->stride[1]; ++r1)
+      for (int r2 = 0; r2 < g->stride[2]; ++r2) {
+        AxisClass a[3] = {axis_class(g->in_dims[0], g->ksize[0], g->stride[0], g->pad[0], r0),
+                          axis_class(g->in_dims[1], g->ksize[1], g->stride[1], g->pad[1], r1),
+                          axis_class(g->in_dims[2], g->ksize[2], g->stride[2], g->pad[2], r2)};
+        if (a[0].ext == 0 || a[1].ext == 0 || a[2].ext == 0) continue;
+        if (a[0].nu * a[1].nu * a[2].nu == 0) need_zero = true;
+      }
+  if (need_zero) {   // some input voxels receive no tap at all (e.g. kernel 1 with stride 2)
+    const int64_t n = (int64_t)g->N * g->in_dims[0] * g->in_dims[1] * g->in_dims[2] * g->Cin;
+    cudaMemsetAsync(dx, 0, (size_t)n * 2, st);
+  }
+  for (int r0 = 0; r0 < g->stride[0]; ++r0)
+    for (int r1 = 0; r1 < g->stride[1]; ++r1)
+      for (int r2 = 0; r2 < g->stride[2]; ++r2) {
+        AxisClass a[3] = {axis_class(g->in_dims[0], g->ksize[0], g->stride[0], g->pad[0], r0),
+                          axis_class(g->in_dims[1], g->ksize[1], g->stride[1], g->pad[1], r1),
+                          axis_class(g->in_dims[2], g->ksize[2], g->stride[2], g->pad[2], r2)};
+        const int ntaps = a[0].nu * a[1].nu * a[2].nu;
+        if (a[0].ext == 0 || a[1].ext == 0 || a[2].ext == 0 || ntaps == 0) continue;
+        int taps[32], nt = 0;
+        for (int u0 = 0; u0 < a[0].nu; ++u0)
+          for (int u1 = 0; u1 < a[1].nu; ++u1)
+            for (int u2 = 0; u2 < a[2].nu; ++u2)
+              taps[nt++] = ((a[0].rho + g->stride[0] * u0) * g->ksize[1] + (a[1].rho + g->stride[1] * u1)) * g->ksize[2] +
+                           (a[2].rho + g->stride[2] * u2);
+        if (filter_transpose_taps(MIG_BF16, w, wp, g->Cout, T, g->Cin, nt, taps, stream)) return 2;
+        BoxGeom b{};
+        b.N = g->N; b.D = a[0].ext; b.H = a[1].ext; b.W = a[2].ext;
+        pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
+        b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
+        b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
+        for (int i = 0; i < 3; ++i) {
+          b.ks[i] = a[i].nu;
+          b.off[i] = a[i].base;
+          b.os[i] = g->stride[i];
+          b.oo[i] = a[i].o;
+        }
+        b.sign = -1;
+        b.Csrc = g->Cout; b.Cdst = g->Cin;
+        b.K = nt * b.Csrc;
+        b.cchunks = b.Csrc / 64;
+        b.OD = g->in_dims[0]; b.OH = g->in_dims[1]; b.OW = g->in_dims[2];
+        int rc = launch_box_conv(b, g->N, g->out_dims, dy, wp, nullptr, nullptr, nullptr, dx, nullptr, 0, stream);
+        if (rc) return rc;
+        wp += ((int64_t)g->Cin * nt * g->Cout * 2 + 255) / 256 * 256;
+      }
+  return 0;
 }
 
 template <int BN, int MT>

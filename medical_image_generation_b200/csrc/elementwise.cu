@@ -778,13 +778,39 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
     float c = a.max_norm / (sqrtf(sumsq[0]) + 1e-6f);
     clip = c < 1.f ? c : 1.f;
   }
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float gi = g[i] * clip;
-    float pi = p[i] * (1.f - a.lr * a.wd);
-    float mi = a.b1 * m[i] + (1.f - a.b1) * gi;
-    float vi = a.b2 * v[i] + (1.f - a.b2) * gi * gi;
-    float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= clip;
+    pi *= (1.f - a.lr * a.wd);
+    mi = a.b1 * mi + (1.f - a.b1) * gi;
+    vi = a.b2 * vi + (1.f - a.b2) * gi * gi;
+    const float denom = sqrtf(vi) / a.bc2_sqrt + a.eps;
     pi -= (a.lr / a.bc1) * (mi / denom);
+  };
+  const bool vec = (n % 4 == 0) && (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) |
+                                      reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(shadow) & 7) == 0);
+  if (vec) {   // 128-bit streaming accesses: 7 fp32 streams + the bf16 shadow, one pass over the flat buffers
+    const int64_t n4 = n / 4;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
+      float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+      upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
+      reinterpret_cast<float4*>(p)[i] = P;
+      reinterpret_cast<float4*>(m)[i] = M;
+      reinterpret_cast<float4*>(v)[i] = V;
+      if (shadow) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(P.x, P.y), hi = __floats2bfloat162_rn(P.z, P.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(shadow)[i] = pk;
+      }
+    }
+    return;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
     p[i] = pi; m[i] = mi; v[i] = vi;
     if (shadow) shadow[i] = __float2bfloat16_rn(pi);
   }

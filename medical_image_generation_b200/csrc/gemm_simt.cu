@@ -370,21 +370,59 @@ int simt_conv_dgrad(const mig_conv_geom* g, int dtype, const void* dy, const voi
 }
 
 // [Cout][T][Cin] -> [Cin][T][Cout] (same dtype)
+// per tap: [Cout][Cin] (row pitch Tn*Cin) -> [Cin][Cout] (row pitch Tn*Cout) through a padded 32x32 smem tile,
+// so both the read (along ci) and the write (along co) are coalesced
 template <typename T>
-__global__ void filter_transpose_kernel(const T* __restrict__ w, T* __restrict__ wt, int Cout, int Tn, int Cin) {
-  const int64_t total = (int64_t)Cout * Tn * Cin;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // i indexes the destination so writes are coalesced
-    int co = (int)(i % Cout);
-    int64_t r = i / Cout;
-    int tp = (int)(r % Tn);
-    int ci = (int)(r / Tn);
-    wt[i] = w[((int64_t)co * Tn + tp) * Cin + ci];
+__global__ void __launch_bounds__(256) filter_transpose_kernel(const T* __restrict__ w, T* __restrict__ wt, int Cout,
+                                                               int Tn, int Cin) {
+  __shared__ T tile[32][33];
+  const int tp = blockIdx.z;
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < Cin) tile[i][threadIdx.x] = w[((int64_t)co * Tn + tp) * Cin + ci];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    if (co < Cout && ci < Cin) wt[((int64_t)ci * Tn + tp) * Cout + co] = tile[threadIdx.x][i];
   }
 }
+// same transpose restricted to a subset of taps: wt[ci][j][co] = w[co][taps[j]][ci] (strided-dgrad sub-filters)
+struct TapList { int n; int t[32]; };
+template <typename T>
+__global__ void __launch_bounds__(256) filter_transpose_taps_kernel(const T* __restrict__ w, T* __restrict__ wt,
+                                                                    int Cout, int Tn, int Cin, TapList taps) {
+  __shared__ T tile[32][33];
+  const int j = blockIdx.z, tp = taps.t[j];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int co = co0 + i, ci = ci0 + threadIdx.x;
+    if (co < Cout && ci < Cin) tile[i][threadIdx.x] = w[((int64_t)co * Tn + tp) * Cin + ci];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ci = ci0 + i, co = co0 + threadIdx.x;
+    if (co < Cout && ci < Cin) wt[((int64_t)ci * taps.n + j) * Cout + co] = tile[threadIdx.x][i];
+  }
+}
+int filter_transpose_taps(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, int ntaps, const int* taps,
+                          void* stream) {
+  MIG_REQUIRE(ntaps >= 1 && ntaps <= 32, "filter_transpose_taps: bad tap count %d", ntaps);
+  TapList tl;
+  tl.n = ntaps;
+  for (int i = 0; i < ntaps; ++i) tl.t[i] = taps[i];
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, ntaps), block(32, 8);
+  MIG_DISPATCH_DTYPE(dtype, T, (filter_transpose_taps_kernel<T><<<grid, block, 0, as_stream(stream)>>>(
+                                   (const T*)w, (T*)wt, Cout, Tn, Cin, tl)));
+  return check_launch("filter_transpose_taps");
+}
+
 int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream) {
-  int64_t total = (int64_t)Cout * Tn * Cin;
-  MIG_DISPATCH_DTYPE(dtype, T, (filter_transpose_kernel<T><<<bw_grid(total, 256), 256, 0, as_stream(stream)>>>(
+  if ((int64_t)Cout * Tn * Cin == 0) return 0;
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, Tn), block(32, 8);
+  MIG_REQUIRE(grid.y < 65536 && grid.z < 65536, "filter_transpose: filter too large");
+  MIG_DISPATCH_DTYPE(dtype, T, (filter_transpose_kernel<T><<<grid, block, 0, as_stream(stream)>>>(
                                    (const T*)w, (T*)wt, Cout, Tn, Cin)));
   return check_launch("filter_transpose");
 }

@@ -59,7 +59,19 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
     const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
     const int64_t r1 = r0 + g.rows_per_cta < g.S ? r0 + g.rows_per_cta : g.S;
     const T* base = x + ((int64_t)n * g.S) * g.C + (int64_t)col * V;
-    for (int64_t r = r0 + trow; r < r1; r += g.rpb) {
+    int64_t r = r0 + trow;
+    const int64_t step = g.rpb;
+    for (; r + 3 * step < r1; r += 4 * step) {   // 4 independent 16-byte loads in flight per thread
+      Vec16<T> v0 = ld16(base + r * g.C), v1 = ld16(base + (r + step) * g.C), v2 = ld16(base + (r + 2 * step) * g.C),
+               v3 = ld16(base + (r + 3 * step) * g.C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float a = v0.get(j), b = v1.get(j), c = v2.get(j), d = v3.get(j);
+        s[j] += (a + b) + (c + d);
+        ss[j] += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+    for (; r < r1; r += step) {
       Vec16<T> v = ld16(base + r * g.C);
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -120,7 +132,23 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
   const int64_t r1 = r0 + g.rows_per_cta < g.S ? r0 + g.rows_per_cta : g.S;
   const int64_t off = ((int64_t)n * g.S) * g.C + (int64_t)col * V;
-  for (int64_t r = r0 + trow; r < r1; r += g.rpb) {
+  int64_t r = r0 + trow;
+  const int64_t step = g.rpb;
+  for (; r + 3 * step < r1; r += 4 * step) {
+    Vec16<T> v[4], o;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = ld16(x + off + (r + u * step) * g.C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float z = fmaf(v[u].get(j), a[j], b[j]);
+        o.set(j, SILU ? silu_f(z) : z);
+      }
+      st16(y + off + (r + u * step) * g.C, o);
+    }
+  }
+  for (; r < r1; r += step) {
     Vec16<T> v = ld16(x + off + r * g.C), o;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -143,11 +171,11 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
   const int n = blockIdx.z, slab = blockIdx.y;
   const int tcol = threadIdx.x % g.cvb, trow = threadIdx.x / g.cvb;
   const int col = slab * g.cvb + tcol;
-  if (col >= g.cv || trow >= g.rpb) return;
+  const bool active = col < g.cv && trow < g.rpb;   // inactive threads still take part in the smem reduction
   float mu[V], rs[V], ga[V], be[V], p1[V], p2[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    int c = col * V + j;
+    int c = active ? col * V + j : 0;
     int grp = c / g.cpg;
     mu[j] = mean[n * g.G + grp];
     rs[j] = rstd[n * g.G + grp];
@@ -156,9 +184,29 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
     p1[j] = p2[j] = 0.f;
   }
   const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
-  const int64_t r1 = r0 + g.rows_per_cta < g.S ? r0 + g.rows_per_cta : g.S;
-  const int64_t off = ((int64_t)n * g.S) * g.C + (int64_t)col * V;
-  for (int64_t r = r0 + trow; r < r1; r += g.rpb) {
+  const int64_t r1 = !active ? r0 : (r0 + g.rows_per_cta < g.S ? r0 + g.rows_per_cta : g.S);
+  const int64_t off = ((int64_t)n * g.S) * g.C + (int64_t)(active ? col : 0) * V;
+  int64_t r = r0 + trow;
+  const int64_t step = g.rpb;
+  for (; r + 3 * step < r1; r += 4 * step) {   // 8 independent 16-byte loads in flight per thread
+    Vec16<T> vx[4], vd[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      vx[u] = ld16(x + off + (r + u * step) * g.C);
+      vd[u] = ld16(dy + off + (r + u * step) * g.C);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float xh = (vx[u].get(j) - mu[j]) * rs[j];
+        float dz = vd[u].get(j);
+        if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+        p1[j] += dz * xh;
+        p2[j] += dz;
+      }
+  }
+  for (; r < r1; r += step) {
     Vec16<T> vx = ld16(x + off + r * g.C), vd = ld16(dy + off + r * g.C);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -169,11 +217,25 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
       p2[j] += dz;
     }
   }
+  // reduce the rpb thread-rows of this CTA through shared memory: one global atomic per (CTA, channel, moment)
+  // instead of one per thread (the same (n, c) address is hit by every CTA of the sample)
+  extern __shared__ float red[];   // [blockDim.x][2V] laid out as [(j*2+m)][thread] -> conflict-free
+  const int nt = blockDim.x;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
-    int c = col * V + j;
-    atomicAdd(&ws[((int64_t)n * g.C + c) * 2], p1[j]);
-    atomicAdd(&ws[((int64_t)n * g.C + c) * 2 + 1], p2[j]);
+    red[(2 * j) * nt + threadIdx.x] = p1[j];
+    red[(2 * j + 1) * nt + threadIdx.x] = p2[j];
+  }
+  __syncthreads();
+  // thread t finishes entry e = t: (column tcol', item q) with q in [0, 2V): loop so any block shape works
+  for (int e = threadIdx.x; e < g.cvb * 2 * V; e += nt) {
+    const int q = e / g.cvb, tc = e - q * g.cvb;
+    const int ccol = slab * g.cvb + tc;
+    if (ccol >= g.cv) continue;
+    float s = 0.f;
+    for (int rr = 0; rr < g.rpb; ++rr) s += red[q * nt + rr * g.cvb + tc];
+    const int c = ccol * V + (q >> 1);
+    atomicAdd(&ws[((int64_t)n * g.C + c) * 2 + (q & 1)], s);
   }
 }
 
@@ -233,7 +295,28 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
   const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
   const int64_t r1 = r0 + g.rows_per_cta < g.S ? r0 + g.rows_per_cta : g.S;
   const int64_t off = ((int64_t)n * g.S) * g.C + (int64_t)col * V;
-  for (int64_t r = r0 + trow; r < r1; r += g.rpb) {
+  int64_t r = r0 + trow;
+  const int64_t step = g.rpb;
+  for (; r + 1 * step < r1; r += 2 * step) {
+    Vec16<T> vx[2], vd[2], o;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      vx[u] = ld16(x + off + (r + u * step) * g.C);
+      vd[u] = ld16(dy + off + (r + u * step) * g.C);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float xh = (vx[u].get(j) - mu[j]) * rs[j];
+        float dz = vd[u].get(j);
+        if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+        o.set(j, rs[j] * (dz * ga[j] - (xh * A[j] + B[j])));
+      }
+      st16(dx + off + (r + u * step) * g.C, o);
+    }
+  }
+  for (; r < r1; r += step) {
     Vec16<T> vx = ld16(x + off + r * g.C), vd = ld16(dy + off + r * g.C), o;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -289,8 +372,8 @@ static int gn_bwd(const void* x, const void* dy, const float* gamma, const float
   float* wsc = (float*)ws;
   float* wsg = wsc + (int64_t)N * C * 2;
   cudaMemsetAsync(wsc, 0, sizeof(float) * (size_t)N * C * 2, st);
-  if (silu) gn_bwd_stats_kernel<T, true><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
-  else gn_bwd_stats_kernel<T, false><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
+  if (silu) gn_bwd_stats_kernel<T, true><<<grid, threads, threads * 2 * Vec16<T>::N * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
+  else gn_bwd_stats_kernel<T, false><<<grid, threads, threads * 2 * Vec16<T>::N * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
   int fin = C > N * G ? C : N * G;
   gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(wsc, gamma, dgamma, dbeta, wsg, N, C, G);
   float inv = 1.f / ((float)S * (float)g.cpg);

@@ -46,6 +46,12 @@ CONV_CASES = [
     (8, 64, 256, (24, 24, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),  # BASELINE-size level 0: fwd uses the 256x256 CTA tile
     (8, 256, 64, (24, 24, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),  # ... and dgrad / wgrad use it here
     (2, 128, 256, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # 6^3: overhanging 2x4x8 boxes, split-K
+    # strided Downsample convs: dgrad runs as stride-residue classes on the TMA kernel
+    (2, 64, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 128, 64, (8, 16, 16), (3, 3, 3), (1, 2, 2), (1, 1, 1)),   # anisotropic stride
+    (1, 64, 64, (16, 16, 8), (3, 3, 1), (2, 2, 1), (1, 1, 0)),    # thin axis: kernel 1 / pad 0 / stride 1
+    (2, 64, 128, (9, 11, 16), (3, 3, 3), (2, 2, 2), (1, 1, 1)),   # odd extents: classes of different size
+    (1, 64, 64, (8, 8, 8), (1, 1, 1), (2, 2, 2), (0, 0, 0)),      # kernel 1 stride 2: most input voxels get zero gradient
 ]
 
 
