@@ -167,8 +167,9 @@ int mig_vae_sample_bwd(int dtype, const void* logvar, const void* eps, const voi
                        const void* dsigma_ext, void* dmu, void* dlogvar, int64_t n, void* stream);
 
 /* ---- K18: optimizer on flat fp32 buffers (ldm:121,171-180) ---------------------------------------- */
-/* out[0] += sum(g^2) over n elements (call per segment, then sqrt on host/device) */
-int mig_sumsq(const float* g, float* out, int64_t n, void* stream);
+/* out[0] = sum(g^2) over n elements, deterministic two-stage reduction (`partials` needs 2048 floats): data-
+ * parallel replicas must derive bit-identical clip coefficients. torch.nn.utils.clip_grad_norm_ (ldm:177) */
+int mig_sumsq(const float* g, float* out, float* partials, int64_t n, void* stream);
 /* AdamW (decoupled weight decay, torch.optim.AdamW semantics); grad pre-scale = min(1, max_norm/(norm+1e-6))
  * read from device scalar sumsq when max_norm > 0. bf16_shadow (optional) receives the updated params in bf16. */
 int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,

@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
        i += (int64_t)gridDim.x * blockDim.x)
     acc += g[i] * g[i];
   acc = block_sum(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0) out[blockIdx.x] = acc;   // per-CTA partial; summed in a fixed order by loss_final_kernel
 }
 
 struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt, max_norm; };
@@ -817,9 +817,14 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
 }
 }  // namespace mig
 
-extern "C" int mig_sumsq(const float* g, float* out, int64_t n, void* stream) {
-  if (n <= 0) return 0;
-  sumsq_kernel<<<bw_grid((n + 3) / 4, 256, 4), 256, 0, as_stream(stream)>>>(g, out, n, aligned16(g));
+extern "C" int mig_sumsq(const float* g, float* out, float* partials, int64_t n, void* stream) {
+  MIG_REQUIRE(n > 0 && partials != nullptr, "sumsq: empty input or missing partials buffer");
+  // deterministic: per-CTA partials, then one CTA adds them in a fixed order (in double). Data-parallel replicas
+  // must compute bit-identical clip coefficients or they drift apart.
+  int grid = bw_grid((n + 3) / 4, 256, 4);
+  if (grid > kLossBlocks) grid = kLossBlocks;
+  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, partials, n, aligned16(g));
+  loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, out, 1.0);
   return check_launch("sumsq");
 }
 extern "C" int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,

@@ -27,6 +27,59 @@ def _dist_on() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
+class GradBuckets:
+    """Contiguous gradient buckets over ONE flat buffer, all-reduced (mean) as soon as every member gradient has
+    been produced. Device-agnostic host logic: NCCL over NVLink on the GPUs, gloo in the CPU tests.
+
+    `sizes[i]` is the (padded) element count of member i in buffer order; members are referred to by index."""
+
+    def __init__(self, flat: torch.Tensor, sizes, cap_elems: int, group=None):
+        self.flat, self.group = flat, group
+        self.world = dist.get_world_size(group)
+        self.avg_native = dist.get_backend(group) == "nccl"   # gloo has no ReduceOp.AVG
+        self.buckets, self.bucket_of = [], []
+        start = count = n = 0
+        for sz in sizes:
+            self.bucket_of.append(len(self.buckets))
+            count += int(sz)
+            n += 1
+            if count >= cap_elems:
+                self.buckets.append(dict(lo=start, hi=start + count, n=n, pending=n, work=None))
+                start, count, n = start + count, 0, 0
+        if n:
+            self.buckets.append(dict(lo=start, hi=start + count, n=n, pending=n, work=None))
+        self.seen = set()
+
+    def _launch(self, bk) -> None:
+        op = dist.ReduceOp.AVG if self.avg_native else dist.ReduceOp.SUM
+        bk["work"] = dist.all_reduce(self.flat[bk["lo"]:bk["hi"]], op=op, group=self.group, async_op=True)
+
+    def ready(self, index: int) -> None:
+        """Member `index` has its final gradient in the flat buffer."""
+        if index in self.seen:
+            return
+        self.seen.add(index)
+        bk = self.buckets[self.bucket_of[index]]
+        bk["pending"] -= 1
+        if bk["pending"] == 0:
+            self._launch(bk)
+
+    def reset(self) -> None:
+        self.seen.clear()
+        for bk in self.buckets:
+            bk["pending"], bk["work"] = bk["n"], None
+
+    def finish(self) -> None:
+        """Reduce the buckets that did not fire during backward (a member unused this step), then wait for all."""
+        for bk in self.buckets:
+            if bk["work"] is None:
+                self._launch(bk)
+        for bk in self.buckets:
+            bk["work"].wait()
+            if not self.avg_native:
+                self.flat[bk["lo"]:bk["hi"]].div_(self.world)
+
+
 class FlatAdamW:
     """AdamW + global-norm clipping over flat buffers; numerics follow torch.optim.AdamW / clip_grad_norm_."""
 
@@ -58,6 +111,7 @@ class FlatAdamW:
         self.v = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
         self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._partials = torch.zeros(2048, dtype=torch.float32, device=dev)
         self.params = []
         off = 0
         for n, p in used + tail:
@@ -73,50 +127,26 @@ class FlatAdamW:
             off += pad(k)
         call("mig_cast", 0, 1, ops._ptr(self.master), ops._ptr(self.shadow), total, ops._stream())
         # ---- gradient buckets (contiguous slices of the used region) ----
-        self.buckets = []
-        self._bucket_of = {}
+        self.buckets = None
+        self._index_of = {}
         if _dist_on():
-            cap = int(bucket_mb * (1 << 20) / 4)
-            start, count, members = 0, 0, []
-            for n, p in used:
-                members.append(p)
-                count += pad(p.numel())
-                if count >= cap:
-                    self.buckets.append(dict(lo=start, hi=start + count, pending=len(members), n=len(members), work=None))
-                    for q in members:
-                        self._bucket_of[id(q)] = len(self.buckets) - 1
-                    start, count, members = start + count, 0, []
-            if members:
-                self.buckets.append(dict(lo=start, hi=start + count, pending=len(members), n=len(members), work=None))
-                for q in members:
-                    self._bucket_of[id(q)] = len(self.buckets) - 1
+            self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
+            self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
             ops.set_grad_ready_hook(self._grad_ready)
-        self._seen = set()
 
     # called from the backward kernels' wrappers once a parameter's gradient is complete in `main_grad`
     def _grad_ready(self, p) -> None:
-        b = self._bucket_of.get(id(p))
-        if b is None or id(p) in self._seen:
-            return
-        self._seen.add(id(p))
-        bk = self.buckets[b]
-        bk["pending"] -= 1
-        if bk["pending"] == 0:
-            bk["work"] = dist.all_reduce(self.grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.AVG, async_op=True)
+        i = self._index_of.get(id(p))
+        if i is not None:
+            self.buckets.ready(i)
 
     def zero_grad(self) -> None:
         self.grad.zero_()
-        self._seen.clear()
-        for bk in self.buckets:
-            bk["pending"], bk["work"] = bk["n"], None
+        if self.buckets is not None:
+            self.buckets.reset()
 
     def finish_grad_sync(self) -> None:
-        """Reduce whatever bucket did not fire during backward (e.g. a parameter unused this step), then wait."""
-        for bk in self.buckets:
-            if bk["work"] is None:
-                bk["work"] = dist.all_reduce(self.grad[bk["lo"]:bk["hi"]], op=dist.ReduceOp.AVG, async_op=True)
-        for bk in self.buckets:
-            bk["work"].wait()
+        self.buckets.finish()
 
     def step(self) -> None:
         # gradients that arrived through plain autograd (.grad) -- e.g. nn.Embedding -- join the flat buffer here
@@ -124,15 +154,14 @@ class FlatAdamW:
             if p.grad is not None:
                 p.main_grad.add_(p.grad)
                 p.grad = None
-        if self.buckets:
+        if self.buckets is not None:
             self.finish_grad_sync()
         self.step_count += 1
         st = ops._stream()
         sumsq_ptr = None
         max_norm = 0.0
         if self.max_grad_norm:
-            self.sumsq.zero_()
-            call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), self.used_numel, st)
+            call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), ops._ptr(self._partials), self.used_numel, st)
             sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
         call("mig_adamw_step", ops._ptr(self.master), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
              self.used_numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),

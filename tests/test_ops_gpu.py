@@ -340,7 +340,11 @@ def test_adamw_and_clip_match_torch():
         opt.step()
         gd = gr.to(DEV)
         ss = torch.zeros(1, device=DEV)
-        _lib.call("mig_sumsq", C.c_void_p(gd.data_ptr()), C.c_void_p(ss.data_ptr()), n, st)
+        parts = torch.zeros(2048, device=DEV)
+        _lib.call("mig_sumsq", C.c_void_p(gd.data_ptr()), C.c_void_p(ss.data_ptr()), C.c_void_p(parts.data_ptr()), n, st)
+        ss2 = torch.zeros(1, device=DEV)
+        _lib.call("mig_sumsq", C.c_void_p(gd.data_ptr()), C.c_void_p(ss2.data_ptr()), C.c_void_p(parts.data_ptr()), n, st)
+        assert torch.equal(ss, ss2)       # deterministic (bit-identical replicas under data parallelism)
         assert rel_err(ss.sqrt(), gr.norm()) < 1e-5
         _lib.call("mig_adamw_step", C.c_void_p(p.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(m.data_ptr()),
                   C.c_void_p(v.data_ptr()), n, 2e-5, 0.9, 0.999, 1e-8, 0.01, step, C.c_void_p(ss.data_ptr()), 1.0,

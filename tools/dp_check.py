@@ -1,0 +1,67 @@
+"""Launched with torchrun on N GPUs: the data-parallel LDMTrainer must (a) keep replicas bit-identical and (b) match a
+single-process run on the concatenated global batch (fp32, small U-Net)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, ".")
+import medical_image_generation_b200 as mig  # noqa: E402
+from medical_image_generation_b200.engine import LDMTrainer  # noqa: E402
+from oracle.golden_util import golden_params  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+g = torch.load("tests/golden/unet3d_small.pt", weights_only=False)
+params = golden_params(g["shapes"], g["seed"])
+kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+
+
+def make(dp):
+    m = mig.DiffusionModelUNet(**g["cfg"], compute_dtype=torch.float32)
+    m.load_state_dict(params)
+    return m.cuda().train()
+
+
+gen = torch.Generator().manual_seed(7)
+B = 2
+steps = 3
+data = [(torch.randn(world * B, 3, 8, 8, 8, generator=gen), torch.randn(world * B, 3, 8, 8, 8, generator=gen),
+         torch.randint(0, 1000, (world * B,), generator=gen)) for _ in range(steps)]
+# data-parallel run: each rank sees its slice
+m_dp = make(True)
+tr = LDMTrainer(m_dp, mig.DDPMScheduler(**kw), lr=1e-3, bucket_mb=1.0)
+assert tr.opt.buckets is not None and len(tr.opt.buckets.buckets) > 1
+for x0, nz, t in data:
+    sl = slice(rank * B, (rank + 1) * B)
+    tr.step(x0[sl].cuda(), noise=nz[sl].cuda(), timesteps=t[sl].cuda())
+flat = tr.opt.master.clone()
+tr.opt.close()
+# replicas identical
+ref = flat.clone()
+dist.broadcast(ref, src=0)
+same = bool(torch.equal(ref, flat))
+# single-process run on the global batch (rank 0 only, no process group involvement: world-size-1 semantics)
+ok_global = True
+if rank == 0:
+    import torch.distributed as d2
+    m1 = make(False)
+    opt = torch.optim.AdamW(m1.parameters(), lr=1e-3)
+    s = mig.DDPMScheduler(**kw)
+    for x0, nz, t in data:
+        pred = m1(s.add_noise(x0.cuda(), nz.cuda(), t.cuda()), t.cuda())
+        loss = mig.ops.mse_loss(pred, nz.cuda())
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m1.parameters(), 1.0)
+        opt.step()
+    pa, pb = dict(m_dp.named_parameters()), dict(m1.named_parameters())
+    worst = max(float((pa[k] - pb[k]).norm() / pb[k].norm().clamp_min(1e-12)) for k in pa)
+    ok_global = worst < 5e-4
+    print(f"dp{world}: replicas identical={same}; vs single-process global batch worst rel diff {worst:.2e}", flush=True)
+flag = torch.tensor([int(same and ok_global)], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(flag) == 1 else 1)
