@@ -171,10 +171,12 @@ int mig_vae_sample_bwd(int dtype, const void* logvar, const void* eps, const voi
  * parallel replicas must derive bit-identical clip coefficients. torch.nn.utils.clip_grad_norm_ (ldm:177) */
 int mig_sumsq(const float* g, float* out, float* partials, int64_t n, void* stream);
 /* AdamW (decoupled weight decay, torch.optim.AdamW semantics); grad pre-scale = min(1, max_norm/(norm+1e-6))
- * read from device scalar sumsq when max_norm > 0. bf16_shadow (optional) receives the updated params in bf16. */
+ * read from device scalar sumsq when max_norm > 0. bf16_shadow (optional) receives the updated params in bf16.
+ * step_device (optional): device int32 holding the 1-based step count; overrides `step` so that a captured CUDA
+ * graph of the training step stays correct on replay. */
 int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int32_t step, const float* sumsq, float max_norm,
-                   void* bf16_shadow, void* stream);
+                   void* bf16_shadow, const int32_t* step_device, void* stream);
 
 #ifdef __cplusplus
 }

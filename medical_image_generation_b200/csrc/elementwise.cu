@@ -771,7 +771,13 @@ struct AdamArgs { float lr, b1, b2, eps, wd, bc1, bc2_sqrt, max_norm; };
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                     AdamArgs a, const float* __restrict__ sumsq,
-                                                    __nv_bfloat16* __restrict__ shadow) {
+                                                    __nv_bfloat16* __restrict__ shadow,
+                                                    const int* __restrict__ step_dev) {
+  if (step_dev) {   // step counter lives on the device (CUDA-graph replay): bias corrections computed here
+    const double t = (double)step_dev[0];
+    a.bc1 = (float)(1.0 - pow((double)a.b1, t));
+    a.bc2_sqrt = (float)sqrt(1.0 - pow((double)a.b2, t));
+  }
   float clip = 1.f;
   if (a.max_norm > 0.f && sumsq) {
     // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
@@ -829,11 +835,13 @@ extern "C" int mig_sumsq(const float* g, float* out, float* partials, int64_t n,
 }
 extern "C" int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
-                              float max_norm, void* bf16_shadow, void* stream) {
+                              float max_norm, void* bf16_shadow, const int32_t* step_device, void* stream) {
   if (n <= 0) return 0;
-  MIG_REQUIRE(step >= 1, "adamw: step counts from 1");
-  AdamArgs a{lr, beta1, beta2, eps, weight_decay, (float)(1.0 - pow((double)beta1, (double)step)),
-             (float)sqrt(1.0 - pow((double)beta2, (double)step)), max_norm};
-  adamw_kernel<<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, sumsq, (__nv_bfloat16*)bf16_shadow);
+  MIG_REQUIRE(step >= 1 || step_device != nullptr, "adamw: step counts from 1");
+  const int s = step >= 1 ? step : 1;
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, (float)(1.0 - pow((double)beta1, (double)s)),
+             (float)sqrt(1.0 - pow((double)beta2, (double)s)), max_norm};
+  adamw_kernel<<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, sumsq, (__nv_bfloat16*)bf16_shadow,
+                                                               step_device);
   return check_launch("adamw");
 }

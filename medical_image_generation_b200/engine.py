@@ -112,6 +112,7 @@ class FlatAdamW:
         self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._partials = torch.zeros(2048, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.params = []
         off = 0
         for n, p in used + tail:
@@ -156,7 +157,8 @@ class FlatAdamW:
                 p.grad = None
         if self.buckets is not None:
             self.finish_grad_sync()
-        self.step_count += 1
+        self.step_count += 1          # host mirror; the kernel reads the device counter (valid under graph replay)
+        self.step_dev.add_(1)
         st = ops._stream()
         sumsq_ptr = None
         max_norm = 0.0
@@ -165,7 +167,8 @@ class FlatAdamW:
             sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
         call("mig_adamw_step", ops._ptr(self.master), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
              self.used_numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-             float(self.weight_decay), int(self.step_count), sumsq_ptr, max_norm, ops._ptr(self.shadow), st)
+             float(self.weight_decay), int(self.step_count), sumsq_ptr, max_norm, ops._ptr(self.shadow),
+             ops._ptr(self.step_dev), st)
 
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm of the last step() (device scalar; no sync)."""
@@ -184,7 +187,8 @@ class LDMTrainer:
     no_grad, exactly as the reference does), data-parallel across the process group when one is initialised."""
 
     def __init__(self, unet, scheduler, lr: float = 2e-5, grad_clip_max_norm: Optional[float] = 1.0,
-                 weight_decay: float = 1e-2, bucket_mb: float = 64.0):
+                 weight_decay: float = 1e-2, bucket_mb: float = 64.0, cuda_graph: bool = False,
+                 graph_warmup_steps: int = 3):
         self.unet, self.scheduler = unet, scheduler
         self.opt = FlatAdamW(unet, lr=lr, weight_decay=weight_decay, max_grad_norm=grad_clip_max_norm,
                              bucket_mb=bucket_mb)
@@ -192,9 +196,52 @@ class LDMTrainer:
             dist.broadcast(self.opt.master, src=0)
             call("mig_cast", 0, 1, ops._ptr(self.opt.master), ops._ptr(self.opt.shadow), self.opt.master.numel(),
                  ops._stream())
+        # CUDA graph of the whole step (add_noise -> U-Net fwd -> MSE -> bwd -> all-reduce -> clip -> AdamW): the
+        # step is ~1300 kernel launches, so replaying one graph removes the launch gaps. The first
+        # `graph_warmup_steps` calls run eagerly (they are real optimiser steps), the next call is captured.
+        self.cuda_graph = cuda_graph
+        self._eager_calls = 0
+        self._warm = graph_warmup_steps
+        self._graph = None
+        self._static_x = self._static_loss = None
+        self._graph_key = None
 
     def step(self, latents_scaled: torch.Tensor, noise: Optional[torch.Tensor] = None,
              timesteps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.cuda_graph and noise is None and timesteps is None:
+            return self._graph_step(latents_scaled)
+        return self._eager_step(latents_scaled, noise, timesteps)
+
+    def _graph_step(self, x0: torch.Tensor) -> torch.Tensor:
+        key = (tuple(x0.shape), x0.dtype, float(self.opt.lr))
+        if self._graph is not None and key != self._graph_key:   # shape or lr changed: capture again
+            self._graph, self._eager_calls = None, 0
+        if self._graph is None:
+            if self._eager_calls < self._warm:
+                self._eager_calls += 1
+                return self._eager_step(x0, None, None)
+            self._static_x = x0.clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph):
+                    self._static_loss = self._eager_step(self._static_x, None, None)
+            except Exception as e:  # noqa: BLE001 -- fall back loudly, never silently change numerics
+                self.cuda_graph = False
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing eagerly")
+                torch.cuda.synchronize()
+                return self._eager_step(x0, None, None)
+            self._graph, self._graph_key = graph, key
+            # capture does not execute: the captured step's host-side counter advanced once, the device one did not
+        else:
+            self._static_x.copy_(x0, non_blocking=True)
+            self.opt.step_count += 1
+        self._graph.replay()
+        return self._static_loss
+
+    def _eager_step(self, latents_scaled: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                    timesteps: Optional[torch.Tensor] = None) -> torch.Tensor:
         s = self.scheduler
         x0 = latents_scaled
         if timesteps is None:  # train_ldm.py:145

@@ -348,7 +348,7 @@ def test_adamw_and_clip_match_torch():
         assert rel_err(ss.sqrt(), gr.norm()) < 1e-5
         _lib.call("mig_adamw_step", C.c_void_p(p.data_ptr()), C.c_void_p(gd.data_ptr()), C.c_void_p(m.data_ptr()),
                   C.c_void_p(v.data_ptr()), n, 2e-5, 0.9, 0.999, 1e-8, 0.01, step, C.c_void_p(ss.data_ptr()), 1.0,
-                  C.c_void_p(shadow.data_ptr()), st)
+                  C.c_void_p(shadow.data_ptr()), None, st)
         assert rel_err(p, pr.detach()) < 1e-6
     assert rel_err(shadow, p) < 4e-3
 
