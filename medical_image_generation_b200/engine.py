@@ -256,3 +256,57 @@ class LDMTrainer:
         loss.backward()
         self.opt.step()
         return loss
+
+
+class AETrainer:
+    """Generator step of train_autoencoder.AutoEncoder.train_generator_step (train_autoencoder.py:399-436) restricted
+    to the terms that need no downloaded networks: L1 reconstruction + kl_weight * KL (train_autoencoder.py:67-72,
+    412-414). Perceptual and adversarial terms are out of scope. Data-parallel like LDMTrainer."""
+
+    def __init__(self, autoencoder, lr: float = 5e-5, kl_weight: float = 1e-7,
+                 grad_clip_max_norm: Optional[float] = 1.0, bucket_mb: float = 64.0):
+        self.ae, self.kl_weight = autoencoder, kl_weight
+        # the reference uses torch.optim.Adam (no weight decay) for the generator (train_autoencoder.py:470)
+        self.opt = FlatAdamW(autoencoder, lr=lr, weight_decay=0.0, max_grad_norm=grad_clip_max_norm,
+                             bucket_mb=bucket_mb, unused=("proj_attn",))
+        if _dist_on():
+            dist.broadcast(self.opt.master, src=0)
+            call("mig_cast", 0, 1, ops._ptr(self.opt.master), ops._ptr(self.opt.shadow), self.opt.master.numel(),
+                 ops._stream())
+
+    def step(self, images: torch.Tensor, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.opt.zero_grad()
+        z_mu, z_sigma = self.ae.encode(images)
+        z = ops.vae_reparam(z_mu, z_sigma, eps) if eps is not None else self.ae.sampling(z_mu, z_sigma)
+        recon = self.ae.decode(z)
+        loss = ops.l1_loss(recon, images) + self.kl_weight * ops.kl_loss(z_mu, z_sigma)
+        loss.backward()
+        self.opt.step()
+        return loss
+
+
+@torch.no_grad()
+def sample_volumes(unet, scheduler, shape, num_volumes: int, base_seed: int = 42, autoencoder=None,
+                   scale_factor: float = 1.0, num_inference_steps: Optional[int] = None, noise_mode: str = "device"):
+    """Sampling sharder: volume v goes to rank v % world, seeded base_seed + v, full reverse process
+    (train_ldm.py:332-366 / train_ddpm.py:238-246) on that rank; NO communication. Returns {volume index: tensor} for
+    the volumes of this rank. `shape` is one volume's (C, *spatial)."""
+    from .inferers import DiffusionInferer, LatentDiffusionInferer
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    dev = next(unet.parameters()).device
+    scheduler.noise_mode = noise_mode
+    scheduler.set_timesteps(num_inference_steps or scheduler.num_train_timesteps)
+    unet.eval()
+    out = {}
+    for v in range(rank, num_volumes, world):
+        with torch.random.fork_rng(devices=[dev]):
+            torch.manual_seed(base_seed + v)                                   # per-volume seed
+            noise = torch.randn(1, *shape).to(dev)                             # CPU draw like train_ldm.py:343-349
+            if autoencoder is not None:
+                inf = LatentDiffusionInferer(scheduler, scale_factor=scale_factor)
+                out[v] = inf.sample(noise, autoencoder_model=autoencoder, diffusion_model=unet, scheduler=scheduler,
+                                    verbose=False)
+            else:
+                out[v] = DiffusionInferer(scheduler).sample(noise, unet, scheduler, verbose=False)
+    return out

@@ -1,0 +1,45 @@
+"""BASELINE config 4: DDPM sampling of 1x128x128x64 volumes with anisotropic strides [[1,1,1],[2,2,1],[2,2,2]].
+Widths are not pinned by the reference: candidate A = (32,64,128), attention on the coarsest level
+with 128-channel heads. Times `steps` reverse steps (U-Net forward + fused scheduler step) and reports the
+1000-step volumes/min this implies (stated as an extrapolation)."""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+import medical_image_generation_b200 as mig  # noqa: E402
+from medical_image_generation_b200 import planner  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+widths = (32, 64, 128) if (len(sys.argv) < 3 or sys.argv[2] == "A") else (64, 128, 256)
+torch.manual_seed(0)
+cfg = dict(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=2, num_channels=list(widths),
+           attention_levels=[False, False, True], num_head_channels=[0, 0, widths[2]], norm_num_groups=32,
+           strides=[[1, 1, 1], [2, 2, 1], [2, 2, 2]], kernel_sizes=[[3, 3, 3]] * 3, paddings=[[1, 1, 1]] * 3)
+m = mig.DiffusionModelUNet(**cfg).cuda().eval()
+with torch.no_grad():
+    for p in m.parameters():
+        if float(p.abs().max()) == 0:
+            p.normal_(0, 0.02)
+s = mig.DDPMScheduler(**planner.LDM_SCHEDULER_KWARGS)
+s.noise_mode = "device"
+s.set_timesteps(1000)
+inf = mig.DiffusionInferer(s)
+x = torch.randn(1, 1, 128, 128, 64, device="cuda")
+ts = s.timesteps[:steps + 3]
+with torch.no_grad():
+    img = x
+    for t in ts[:3]:
+        out = m(img, timesteps=torch.Tensor((t,)).cuda())
+        img, _ = s.step(out, t, img)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in ts[3:]:
+        out = m(img, timesteps=torch.Tensor((t,)).cuda())
+        img, _ = s.step(out, t, img)
+    e1.record()
+    torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+print(f"DDPM sampling widths {widths}: {ms:.2f} ms per reverse step -> {1000 * ms / 1e3:.1f} s per 1000-step volume -> "
+      f"{60.0 / (1000 * ms / 1e3):.2f} volumes/min/GPU (extrapolated from {steps} timed steps); finite={bool(torch.isfinite(img).all())}")
