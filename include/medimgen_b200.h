@@ -77,6 +77,13 @@ typedef struct {
 int mig_gemm_strided(const mig_gemm_desc* d, int dtype_ab, int dtype_c, const void* A, const void* B, void* C,
                      int engine, void* stream);
 
+/* Fused flash-style attention forward on tcgen05 (replaces xformers.ops.memory_efficient_attention unet:128-135,403
+ * and the baddbmm/softmax/bmm chain unet:406-416 when no gradient is needed): out = softmax(scale * q k^T) v per
+ * (batch, head). q (B,Lq,H*dh), k/v (B,Lk,H*dh), out (B,Lq,H*dh): contiguous bf16. lse: workspace of B*H*Lq floats
+ * (receives the log2-domain log-sum-exp). dh must be a multiple of 64 (above 256: a multiple of 256). */
+int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B, int32_t H,
+                            int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream);
+
 /* ---- K4/K5: GroupNorm (+SiLU), nn.GroupNorm at unet:628,648,275,377,1932; ae:157,167,238,451,604 ----
  * x,y: [N][S][C] channels-last, S = D*H*W. mean/rstd: [N][G] fp32 (saved for backward). */
 int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,

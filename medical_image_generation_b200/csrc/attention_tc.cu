@@ -1,0 +1,325 @@
+// Fused flash-style attention forward on tcgen05 (replaces xformers.ops.memory_efficient_attention, unet:128-135,403;
+// and the baddbmm -> softmax -> bmm chain unet:406-416 when no gradient is required).
+//
+//   O[b, q, h*dh + :] = softmax_k(scale * Q K^T) V        per (batch b, head h); heads live inside the channel dim.
+//
+// The L x L score matrix never goes to HBM. Two passes, both with S = Q K^T accumulated in tensor memory:
+//   pass 0 (stats)  : per row running max / sum over all key tiles  ->  lse[row] = max + log2(sum)  (log2 domain)
+//   pass 1 (output) : P = exp2(S * scale*log2e - lse) is ALREADY normalised, so O += P V needs no rescaling of the
+//                     accumulator (no TMEM read-modify-write, no correction warps); S is double-buffered in TMEM so
+//                     the softmax of key tile j overlaps the Q K^T of tile j+1.
+// Head dims above 256 (the LDM default uses single heads of 512 / 768 channels) do not fit TMEM next to S: the
+// value/output dim is cut into 256-column slices, one CTA per slice (each recomputes S).
+//
+// Roles (192 threads): warps 0-3 softmax + epilogue (thread = query row = TMEM lane), warp 4 UMMA issuer + TMEM
+// allocator, warp 5 TMA issuer. Shared memory: 3-stage ring for (Q chunk, K chunk) pairs, one P tile (bf16,
+// K-major, 128B swizzle = the A operand of P V), 2-stage ring for V half-tiles (MN-major B operand).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace mig {
+
+using namespace tc;
+
+constexpr int FA_THREADS = 192;
+constexpr int FA_BM = 128, FA_BN = 128;         // query rows / keys per tile
+constexpr int FA_QK_STAGES = 3, FA_V_STAGES = 2;
+constexpr int FA_QK_STAGE_BYTES = 2 * FA_BM * 128;   // Q chunk + K chunk, 64 channels each
+constexpr int FA_P_BYTES = 2 * FA_BM * 128;          // 128 x 128 bf16 as two 64-key panels
+constexpr int FA_PANEL = 64 * 128;
+
+struct FlashParams {
+  int B, H, Lq, Lk, dh, DV;   // DV = value/output columns handled by one CTA (<= 256)
+  float scale_log2;           // softmax scale * log2(e)
+  float* lse;                 // [B*H][Lq], log2 domain
+  __nv_bfloat16* out;         // (B, Lq, H*dh)
+};
+
+// bars: qk_full[3] qk_empty[3] v_full[2] v_empty[2] s_full[2] s_empty[2] p_full p_empty o_full
+template <int PASS>
+__global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_constant__ CUtensorMap qmap,
+                                                                  const __grid_constant__ CUtensorMap kmap,
+                                                                  const __grid_constant__ CUtensorMap vmap,
+                                                                  FlashParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t qk_smem = smem_base;
+  const uint32_t p_smem = qk_smem + FA_QK_STAGES * FA_QK_STAGE_BYTES;
+  const uint32_t v_smem = p_smem + FA_P_BYTES;
+  __shared__ __align__(8) uint64_t bars[17];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t b0 = smem_u32(&bars[0]);
+  const uint32_t qk_full = b0, qk_empty = b0 + 8 * 3, v_full = b0 + 8 * 6, v_empty = b0 + 8 * 8, s_full = b0 + 8 * 10,
+                 s_empty = b0 + 8 * 12, p_full = b0 + 8 * 14, p_empty = b0 + 8 * 15, o_full = b0 + 8 * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * FA_BM;
+  const int slice = blockIdx.y;
+  const int b = blockIdx.z / p.H, h = blockIdx.z - b * p.H;
+  const int nkv = (p.Lk + FA_BN - 1) / FA_BN;
+  const int nkc = p.dh / 64;
+  const int v_stage_bytes = (p.DV / 64) * FA_PANEL;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(qk_full + 8 * i, 1); mbar_init(qk_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 128);
+    }
+    mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<512>(smem_u32(&tmem_slot));
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t tmem_o = tmem_base + 256;   // S buffers at columns [0,128) and [128,256)
+
+  if (warp < 4) {
+    // ============================ softmax / epilogue: one thread per query row ============================
+    const int r = warp * 32 + lane;
+    const int q = q0 + r;
+    const bool qok = q < p.Lq;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    float lse_r = 0.f;
+    if (PASS == 1) lse_r = qok ? p.lse[(int64_t)blockIdx.z * p.Lq + q] : 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int buf = j & 1;
+      mbar_wait(s_full + 8 * buf, (uint32_t)(j >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t ts = tmem_base + lane_off + buf * FA_BN;
+      const int kbase = j * FA_BN;
+      if (PASS == 0) {
+        float tmax = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(ts + c0, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (kbase + c0 + e < p.Lk) tmax = fmaxf(tmax, v[e] * p.scale_log2);
+        }
+        const float m_new = fmaxf(m_run, tmax);
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(ts + c0, v);
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (kbase + c0 + e < p.Lk) sum += exp2f(v[e] * p.scale_log2 - m_new);
+        }
+        l_run = l_run * exp2f(m_run - m_new) + sum;
+        m_run = m_new;
+        tcgen05_fence_before();
+        mbar_arrive(s_empty + 8 * buf);
+      } else {
+        mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile has consumed the P buffer
+#pragma unroll 1
+        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
+          float v[16];
+          tmem_ld16(ts + c0, v);
+          uint4 o0, o1;
+          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+          float pr[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            pr[e] = (kbase + c0 + e < p.Lk) ? exp2f(v[e] * p.scale_log2 - lse_r) : 0.f;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            h0[e] = __floats2bfloat162_rn(pr[2 * e], pr[2 * e + 1]);
+            h1[e] = __floats2bfloat162_rn(pr[8 + 2 * e], pr[8 + 2 * e + 1]);
+          }
+          const int panel = c0 >> 6, ch = (c0 & 63) >> 3;   // 16-byte chunk index within the 128-byte row
+          const uint32_t base = p_smem + panel * (FA_BM * 128);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, ch)), "r"(o0.x), "r"(o0.y),
+                       "r"(o0.z), "r"(o0.w) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, ch + 1)), "r"(o1.x), "r"(o1.y),
+                       "r"(o1.z), "r"(o1.w) : "memory");
+        }
+        tcgen05_fence_before();
+        mbar_arrive(s_empty + 8 * buf);
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the UMMA (async proxy)
+        mbar_arrive(p_full);
+      }
+    }
+    if (PASS == 0) {
+      if (qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
+    } else {
+      mbar_wait(o_full, 0);
+      tcgen05_fence_after();
+      const uint32_t to = tmem_o + lane_off;
+      __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + q) * ((int64_t)p.H * p.dh) + (int64_t)h * p.dh + slice * p.DV;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.DV; c0 += 16) {
+        float v[16];
+        tmem_ld16(to + c0, v);
+        if (!qok) continue;
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+          h1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+        }
+        reinterpret_cast<uint4*>(orow + c0)[0] = o0;
+        reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    // ============================ UMMA issuer ============================
+    const uint32_t idesc_s = make_idesc(FA_BM, FA_BN, 0, 0);
+    const uint32_t idesc_o = make_idesc(FA_BM, p.DV, 0, 1);
+    int qs = 0;      // QK ring position
+    uint32_t qph = 0;
+    int vs = 0;
+    uint32_t vph = 0;
+    auto issue_qk = [&](int j) {
+      const int buf = j & 1;
+      mbar_wait(s_empty + 8 * buf, ((uint32_t)(j >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      for (int c = 0; c < nkc; ++c) {
+        mbar_wait(qk_full + 8 * qs, qph);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t a = qk_smem + qs * FA_QK_STAGE_BYTES, bsm = a + FA_BM * 128;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + buf * FA_BN, make_smem_desc(a + kk * 32, 16, 1024), make_smem_desc(bsm + kk * 32, 16, 1024),
+                      idesc_s, (c | kk) ? 1u : 0u);
+          umma_commit(qk_empty + 8 * qs);
+          if (c == nkc - 1) umma_commit(s_full + 8 * buf);
+        }
+        __syncwarp();
+        if (++qs == FA_QK_STAGES) { qs = 0; qph ^= 1u; }
+      }
+    };
+    issue_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_qk(j + 1);
+      if (PASS == 1) {
+        mbar_wait(p_full, (uint32_t)j & 1u);
+        tcgen05_fence_after();
+        for (int half = 0; half < 2; ++half) {
+          mbar_wait(v_full + 8 * vs, vph);
+          tcgen05_fence_after();
+          if (lane == 0) {
+            const uint32_t a = p_smem + half * (FA_BM * 128), bsm = v_smem + vs * v_stage_bytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tmem_o, make_smem_desc(a + kk * 32, 16, 1024), make_smem_desc(bsm + kk * 2048, FA_PANEL, 1024),
+                        idesc_o, (j | half | kk) ? 1u : 0u);
+            umma_commit(v_empty + 8 * vs);
+            if (half == 1) {
+              umma_commit(p_empty);
+              if (j == nkv - 1) umma_commit(o_full);
+            }
+          }
+          __syncwarp();
+          if (++vs == FA_V_STAGES) { vs = 0; vph ^= 1u; }
+        }
+      }
+    }
+  } else if (lane == 0) {
+    // ============================ TMA issuer ============================
+    int qs = 0, vs = 0;
+    uint32_t qph = 0, vph = 0;
+    auto load_qk = [&](int j) {
+      for (int c = 0; c < nkc; ++c) {
+        mbar_wait(qk_empty + 8 * qs, qph ^ 1u);
+        const uint32_t a = qk_smem + qs * FA_QK_STAGE_BYTES, bar = qk_full + 8 * qs;
+        mbar_arrive_expect_tx(bar, FA_QK_STAGE_BYTES);
+        tma_load_4d(a, &qmap, bar, c * 64, h, q0, b);
+        tma_load_4d(a + FA_BM * 128, &kmap, bar, c * 64, h, j * FA_BN, b);
+        if (++qs == FA_QK_STAGES) { qs = 0; qph ^= 1u; }
+      }
+    };
+    auto load_v = [&](int j) {
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(v_empty + 8 * vs, vph ^ 1u);
+        const uint32_t dst = v_smem + vs * v_stage_bytes, bar = v_full + 8 * vs;
+        mbar_arrive_expect_tx(bar, v_stage_bytes);
+        for (int pn = 0; pn < p.DV / 64; ++pn)
+          tma_load_4d(dst + pn * FA_PANEL, &vmap, bar, slice * p.DV + pn * 64, h, j * FA_BN + half * 64, b);
+        if (++vs == FA_V_STAGES) { vs = 0; vph ^= 1u; }
+      }
+    };
+    load_qk(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) load_qk(j + 1);
+      if (PASS == 1) load_v(j);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// 4-d map over a contiguous (B, L, H*dh) bf16 tensor: dims (dh, H, L, B); box (64, 1, rows, 1)
+static int bhld_map(CUtensorMap* m, const void* base, int B, int H, int L, int dh, uint32_t box_rows) {
+  const uint64_t C = (uint64_t)H * dh;
+  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)L, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)dh * 2, C * 2, (uint64_t)L * C * 2};
+  uint32_t box[4] = {64, 1, box_rows, 1};
+  return make_map(m, base, 4, dims, strides, box);
+}
+
+bool flash_eligible(int H, int dh) {
+  if (dh % 64 != 0) return false;
+  if (dh > 256 && dh % 256 != 0) return false;
+  return H >= 1;
+}
+
+template <int PASS>
+static int launch_flash(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, const FlashParams& p,
+                        dim3 grid, cudaStream_t st) {
+  const int smem = FA_QK_STAGES * FA_QK_STAGE_BYTES + FA_P_BYTES + FA_V_STAGES * 4 * FA_PANEL + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MIG_REQUIRE(e == cudaSuccess, "flash_attention: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = true;
+  }
+  flash_fwd_kernel<PASS><<<grid, FA_THREADS, smem, st>>>(qm, km, vm, p);
+  return check_launch("flash_fwd_kernel");
+}
+
+}  // namespace mig
+
+using namespace mig;
+
+extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B,
+                                       int32_t H, int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream) {
+  MIG_REQUIRE(q && k && v && out && lse, "flash_attention: null argument");
+  MIG_REQUIRE(mig_has_tcgen05(), "flash_attention: needs an sm_100 device");
+  MIG_REQUIRE(flash_eligible(H, dh), "flash_attention: head dim %d not supported (multiple of 64; above 256 a multiple of 256)", dh);
+  MIG_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && (int64_t)B * H < 65536, "flash_attention: bad sizes");
+  MIG_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+                reinterpret_cast<uintptr_t>(out)) & 15) == 0, "flash_attention: tensors must be 16-byte aligned");
+  CUtensorMap qm, km, vm;
+  if (bhld_map(&qm, q, B, H, Lq, dh, FA_BM)) return 1;
+  if (bhld_map(&km, k, B, H, Lk, dh, FA_BN)) return 1;
+  if (bhld_map(&vm, v, B, H, Lk, dh, 64)) return 1;
+  FlashParams p{};
+  p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.dh = dh;
+  p.DV = dh > 256 ? 256 : dh;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.lse = lse;
+  p.out = (__nv_bfloat16*)out;
+  cudaStream_t st = as_stream(stream);
+  const unsigned mt = (Lq + FA_BM - 1) / FA_BM;
+  if (launch_flash<0>(qm, km, vm, p, dim3(mt, 1, B * H), st)) return 2;
+  return launch_flash<1>(qm, km, vm, p, dim3(mt, dh / p.DV, B * H), st);
+}

@@ -736,7 +736,42 @@ class _SdpaFn(Function):
 def sdpa(q, k, v, heads: int, scale_: float):
     """softmax(scale * q k^T) v per head; q (B,Lq,C), k/v (B,Lk,C), heads split the channel dim."""
     _require_cuda(q, "sdpa")
-    return _SdpaFn.apply(q.contiguous(), k.contiguous(), v.contiguous(), int(heads), float(scale_))
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    if flash_attention_usable(q, k, v, heads):
+        return flash_attention(q, k, v, int(heads), float(scale_))
+    return _SdpaFn.apply(q, k, v, int(heads), float(scale_))
+
+
+_FLASH = True
+
+
+def set_flash_attention(enabled: bool) -> None:
+    global _FLASH
+    _FLASH = bool(enabled)
+
+
+def flash_attention_usable(q, k, v, heads: int) -> bool:
+    """The fused tcgen05 kernel is forward-only: used when no gradient is needed (sampling, validation, the frozen
+    autoencoder) and the head dim fits (multiple of 64; above 256 a multiple of 256)."""
+    if not _FLASH or _ENGINE == _lib.ENGINE_SIMT or q.dtype != torch.bfloat16:
+        return False
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        return False
+    dh = q.shape[-1] // heads
+    if dh % 64 != 0 or (dh > 256 and dh % 256 != 0) or q.shape[0] * heads >= 65536:
+        return False
+    return bool(_lib.load().mig_has_tcgen05())
+
+
+def flash_attention(q, k, v, heads: int, scale_: float):
+    """softmax(scale * q k^T) v without materialising the score matrix (unet:128-135 / 406-416). No autograd."""
+    B, Lq, Cc = q.shape
+    Lk = k.shape[1]
+    out = torch.empty_like(q)
+    lse = torch.empty((B * heads, Lq), dtype=torch.float32, device=q.device)
+    call("mig_flash_attention_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, Lq, Lk, Cc // heads,
+         float(scale_), _stream())
+    return out
 
 
 # ----------------------------------------------------------------------------------------------

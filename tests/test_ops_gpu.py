@@ -365,3 +365,34 @@ def test_errors_are_loud():
         ops.conv_nd(torch.randn(1, 8, 1, 1, 1, device=DEV), torch.randn(4, 8, 3, 3, 3, device=DEV), None, 1, 0)
     with pytest.raises(TypeError):
         ops.silu(torch.zeros(4, device=DEV, dtype=torch.float16))
+
+
+@pytest.mark.parametrize("B,Lq,Lk,C,heads", [(2, 256, 256, 128, 1), (1, 200, 333, 128, 2), (2, 216, 216, 768, 1),
+                                              (1, 1728, 1728, 512, 1), (1, 130, 70, 64, 1), (1, 5, 3, 256, 4),
+                                              (1, 1024, 4096, 128, 1)])
+def test_flash_attention_forward(B, Lq, Lk, C, heads):
+    """Fused tcgen05 flash-style attention (forward only) vs fp32 softmax attention on the CPU; includes ragged tails,
+    cross-attention lengths, multi-head and the 512/768-channel single heads of the LDM default (value-dim slicing)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(Lq + Lk + C)
+    q, k, v = (bf16_round(torch.randn(B, L, C, generator=g)) for L in (Lq, Lk, Lk))
+    scale = 1 / math.sqrt(C / heads)
+
+    def split(t):
+        return t.reshape(B, -1, heads, C // heads).permute(0, 2, 1, 3)
+
+    p = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1)
+    want = (p @ split(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    qd, kd, vd = (t.to(DEV).bfloat16() for t in (q, k, v))
+    assert ops.flash_attention_usable(qd, kd, vd, heads)
+    with torch.no_grad():
+        got = ops.sdpa(qd, kd, vd, heads, scale)
+    assert got.shape == want.shape and rel_err(got, want) < BF16_TOL
+    # and it agrees with the GEMM-composed training path
+    ops.set_flash_attention(False)
+    try:
+        with torch.no_grad():
+            ref2 = ops.sdpa(qd, kd, vd, heads, scale)
+    finally:
+        ops.set_flash_attention(True)
+    assert rel_err(got, ref2) < BF16_TOL
