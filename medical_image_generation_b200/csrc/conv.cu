@@ -79,8 +79,26 @@ static bool want_pad(const mig_conv_geom* g, int dtype, int which, int engine) {
   return g->Cin % 8 != 0 || g->Cout % 8 != 0;                   // wgrad needs both
 }
 
+// conv_halo.cu: 32-channel layers with a smem-resident halo tile
+bool halo_conv_eligible(const mig_conv_geom* g, int which);
+int halo_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
+                  const void* residual, void* y, void* stream);
+int halo_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                    void* stream);
+static bool halo_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MIG_DISABLE_HALO_CONV");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static int run_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
                    const void* residual, void* y, void* ws, int64_t wsb, void* stream) {
+  if (halo_enabled() && halo_conv_eligible(g, 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
+      (!residual || aligned16(residual)))
+    return halo_conv_fwd(g, x, w, bias, chan_bias, residual, y, stream);
   if (tma_enabled() && tma_conv_eligible(g, 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
       (!residual || aligned16(residual)))
     return tma_conv_fwd(g, x, w, bias, chan_bias, residual, y, ws, wsb, stream);
@@ -88,6 +106,8 @@ static int run_fwd(const mig_conv_geom* g, const void* x, const void* w, const f
 }
 static int run_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t wsb,
                      void* stream) {
+  if (halo_enabled() && halo_conv_eligible(g, 1) && aligned16(dy) && aligned16(w) && aligned16(dx))
+    return halo_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
   if (tma_enabled() && aligned16(dy) && aligned16(w) && aligned16(dx)) {
     if (tma_conv_eligible(g, 1)) return tma_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
     if (tma_dgrad_strided_eligible(g)) return tma_conv_dgrad_strided(g, dy, w, dx, ws, wsb, stream);

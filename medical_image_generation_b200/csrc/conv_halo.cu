@@ -1,0 +1,326 @@
+// tcgen05 engine, part 4: narrow-channel convolution (Cin = 32, Cout <= 32, stride 1) with a shared-memory-resident
+// halo tile -- the 32-channel full-resolution layers of the AutoencoderKL (ae:158-176 at 96^3) and of pixel-space
+// DDPM U-Nets (BASELINE configs 2 and 4).
+//
+// With 32 channels an implicit GEMM has N = 32 and K = 27*32: the tensor cores are idle and the cost is operand feed.
+// The generic kernels read every input voxel once per tap (27x). Here a persistent CTA
+//   1. keeps the WHOLE filter (27 x 32 x Cout bf16 = 55 KB) in shared memory for its lifetime,
+//   2. TMA-loads an output tile's input footprint (8x16x1 voxels + halo = 10x18x3 voxels x 64 B) ONCE,
+//   3. re-lays it out in smem as four 8-channel planes [chunk][voxel] x 16 B, which is the UMMA "no swizzle" K-major
+//      core-matrix format (8 rows x 16 B contiguous): a filter tap is then just a different START ADDRESS of the same
+//      planes (leading byte offset = plane stride, stride byte offset = one voxel line), no data movement,
+//   4. issues 27 taps x 2 UMMAs (128 x N x 16) into a double-buffered TMEM accumulator, while the next tile's halo
+//      is in flight and the previous tile's epilogue (+bias, +time embedding, +residual, bf16 store) runs.
+// Input traffic drops from 27x to 4.2x (halo overhead) and all address arithmetic disappears from the main loop.
+// fwd and dgrad (mirrored taps, transposed filter) share the kernel.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_host.cuh"
+
+namespace mig {
+
+using namespace tc;
+
+int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream);
+
+constexpr int HT_X = 8, HT_Y = 16;            // output tile: 8 (x) x 16 (y) x 1 (z) = 128 voxels = UMMA M
+constexpr int H_THREADS = 192;
+constexpr int H_C = 32;                        // source channels
+constexpr int H_MAXVOX = (HT_X + 2) * (HT_Y + 2) * 3;
+
+__device__ __forceinline__ void tma_load_5d_h(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
+                                              int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(dst),
+      "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// no-swizzle K-major descriptor: core matrix = 8 rows x 16 bytes stored contiguously (128 B);
+// LBO = byte distance between the two 8-element K chunks of one UMMA, SBO = byte distance between 8-row groups
+__device__ __forceinline__ uint64_t make_desc_noswz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100); layout type bits [61,64) = 0: no swizzle
+  return d;
+}
+
+struct HaloParams {
+  int N, D, H, W;         // SOURCE extent
+  int OD, OH, OW;         // output extent
+  int ks[3];              // filter size (each <= 3)
+  int lo[3];              // halo origin relative to the output coordinate: src = out + lo + h, h in [0, hz/hy/hx)
+  int hz, hy, hx;         // halo extent: 1+kz-1, 16+ky-1, 8+kx-1
+  int sign;               // +1 fwd (halo offset of tap t = t), -1 dgrad (ks-1-t)
+  int Cdst, Npad;         // output channels, UMMA N (16 or 32)
+  int tiles_x, tiles_y;
+  int64_t num_tiles;      // N*OD*tiles_y*tiles_x
+  const __nv_bfloat16* w; // [Cdst][taps][32]
+  const float* bias;
+  const float* chan_bias;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+};
+
+__global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap xmap, HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int T = p.ks[0] * p.ks[1] * p.ks[2];
+  const int nvox = p.hz * p.hy * p.hx;
+  const uint32_t plane = (uint32_t)nvox * 16u;          // one 8-channel plane
+  const uint32_t stage_bytes = (uint32_t)nvox * 64u;    // TMA staging [voxel][32 ch]
+  const uint32_t w_bytes = (uint32_t)T * 4u * p.Npad * 16u;
+  const uint32_t w_smem = smem_base;
+  const uint32_t stg_smem = (w_smem + w_bytes + 127u) & ~127u;
+  const uint32_t stg_stride = (stage_bytes + 127u) & ~127u;
+  const uint32_t pl_smem = stg_smem + 2 * stg_stride;
+  const uint32_t pl_stride = (4u * plane + 127u) & ~127u;
+  __shared__ __align__(8) uint64_t bars[12];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t b0 = smem_u32(&bars[0]);
+  const uint32_t stg_full = b0, stg_empty = b0 + 16, pl_full = b0 + 32, pl_empty = b0 + 48, acc_full = b0 + 64,
+                 acc_empty = b0 + 80;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(stg_full + 8 * i, 1);  mbar_init(stg_empty + 8 * i, 128);
+      mbar_init(pl_full + 8 * i, 128); mbar_init(pl_empty + 8 * i, 1);
+      mbar_init(acc_full + 8 * i, 1);  mbar_init(acc_empty + 8 * i, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<64>(smem_u32(&tmem_slot));
+  if (warp == 5 && lane == 0) tma_prefetch_desc(&xmap);
+  // resident filter: global [co][tap][32] -> smem [tap][chunk][n][8 ch] (16-byte units), rows n >= Cdst are zero
+  for (int i = threadIdx.x; i < T * 4 * p.Npad; i += H_THREADS) {
+    const int n = i % p.Npad, c = (i / p.Npad) & 3, tap = i / (p.Npad * 4);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < p.Cdst) v = *reinterpret_cast<const uint4*>(p.w + ((int64_t)n * T + tap) * H_C + c * 8);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(w_smem + (uint32_t)i * 16u), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w) : "memory");
+  }
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const int64_t my_tiles = p.num_tiles > blockIdx.x ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  auto tile_coords = [&](int64_t i, int& n, int& z, int& y0, int& x0) {
+    int64_t t = (int64_t)blockIdx.x + i * gridDim.x;
+    x0 = (int)(t % p.tiles_x) * HT_X; t /= p.tiles_x;
+    y0 = (int)(t % p.tiles_y) * HT_Y; t /= p.tiles_y;
+    z = (int)(t % p.OD);
+    n = (int)(t / p.OD);
+  };
+
+  if (warp < 4) {
+    // ============ workers: re-layout staging -> planes, then the epilogue of the previous tile ============
+    const int r = warp * 32 + lane;
+    auto epilogue = [&](int64_t i) {
+      const int a = (int)(i & 1);
+      mbar_wait(acc_full + 8 * a, (uint32_t)(i >> 1) & 1u);
+      tcgen05_fence_after();
+      int n, z, y0, x0;
+      tile_coords(i, n, z, y0, x0);
+      const int y = y0 + (r >> 3), x = x0 + (r & 7);
+      const bool ok = y < p.OH && x < p.OW;
+      const int64_t m = (((int64_t)n * p.OD + z) * p.OH + y) * p.OW + x;
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + c0, v);
+        if (!ok) continue;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int col = c0 + e;
+          if (col < p.Cdst) {
+            if (p.bias) v[e] += p.bias[col];
+            if (p.chan_bias) v[e] += p.chan_bias[(int64_t)n * p.Cdst + col];
+          }
+        }
+        __nv_bfloat16* dst = p.out + m * p.Cdst + c0;
+        if (c0 + 16 <= p.Cdst && (p.Cdst & 7) == 0) {
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * p.Cdst + c0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+            const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+          }
+          reinterpret_cast<uint4*>(dst)[0] = o0;
+          reinterpret_cast<uint4*>(dst)[1] = o1;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (c0 + e < p.Cdst) {
+              float rr = p.residual ? __bfloat162float(p.residual[m * p.Cdst + c0 + e]) : 0.f;
+              dst[e] = __float2bfloat16_rn(v[e] + rr);
+            }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty + 8 * a);
+    };
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(stg_full + 8 * s, ph);
+      mbar_wait(pl_empty + 8 * s, ph ^ 1u);
+      const uint32_t src = stg_smem + s * stg_stride, dst = pl_smem + s * pl_stride;
+      for (int idx = r; idx < nvox * 4; idx += 128) {
+        const int vox = idx >> 2, c = idx & 3;
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src + idx * 16));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + c * plane + vox * 16), "r"(a0), "r"(a1), "r"(a2),
+                     "r"(a3) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(pl_full + 8 * s);
+      mbar_arrive(stg_empty + 8 * s);
+      if (i >= 1) epilogue(i - 1);
+    }
+    if (my_tiles >= 1) epilogue(my_tiles - 1);
+  } else if (warp == 4) {
+    // ============ UMMA issuer: 27 taps x 2 K-steps per tile, A = shifted windows of the planes ============
+    const uint32_t idesc = make_idesc(128, p.Npad, 0, 0);
+    const uint32_t sbo_a = (uint32_t)p.hx * 16u;
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(pl_full + 8 * s, ph);
+      mbar_wait(acc_empty + 8 * s, ph ^ 1u);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        const uint32_t pl = pl_smem + s * pl_stride;
+        const uint32_t acc = tmem_base + s * 32;
+        int tap = 0;
+        for (int t0 = 0; t0 < p.ks[0]; ++t0)
+          for (int t1 = 0; t1 < p.ks[1]; ++t1)
+            for (int t2 = 0; t2 < p.ks[2]; ++t2, ++tap) {
+              const int h0 = p.sign > 0 ? t0 : p.ks[0] - 1 - t0;
+              const int h1 = p.sign > 0 ? t1 : p.ks[1] - 1 - t1;
+              const int h2 = p.sign > 0 ? t2 : p.ks[2] - 1 - t2;
+              const uint32_t voff = (uint32_t)((h0 * p.hy + h1) * p.hx + h2) * 16u;
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ad = make_desc_noswz(pl + (2 * ks) * plane + voff, plane, sbo_a);
+                const uint64_t bd = make_desc_noswz(w_smem + (uint32_t)((tap * 4 + 2 * ks) * p.Npad) * 16u, p.Npad * 16u, 128u);
+                umma_bf16(acc, ad, bd, idesc, (tap | ks) ? 1u : 0u);
+              }
+            }
+        umma_commit(pl_empty + 8 * s);
+        umma_commit(acc_full + 8 * s);
+      }
+      __syncwarp();
+    }
+  } else if (lane == 0) {
+    // ============ TMA issuer: one halo box per tile ============
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      mbar_wait(stg_empty + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      int n, z, y0, x0;
+      tile_coords(i, n, z, y0, x0);
+      mbar_arrive_expect_tx(stg_full + 8 * s, stage_bytes);
+      tma_load_5d_h(stg_smem + s * stg_stride, &xmap, stg_full + 8 * s, 0, x0 + p.lo[2], y0 + p.lo[1], z + p.lo[0], n);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<64>(tmem_base);
+  }
+}
+
+// which: 0 fwd, 1 dgrad
+bool halo_conv_eligible(const mig_conv_geom* g, int which) {
+  const int csrc = which == 1 ? g->Cout : g->Cin, cdst = which == 1 ? g->Cin : g->Cout;
+  if (csrc != H_C || cdst < 1 || cdst > 32) return false;
+  for (int i = 0; i < 3; ++i)
+    if (g->stride[i] != 1 || g->ksize[i] > 3) return false;
+  const int64_t vox = (int64_t)g->N * g->out_dims[0] * g->out_dims[1] * g->out_dims[2];
+  const int32_t* od = which == 1 ? g->in_dims : g->out_dims;
+  return vox >= 32768 && od[2] >= HT_X && od[1] >= HT_Y / 2;
+}
+
+static int run_halo(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
+                    const float* chan_bias, const void* residual, void* out, void* stream) {
+  HaloParams p{};
+  const int32_t* sd = which == 1 ? g->out_dims : g->in_dims;   // source extent
+  const int32_t* od = which == 1 ? g->in_dims : g->out_dims;   // extent of the tensor being produced
+  p.N = g->N; p.D = sd[0]; p.H = sd[1]; p.W = sd[2];
+  p.OD = od[0]; p.OH = od[1]; p.OW = od[2];
+  p.sign = which == 1 ? -1 : 1;
+  for (int i = 0; i < 3; ++i) {
+    p.ks[i] = g->ksize[i];
+    const int off = which == 1 ? g->pad[i] : -g->pad[i];
+    p.lo[i] = off + (p.sign > 0 ? 0 : -(g->ksize[i] - 1));
+  }
+  p.hz = 1 + p.ks[0] - 1; p.hy = HT_Y + p.ks[1] - 1; p.hx = HT_X + p.ks[2] - 1;
+  p.Cdst = which == 1 ? g->Cin : g->Cout;
+  p.Npad = p.Cdst <= 16 ? 16 : 32;
+  p.tiles_x = (p.OW + HT_X - 1) / HT_X;
+  p.tiles_y = (p.OH + HT_Y - 1) / HT_Y;
+  p.num_tiles = (int64_t)p.N * p.OD * p.tiles_y * p.tiles_x;
+  p.w = (const __nv_bfloat16*)wk;
+  p.bias = bias; p.chan_bias = chan_bias;
+  p.residual = (const __nv_bfloat16*)residual;
+  p.out = (__nv_bfloat16*)out;
+  // 5-d source map (C, W, H, D, N), box (32, hx, hy, hz, 1), no swizzle: staging rows are plain 64-byte voxels
+  EncodeTiledFn enc = get_encode();
+  MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  CUtensorMap xm;
+  cuuint64_t gd[5] = {(cuuint64_t)H_C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, (cuuint64_t)p.N};
+  cuuint64_t gs[4] = {(cuuint64_t)H_C * 2, (cuuint64_t)p.W * H_C * 2, (cuuint64_t)p.H * p.W * H_C * 2,
+                      (cuuint64_t)p.D * p.H * p.W * H_C * 2};
+  cuuint32_t bx[5] = {(cuuint32_t)H_C, (cuuint32_t)p.hx, (cuuint32_t)p.hy, (cuuint32_t)p.hz, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(&xm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(src), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo map) failed with %d", (int)r);
+  const int T = p.ks[0] * p.ks[1] * p.ks[2];
+  const int nvox = p.hz * p.hy * p.hx;
+  const int smem = T * 4 * p.Npad * 16 + 2 * (nvox * 64 + 128) + 2 * (nvox * 64 + 128) + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MIG_REQUIRE(e == cudaSuccess, "conv_halo: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  int64_t grid = device_info().sm_count;
+  if (grid > p.num_tiles) grid = p.num_tiles;
+  conv_halo_kernel<<<(unsigned)grid, H_THREADS, smem, as_stream(stream)>>>(xm, p);
+  return check_launch("conv_halo_kernel");
+}
+
+int halo_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
+                  const void* residual, void* y, void* stream) {
+  return run_halo(g, 0, x, w, bias, chan_bias, residual, y, stream);
+}
+
+int halo_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                    void* stream) {
+  const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
+  const int64_t wt_bytes = (int64_t)g->Cin * T * g->Cout * 2;
+  MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(halo): workspace too small");
+  if (filter_transpose(MIG_BF16, w, ws, g->Cout, T, g->Cin, stream)) return 2;
+  return run_halo(g, 1, dy, ws, nullptr, nullptr, nullptr, dx, stream);
+}
+
+}  // namespace mig

@@ -52,6 +52,12 @@ CONV_CASES = [
     (1, 64, 64, (16, 16, 8), (3, 3, 1), (2, 2, 1), (1, 1, 0)),    # thin axis: kernel 1 / pad 0 / stride 1
     (2, 64, 128, (9, 11, 16), (3, 3, 3), (2, 2, 2), (1, 1, 1)),   # odd extents: classes of different size
     (1, 64, 64, (8, 8, 8), (1, 1, 1), (2, 2, 2), (0, 0, 0)),      # kernel 1 stride 2: most input voxels get zero gradient
+    # 32-channel full-resolution layers: smem-resident halo-tile kernel (fwd + dgrad)
+    (1, 32, 32, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),
+    (2, 32, 32, (12, 40, 44), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # ragged tiles in x and y
+    (1, 32, 1, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # out conv of the AE: one output channel (N padded to 16)
+    (1, 32, 16, (16, 48, 48), (3, 3, 1), (1, 1, 1), (1, 1, 0)),   # anisotropic kernel
+    (4, 32, 32, (96, 96), (3, 3), (1, 1), (1, 1)),                # 2-D
 ]
 
 
