@@ -85,6 +85,8 @@ int halo_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const fl
                   const void* residual, void* y, void* stream);
 int halo_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
                     void* stream);
+bool halo_wgrad_eligible(const mig_conv_geom* g);
+int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
 static bool halo_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -116,6 +118,8 @@ static int run_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void
 }
 static int run_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* ws, int64_t wsb,
                      void* stream) {
+  if (halo_enabled() && halo_wgrad_eligible(g) && aligned16(x) && aligned16(dy) && aligned16(dw))
+    return halo_conv_wgrad(g, x, dy, dw, stream);
   if (tma_enabled() && tma_conv_eligible(g, 2) && aligned16(x) && aligned16(dy)) return tma_conv_wgrad(g, x, dy, dw, stream);
   return tc_conv_wgrad(g, x, dy, dw, ws, wsb, stream);
 }

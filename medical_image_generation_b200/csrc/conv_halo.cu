@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   const int T = p.ks[0] * p.ks[1] * p.ks[2];
   const int nvox = p.hz * p.hy * p.hx;
-  const uint32_t plane = (uint32_t)nvox * 16u;          // one 8-channel plane
+  const uint32_t plane = (uint32_t)nvox * 16u + 16u;    // one 8-channel plane (+16 B: planes start on different banks)
   const uint32_t stage_bytes = (uint32_t)nvox * 64u;    // TMA staging [voxel][32 ch]
   const uint32_t w_bytes = (uint32_t)T * 4u * p.Npad * 16u;
   const uint32_t w_smem = smem_base;
@@ -207,23 +207,30 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       mbar_wait(acc_empty + 8 * s, ph ^ 1u);
       tcgen05_fence_after();
       if (lane == 0) {
-        const uint32_t pl = pl_smem + s * pl_stride;
+        // The UMMAs are tiny (128 x N x 16 = 16 tensor cycles), so the single issuing thread is the limiter: the
+        // descriptors are built once per tile and advanced with ONE 64-bit add per UMMA (the start-address field is
+        // the low 14 bits in 16-byte units; shared-memory addresses never carry out of it).
         const uint32_t acc = tmem_base + s * 32;
-        int tap = 0;
-        for (int t0 = 0; t0 < p.ks[0]; ++t0)
-          for (int t1 = 0; t1 < p.ks[1]; ++t1)
-            for (int t2 = 0; t2 < p.ks[2]; ++t2, ++tap) {
-              const int h0 = p.sign > 0 ? t0 : p.ks[0] - 1 - t0;
-              const int h1 = p.sign > 0 ? t1 : p.ks[1] - 1 - t1;
-              const int h2 = p.sign > 0 ? t2 : p.ks[2] - 1 - t2;
-              const uint32_t voff = (uint32_t)((h0 * p.hy + h1) * p.hx + h2) * 16u;
-#pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                const uint64_t ad = make_desc_noswz(pl + (2 * ks) * plane + voff, plane, sbo_a);
-                const uint64_t bd = make_desc_noswz(w_smem + (uint32_t)((tap * 4 + 2 * ks) * p.Npad) * 16u, p.Npad * 16u, 128u);
-                umma_bf16(acc, ad, bd, idesc, (tap | ks) ? 1u : 0u);
-              }
+        const uint64_t a0 = make_desc_noswz(pl_smem + s * pl_stride, plane, sbo_a);
+        const uint64_t a_ks = (uint64_t)((2u * plane) >> 4);
+        uint64_t bd = make_desc_noswz(w_smem, p.Npad * 16u, 128u);
+        const uint64_t b_ks = (uint64_t)((2u * p.Npad * 16u) >> 4);
+        uint32_t first = 0;
+        for (int t0 = 0; t0 < p.ks[0]; ++t0) {
+          const int h0 = p.sign > 0 ? t0 : p.ks[0] - 1 - t0;
+          for (int t1 = 0; t1 < p.ks[1]; ++t1) {
+            const int h1 = p.sign > 0 ? t1 : p.ks[1] - 1 - t1;
+            const uint64_t row = a0 + (uint64_t)((h0 * p.hy + h1) * p.hx);
+#pragma unroll 3
+            for (int t2 = 0; t2 < p.ks[2]; ++t2) {
+              const uint64_t ad = row + (uint64_t)(p.sign > 0 ? t2 : p.ks[2] - 1 - t2);
+              umma_bf16(acc, ad, bd, idesc, first);
+              first = 1u;
+              umma_bf16(acc, ad + a_ks, bd + b_ks, idesc, 1u);
+              bd += 2 * b_ks;
             }
+          }
+        }
         umma_commit(pl_empty + 8 * s);
         umma_commit(acc_full + 8 * s);
       }
@@ -296,7 +303,7 @@ static int run_halo(const mig_conv_geom* g, int which, const void* src, const vo
   MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo map) failed with %d", (int)r);
   const int T = p.ks[0] * p.ks[1] * p.ks[2];
   const int nvox = p.hz * p.hy * p.hx;
-  const int smem = T * 4 * p.Npad * 16 + 2 * (nvox * 64 + 128) + 2 * (nvox * 64 + 128) + 512;
+  const int smem = T * 4 * p.Npad * 16 + 2 * (nvox * 64 + 128) + 2 * (nvox * 64 + 64 + 128) + 512;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -307,6 +314,228 @@ static int run_halo(const mig_conv_geom* g, int which, const void* src, const vo
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv_halo_kernel<<<(unsigned)grid, H_THREADS, smem, as_stream(stream)>>>(xm, p);
   return check_launch("conv_halo_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// wgrad for the same layers: dW[co][tap*32 + ci] += sum_v dY[v][co] * X[v + tap][ci]
+// ---------------------------------------------------------------------------------------------------
+// Both operands are MN-major no-swizzle planes in shared memory: X halo planes [ci chunk][voxel] x 16 B (the same
+// re-layout as the forward kernel; a tap is a start-address offset) and dY planes [co chunk][voxel] x 16 B. One UMMA
+// (128 x 32 x 16) reduces 16 voxels (two 8-voxel lines) of one tap; a CTA owns half of the taps (grid parity) and
+// keeps ALL of its tap accumulators (<= 14 x 32 columns) in tensor memory over its whole tile loop, so the fp32
+// reduction into dW happens once per CTA. Output channels occupy TMEM lanes 0..Cout-1; the chunks above Cout read
+// zero planes.
+struct HaloWgradParams {
+  int N, D, H, W;          // X extent
+  int OD, OH, OW;          // dY extent
+  int ks[3], lo[3];
+  int hz, hy, hx;
+  int Cout;                // <= 32, multiple of 8
+  int tiles_x, tiles_y;
+  int64_t num_tiles;
+  int taps_total, taps_per_half;
+  float* dw;               // [Cout][taps][32]
+};
+
+__global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                                  const __grid_constant__ CUtensorMap dymap,
+                                                                  HaloWgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const int nvox = p.hz * p.hy * p.hx;
+  // plane strides are padded by 16 B so that consecutive channel-chunk planes start in different shared-memory banks
+  // (a multiple of 128 B would put every chunk of a UMMA operand fetch on the same banks)
+  const uint32_t xplane = (uint32_t)nvox * 16u + 16u;
+  const uint32_t x_stage_bytes = (uint32_t)nvox * 64u;
+  const uint32_t dy_stage_bytes = 128u * (uint32_t)p.Cout * 2u;
+  constexpr uint32_t dyplane = 128u * 16u + 16u;              // one 8-channel plane of the 128-voxel dY tile
+  // layout: [X staging][dY staging][X planes x2][dY planes x2 (16 chunk planes each; chunks >= Cout/8 stay zero)]
+  const uint32_t xs_smem = smem_base;
+  const uint32_t dys_smem = (xs_smem + x_stage_bytes + 127u) & ~127u;
+  const uint32_t xp_smem = (dys_smem + dy_stage_bytes + 127u) & ~127u;
+  const uint32_t xp_stride = (4u * xplane + 127u) & ~127u;
+  const uint32_t dyp_smem = xp_smem + 2 * xp_stride;
+  constexpr uint32_t dyp_stride = 16u * dyplane;
+  __shared__ __align__(8) uint64_t bars[8];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t b0 = smem_u32(&bars[0]);
+  const uint32_t stg_full = b0, stg_empty = b0 + 8, pl_full = b0 + 16 /*2*/, pl_empty = b0 + 32 /*2*/, acc_done = b0 + 48;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = blockIdx.x & 1;
+  const int tap_begin = half * p.taps_per_half;
+  const int ntap = min(p.taps_total, tap_begin + p.taps_per_half) - tap_begin;
+  const int cta = blockIdx.x >> 1, nctas = gridDim.x >> 1;
+  const int64_t my_tiles = p.num_tiles > cta ? (p.num_tiles - cta + nctas - 1) / nctas : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(stg_full, 1); mbar_init(stg_empty, 128);
+    for (int i = 0; i < 2; ++i) { mbar_init(pl_full + 8 * i, 128); mbar_init(pl_empty + 8 * i, 1); }
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<512>(smem_u32(&tmem_slot));
+  if (warp == 5 && lane == 0) { tma_prefetch_desc(&xmap); tma_prefetch_desc(&dymap); }
+  // zero the dY planes once (the chunk planes >= Cout/8 are never written again)
+  for (uint32_t i = threadIdx.x; i < 2 * dyp_stride / 16; i += H_THREADS)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dyp_smem + i * 16u), "r"(0u) : "memory");
+  fence_proxy_async();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  auto tile_coords = [&](int64_t i, int& n, int& z, int& y0, int& x0) {
+    int64_t t = (int64_t)cta + i * nctas;
+    x0 = (int)(t % p.tiles_x) * HT_X; t /= p.tiles_x;
+    y0 = (int)(t % p.tiles_y) * HT_Y; t /= p.tiles_y;
+    z = (int)(t % p.OD);
+    n = (int)(t / p.OD);
+  };
+
+  if (warp < 4) {
+    const int r = warp * 32 + lane;
+    const int nchunk = p.Cout / 8;
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+      mbar_wait(stg_full, (uint32_t)i & 1u);
+      mbar_wait(pl_empty + 8 * s, ph ^ 1u);
+      const uint32_t xdst = xp_smem + s * xp_stride, ddst = dyp_smem + s * dyp_stride;
+      for (int idx = r; idx < nvox * 4; idx += 128) {
+        const int vox = idx >> 2, c = idx & 3;
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(xs_smem + idx * 16));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xdst + c * xplane + vox * 16), "r"(a0), "r"(a1), "r"(a2),
+                     "r"(a3) : "memory");
+      }
+      // dY tile: TMA staged [voxel r][Cout] -> planes [chunk][voxel]; out-of-range voxels were zero-filled by TMA
+      for (int c = 0; c < nchunk; ++c) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(dys_smem + (uint32_t)r * p.Cout * 2u + c * 16u));
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ddst + c * dyplane + r * 16), "r"(a0), "r"(a1), "r"(a2),
+                     "r"(a3) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(pl_full + 8 * s);
+      mbar_arrive(stg_empty);
+    }
+    // ---- epilogue: TMEM lanes 0..Cout-1 hold dW rows; only warp 0's quadrant carries data ----
+    mbar_wait(acc_done, 0);
+    tcgen05_fence_after();
+    if (warp == 0 && my_tiles > 0) {
+      const bool cok = lane < p.Cout;
+      for (int t = 0; t < ntap; ++t) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + t * 32 + c0, v);
+          if (cok) red_add_16(p.dw + ((int64_t)lane * p.taps_total + tap_begin + t) * H_C + c0, v, 16);
+        }
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == 4) {
+    const uint32_t idesc = make_idesc(128, 32, 1, 1);
+    const uint32_t lbo_b = (uint32_t)p.hx * 16u;   // next 8-voxel line of the X halo
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      const int s = (int)(i & 1);
+      mbar_wait(pl_full + 8 * s, (uint32_t)(i >> 1) & 1u);
+      tcgen05_fence_after();
+      if (lane == 0) {
+        // descriptors built once per tile, advanced by one add per UMMA (the issuing thread is the limiter here)
+        // A: dY planes, M = co chunks (SBO = plane), K = 16 voxels = lines 2yk, 2yk+1 (LBO = one 8-voxel line)
+        const uint64_t a0 = make_desc_noswz(dyp_smem + s * dyp_stride, HT_X * 16u, dyplane);
+        // B: X halo planes, N = ci chunks (SBO = plane), K = the same voxels shifted by the tap
+        const uint64_t b0d = make_desc_noswz(xp_smem + s * xp_stride, lbo_b, xplane);
+        const uint64_t a_inc = (uint64_t)(2 * HT_X), b_inc = (uint64_t)(2 * p.hx);   // two voxel lines, 16-byte units
+        const uint32_t acc_flag = i ? 1u : 0u;
+        int tap = tap_begin;
+        int t2 = tap % p.ks[2], t1 = (tap / p.ks[2]) % p.ks[1], t0 = tap / (p.ks[2] * p.ks[1]);
+        for (int t = 0; t < ntap; ++t) {
+          const uint64_t bt = b0d + (uint64_t)((t0 * p.hy + t1) * p.hx + t2);
+          const uint32_t acc = tmem_base + t * 32;
+          umma_bf16(acc, a0, bt, idesc, acc_flag);
+#pragma unroll
+          for (int yk = 1; yk < HT_Y / 2; ++yk) umma_bf16(acc, a0 + yk * a_inc, bt + yk * b_inc, idesc, 1u);
+          if (++t2 == p.ks[2]) { t2 = 0; if (++t1 == p.ks[1]) { t1 = 0; ++t0; } }
+        }
+        umma_commit(pl_empty + 8 * s);
+        if (i == my_tiles - 1) umma_commit(acc_done);
+      }
+      __syncwarp();
+    }
+    if (my_tiles == 0 && lane == 0) mbar_arrive(acc_done);
+  } else if (lane == 0) {
+    for (int64_t i = 0; i < my_tiles; ++i) {
+      mbar_wait(stg_empty, ((uint32_t)i & 1u) ^ 1u);
+      int n, z, y0, x0;
+      tile_coords(i, n, z, y0, x0);
+      mbar_arrive_expect_tx(stg_full, x_stage_bytes + dy_stage_bytes);
+      tma_load_5d_h(xs_smem, &xmap, stg_full, 0, x0 + p.lo[2], y0 + p.lo[1], z + p.lo[0], n);
+      tma_load_5d_h(dys_smem, &dymap, stg_full, 0, x0, y0, z, n);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+bool halo_wgrad_eligible(const mig_conv_geom* g) {
+  if (g->Cin != H_C || g->Cout > 32 || g->Cout < 8 || g->Cout % 8 != 0) return false;
+  for (int i = 0; i < 3; ++i)
+    if (g->stride[i] != 1 || g->ksize[i] > 3) return false;
+  const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
+  if ((T + 1) / 2 * 32 > 512) return false;
+  const int64_t vox = (int64_t)g->N * g->out_dims[0] * g->out_dims[1] * g->out_dims[2];
+  return vox >= 32768 && g->out_dims[2] >= HT_X && g->out_dims[1] >= HT_Y / 2;
+}
+
+static int halo_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bx_, int by_, int bz_) {
+  EncodeTiledFn enc = get_encode();
+  MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gd[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gs[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t bx[5] = {(cuuint32_t)C, (cuuint32_t)bx_, (cuuint32_t)by_, (cuuint32_t)bz_, 1};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo map) failed with %d", (int)r);
+  return 0;
+}
+
+int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream) {
+  HaloWgradParams p{};
+  p.N = g->N; p.D = g->in_dims[0]; p.H = g->in_dims[1]; p.W = g->in_dims[2];
+  p.OD = g->out_dims[0]; p.OH = g->out_dims[1]; p.OW = g->out_dims[2];
+  for (int i = 0; i < 3; ++i) { p.ks[i] = g->ksize[i]; p.lo[i] = -g->pad[i]; }
+  p.hz = p.ks[0]; p.hy = HT_Y + p.ks[1] - 1; p.hx = HT_X + p.ks[2] - 1;
+  p.Cout = g->Cout;
+  p.tiles_x = (p.OW + HT_X - 1) / HT_X;
+  p.tiles_y = (p.OH + HT_Y - 1) / HT_Y;
+  p.num_tiles = (int64_t)p.N * p.OD * p.tiles_y * p.tiles_x;
+  p.taps_total = p.ks[0] * p.ks[1] * p.ks[2];
+  p.taps_per_half = (p.taps_total + 1) / 2;
+  p.dw = dw;
+  CUtensorMap xm, dym;
+  if (halo_map(&xm, x, p.N, p.D, p.H, p.W, H_C, p.hx, p.hy, p.hz)) return 1;
+  if (halo_map(&dym, dy, p.N, p.OD, p.OH, p.OW, p.Cout, HT_X, HT_Y, 1)) return 1;
+  const int nvox = p.hz * p.hy * p.hx;
+  const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 64 + 128) + 2 * 16 * (128 * 16 + 16) + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    MIG_REQUIRE(e == cudaSuccess, "wgrad_halo: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
+    configured = smem;
+  }
+  int64_t pairs = device_info().sm_count / 2;
+  if (pairs > p.num_tiles) pairs = p.num_tiles;
+  if (pairs < 1) pairs = 1;
+  wgrad_halo_kernel<<<(unsigned)(2 * pairs), H_THREADS, smem, as_stream(stream)>>>(xm, dym, p);
+  return check_launch("wgrad_halo_kernel");
 }
 
 int halo_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
