@@ -37,6 +37,9 @@ int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* 
                    void* stream);
 int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
 bool tma_dgrad_strided_eligible(const mig_conv_geom* g);
+bool halo_dgrad_strided_eligible(const mig_conv_geom* g);
+int halo_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                            void* stream);
 int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
                            void* stream);
 // small_ops.cu
@@ -110,6 +113,8 @@ static int run_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void
                      void* stream) {
   if (halo_enabled() && halo_conv_eligible(g, 1) && aligned16(dy) && aligned16(w) && aligned16(dx))
     return halo_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
+  if (halo_enabled() && halo_dgrad_strided_eligible(g) && aligned16(dy) && aligned16(w) && aligned16(dx))
+    return halo_conv_dgrad_strided(g, dy, w, dx, ws, wsb, stream);
   if (tma_enabled() && aligned16(dy) && aligned16(w) && aligned16(dx)) {
     if (tma_conv_eligible(g, 1)) return tma_conv_dgrad(g, dy, w, dx, ws, wsb, stream);
     if (tma_dgrad_strided_eligible(g)) return tma_conv_dgrad_strided(g, dy, w, dx, ws, wsb, stream);

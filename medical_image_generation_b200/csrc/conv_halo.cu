@@ -57,6 +57,9 @@ struct HaloParams {
   int hz, hy, hx;         // halo extent: 1+kz-1, 16+ky-1, 8+kx-1
   int sign;               // +1 fwd (halo offset of tap t = t), -1 dgrad (ks-1-t)
   int Cdst, Npad;         // output channels, UMMA N (16 or 32)
+  // where an output row lands: coordinate = row*os + oo inside a (TD,TH,TW) tensor (identity except strided dgrad,
+  // where each stride-residue class of input voxels is its own dense problem)
+  int os[3], oo[3], TD, TH, TW;
   int tiles_x, tiles_y;
   int64_t num_tiles;      // N*OD*tiles_y*tiles_x
   const __nv_bfloat16* w; // [Cdst][taps][32]
@@ -77,7 +80,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const uint32_t w_smem = smem_base;
   const uint32_t stg_smem = (w_smem + w_bytes + 127u) & ~127u;
   const uint32_t stg_stride = (stage_bytes + 127u) & ~127u;
-  const uint32_t pl_smem = stg_smem + 2 * stg_stride;
+  // two staging buffers when they fit; with a 64-wide filter (110 KB resident) only one
+  const int nstg = p.Npad > 32 ? 1 : 2;
+  const uint32_t pl_smem = stg_smem + nstg * stg_stride;
   const uint32_t pl_stride = (4u * plane + 127u) & ~127u;
   __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_slot;
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     }
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<64>(smem_u32(&tmem_slot));
+  if (warp == 4) tmem_alloc<128>(smem_u32(&tmem_slot));
   if (warp == 5 && lane == 0) tma_prefetch_desc(&xmap);
   // resident filter: global [co][tap][32] -> smem [tap][chunk][n][8 ch] (16-byte units), rows n >= Cdst are zero
   for (int i = threadIdx.x; i < T * 4 * p.Npad; i += H_THREADS) {
@@ -130,8 +135,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       tile_coords(i, n, z, y0, x0);
       const int y = y0 + (r >> 3), x = x0 + (r & 7);
       const bool ok = y < p.OH && x < p.OW;
-      const int64_t m = (((int64_t)n * p.OD + z) * p.OH + y) * p.OW + x;
-      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * 32;
+      const int64_t m = (((int64_t)n * p.TD + z * p.os[0] + p.oo[0]) * p.TH + y * p.os[1] + p.oo[1]) * p.TW +
+                        x * p.os[2] + p.oo[2];
+      const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * 64;
 #pragma unroll 1
       for (int c0 = 0; c0 < p.Npad; c0 += 16) {
         float v[16];
@@ -180,9 +186,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int s = (int)(i & 1);
       const uint32_t ph = (uint32_t)(i >> 1) & 1u;
-      mbar_wait(stg_full + 8 * s, ph);
+      const int ss = nstg == 2 ? s : 0;
+      mbar_wait(stg_full + 8 * ss, nstg == 2 ? ph : (uint32_t)i & 1u);
       mbar_wait(pl_empty + 8 * s, ph ^ 1u);
-      const uint32_t src = stg_smem + s * stg_stride, dst = pl_smem + s * pl_stride;
+      const uint32_t src = stg_smem + ss * stg_stride, dst = pl_smem + s * pl_stride;
       for (int idx = r; idx < nvox * 4; idx += 128) {
         const int vox = idx >> 2, c = idx & 3;
         uint32_t a0, a1, a2, a3;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       }
       fence_proxy_async();
       mbar_arrive(pl_full + 8 * s);
-      mbar_arrive(stg_empty + 8 * s);
+      mbar_arrive(stg_empty + 8 * ss);
       if (i >= 1) epilogue(i - 1);
     }
     if (my_tiles >= 1) epilogue(my_tiles - 1);
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         // The UMMAs are tiny (128 x N x 16 = 16 tensor cycles), so the single issuing thread is the limiter: the
         // descriptors are built once per tile and advanced with ONE 64-bit add per UMMA (the start-address field is
         // the low 14 bits in 16-byte units; shared-memory addresses never carry out of it).
-        const uint32_t acc = tmem_base + s * 32;
+        const uint32_t acc = tmem_base + s * 64;
         const uint64_t a0 = make_desc_noswz(pl_smem + s * pl_stride, plane, sbo_a);
         const uint64_t a_ks = (uint64_t)((2u * plane) >> 4);
         uint64_t bd = make_desc_noswz(w_smem, p.Npad * 16u, 128u);
@@ -239,8 +246,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   } else if (lane == 0) {
     // ============ TMA issuer: one halo box per tile ============
     for (int64_t i = 0; i < my_tiles; ++i) {
-      const int s = (int)(i & 1);
-      mbar_wait(stg_empty + 8 * s, ((uint32_t)(i >> 1) & 1u) ^ 1u);
+      const int s = nstg == 2 ? (int)(i & 1) : 0;
+      mbar_wait(stg_empty + 8 * s, ((nstg == 2 ? (uint32_t)(i >> 1) : (uint32_t)i) & 1u) ^ 1u);
       int n, z, y0, x0;
       tile_coords(i, n, z, y0, x0);
       mbar_arrive_expect_tx(stg_full + 8 * s, stage_bytes);
@@ -250,14 +257,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   __syncthreads();
   if (warp == 4) {
     tcgen05_fence_after();
-    tmem_dealloc<64>(tmem_base);
+    tmem_dealloc<128>(tmem_base);
   }
 }
 
 // which: 0 fwd, 1 dgrad
 bool halo_conv_eligible(const mig_conv_geom* g, int which) {
   const int csrc = which == 1 ? g->Cout : g->Cin, cdst = which == 1 ? g->Cin : g->Cout;
-  if (csrc != H_C || cdst < 1 || cdst > 32) return false;
+  if (csrc != H_C || cdst < 1 || cdst > 64) return false;
   for (int i = 0; i < 3; ++i)
     if (g->stride[i] != 1 || g->ksize[i] > 3) return false;
   const int64_t vox = (int64_t)g->N * g->out_dims[0] * g->out_dims[1] * g->out_dims[2];
@@ -265,22 +272,28 @@ bool halo_conv_eligible(const mig_conv_geom* g, int which) {
   return vox >= 32768 && od[2] >= HT_X && od[1] >= HT_Y / 2;
 }
 
-static int run_halo(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
-                    const float* chan_bias, const void* residual, void* out, void* stream) {
+// one dense stride-1 problem: rows (n, z, y, x) over ext[], source voxel = row + lo + halo offset
+struct HaloProblem {
+  int N;
+  int src[3];       // source extent
+  int ext[3];       // row extent (the output tensor itself, or one stride-residue class of it)
+  int ks[3], lo[3];
+  int sign;
+  int Cdst;
+  int os[3], oo[3], tgt[3];   // row -> output coordinate = row*os + oo inside tgt[]
+};
+
+static int launch_halo(const HaloProblem& h, const void* src, const void* wk, const float* bias, const float* chan_bias,
+                       const void* residual, void* out, void* stream) {
   HaloParams p{};
-  const int32_t* sd = which == 1 ? g->out_dims : g->in_dims;   // source extent
-  const int32_t* od = which == 1 ? g->in_dims : g->out_dims;   // extent of the tensor being produced
-  p.N = g->N; p.D = sd[0]; p.H = sd[1]; p.W = sd[2];
-  p.OD = od[0]; p.OH = od[1]; p.OW = od[2];
-  p.sign = which == 1 ? -1 : 1;
-  for (int i = 0; i < 3; ++i) {
-    p.ks[i] = g->ksize[i];
-    const int off = which == 1 ? g->pad[i] : -g->pad[i];
-    p.lo[i] = off + (p.sign > 0 ? 0 : -(g->ksize[i] - 1));
-  }
+  p.N = h.N; p.D = h.src[0]; p.H = h.src[1]; p.W = h.src[2];
+  p.OD = h.ext[0]; p.OH = h.ext[1]; p.OW = h.ext[2];
+  p.sign = h.sign;
+  for (int i = 0; i < 3; ++i) { p.ks[i] = h.ks[i]; p.lo[i] = h.lo[i]; p.os[i] = h.os[i]; p.oo[i] = h.oo[i]; }
+  p.TD = h.tgt[0]; p.TH = h.tgt[1]; p.TW = h.tgt[2];
   p.hz = 1 + p.ks[0] - 1; p.hy = HT_Y + p.ks[1] - 1; p.hx = HT_X + p.ks[2] - 1;
-  p.Cdst = which == 1 ? g->Cin : g->Cout;
-  p.Npad = p.Cdst <= 16 ? 16 : 32;
+  p.Cdst = h.Cdst;
+  p.Npad = p.Cdst <= 16 ? 16 : p.Cdst <= 32 ? 32 : 64;
   p.tiles_x = (p.OW + HT_X - 1) / HT_X;
   p.tiles_y = (p.OH + HT_Y - 1) / HT_Y;
   p.num_tiles = (int64_t)p.N * p.OD * p.tiles_y * p.tiles_x;
@@ -303,7 +316,8 @@ static int run_halo(const mig_conv_geom* g, int which, const void* src, const vo
   MIG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(halo map) failed with %d", (int)r);
   const int T = p.ks[0] * p.ks[1] * p.ks[2];
   const int nvox = p.hz * p.hy * p.hx;
-  const int smem = T * 4 * p.Npad * 16 + 2 * (nvox * 64 + 128) + 2 * (nvox * 64 + 64 + 128) + 512;
+  const int nstg = p.Npad > 32 ? 1 : 2;
+  const int smem = T * 4 * p.Npad * 16 + nstg * (nvox * 64 + 128) + 2 * (nvox * 64 + 64 + 128) + 512;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -314,6 +328,106 @@ static int run_halo(const mig_conv_geom* g, int which, const void* src, const vo
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv_halo_kernel<<<(unsigned)grid, H_THREADS, smem, as_stream(stream)>>>(xm, p);
   return check_launch("conv_halo_kernel");
+}
+
+static int run_halo(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
+                    const float* chan_bias, const void* residual, void* out, void* stream) {
+  HaloProblem h{};
+  const int32_t* sd = which == 1 ? g->out_dims : g->in_dims;   // source extent
+  const int32_t* od = which == 1 ? g->in_dims : g->out_dims;   // extent of the tensor being produced
+  h.N = g->N;
+  h.sign = which == 1 ? -1 : 1;
+  for (int i = 0; i < 3; ++i) {
+    h.src[i] = sd[i]; h.ext[i] = od[i]; h.tgt[i] = od[i]; h.os[i] = 1; h.oo[i] = 0;
+    h.ks[i] = g->ksize[i];
+    const int off = which == 1 ? g->pad[i] : -g->pad[i];
+    h.lo[i] = off + (h.sign > 0 ? 0 : -(g->ksize[i] - 1));
+  }
+  h.Cdst = which == 1 ? g->Cin : g->Cout;
+  return launch_halo(h, src, wk, bias, chan_bias, residual, out, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// strided dgrad (the backward of the 32-channel Downsample convolution) by stride-residue classes
+// ---------------------------------------------------------------------------------------------------
+// Same decomposition as conv_tma.cu: input voxels with the same residue (i + pad) mod stride see the same tap subset, so
+// every class is a dense stride-1 problem with a sub-filter (8 classes of 1..8 taps for k = 3, s = 2), whose rows
+// scatter into dx with the stride. Here each class runs on the halo kernel.
+int filter_transpose_taps(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, int ntaps, const int* taps,
+                          void* stream);
+
+struct HaloAxisClass { int o, ext, nu, base, rho; };
+static HaloAxisClass halo_axis_class(int in, int k, int s, int p, int rho) {
+  HaloAxisClass a;
+  a.rho = rho;
+  a.o = ((rho - p) % s + s) % s;                  // first input coordinate of the class
+  a.ext = in > a.o ? (in - a.o + s - 1) / s : 0;  // how many input coordinates it holds
+  a.nu = rho < k ? (k - rho + s - 1) / s : 0;     // taps rho, rho+s, ...
+  a.base = (a.o + p - rho) / s;                   // dy coordinate of (class row 0, tap rho)
+  return a;
+}
+
+bool halo_dgrad_strided_eligible(const mig_conv_geom* g) {
+  if (g->Cout != H_C || g->Cin < 1 || g->Cin > 64) return false;
+  bool any = false;
+  for (int i = 0; i < 3; ++i) {
+    if (g->stride[i] < 1 || g->stride[i] > 2 || g->ksize[i] > 3) return false;
+    any = any || g->stride[i] == 2;
+  }
+  if (!any) return false;
+  const int64_t vox = (int64_t)g->N * g->in_dims[0] * g->in_dims[1] * g->in_dims[2];
+  if (vox < 32768) return false;
+  for (int r1 = 0; r1 < g->stride[1]; ++r1)
+    if (halo_axis_class(g->in_dims[1], g->ksize[1], g->stride[1], g->pad[1], r1).ext < HT_Y / 2) return false;
+  for (int r2 = 0; r2 < g->stride[2]; ++r2)
+    if (halo_axis_class(g->in_dims[2], g->ksize[2], g->stride[2], g->pad[2], r2).ext < HT_X) return false;
+  return true;
+}
+
+int halo_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
+                            void* stream) {
+  const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
+  const int64_t wt_bytes = ((int64_t)g->Cin * T * g->Cout * 2 + 255) / 256 * 256 + 27 * 256;
+  MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(halo, strided): workspace too small");
+  bool need_zero = false;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint8_t* wp = (uint8_t*)ws;
+    for (int r0 = 0; r0 < g->stride[0]; ++r0)
+      for (int r1 = 0; r1 < g->stride[1]; ++r1)
+        for (int r2 = 0; r2 < g->stride[2]; ++r2) {
+          HaloAxisClass a[3] = {halo_axis_class(g->in_dims[0], g->ksize[0], g->stride[0], g->pad[0], r0),
+                                halo_axis_class(g->in_dims[1], g->ksize[1], g->stride[1], g->pad[1], r1),
+                                halo_axis_class(g->in_dims[2], g->ksize[2], g->stride[2], g->pad[2], r2)};
+          if (a[0].ext == 0 || a[1].ext == 0 || a[2].ext == 0) continue;
+          const int ntaps = a[0].nu * a[1].nu * a[2].nu;
+          if (pass == 0) { need_zero = need_zero || ntaps == 0; continue; }
+          if (ntaps == 0) continue;
+          int taps[27], nt = 0;
+          for (int u0 = 0; u0 < a[0].nu; ++u0)
+            for (int u1 = 0; u1 < a[1].nu; ++u1)
+              for (int u2 = 0; u2 < a[2].nu; ++u2)
+                taps[nt++] = ((a[0].rho + g->stride[0] * u0) * g->ksize[1] + (a[1].rho + g->stride[1] * u1)) * g->ksize[2] +
+                             (a[2].rho + g->stride[2] * u2);
+          if (filter_transpose_taps(MIG_BF16, w, wp, g->Cout, T, g->Cin, nt, taps, stream)) return 2;
+          HaloProblem h{};
+          h.N = g->N;
+          h.sign = -1;
+          h.Cdst = g->Cin;
+          for (int i = 0; i < 3; ++i) {
+            h.src[i] = g->out_dims[i]; h.ext[i] = a[i].ext; h.tgt[i] = g->in_dims[i];
+            h.ks[i] = a[i].nu; h.lo[i] = a[i].base - (a[i].nu - 1);
+            h.os[i] = g->stride[i]; h.oo[i] = a[i].o;
+          }
+          int rc = launch_halo(h, dy, wp, nullptr, nullptr, nullptr, dx, stream);
+          if (rc) return rc;
+          wp += ((int64_t)g->Cin * nt * g->Cout * 2 + 255) / 256 * 256;
+        }
+    if (pass == 0 && need_zero) {   // some input voxels receive no tap at all (kernel 1 with stride 2)
+      const int64_t n = (int64_t)g->N * g->in_dims[0] * g->in_dims[1] * g->in_dims[2] * g->Cin;
+      cudaMemsetAsync(dx, 0, (size_t)n * 2, as_stream(stream));
+    }
+  }
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------

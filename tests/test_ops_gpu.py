@@ -58,6 +58,14 @@ CONV_CASES = [
     (1, 32, 1, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # out conv of the AE: one output channel (N padded to 16)
     (1, 32, 16, (16, 48, 48), (3, 3, 1), (1, 1, 1), (1, 1, 0)),   # anisotropic kernel
     (4, 32, 32, (96, 96), (3, 3), (1, 1), (1, 1)),                # 2-D
+    (1, 32, 64, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # 64 outputs: single staging buffer, N = 64
+    (1, 64, 32, (16, 40, 48), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # dgrad produces 64 channels from 32
+    (1, 32, 48, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # 48 outputs padded to N = 64
+    # strided 32-channel Downsample: dgrad = stride-residue classes on the halo kernel
+    (1, 32, 32, (32, 32, 32), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+    (1, 32, 32, (33, 35, 37), (3, 3, 3), (2, 2, 2), (1, 1, 1)),   # odd extents: classes of different size
+    (2, 32, 32, (8, 64, 64), (3, 3, 1), (2, 2, 1), (1, 1, 0)),    # anisotropic stride / kernel
+    (8, 24, 32, (64, 64), (3, 3), (2, 2), (1, 1)),                # 2-D, 24 input channels
 ]
 
 
