@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
       for (int c = 0; c < nkc; ++c) {
         mbar_wait(qk_full + 8 * qs, qph);
         tcgen05_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a = qk_smem + qs * FA_QK_STAGE_BYTES, bsm = a + FA_BM * 128;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         for (int half = 0; half < 2; ++half) {
           mbar_wait(v_full + 8 * vs, vph);
           tcgen05_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t a = p_smem + half * (FA_BM * 128), bsm = v_smem + vs * v_stage_bytes;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         }
       }
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ============================ TMA issuer ============================
     int qs = 0, vs = 0;
     uint32_t qph = 0, vph = 0;

@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   const int T = p.ks[0] * p.ks[1] * p.ks[2];
   const int nvox = p.hz * p.hy * p.hx;
-  const uint32_t plane = (uint32_t)nvox * 16u + 16u;    // one 8-channel plane (+16 B: planes start on different banks)
+  // one 8-channel plane, padded so that the four planes start 32 B apart modulo 128 B: the 16-byte re-layout stores of
+  // a quarter warp (2 voxels x 4 planes) then hit eight different 16-byte bank groups
+  const uint32_t plane = (uint32_t)nvox * 16u + ((160u - ((uint32_t)nvox * 16u) % 128u) % 128u);
   const uint32_t stage_bytes = (uint32_t)nvox * 64u;    // TMA staging [voxel][32 ch]
   const uint32_t w_bytes = (uint32_t)T * 4u * p.Npad * 16u;
   const uint32_t w_smem = smem_base;
@@ -86,6 +88,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const uint32_t pl_stride = (4u * plane + 127u) & ~127u;
   __shared__ __align__(8) uint64_t bars[12];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float add_s[2][64];   // bias + per-sample channel bias of the tile in accumulator a
   const uint32_t b0 = smem_u32(&bars[0]);
   const uint32_t stg_full = b0, stg_empty = b0 + 16, pl_full = b0 + 32, pl_empty = b0 + 48, acc_full = b0 + 64,
                  acc_empty = b0 + 80;
@@ -143,13 +146,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         float v[16];
         tmem_ld16(trow + c0, v);
         if (!ok) continue;
+        const float4* ap = reinterpret_cast<const float4*>(&add_s[a][c0]);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const int col = c0 + e;
-          if (col < p.Cdst) {
-            if (p.bias) v[e] += p.bias[col];
-            if (p.chan_bias) v[e] += p.chan_bias[(int64_t)n * p.Cdst + col];
-          }
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = ap[e];
+          v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
         }
         __nv_bfloat16* dst = p.out + m * p.Cdst + c0;
         if (c0 + 16 <= p.Cdst && (p.Cdst & 7) == 0) {
@@ -189,6 +190,19 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       const int ss = nstg == 2 ? s : 0;
       mbar_wait(stg_full + 8 * ss, nstg == 2 ? ph : (uint32_t)i & 1u);
       mbar_wait(pl_empty + 8 * s, ph ^ 1u);
+      // every worker is past epilogue(i-2), the last reader of add_s[s]; the barrier of iteration i+1 (or the one
+      // before the final epilogue) orders these writes before epilogue(i) reads them
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (r < 64) {
+        float add = 0.f;
+        if (r < p.Cdst) {
+          int n, z, y0, x0;
+          tile_coords(i, n, z, y0, x0);
+          if (p.bias) add += p.bias[r];
+          if (p.chan_bias) add += p.chan_bias[(int64_t)n * p.Cdst + r];
+        }
+        add_s[s][r] = add;
+      }
       const uint32_t src = stg_smem + ss * stg_stride, dst = pl_smem + s * pl_stride;
       for (int idx = r; idx < nvox * 4; idx += 128) {
         const int vox = idx >> 2, c = idx & 3;
@@ -202,6 +216,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       mbar_arrive(stg_empty + 8 * ss);
       if (i >= 1) epilogue(i - 1);
     }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
     if (my_tiles >= 1) epilogue(my_tiles - 1);
   } else if (warp == 4) {
     // ============ UMMA issuer: 27 taps x 2 K-steps per tile, A = shifted windows of the planes ============
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       mbar_wait(pl_full + 8 * s, ph);
       mbar_wait(acc_empty + 8 * s, ph ^ 1u);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         // The UMMAs are tiny (128 x N x 16 = 16 tensor cycles), so the single issuing thread is the limiter: the
         // descriptors are built once per tile and advanced with ONE 64-bit add per UMMA (the start-address field is
         // the low 14 bits in 16-byte units; shared-memory addresses never carry out of it).
@@ -243,7 +258,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       }
       __syncwarp();
     }
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     // ============ TMA issuer: one halo box per tile ============
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int s = nstg == 2 ? (int)(i & 1) : 0;
@@ -317,7 +332,7 @@ static int launch_halo(const HaloProblem& h, const void* src, const void* wk, co
   const int T = p.ks[0] * p.ks[1] * p.ks[2];
   const int nvox = p.hz * p.hy * p.hx;
   const int nstg = p.Npad > 32 ? 1 : 2;
-  const int smem = T * 4 * p.Npad * 16 + nstg * (nvox * 64 + 128) + 2 * (nvox * 64 + 64 + 128) + 512;
+  const int smem = T * 4 * p.Npad * 16 + nstg * (nvox * 64 + 128) + 2 * (nvox * 64 + 512 + 128) + 512;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -459,7 +474,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
   const int nvox = p.hz * p.hy * p.hx;
   // plane strides are padded by 16 B so that consecutive channel-chunk planes start in different shared-memory banks
   // (a multiple of 128 B would put every chunk of a UMMA operand fetch on the same banks)
-  const uint32_t xplane = (uint32_t)nvox * 16u + 16u;
+  const uint32_t xplane = (uint32_t)nvox * 16u + ((160u - ((uint32_t)nvox * 16u) % 128u) % 128u);
   const uint32_t x_stage_bytes = (uint32_t)nvox * 64u;
   const uint32_t dy_stage_bytes = 128u * (uint32_t)p.Cout * 2u;
   constexpr uint32_t dyplane = 128u * 16u + 16u;              // one 8-channel plane of the 128-voxel dY tile
@@ -556,7 +571,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
       const int s = (int)(i & 1);
       mbar_wait(pl_full + 8 * s, (uint32_t)(i >> 1) & 1u);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         // descriptors built once per tile, advanced by one add per UMMA (the issuing thread is the limiter here)
         // A: dY planes, M = co chunks (SBO = plane), K = 16 voxels = lines 2yk, 2yk+1 (LBO = one 8-voxel line)
         const uint64_t a0 = make_desc_noswz(dyp_smem + s * dyp_stride, HT_X * 16u, dyplane);
@@ -580,7 +595,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
       __syncwarp();
     }
     if (my_tiles == 0 && lane == 0) mbar_arrive(acc_done);
-  } else if (lane == 0) {
+  } else if (elect_one()) {
     for (int64_t i = 0; i < my_tiles; ++i) {
       mbar_wait(stg_empty, ((uint32_t)i & 1u) ^ 1u);
       int n, z, y0, x0;
@@ -638,7 +653,7 @@ int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float
   if (halo_map(&xm, x, p.N, p.D, p.H, p.W, H_C, p.hx, p.hy, p.hz)) return 1;
   if (halo_map(&dym, dy, p.N, p.OD, p.OH, p.OW, p.Cout, HT_X, HT_Y, 1)) return 1;
   const int nvox = p.hz * p.hy * p.hx;
-  const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 64 + 128) + 2 * 16 * (128 * 16 + 16) + 512;
+  const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 512 + 128) + 2 * 16 * (128 * 16 + 16) + 512;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       const int s = it % STAGES;
       mbar_wait(full0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TBK / 16; ++kk) {
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
       const int s = it % STAGES;
       mbar_wait(full0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TBK / 16; ++kk) {

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       mbar_wait(full0 + 8 * s, ph);
       tcgen05_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TBK / 16; ++kk) {
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     if (nkb == 0 && lane == 0) mbar_arrive(accbar);
   } else {
     // ===================== TMA issuer (filters) ======================
-    if (lane == 0) {
+    if (elect_one()) {
       for (int it = 0; it < nkb; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;

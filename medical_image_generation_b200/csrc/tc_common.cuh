@@ -97,6 +97,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a CONVERGED warp. Branching on this instead of `lane == 0` matters: ptxas knows a single thread is active,
+// so descriptor arithmetic stays in uniform registers next to UTCHMMA / UTMALDG; with `lane == 0` every tcgen05.mma is
+// wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~20 instructions per MMA on the issuing thread).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // all previously issued MMAs of this thread complete -> one arrive on the mbarrier
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
