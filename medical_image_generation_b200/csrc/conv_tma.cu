@@ -45,7 +45,9 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
 
 struct BoxGeom {
   int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad)
-  int bd, bh, bw;        // box (bd*bh*bw == 64); boxes may overhang the tensor
+  int bd, bh, bw;        // box; boxes may overhang the tensor
+  int rb, nb;            // rows per shared-memory slot (64 or 128) and valid rows per box (bd*bh*bw <= rb);
+                         // wgrad: rb = 64 and nb a multiple of 16 (the box is one K stage of nb/16 UMMAs)
   int nbd, nbh, nbw;     // boxes per axis (ceil)
   int64_t num_boxes;     // N*nbd*nbh*nbw
   int ks[3];             // kernel
@@ -88,10 +90,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float add_s[2 * MT][BN];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BoxGeom& g = p.g;
-  const int64_t box0 = (int64_t)blockIdx.x * (2 * MT);
+  const int spt = TBM / g.rb;            // boxes per 128-row accumulator
+  const int nslot = MT * spt;
+  const int64_t box0 = (int64_t)blockIdx.x * nslot;
   const int n0 = blockIdx.y * BN;
   const int kb_begin = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
@@ -114,14 +119,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   if (warp < 4) {
     // ===================== epilogue =====================
     const int row = warp * 32 + lane;
-    const int r = row & 63;
+    const int r = row & (g.rb - 1), slot = row / g.rb;
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
+    // while the main loop runs: bias + per-sample channel bias of this CTA's columns, one row per box (a box lies
+    // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
+    if (!p.partial) {
+      for (int j = 0; j < nslot; ++j) {
+        int n = 0, d0, h0, w0;
+        if (box0 + j < g.num_boxes) box_origin(g, box0 + j, n, d0, h0, w0);
+        for (int c = row; c < BN; c += 128) {
+          const int col = n0 + c;
+          float a = 0.f;
+          if (col < g.Cdst) {
+            if (p.bias) a += p.bias[col];
+            if (p.chan_bias) a += p.chan_bias[(int64_t)n * g.Cdst + col];
+          }
+          add_s[j][c] = a;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(accbar, 0);
     tcgen05_fence_after();
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-      const int64_t box = box0 + mt * 2 + (row >> 6);
-      bool mok = box < g.num_boxes;
+      const int64_t box = box0 + mt * spt + slot;
+      bool mok = box < g.num_boxes && r < g.nb;
       int n = 0, d0 = 0, h0 = 0, w0 = 0;
       if (mok) box_origin(g, box, n, d0, h0, w0);
       mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
@@ -140,14 +163,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           continue;
         }
         const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
-        if (p.bias) {
+        const float4* ap = reinterpret_cast<const float4*>(&add_s[mt * spt + slot][c0]);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += p.bias[col0 + e];
-        }
-        if (p.chan_bias) {
-          const float* cb = p.chan_bias + (int64_t)n * g.Cdst + col0;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) if (col0 + e < g.Cdst) v[e] += cb[e];
+        for (int e = 0; e < 4; ++e) {
+          const float4 b4 = ap[e];
+          v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
         }
         __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
         if (full16) {
@@ -205,24 +225,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   } else {
     // ============ TMA issuers: lanes 0..2MT-1 -> the A boxes, lane 2MT -> the filter box ============
     int bn_ = g.N, bd_ = 0, bh_ = 0, bw_ = 0;   // default: fully out of bounds -> zero rows (tile tail)
-    if (lane < 2 * MT && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
+    if (lane < nslot && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
+    const uint32_t tx_bytes = (uint32_t)(nslot * g.nb) * 128u + B_BYTES;   // a box transfers its nb rows (zero-filled when out of bounds)
     for (int it = 0; it < nkb; ++it) {
       const int s = it % STAGES;
       const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
       const int kb = kb_begin + it;
       if (lane == 0) {  // one lane polls the barrier; the others park at the warp barrier
         mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        mbar_arrive_expect_tx(bar, tx_bytes);
       }
       __syncwarp();
-      if (lane < 2 * MT) {
+      if (lane < nslot) {
         int tap = kb / g.cchunks;
         const int c0 = (kb - tap * g.cchunks) * 64;
         const int t2 = tap % g.ks[2]; tap /= g.ks[2];
         const int t1 = tap % g.ks[1];
         const int t0 = tap / g.ks[1];
         const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
-        tma_load_5d(a_smem + lane * PANEL, &xmap, bar, c0, bw_ + dx, bh_ + dy, bd_ + dz, bn_);
+        tma_load_5d(a_smem + lane * (g.rb * 128), &xmap, bar, c0, bw_ + dx, bh_ + dy, bd_ + dz, bn_);
       } else if (lane == 2 * MT) {
         tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
       }
@@ -249,6 +270,42 @@ __global__ void __launch_bounds__(256) tma_splitk_finish(const float* __restrict
     if (chan_bias) v += chan_bias[(m / Mo) * C + c];
     if (residual) v += __bfloat162float(residual[i]);
     out[i] = __float2bfloat16_rn(v);
+  }
+}
+// the same, 8 channels per thread (C % 8 == 0, all pointers 16-byte aligned)
+__global__ void __launch_bounds__(256) tma_splitk_finish8(const float* __restrict__ partial, const float* __restrict__ bias,
+                                                          const float* __restrict__ chan_bias,
+                                                          const __nv_bfloat16* __restrict__ residual,
+                                                          __nv_bfloat16* __restrict__ out, int64_t M, int C, int64_t Mo) {
+  const int C8 = C >> 3;
+  const int64_t total = M * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / C8;
+    const int c = (int)(i - m * C8) * 8;
+    const float4* pp = reinterpret_cast<const float4*>(partial + i * 8);
+    float4 a = pp[0], b = pp[1];
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (bias) {
+      const float4* q = reinterpret_cast<const float4*>(bias + c);
+      a = q[0]; b = q[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (chan_bias) {
+      const float4* q = reinterpret_cast<const float4*>(chan_bias + (m / Mo) * C + c);
+      a = q[0]; b = q[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (residual) {
+      const uint4 r = *reinterpret_cast<const uint4*>(residual + i * 8);
+      const __nv_bfloat16* rb = reinterpret_cast<const __nv_bfloat16*>(&r);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += __bfloat162float(rb[e]);
+    }
+    uint4 o;
+    __nv_bfloat162* q = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) q[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+    *reinterpret_cast<uint4*>(out + i * 8) = o;
   }
 }
 
@@ -325,6 +382,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
         const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < TBK / 16; ++kk) {
+          if (kk * 16 >= g.nb) break;   // boxes of 16/32/48 voxels use the first rows of each 64-row panel
           const uint64_t bd = make_smem_desc(b_smem + kk * 2048, PANEL, 1024);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
@@ -356,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
       const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
       if (lane == 0) {
         mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar, STAGE_BYTES);
+        mbar_arrive_expect_tx(bar, (uint32_t)((APAN + NPAN) * g.nb) * 128u);
       }
       __syncwarp();
       if (lane < APAN + NPAN) {
@@ -404,6 +462,58 @@ static bool pick_box(int D, int H, int W, int* bd, int* bh, int* bw) {
   return best >= 0.5;   // below that the cp.async gather kernels are the better choice
 }
 
+// wgrad: a box is one K stage, so its voxel count only has to be a multiple of 16 (the UMMA K). Besides the 64-voxel
+// shapes, 48/32/16-voxel boxes are tried for volumes the 64-voxel boxes tile badly (6^3: 4x2x6 boxes, 75 % instead of
+// 56 % useful rows); smaller stages pay relatively more per-stage overhead, hence the discount.
+static bool pick_box_k(int D, int H, int W, int* bd, int* bh, int* bw) {
+  bool ok = pick_box(D, H, W, bd, bh, bw);
+  double best = 0.0;
+  if (ok) {
+    const double cover = (double)((D + *bd - 1) / *bd * *bd) * ((H + *bh - 1) / *bh * *bh) * ((W + *bw - 1) / *bw * *bw);
+    best = (double)D * H * W / cover;
+  }
+  if (best >= 0.8) return true;
+  double best_s = best * 64.0 / 72.0;
+  for (int d = 1; d <= D && d <= 64; ++d)
+    for (int h = 1; h <= H && d * h <= 64; ++h)
+      for (int w = 1; w <= W && d * h * w <= 64; ++w) {
+        const int nb = d * h * w;
+        if (nb % 16 != 0) continue;
+        const double boxes = (double)((D + d - 1) / d) * ((H + h - 1) / h) * ((W + w - 1) / w);
+        const double sc = (double)D * H * W / (boxes * nb) * nb / (nb + 8.0);
+        if (sc > best_s + 0.05) { best_s = sc; *bd = d; *bh = h; *bw = w; ok = true; }
+      }
+  return ok && best_s * 72.0 / 64.0 >= 0.5;
+}
+
+// fwd / dgrad only: a box may also fill one whole 128-row slot with FEWER than 128 voxels (the unused rows compute
+// garbage accumulator rows that the epilogue never reads), which tiles small odd volumes much better than overhanging
+// 64-voxel boxes: 6^3 -> two 3x6x6 boxes per sample (84 % useful rows instead of 56 %).
+static bool pick_box_rows(int D, int H, int W, int* bd, int* bh, int* bw, int* rb) {
+  *rb = 64;
+  double best = 0.0;
+  bool ok = pick_box(D, H, W, bd, bh, bw);
+  if (ok) {
+    const double cover = (double)((D + *bd - 1) / *bd * *bd) * ((H + *bh - 1) / *bh * *bh) * ((W + *bw - 1) / *bw * *bw);
+    best = (double)D * H * W / cover;
+  }
+  if (best >= 0.8) return true;
+  double best128 = 0.0;
+  int c[3] = {0, 0, 0};
+  for (int d = 1; d <= D && d <= 128; ++d)
+    for (int h = 1; h <= H && d * h <= 128; ++h)
+      for (int w = 1; w <= W && d * h * w <= 128; ++w) {
+        const double boxes = (double)((D + d - 1) / d) * ((H + h - 1) / h) * ((W + w - 1) / w);
+        const double eff = (double)D * H * W / (boxes * 128.0);
+        if (eff > best128 + 1e-9 || (eff > best128 - 1e-9 && w > c[2])) { best128 = eff; c[0] = d; c[1] = h; c[2] = w; }
+      }
+  if (best128 > best + 0.1) {
+    *bd = c[0]; *bh = c[1]; *bw = c[2]; *rb = 128;
+    return best128 >= 0.5;
+  }
+  return ok;
+}
+
 // which: 0 fwd, 1 dgrad, 2 wgrad
 bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   for (int i = 0; i < 3; ++i)
@@ -411,10 +521,10 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   const int csrc = which == 1 ? g->Cout : g->Cin;
   if (csrc % 64 != 0) return false;
   if (which == 2 && g->Cout % 8 != 0) return false;
-  if (which != 2 && (which == 0 ? g->Cout : g->Cin) < 8) return false;
   const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
-  int bd, bh, bw;
-  return pick_box(dims[0], dims[1], dims[2], &bd, &bh, &bw);
+  int bd, bh, bw, rb;
+  if (which != 2) return pick_box_rows(dims[0], dims[1], dims[2], &bd, &bh, &bw, &rb);
+  return pick_box_k(dims[0], dims[1], dims[2], &bd, &bh, &bw);
 }
 
 static int make_act_map(CUtensorMap* m, const void* base, int N, const int32_t dims[3], int C, int bd, int bh, int bw) {
@@ -437,7 +547,10 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   BoxGeom b{};
   const int32_t* rows = which == 1 ? g->in_dims : g->out_dims;
   b.N = g->N; b.D = rows[0]; b.H = rows[1]; b.W = rows[2];
-  pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
+  b.rb = 64;
+  if (which == 2) pick_box_k(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
+  else pick_box_rows(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw, &b.rb);
+  b.nb = b.bd * b.bh * b.bw;
   b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
   b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
   int taps = 1;
@@ -515,8 +628,9 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     double best = 1e30;
     static const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
     for (int m_ = 1; m_ <= (bn == 256 ? 2 : 1); ++m_) {
-      const int64_t mtiles_ = (b.num_boxes + 2 * m_ - 1) / (2 * m_);
-      const double t_stage = fmax(512.0 * m_ * bn / 256.0, 128.0 * m_ * 3.5 + bn * 1.5);
+      const int nslot_ = m_ * (TBM / b.rb);
+      const int64_t mtiles_ = (b.num_boxes + nslot_ - 1) / nslot_;
+      const double t_stage = fmax(512.0 * m_ * bn / 256.0, (double)nslot_ * b.nb * 3.5 + bn * 1.5);
       for (int s_ : cand_s) {
         if (s_ > 1 && (!ws_ok || p.num_kb / s_ < 4)) continue;
         const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
@@ -528,7 +642,8 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
       }
     }
   }
-  const int64_t mtiles = (b.num_boxes + 2 * mt - 1) / (2 * mt);
+  const int nslot = mt * (TBM / b.rb);
+  const int64_t mtiles = (b.num_boxes + nslot - 1) / nslot;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   if (splits > 1) {
@@ -544,9 +659,16 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   else rc = launch_conv_tma<32, 1>(xm, wm, p, grid, st);
   if (rc) return rc;
   if (splits > 1) {
-    tma_splitk_finish<<<bw_grid(M * b.Cdst, 256), 256, 0, st>>>((const float*)ws, bias, chan_bias,
-                                                                (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M,
-                                                                b.Cdst, (int64_t)b.D * b.H * b.W);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (b.Cdst % 8 == 0 && al16(ws) && al16(bias) && al16(chan_bias) && al16(residual) && al16(out))
+      tma_splitk_finish8<<<bw_grid(M * b.Cdst / 8, 256), 256, 0, st>>>((const float*)ws, bias, chan_bias,
+                                                                       (const __nv_bfloat16*)residual,
+                                                                       (__nv_bfloat16*)out, M, b.Cdst,
+                                                                       (int64_t)b.D * b.H * b.W);
+    else
+      tma_splitk_finish<<<bw_grid(M * b.Cdst, 256), 256, 0, st>>>((const float*)ws, bias, chan_bias,
+                                                                  (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M,
+                                                                  b.Cdst, (int64_t)b.D * b.H * b.W);
     return check_launch("tma_splitk_finish");
   }
   return 0;
@@ -646,7 +768,9 @@ int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w
         if (filter_transpose_taps(MIG_BF16, w, wp, g->Cout, T, g->Cin, nt, taps, stream)) return 2;
         BoxGeom b{};
         b.N = g->N; b.D = a[0].ext; b.H = a[1].ext; b.W = a[2].ext;
+        b.rb = 64;
         pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
+        b.nb = b.bd * b.bh * b.bw;
         b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
         b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
         for (int i = 0; i < 3; ++i) {
@@ -701,7 +825,7 @@ int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float*
       if (bn_ > 64 && b.K <= bn_ / 2) continue;
       if (mt_ == 2 && g->Cout <= 128) continue;
       const int64_t tiles = (int64_t)((g->Cout + TBM * mt_ - 1) / (TBM * mt_)) * ((b.K + bn_ - 1) / bn_);
-      const double t_stage = fmax(512.0 * mt_ * bn_ / 256.0, 64.0 * 3.5 * (2 * mt_ + bn_ / 64));
+      const double t_stage = fmax(512.0 * mt_ * bn_ / 256.0 * b.nb / 64.0, b.nb * 3.5 * (2 * mt_ + bn_ / 64));
       const double t_epi = 2500.0 + mt_ * 128.0 * bn_ / 5.0;
       for (int64_t s_ = 1; s_ <= b.num_boxes && s_ <= 4096; s_ = s_ < 8 ? s_ + 1 : s_ + s_ / 4) {
         const double waves = (double)((tiles * s_ + sms - 1) / sms);

@@ -388,6 +388,39 @@ __global__ void __launch_bounds__(256) filter_transpose_kernel(const T* __restri
     if (co < Cout && ci < Cin) wt[((int64_t)ci * Tn + tp) * Cout + co] = tile[threadIdx.x][i];
   }
 }
+// bf16 fast path (Cin % 8 == 0, Cout % 8 == 0, 16-byte aligned): 64x64 tiles, 16-byte global reads along ci and
+// 16-byte global writes along co (full 128-byte lines both ways); the 2-byte transposition happens in shared memory
+__global__ void __launch_bounds__(256) filter_transpose64_kernel(const __nv_bfloat16* __restrict__ w,
+                                                                 __nv_bfloat16* __restrict__ wt, int Cout, int Tn,
+                                                                 int Cin) {
+  constexpr int PITCH = 66;   // half-words per tile row: 33 words, so a column walk touches 32 different banks
+  __shared__ __align__(16) uint16_t tile[64 * PITCH];
+  const int tp = blockIdx.z;
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
+  const uint16_t* wu = reinterpret_cast<const uint16_t*>(w);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + 256 * k, row = idx >> 3, v = idx & 7;
+    const int co = co0 + row, ci = ci0 + v * 8;
+    uint4 q = make_uint4(0, 0, 0, 0);
+    if (co < Cout && ci < Cin) q = *reinterpret_cast<const uint4*>(wu + ((int64_t)co * Tn + tp) * Cin + ci);
+    uint32_t* d = reinterpret_cast<uint32_t*>(tile + row * PITCH + v * 8);
+    d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int idx = threadIdx.x + 256 * k, ci = idx >> 3, cv = idx & 7;
+    if (co0 + cv * 8 >= Cout || ci0 + ci >= Cin) continue;
+    uint16_t e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e[j] = tile[(cv * 8 + j) * PITCH + ci];
+    uint4 q;
+    q.x = e[0] | ((uint32_t)e[1] << 16); q.y = e[2] | ((uint32_t)e[3] << 16);
+    q.z = e[4] | ((uint32_t)e[5] << 16); q.w = e[6] | ((uint32_t)e[7] << 16);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(wt) + ((int64_t)(ci0 + ci) * Tn + tp) * Cout + co0 + cv * 8) = q;
+  }
+}
 // same transpose restricted to a subset of taps: wt[ci][j][co] = w[co][taps[j]][ci] (strided-dgrad sub-filters)
 struct TapList { int n; int t[32]; };
 template <typename T>
@@ -420,6 +453,13 @@ int filter_transpose_taps(int dtype, const void* w, void* wt, int Cout, int Tn, 
 
 int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream) {
   if ((int64_t)Cout * Tn * Cin == 0) return 0;
+  if (dtype == MIG_BF16 && Cin % 8 == 0 && Cout % 8 == 0 && ((reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(wt)) & 15) == 0 &&
+      (Cout + 63) / 64 < 65536 && Tn < 65536) {
+    dim3 grid64((Cin + 63) / 64, (Cout + 63) / 64, Tn);
+    filter_transpose64_kernel<<<grid64, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)wt, Cout, Tn,
+                                                                     Cin);
+    return check_launch("filter_transpose64");
+  }
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, Tn), block(32, 8);
   MIG_REQUIRE(grid.y < 65536 && grid.z < 65536, "filter_transpose: filter too large");
   MIG_DISPATCH_DTYPE(dtype, T, (filter_transpose_kernel<T><<<grid, block, 0, as_stream(stream)>>>(

@@ -23,8 +23,13 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         tr.step(x)
     torch.cuda.synchronize()
 ev = prof.key_averages()
-rows = sorted(((e.device_time_total, e.count, e.key) for e in ev if e.device_time_total > 0), reverse=True)
-tot = sum(r[0] for r in rows if "ProfilerStep" not in r[2])
+def _is_kernel(k):
+    return k.startswith(("void ", "mig::", "Memset", "Memcpy", "nccl"))
+
+
+rows = sorted(((e.device_time_total, e.count, e.key) for e in ev if e.device_time_total > 0 and _is_kernel(e.key)),
+              reverse=True)
+tot = sum(r[0] for r in rows)
 print(f"total device time per step: {tot / 2 / 1e3:.2f} ms")
 for t, c, k in rows[:45]:
     print(f"{t / 2 / 1e3:9.3f} ms {100 * t / tot:5.1f}%  x{c // 2:<5d} {k[:110]}")
