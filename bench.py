@@ -256,7 +256,7 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t)
     clocks = sampler.stop(w0, w1) if rank == 0 else None
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
 
     # ---- timed region 2: end to end through the public API with HOST (pinned) inputs -> `e2e` ----
     sync_all()
@@ -299,7 +299,7 @@ def run_b200(args):
                     "eager_ms_per_step": eager_ms_per_step,
                     "whole_step_model_tflops": 4.302e12 * B * args.steps / (ms_total * 1e-3) / 1e12}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the contract: rank 0 at N=1 only
             sps, cores, sec = cpu_reference_steps(args.cpu_steps, 0)
             cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": f"{args.cpu_steps} optimiser steps at batch 1 of the same U-Net (oracle port, fp32, "
@@ -320,12 +320,27 @@ def run_b200(args):
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # Teardown: the captured step graph holds NCCL work; destroying the communicator with such a graph alive can
+        # block for minutes. Drop the graph, drain the device, meet at a barrier and leave without the interpreter's
+        # teardown (every result is already printed and flushed).
+        trainer._graph = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
     args = parse()
+    # failsafe: a wedged collective must not hold the GPUs until the caller's limit
+    limit = float(os.environ.get("MIG_BENCH_LIMIT_S", "1500"))
+    watchdog = threading.Timer(limit, lambda: (sys.stderr.write("bench.py: time limit reached, aborting\n"), os._exit(3)))
+    watchdog.daemon = True
+    watchdog.start()
     if args.impl == "reference":
         run_reference(args)
     else:
