@@ -90,6 +90,19 @@ int halo_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void*
                     void* stream);
 bool halo_wgrad_eligible(const mig_conv_geom* g);
 int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
+// conv_thin.cu: CUDA-core kernels for the 1..4-channel ends (conv_in / out conv at full resolution)
+bool thin_conv_eligible(const mig_conv_geom* g, int which);
+int thin_conv(const mig_conv_geom* g, int which, const void* thin, const void* w, const float* bias,
+              const float* chan_bias, const void* residual, void* out, void* stream);
+int thin_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
+static bool thin_ok(const mig_conv_geom* g, int dtype, int which, int engine) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MIG_DISABLE_THIN_CONV");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1 && dtype == MIG_BF16 && engine != 1 && thin_conv_eligible(g, which);
+}
 static bool halo_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -163,6 +176,8 @@ extern "C" int mig_conv_fwd(const mig_conv_geom* g, int dtype, const void* x, co
                             int64_t workspace_bytes, void* stream) {
   MIG_REQUIRE(g && x && w && y, "conv_fwd: null argument");
   if (skinny_eligible(g) && !chan_bias && !residual) return skinny_fwd(g, dtype, x, w, bias, nullptr, nullptr, y, stream);
+  if (thin_ok(g, dtype, 0, engine) && aligned16(y) && (!residual || aligned16(residual)))
+    return thin_conv(g, 0, x, w, bias, chan_bias, residual, y, stream);
   if (use_tc(g, dtype, 0, engine)) return run_fwd(g, x, w, bias, chan_bias, residual, y, workspace, workspace_bytes, stream);
   if (want_pad(g, dtype, 0, engine) && workspace && workspace_bytes >= mig_conv_workspace_bytes(g, dtype, 0, engine)) {
     // pad the input channels of x and of the filter to a multiple of 8 (zeros), then the normal tensor-core path
@@ -183,6 +198,7 @@ extern "C" int mig_conv_dgrad(const mig_conv_geom* g, int dtype, const void* dy,
                               void* workspace, int64_t workspace_bytes, void* stream) {
   MIG_REQUIRE(g && dy && w && dx, "conv_dgrad: null argument");
   if (skinny_eligible(g)) return skinny_dgrad(g, dtype, dy, w, dx, stream);
+  if (thin_ok(g, dtype, 1, engine) && aligned16(dx)) return thin_conv(g, 1, dy, w, nullptr, nullptr, nullptr, dx, stream);
   if (use_tc(g, dtype, 1, engine)) return run_dgrad(g, dy, w, dx, workspace, workspace_bytes, stream);
   if (want_pad(g, dtype, 1, engine) && workspace && workspace_bytes >= mig_conv_workspace_bytes(g, dtype, 1, engine)) {
     // pad the output channels: dy gets zero channels, the filter gets zero rows
@@ -213,6 +229,7 @@ extern "C" int mig_conv_wgrad(const mig_conv_geom* g, int dtype, const void* x, 
   }
   if (!dw) return 0;
   if (skinny_eligible(g)) return skinny_wgrad(g, dtype, x, dy, dw, stream);
+  if (thin_ok(g, dtype, 2, engine)) return thin_conv_wgrad(g, x, dy, dw, stream);
   if (use_tc(g, dtype, 2, engine)) return run_wgrad(g, x, dy, dw, workspace, workspace_bytes, stream);
   if (want_pad(g, dtype, 2, engine) && workspace && workspace_bytes >= mig_conv_workspace_bytes(g, dtype, 2, engine)) {
     const int cin = pad8(g->Cin), cout = pad8(g->Cout), T = taps(g);

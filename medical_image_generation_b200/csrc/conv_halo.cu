@@ -450,9 +450,9 @@ int halo_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* 
 // ---------------------------------------------------------------------------------------------------
 // Both operands are MN-major no-swizzle planes in shared memory: X halo planes [ci chunk][voxel] x 16 B (the same
 // re-layout as the forward kernel; a tap is a start-address offset) and dY planes [co chunk][voxel] x 16 B. One UMMA
-// (128 x 32 x 16) reduces 16 voxels (two 8-voxel lines) of one tap; a CTA owns half of the taps (grid parity) and
+// (64 x 32 x 16) reduces 16 voxels (two 8-voxel lines) of one tap; a CTA owns half of the taps (grid parity) and
 // keeps ALL of its tap accumulators (<= 14 x 32 columns) in tensor memory over its whole tile loop, so the fp32
-// reduction into dW happens once per CTA. Output channels occupy TMEM lanes 0..Cout-1; the chunks above Cout read
+// reduction into dW happens once per CTA. Output channel m sits in TMEM lane (m % 16) + 32 (m / 16) (M = 64 layout); the chunks above Cout read
 // zero planes.
 struct HaloWgradParams {
   int N, D, H, W;          // X extent
@@ -478,13 +478,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
   const uint32_t x_stage_bytes = (uint32_t)nvox * 64u;
   const uint32_t dy_stage_bytes = 128u * (uint32_t)p.Cout * 2u;
   constexpr uint32_t dyplane = 128u * 16u + 16u;              // one 8-channel plane of the 128-voxel dY tile
-  // layout: [X staging][dY staging][X planes x2][dY planes x2 (16 chunk planes each; chunks >= Cout/8 stay zero)]
+  // layout: [X staging][dY staging][X planes x2][dY planes x2 (8 chunk planes each = the 64 rows of an M = 64 UMMA;
+  // chunks >= Cout/8 stay zero)]
   const uint32_t xs_smem = smem_base;
   const uint32_t dys_smem = (xs_smem + x_stage_bytes + 127u) & ~127u;
   const uint32_t xp_smem = (dys_smem + dy_stage_bytes + 127u) & ~127u;
   const uint32_t xp_stride = (4u * xplane + 127u) & ~127u;
   const uint32_t dyp_smem = xp_smem + 2 * xp_stride;
-  constexpr uint32_t dyp_stride = 16u * dyplane;
+  constexpr uint32_t dyp_stride = 8u * dyplane;
   __shared__ __align__(8) uint64_t bars[8];
   __shared__ uint32_t tmem_slot;
   const uint32_t b0 = smem_u32(&bars[0]);
@@ -549,23 +550,25 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
       mbar_arrive(pl_full + 8 * s);
       mbar_arrive(stg_empty);
     }
-    // ---- epilogue: TMEM lanes 0..Cout-1 hold dW rows; only warp 0's quadrant carries data ----
+    // ---- epilogue: an M = 64 accumulator keeps row m in TMEM lane (m % 16) + 32 * (m / 16): warp w reads the dW rows
+    // 16w .. 16w+15 from the first 16 lanes of its own quadrant; Cout <= 32 -> warps 0 and 1 carry data ----
     mbar_wait(acc_done, 0);
     tcgen05_fence_after();
-    if (warp == 0 && my_tiles > 0) {
-      const bool cok = lane < p.Cout;
+    if (warp * 16 < p.Cout && my_tiles > 0) {
+      const int co = warp * 16 + lane;
+      const bool cok = lane < 16 && co < p.Cout;
       for (int t = 0; t < ntap; ++t) {
 #pragma unroll 1
         for (int c0 = 0; c0 < 32; c0 += 16) {
           float v[16];
-          tmem_ld16(tmem_base + t * 32 + c0, v);
-          if (cok) red_add_16(p.dw + ((int64_t)lane * p.taps_total + tap_begin + t) * H_C + c0, v, 16);
+          tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + t * 32 + c0, v);
+          if (cok) red_add_16(p.dw + ((int64_t)co * p.taps_total + tap_begin + t) * H_C + c0, v, 16);
         }
       }
     }
     tcgen05_fence_before();
   } else if (warp == 4) {
-    const uint32_t idesc = make_idesc(128, 32, 1, 1);
+    const uint32_t idesc = make_idesc(64, 32, 1, 1);   // M = 64: the A fetch is 2 KB instead of 4 KB per UMMA
     const uint32_t lbo_b = (uint32_t)p.hx * 16u;   // next 8-voxel line of the X halo
     for (int64_t i = 0; i < my_tiles; ++i) {
       const int s = (int)(i & 1);
@@ -653,7 +656,7 @@ int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float
   if (halo_map(&xm, x, p.N, p.D, p.H, p.W, H_C, p.hx, p.hy, p.hz)) return 1;
   if (halo_map(&dym, dy, p.N, p.OD, p.OH, p.OW, p.Cout, HT_X, HT_Y, 1)) return 1;
   const int nvox = p.hz * p.hy * p.hx;
-  const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 512 + 128) + 2 * 16 * (128 * 16 + 16) + 512;
+  const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 512 + 128) + 2 * 8 * (128 * 16 + 16) + 512;
   static int configured = 0;
   if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

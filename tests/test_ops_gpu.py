@@ -64,6 +64,13 @@ CONV_CASES = [
     (1, 32, 64, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # 64 outputs: single staging buffer, N = 64
     (1, 64, 32, (16, 40, 48), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # dgrad produces 64 channels from 32
     (1, 32, 48, (32, 32, 32), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # 48 outputs padded to N = 64
+    # thin ends on CUDA cores (conv_in / out conv of the AE and of pixel-space DDPM U-Nets)
+    (2, 1, 32, (12, 20, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # conv_in 1 -> 32, ragged tiles
+    (1, 2, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # image + label input
+    (1, 32, 2, (16, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # out conv 32 -> 2: thin dgrad + wgrad
+    (1, 3, 64, (8, 16, 16), (3, 3, 1), (1, 1, 1), (1, 1, 0)),     # 3 -> 64 (wgrad stays on the padded path), flat kernel
+    (3, 1, 64, (40, 40), (3, 3), (1, 1), (1, 1)),                 # 2-D
+    (2, 64, 1, (40, 40), (3, 3), (1, 1), (1, 1)),                 # 2-D out conv
     # strided 32-channel Downsample: dgrad = stride-residue classes on the halo kernel
     (1, 32, 32, (32, 32, 32), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     (1, 32, 32, (33, 35, 37), (3, 3, 3), (2, 2, 2), (1, 1, 1)),   # odd extents: classes of different size
