@@ -371,10 +371,119 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, fl
     atomicAdd(out + b * C + c, t);
   }
 }
+// Vector path (C a multiple of the 16-byte vector width): a thread owns one 16-byte column vector and walks down rows
+// with four independent loads in flight; the thread rows of a CTA are merged through shared memory, then one atomic per
+// (CTA, column). grid (slabs, chunks, B), block cvb*rpb <= 256.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t R, int C,
+                                                         int cvb, int rpb, int64_t rows_per_cta) {
+  constexpr int V = Vec16<T>::N;
+  __shared__ float red[256 * V];
+  const int cv = C / V;
+  const int tcol = threadIdx.x % cvb, trow = threadIdx.x / cvb;
+  const int col = blockIdx.x * cvb + tcol;
+  const bool active = col < cv && trow < rpb;
+  float s[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) s[j] = 0.f;
+  if (active) {
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r1 = r0 + rows_per_cta < R ? r0 + rows_per_cta : R;
+    const T* base = x + (int64_t)blockIdx.z * R * C + (int64_t)col * V;
+    int64_t r = r0 + trow;
+    const int64_t step = rpb;
+    for (; r + 3 * step < r1; r += 4 * step) {
+      Vec16<T> v0 = ld16(base + r * C), v1 = ld16(base + (r + step) * C), v2 = ld16(base + (r + 2 * step) * C),
+               v3 = ld16(base + (r + 3 * step) * C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s[j] += (v0.get(j) + v1.get(j)) + (v2.get(j) + v3.get(j));
+    }
+    for (; r < r1; r += step) {
+      Vec16<T> v = ld16(base + r * C);
+#pragma unroll
+      for (int j = 0; j < V; ++j) s[j] += v.get(j);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < V; ++j) red[j * 256 + threadIdx.x] = s[j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < cvb * V; e += blockDim.x) {
+    const int j = e / cvb, tc = e - j * cvb;
+    const int ccol = blockIdx.x * cvb + tc;
+    if (ccol >= cv) continue;
+    float t = 0.f;
+    for (int rr = 0; rr < rpb; ++rr) t += red[j * 256 + rr * cvb + tc];
+    atomicAdd(out + (int64_t)blockIdx.z * C + ccol * V + j, t);
+  }
+}
+// Few columns (C <= 8, e.g. the 1/2/3-channel ends): one thread per row, consecutive threads read consecutive rows.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_thin_kernel(const T* __restrict__ x, float* __restrict__ out, int64_t R,
+                                                          int C) {
+  __shared__ float red[8][8];
+  const T* xs = x + (int64_t)blockIdx.z * R * C;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; r + 3 * stride < R; r += 4 * stride) {
+    float a[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[u][j] = j < C ? to_f(xs[(r + u * stride) * C + j]) : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += (a[0][j] + a[1][j]) + (a[2][j] + a[3][j]);
+  }
+  for (; r < R; r += stride)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += j < C ? to_f(xs[r * C + j]) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = s[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + (int64_t)blockIdx.z * C + threadIdx.x, t);
+  }
+}
 template <typename T>
 static int launch_colsum(const void* x, float* out, int B, int64_t R, int C, int accumulate, void* stream) {
   if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C, as_stream(stream));
   if (B * R * C == 0) return 0;
+  constexpr int V = Vec16<T>::N;
+  const int64_t target = (int64_t)device_info().sm_count * 4;
+  if (C % V == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // 4 column vectors (64 B of a row) per CTA: the CTA count that saturates HBM then issues 32..64 atomics each,
+    // not one per column of the whole row
+    const int cv = C / V, cvb = cv < 4 ? cv : 4, rpb = 256 / cvb, slabs = (cv + cvb - 1) / cvb;
+    int64_t chunks = target / ((int64_t)B * slabs);
+    if (chunks < 1) chunks = 1;
+    int64_t rows = (R + chunks - 1) / chunks;
+    if (rows < (int64_t)rpb * 4) rows = (int64_t)rpb * 4;
+    chunks = (R + rows - 1) / rows;
+    if (chunks <= 65535) {
+      dim3 grid(slabs, (unsigned)chunks, B);
+      colsum_vec_kernel<T><<<grid, cvb * rpb, 0, as_stream(stream)>>>((const T*)x, out, R, C, cvb, rpb, rows);
+      return check_launch("colsum_vec");
+    }
+  }
+  if (C <= 8) {
+    int64_t blocks = (R + 256 * 8 - 1) / (256 * 8);
+    if (blocks > target) blocks = target;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, 1, B);
+    colsum_thin_kernel<T><<<grid, 256, 0, as_stream(stream)>>>((const T*)x, out, R, C);
+    return check_launch("colsum_thin");
+  }
   int ctiles = (C + 31) / 32;
   int64_t want = (int64_t)device_info().sm_count * 4 / (ctiles * (int64_t)B) + 1;
   int64_t maxchunks = (R + 7) / 8;
