@@ -223,29 +223,39 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       __syncwarp();
     }
   } else {
-    // ============ TMA issuers: lanes 0..2MT-1 -> the A boxes, lane 2MT -> the filter box ============
-    int bn_ = g.N, bd_ = 0, bh_ = 0, bw_ = 0;   // default: fully out of bounds -> zero rows (tile tail)
-    if (lane < nslot && box0 + lane < g.num_boxes) box_origin(g, box0 + lane, bn_, bd_, bh_, bw_);
-    const uint32_t tx_bytes = (uint32_t)(nslot * g.nb) * 128u + B_BYTES;   // a box transfers its nb rows (zero-filled when out of bounds)
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % STAGES;
-      const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
-      const int kb = kb_begin + it;
-      if (lane == 0) {  // one lane polls the barrier; the others park at the warp barrier
+    // ============ TMA issuer: ONE elected thread, all address arithmetic warp-uniform ============
+    // (The earlier one-lane-per-box scheme made ptxas wrap every UTMALDG in a divergence "waterfall" loop and redid the
+    // tap / box index divisions every stage; this thread is the producer's critical path, so the k-block -> (tap,
+    // channel chunk) mapping is an odometer and the box origins are computed once.)
+    if (elect_one()) {
+      int bn_[2 * MT], bd_[2 * MT], bh_[2 * MT], bw_[2 * MT];
+#pragma unroll
+      for (int j = 0; j < 2 * MT; ++j) {
+        bn_[j] = g.N; bd_[j] = 0; bh_[j] = 0; bw_[j] = 0;   // default: fully out of bounds -> zero rows (tile tail)
+        if (j < nslot && box0 + j < g.num_boxes) box_origin(g, box0 + j, bn_[j], bd_[j], bh_[j], bw_[j]);
+      }
+      const uint32_t tx_bytes = (uint32_t)(nslot * g.nb) * 128u + B_BYTES;   // a box transfers its nb rows (zero-filled when out of bounds)
+      const uint32_t slot_bytes = (uint32_t)g.rb * 128u;
+      int tap = kb_begin / g.cchunks;
+      int cch = kb_begin - tap * g.cchunks;
+      int t2 = tap % g.ks[2]; tap /= g.ks[2];
+      int t1 = tap % g.ks[1];
+      int t0 = tap / g.ks[1];
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
         mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
         mbar_arrive_expect_tx(bar, tx_bytes);
-      }
-      __syncwarp();
-      if (lane < nslot) {
-        int tap = kb / g.cchunks;
-        const int c0 = (kb - tap * g.cchunks) * 64;
-        const int t2 = tap % g.ks[2]; tap /= g.ks[2];
-        const int t1 = tap % g.ks[1];
-        const int t0 = tap / g.ks[1];
         const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
-        tma_load_5d(a_smem + lane * (g.rb * 128), &xmap, bar, c0, bw_ + dx, bh_ + dy, bd_ + dz, bn_);
-      } else if (lane == 2 * MT) {
-        tma_load_2d(b_smem, &wmap, bar, kb * TBK, n0);
+        const int c0 = cch * 64;
+#pragma unroll
+        for (int j = 0; j < 2 * MT; ++j)
+          if (j < nslot) tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] + dx, bh_[j] + dy, bd_[j] + dz, bn_[j]);
+        tma_load_2d(b_smem, &wmap, bar, (kb_begin + it) * TBK, n0);
+        if (++cch == g.cchunks) {
+          cch = 0;
+          if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
+        }
       }
     }
   }
@@ -396,37 +406,41 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
     }
     if (nst <= 0 && lane == 0) mbar_arrive(accbar);
   } else {
-    // TMA issuers, one lane per box: lanes 0..APAN-1 -> the dY panels; lanes APAN..APAN+NPAN-1 -> the im2col(X)
-    // panels. Each X panel is one fixed (tap, 64-channel chunk) for the whole kernel.
-    const int q = lane - APAN;
-    int dz = 0, dy = 0, dx = 0, cc = -1;
-    if (q >= 0 && q < NPAN) {
-      const int k = n0 + q * 64;
-      int tap = k / g.Csrc;
-      cc = k < g.K ? k - tap * g.Csrc : -1;
-      const int t2 = tap % g.ks[2]; tap /= g.ks[2];
-      const int t1 = tap % g.ks[1];
-      const int t0 = tap / g.ks[1];
-      dz = t0 + g.off[0]; dy = t1 + g.off[1]; dx = t2 + g.off[2];
-    }
-    for (int it = 0; it < nst; ++it) {
-      const int s = it % STAGES;
-      const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
-      if (lane == 0) {
-        mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar, (uint32_t)((APAN + NPAN) * g.nb) * 128u);
+    // TMA issuer: one elected thread, warp-uniform arithmetic (see the forward kernel). Each im2col(X) panel is one
+    // fixed (tap, 64-channel chunk) for the whole kernel; the voxel box walks the volume as an odometer.
+    if (elect_one()) {
+      int dz[NPAN], dy[NPAN], dx[NPAN], cc[NPAN];
+#pragma unroll
+      for (int q = 0; q < NPAN; ++q) {
+        const int k = n0 + q * 64;
+        int tap = k / g.Csrc;
+        cc[q] = k < g.K ? k - tap * g.Csrc : -1;
+        const int t2 = tap % g.ks[2]; tap /= g.ks[2];
+        const int t1 = tap % g.ks[1];
+        const int t0 = tap / g.ks[1];
+        dz[q] = t0 + g.off[0]; dy[q] = t1 + g.off[1]; dx[q] = t2 + g.off[2];
       }
-      __syncwarp();
-      if (lane < APAN + NPAN) {
-        int n, d0, h0, w0;
-        box_origin(g, bb + it, n, d0, h0, w0);
-        if (lane < APAN) {
-          tma_load_5d(a_smem + lane * PANEL, &dymap, bar, co0 + lane * 64, w0, h0, d0, n);
-        } else if (cc >= 0) {
-          tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc, w0 + dx, h0 + dy, d0 + dz, n);
-        } else {
+      int n = 0, d0 = 0, h0 = 0, w0 = 0;
+      if (nst > 0) box_origin(g, bb, n, d0, h0, w0);
+      const int wend = g.nbw * g.bw, hend = g.nbh * g.bh, dend = g.nbd * g.bd;
+      const uint32_t tx_bytes = (uint32_t)((APAN + NPAN) * g.nb) * 128u;
+      for (int it = 0; it < nst; ++it) {
+        const int s = it % STAGES;
+        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
+        mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar, tx_bytes);
+#pragma unroll
+        for (int a = 0; a < APAN; ++a) tma_load_5d(a_smem + a * PANEL, &dymap, bar, co0 + a * 64, w0, h0, d0, n);
+#pragma unroll
+        for (int q = 0; q < NPAN; ++q) {
+          if (cc[q] >= 0) tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc[q], w0 + dx[q], h0 + dy[q], d0 + dz[q], n);
           // a panel past the end of K is loaded fully out of bounds (n = N) -> zeros, keeps the byte count fixed
-          tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
+          else tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
+        }
+        w0 += g.bw;
+        if (w0 >= wend) {
+          w0 = 0; h0 += g.bh;
+          if (h0 >= hend) { h0 = 0; d0 += g.bd; if (d0 >= dend) { d0 = 0; ++n; } }
         }
       }
     }
