@@ -137,6 +137,28 @@ __device__ __forceinline__ float silu_grad_f(float x) {
   return s * fmaf(x, 1.f - s, 1.f);
 }
 
+// bf16 activations: sigmoid through ONE MUFU op (tanh.approx, rel. error ~2^-11, far below bf16 resolution) instead
+// of ex2 + rcp; the fp32 parity path keeps the forms above.
+__device__ __forceinline__ float sigmoid_tanh_f(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+template <typename T>
+__device__ __forceinline__ float silu_t(float x) {
+  if constexpr (sizeof(T) == 2) return x * sigmoid_tanh_f(x);
+  else return silu_f(x);
+}
+template <typename T>
+__device__ __forceinline__ float silu_grad_t(float x) {
+  if constexpr (sizeof(T) == 2) {
+    const float s = sigmoid_tanh_f(x);
+    return s * fmaf(x, 1.f - s, 1.f);
+  } else {
+    return silu_grad_f(x);
+  }
+}
+
 // grid sizing for bandwidth kernels: enough CTAs to fill 148 SMs a few times over, capped.
 inline int bw_grid(int64_t work_items, int threads, int per_sm = 8) {
   int64_t blocks = (work_items + threads - 1) / threads;

@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         float z = fmaf(v[u].get(j), a[j], b[j]);
-        o.set(j, SILU ? silu_f(z) : z);
+        o.set(j, SILU ? silu_t<T>(z) : z);
       }
       st16(y + off + (r + u * step) * g.C, o);
     }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float z = fmaf(v.get(j), a[j], b[j]);
-      o.set(j, SILU ? silu_f(z) : z);
+      o.set(j, SILU ? silu_t<T>(z) : z);
     }
     st16(y + off + r * g.C, o);
   }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
       for (int j = 0; j < V; ++j) {
         float xh = (vx[u].get(j) - mu[j]) * rs[j];
         float dz = vd[u].get(j);
-        if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+        if (SILU) dz *= silu_grad_t<T>(fmaf(xh, ga[j], be[j]));
         p1[j] += dz * xh;
         p2[j] += dz;
       }
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(256) gn_bwd_stats_kernel(const T* __restrict__
     for (int j = 0; j < V; ++j) {
       float xh = (vx.get(j) - mu[j]) * rs[j];
       float dz = vd.get(j);
-      if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+      if (SILU) dz *= silu_grad_t<T>(fmaf(xh, ga[j], be[j]));
       p1[j] += dz * xh;
       p2[j] += dz;
     }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
       for (int j = 0; j < V; ++j) {
         float xh = (vx[u].get(j) - mu[j]) * rs[j];
         float dz = vd[u].get(j);
-        if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+        if (SILU) dz *= silu_grad_t<T>(fmaf(xh, ga[j], be[j]));
         o.set(j, rs[j] * (dz * ga[j] - (xh * A[j] + B[j])));
       }
       st16(dx + off + (r + u * step) * g.C, o);
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(const T* __restrict__
     for (int j = 0; j < V; ++j) {
       float xh = (vx.get(j) - mu[j]) * rs[j];
       float dz = vd.get(j);
-      if (SILU) dz *= silu_grad_f(fmaf(xh, ga[j], be[j]));
+      if (SILU) dz *= silu_grad_t<T>(fmaf(xh, ga[j], be[j]));
       o.set(j, rs[j] * (dz * ga[j] - (xh * A[j] + B[j])));
     }
     st16(dx + off + r * g.C, o);

@@ -7,10 +7,13 @@
 namespace mig {
 
 // ---- skinny linear: y[r][o] = sum_k x[r][k] w[o][k] + b[o], rows <= 32 --------------------------------
+// One warp per output feature. The filter row is read with 16-byte loads, four of them in flight per lane (the layer
+// is a 3 MB read that must not degenerate into a chain of dependent scalar loads); x rows come from L1/L2.
 template <typename T, int R>
-__global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
+__global__ void __launch_bounds__(128) skinny_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w,
                                                          const float* __restrict__ bias, T* __restrict__ y, int rows,
-                                                         int K, int O) {
+                                                         int K, int O, int vec) {
+  constexpr int V = Vec16<T>::N;
   const int lane = threadIdx.x & 31;
   const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (o >= O) return;
@@ -18,11 +21,26 @@ __global__ void __launch_bounds__(256) skinny_fwd_kernel(const T* __restrict__ x
     float acc[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) acc[i] = 0.f;
-    for (int k = lane; k < K; k += 32) {
-      const float wv = to_f(w[(int64_t)o * K + k]);
+    if (vec) {
+      const T* wr = w + (int64_t)o * K;
+#pragma unroll 4
+      for (int k = lane * V; k < K; k += 32 * V) {
+        const Vec16<T> wv = ld16(wr + k);
 #pragma unroll
-      for (int i = 0; i < R; ++i)
-        if (r0 + i < rows) acc[i] = fmaf(to_f(x[(int64_t)(r0 + i) * K + k]), wv, acc[i]);
+        for (int i = 0; i < R; ++i)
+          if (r0 + i < rows) {
+            const Vec16<T> xv = ld16(x + (int64_t)(r0 + i) * K + k);
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[i] = fmaf(xv.get(j), wv.get(j), acc[i]);
+          }
+      }
+    } else {
+      for (int k = lane; k < K; k += 32) {
+        const float wv = to_f(w[(int64_t)o * K + k]);
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+          if (r0 + i < rows) acc[i] = fmaf(to_f(x[(int64_t)(r0 + i) * K + k]), wv, acc[i]);
+      }
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
@@ -90,8 +108,9 @@ int skinny_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, 
                const float* chan_bias, const void* residual, void* y, void* stream) {
   MIG_REQUIRE(!chan_bias && !residual, "skinny linear: fused epilogue inputs are not supported");
   const int rows = rows_of(g), K = g->Cin, O = g->Cout;
-  MIG_DISPATCH_DTYPE(dtype, T, (skinny_fwd_kernel<T, 8><<<(O + 7) / 8, 256, 0, as_stream(stream)>>>(
-                                   (const T*)x, (const T*)w, bias, (T*)y, rows, K, O)));
+  const int vec = (K % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
+  MIG_DISPATCH_DTYPE(dtype, T, (skinny_fwd_kernel<T, 8><<<(O + 3) / 4, 128, 0, as_stream(stream)>>>(
+                                   (const T*)x, (const T*)w, bias, (T*)y, rows, K, O, vec)));
   return check_launch("skinny_fwd");
 }
 int skinny_dgrad(const mig_conv_geom* g, int dtype, const void* dy, const void* w, void* dx, void* stream) {
