@@ -43,6 +43,16 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// shared -> global box store (bulk async group); out-of-bounds elements of the box are not written
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(m), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 struct BoxGeom {
   int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad)
   int bd, bh, bw;        // box; boxes may overhang the tensor
@@ -76,12 +86,14 @@ struct ConvTmaParams {
   __nv_bfloat16* out;
   float* partial;
   int num_kb, kb_per_split;
+  int tma_store;   // epilogue stages the bf16 tile in shared memory and writes it with TMA box stores (ymap)
 };
 
 // BN: output-channel tile; MT: number of stacked 128-row accumulators (CTA tile = MT*128 voxels x BN channels)
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                const __grid_constant__ CUtensorMap wmap,
+                                                               const __grid_constant__ CUtensorMap ymap,
                                                                ConvTmaParams p) {
   constexpr int A_BYTES = MT * TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = stages_of(STAGE_BYTES);
@@ -151,12 +163,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
                             g.OW + (w0 + lw) * g.os[2] + g.oo[2];
       const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
+      constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load (one round trip each)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int cw = 0; cw < BN; cw += LDW) {
+        if (n0 + cw >= g.Cdst) break;
+        float vw[LDW];
+        if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
+        else tmem_ld16(trow + cw, vw);
+#pragma unroll
+      for (int c0 = cw; c0 < cw + LDW; c0 += 16) {
         if (n0 + c0 >= g.Cdst) break;
-        float v[16];
-        tmem_ld16(trow + c0, v);
-        if (!mok) continue;
+        float* v = vw + (c0 - cw);
+        if (!mok && !p.tma_store) continue;
         const int col0 = n0 + c0;
         if (p.partial) {
           red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
@@ -170,6 +188,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
         }
         __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
+        if (p.tma_store) {
+          // stage the row in the (now idle) pipeline buffers as [box][64-channel chunk][row][128 B], 128B-swizzled like
+          // the operand tiles; one thread then stores each (box, chunk) with a TMA box store: full 128-byte lines,
+          // overhang clipped by the TMA unit, no per-thread 32-byte global stores
+          if (mok && p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+            const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
+          }
+          uint32_t o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            o[e] = *reinterpret_cast<uint32_t*>(&q);
+          }
+          const uint32_t tile = smem_base + (uint32_t)((mt * spt + slot) * (BN / 64) + (c0 >> 6)) * ((uint32_t)g.rb * 128u);
+          const int j0 = (c0 & 63) >> 3;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile + sw128_offset(r, j0)), "r"(o[0]), "r"(o[1]),
+                       "r"(o[2]), "r"(o[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile + sw128_offset(r, j0 + 1)), "r"(o[4]), "r"(o[5]),
+                       "r"(o[6]), "r"(o[7]) : "memory");
+          continue;
+        }
         if (full16) {
           if (p.residual) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
@@ -197,6 +241,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
               dst[e] = __float2bfloat16_rn(v[e] + rr);
             }
         }
+      }
+      }
+    }
+    if (p.tma_store) {
+      fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA unit
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 0) {
+        for (int j = 0; j < nslot; ++j) {
+          if (box0 + j >= g.num_boxes) break;
+          int n, d0, h0, w0;
+          box_origin(g, box0 + j, n, d0, h0, w0);
+          for (int c = 0; c < BN / 64; ++c) {
+            if (n0 + c * 64 >= g.Cdst) break;
+            tma_store_5d(&ymap, smem_base + (uint32_t)(j * (BN / 64) + c) * ((uint32_t)g.rb * 128u), n0 + c * 64, w0, h0, d0, n);
+          }
+        }
+        tma_store_commit_wait_read();   // shared memory may be handed to the next CTA once the TMA unit has read it
       }
     }
     tcgen05_fence_before();
@@ -373,12 +434,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
       const bool cok = co < g.Cdst && nst > 0;
       const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        if (n0 + c0 >= g.K) break;
-        float v[16];
-        tmem_ld16(trow + c0, v);
+      for (int cw = 0; cw < BN; cw += 64) {
+        if (n0 + cw >= g.K) break;
+        float vw[64];
+        tmem_ld64(trow + cw, vw);
         if (!cok) continue;
-        red_add_16(p.dw + (int64_t)co * g.K + n0 + c0, v, g.K - n0 - c0);
+#pragma unroll
+        for (int c0 = cw; c0 < cw + 64; c0 += 16) {
+          if (n0 + c0 >= g.K) break;
+          red_add_16(p.dw + (int64_t)co * g.K + n0 + c0, vw + (c0 - cw), g.K - n0 - c0);
+        }
       }
     }
     tcgen05_fence_before();
@@ -584,8 +649,8 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
 }
 
 template <int BN, int MT>
-static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const ConvTmaParams& p, dim3 grid,
-                           cudaStream_t st) {
+static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const CUtensorMap& ym, const ConvTmaParams& p,
+                           dim3 grid, cudaStream_t st) {
   constexpr int stage = MT * TBM * 128 + BN * 128;
   constexpr int smem = stages_of(stage) * stage + 1024;
   static bool configured = false;
@@ -594,7 +659,7 @@ static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const C
     MIG_REQUIRE(e == cudaSuccess, "conv_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, p);
+  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, ym, p);
   return check_launch("conv_tma_kernel");
 }
 
@@ -666,11 +731,25 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   }
   dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
   int rc;
-  if (mt == 2) rc = launch_conv_tma<256, 2>(xm, wm, p, grid, st);
-  else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, p, grid, st);
-  else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, p, grid, st);
-  else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, p, grid, st);
-  else rc = launch_conv_tma<32, 1>(xm, wm, p, grid, st);
+  // TMA-store epilogue: rows map 1:1 to the output tensor, whole 64-channel chunks, no split-K partials
+  CUtensorMap ym = xm;
+  static int store_ok = -1;
+  if (store_ok < 0) {
+    const char* e = getenv("MIG_DISABLE_TMA_STORE");
+    store_ok = (e && e[0] == '1') ? 0 : 1;
+  }
+  const bool dense_rows = b.os[0] == 1 && b.os[1] == 1 && b.os[2] == 1 && b.oo[0] == 0 && b.oo[1] == 0 && b.oo[2] == 0 &&
+                          b.OD == b.D && b.OH == b.H && b.OW == b.W;
+  if (store_ok && splits == 1 && dense_rows && b.Cdst % 64 == 0 && bn >= 64) {
+    const int32_t rdims[3] = {b.D, b.H, b.W};
+    if (make_act_map(&ym, out, b.N, rdims, b.Cdst, b.bd, b.bh, b.bw)) return 1;
+    p.tma_store = 1;
+  }
+  if (mt == 2) rc = launch_conv_tma<256, 2>(xm, wm, ym, p, grid, st);
+  else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, ym, p, grid, st);
+  else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, ym, p, grid, st);
+  else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, ym, p, grid, st);
+  else rc = launch_conv_tma<32, 1>(xm, wm, ym, p, grid, st);
   if (rc) return rc;
   if (splits > 1) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

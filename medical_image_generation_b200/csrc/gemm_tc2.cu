@@ -303,18 +303,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const bool mok = m < p.M;
     const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16);
     const int64_t cbase = (int64_t)bo * p.c_outer + (int64_t)bi * p.c_inner + (int64_t)m * p.c_m;
+    constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load: short-K GEMMs are epilogue-bound, and the
+                                              // epilogue is bound by TMEM round trips
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= p.N) break;
-      float v[16];
-      tmem_ld16(trow + c0, v);
+    for (int cw = 0; cw < BN; cw += LDW) {
+      if (n0 + cw >= p.N) break;
+      float vw[LDW];
+      if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
+      else tmem_ld16(trow + cw, vw);
       if (!mok) continue;
+#pragma unroll
+    for (int c0 = cw; c0 < cw + LDW; c0 += 16) {
+      if (n0 + c0 >= p.N) break;
+      const float* v = vw + (c0 - cw);
       const int col0 = n0 + c0;
       if (p.c_f32) {
         float* dst = reinterpret_cast<float*>(p.C) + cbase + col0;
+        if (col0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          float4* d4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (col0 + e < p.N) dst[e] = p.accumulate ? dst[e] + p.alpha * v[e] : p.alpha * v[e];
+          for (int e = 0; e < 4; ++e) {
+            float4 o = make_float4(p.alpha * v[4 * e], p.alpha * v[4 * e + 1], p.alpha * v[4 * e + 2], p.alpha * v[4 * e + 3]);
+            if (p.accumulate) {
+              const float4 q = d4[e];
+              o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+            }
+            d4[e] = o;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (col0 + e < p.N) dst[e] = p.accumulate ? dst[e] + p.alpha * v[e] : p.alpha * v[e];
+        }
       } else {
         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + cbase + col0;
         if (col0 + 16 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -334,6 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             if (col0 + e < p.N) dst[e] = __float2bfloat16_rn(p.alpha * v[e]);
         }
       }
+    }
     }
     tcgen05_fence_before();
   } else if (warp == 4) {

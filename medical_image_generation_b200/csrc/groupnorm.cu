@@ -24,11 +24,11 @@ struct GnGeom {
 };
 
 template <typename T>
-static GnGeom make_geom(int N, int64_t S, int C, int G, int64_t target_ctas) {
+static GnGeom make_geom(int N, int64_t S, int C, int G, int64_t target_ctas, int max_cvb = 256) {
   GnGeom g;
   g.N = N; g.C = C; g.G = G; g.cpg = C / G; g.S = S;
   g.cv = C / Vec16<T>::N;
-  g.cvb = g.cv < 256 ? g.cv : 256;
+  g.cvb = g.cv < max_cvb ? g.cv : max_cvb;
   g.rpb = 256 / g.cvb;
   if (g.rpb < 1) g.rpb = 1;
   g.slabs = (g.cv + g.cvb - 1) / g.cvb;
@@ -372,8 +372,17 @@ static int gn_bwd(const void* x, const void* dy, const float* gamma, const float
   float* wsc = (float*)ws;
   float* wsg = wsc + (int64_t)N * C * 2;
   cudaMemsetAsync(wsc, 0, sizeof(float) * (size_t)N * C * 2, st);
-  if (silu) gn_bwd_stats_kernel<T, true><<<grid, threads, threads * 2 * Vec16<T>::N * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
-  else gn_bwd_stats_kernel<T, false><<<grid, threads, threads * 2 * Vec16<T>::N * sizeof(float), st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, g);
+  {
+    // the statistics pass ends in one atomic per (CTA, channel, moment): give a CTA a 64-byte column slab and many rows
+    // (64 atomics per CTA) instead of every column of a few rows (2*C atomics per CTA, ~300 k per launch)
+    GnGeom gs = make_geom<T>(N, S, C, G, (int64_t)device_info().sm_count * 4, 4);
+    const int schunks = (int)((S + gs.rows_per_cta - 1) / gs.rows_per_cta);
+    dim3 sgrid(schunks, gs.slabs, N);
+    const int sthreads = gs.cvb * gs.rpb;
+    const size_t ssmem = (size_t)sthreads * 2 * Vec16<T>::N * sizeof(float);
+    if (silu) gn_bwd_stats_kernel<T, true><<<sgrid, sthreads, ssmem, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, gs);
+    else gn_bwd_stats_kernel<T, false><<<sgrid, sthreads, ssmem, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsc, gs);
+  }
   int fin = C > N * G ? C : N * G;
   gn_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(wsc, gamma, dgamma, dbeta, wsg, N, C, G);
   float inv = 1.f / ((float)S * (float)g.cpg);
