@@ -119,12 +119,16 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
   const uint32_t tmem_base = tmem_slot;
   const int64_t my_tiles = p.num_tiles > blockIdx.x ? (p.num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
+  // 32-bit arithmetic (the host refuses more than 2^31 tiles): these divisions sit on every role's per-tile path
   auto tile_coords = [&](int64_t i, int& n, int& z, int& y0, int& x0) {
-    int64_t t = (int64_t)blockIdx.x + i * gridDim.x;
-    x0 = (int)(t % p.tiles_x) * HT_X; t /= p.tiles_x;
-    y0 = (int)(t % p.tiles_y) * HT_Y; t /= p.tiles_y;
-    z = (int)(t % p.OD);
-    n = (int)(t / p.OD);
+    uint32_t t = blockIdx.x + (uint32_t)i * gridDim.x;
+    uint32_t q = t / (uint32_t)p.tiles_x;
+    x0 = (int)(t - q * p.tiles_x) * HT_X; t = q;
+    q = t / (uint32_t)p.tiles_y;
+    y0 = (int)(t - q * p.tiles_y) * HT_Y; t = q;
+    q = t / (uint32_t)p.OD;
+    z = (int)(t - q * p.OD);
+    n = (int)q;
   };
 
   if (warp < 4) {
@@ -141,11 +145,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
       const int64_t m = (((int64_t)n * p.TD + z * p.os[0] + p.oo[0]) * p.TH + y * p.os[1] + p.oo[1]) * p.TW +
                         x * p.os[2] + p.oo[2];
       const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16) + a * 64;
-#pragma unroll 1
-      for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + c0, v);
-        if (!ok) continue;
+      // one TMEM round trip for the whole 64-column accumulator slot (columns >= Npad are stale and ignored)
+      float vw[64];
+      tmem_ld64(trow, vw);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        if (c0 >= p.Npad || !ok) continue;
+        float* v = vw + c0;
         const float4* ap = reinterpret_cast<const float4*>(&add_s[a][c0]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -204,12 +210,24 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_halo_kernel(const __grid_co
         add_s[s][r] = add;
       }
       const uint32_t src = stg_smem + ss * stg_stride, dst = pl_smem + s * pl_stride;
-      for (int idx = r; idx < nvox * 4; idx += 128) {
-        const int vox = idx >> 2, c = idx & 3;
-        uint32_t a0, a1, a2, a3;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(src + idx * 16));
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + c * plane + vox * 16), "r"(a0), "r"(a1), "r"(a2),
-                     "r"(a3) : "memory");
+      // six 16-byte moves per round: the loads are issued back to back, then the stores (one dependent load -> store
+      // pair per iteration left the workers waiting on shared-memory latency 17 times per tile)
+      for (int idx0 = r; idx0 < nvox * 4; idx0 += 6 * 128) {
+        uint32_t a[6][4];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = idx0 + u * 128;
+          if (idx < nvox * 4)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u][0]), "=r"(a[u][1]), "=r"(a[u][2]), "=r"(a[u][3])
+                         : "r"(src + idx * 16));
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = idx0 + u * 128;
+          if (idx < nvox * 4)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + (idx & 3) * plane + (idx >> 2) * 16), "r"(a[u][0]),
+                         "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]) : "memory");
+        }
       }
       fence_proxy_async();
       mbar_arrive(pl_full + 8 * s);
@@ -515,11 +533,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
   const uint32_t tmem_base = tmem_slot;
 
   auto tile_coords = [&](int64_t i, int& n, int& z, int& y0, int& x0) {
-    int64_t t = (int64_t)cta + i * nctas;
-    x0 = (int)(t % p.tiles_x) * HT_X; t /= p.tiles_x;
-    y0 = (int)(t % p.tiles_y) * HT_Y; t /= p.tiles_y;
-    z = (int)(t % p.OD);
-    n = (int)(t / p.OD);
+    uint32_t t = (uint32_t)cta + (uint32_t)i * (uint32_t)nctas;
+    uint32_t q = t / (uint32_t)p.tiles_x;
+    x0 = (int)(t - q * p.tiles_x) * HT_X; t = q;
+    q = t / (uint32_t)p.tiles_y;
+    y0 = (int)(t - q * p.tiles_y) * HT_Y; t = q;
+    q = t / (uint32_t)p.OD;
+    z = (int)(t - q * p.OD);
+    n = (int)q;
   };
 
   if (warp < 4) {
@@ -531,12 +552,22 @@ __global__ void __launch_bounds__(H_THREADS, 1) wgrad_halo_kernel(const __grid_c
       mbar_wait(stg_full, (uint32_t)i & 1u);
       mbar_wait(pl_empty + 8 * s, ph ^ 1u);
       const uint32_t xdst = xp_smem + s * xp_stride, ddst = dyp_smem + s * dyp_stride;
-      for (int idx = r; idx < nvox * 4; idx += 128) {
-        const int vox = idx >> 2, c = idx & 3;
-        uint32_t a0, a1, a2, a3;
-        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(xs_smem + idx * 16));
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xdst + c * xplane + vox * 16), "r"(a0), "r"(a1), "r"(a2),
-                     "r"(a3) : "memory");
+      for (int idx0 = r; idx0 < nvox * 4; idx0 += 6 * 128) {
+        uint32_t a[6][4];
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = idx0 + u * 128;
+          if (idx < nvox * 4)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a[u][0]), "=r"(a[u][1]), "=r"(a[u][2]), "=r"(a[u][3])
+                         : "r"(xs_smem + idx * 16));
+        }
+#pragma unroll
+        for (int u = 0; u < 6; ++u) {
+          const int idx = idx0 + u * 128;
+          if (idx < nvox * 4)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xdst + (idx & 3) * xplane + (idx >> 2) * 16), "r"(a[u][0]),
+                         "r"(a[u][1]), "r"(a[u][2]), "r"(a[u][3]) : "memory");
+        }
       }
       // dY tile: TMA staged [voxel r][Cout] -> planes [chunk][voxel]; out-of-range voxels were zero-filled by TMA
       for (int c = 0; c < nchunk; ++c) {
