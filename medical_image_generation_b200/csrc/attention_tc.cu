@@ -33,6 +33,12 @@ constexpr int FA_QK_STAGE_BYTES = 2 * FA_BM * 128;   // Q chunk + K chunk, 64 ch
 constexpr int FA_P_BYTES = 2 * FA_BM * 128;          // 128 x 128 bf16 as two 64-key panels
 constexpr int FA_PANEL = 64 * 128;
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct FlashParams {
   int B, H, Lq, Lk, dh, DV;   // DV = value/output columns handled by one CTA (<= 256)
   float scale_log2;           // softmax scale * log2(e)
@@ -96,54 +102,53 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
       tcgen05_fence_after();
       const uint32_t ts = tmem_base + lane_off + buf * FA_BN;
       const int kbase = j * FA_BN;
+      // The S row is read in two 64-column TMEM loads (one round trip each): with 16-column loads the softmax warps
+      // spent most of their time waiting for tcgen05.ld round trips (8-16 per tile), not computing.
       if (PASS == 0) {
-        float tmax = -INFINITY;
 #pragma unroll 1
-        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(ts + c0, v);
+        for (int half = 0; half < 2; ++half) {
+          float v[64];
+          tmem_ld64(ts + half * 64, v);
+          const int kb = kbase + half * 64;
+          float tmax = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (kbase + c0 + e < p.Lk) tmax = fmaxf(tmax, v[e] * p.scale_log2);
-        }
-        const float m_new = fmaxf(m_run, tmax);
-        float sum = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(ts + c0, v);
+          for (int e = 0; e < 64; ++e) {
+            v[e] = (kb + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
+            tmax = fmaxf(tmax, v[e]);
+          }
+          if (tmax > -INFINITY) {   // online update per 64 keys
+            const float m_new = fmaxf(m_run, tmax);
+            float sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (kbase + c0 + e < p.Lk) sum += exp2f(v[e] * p.scale_log2 - m_new);
+            for (int e = 0; e < 64; ++e) sum += fast_ex2(v[e] - m_new);
+            l_run = l_run * fast_ex2(m_run - m_new) + sum;
+            m_run = m_new;
+          }
         }
-        l_run = l_run * exp2f(m_run - m_new) + sum;
-        m_run = m_new;
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);
       } else {
         mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile has consumed the P buffer
 #pragma unroll 1
-        for (int c0 = 0; c0 < FA_BN; c0 += 16) {
-          float v[16];
-          tmem_ld16(ts + c0, v);
-          uint4 o0, o1;
-          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-          float pr[16];
+        for (int half = 0; half < 2; ++half) {
+          float v[64];
+          tmem_ld64(ts + half * 64, v);
+          const int kb = kbase + half * 64;
+          const uint32_t base = p_smem + half * (FA_BM * 128);   // one 64-key panel per half
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            pr[e] = (kbase + c0 + e < p.Lk) ? exp2f(v[e] * p.scale_log2 - lse_r) : 0.f;
+          for (int c = 0; c < 8; ++c) {                          // 16-byte chunks of the 128-byte row
+            uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            h0[e] = __floats2bfloat162_rn(pr[2 * e], pr[2 * e + 1]);
-            h1[e] = __floats2bfloat162_rn(pr[8 + 2 * e], pr[8 + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) {
+              const int k0 = c * 8 + 2 * e;
+              const float p0 = (kb + k0 < p.Lk) ? fast_ex2(fmaf(v[k0], p.scale_log2, -lse_r)) : 0.f;
+              const float p1 = (kb + k0 + 1 < p.Lk) ? fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -lse_r)) : 0.f;
+              __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
+              o[e] = *reinterpret_cast<uint32_t*>(&q2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, c)), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3]) : "memory");
           }
-          const int panel = c0 >> 6, ch = (c0 & 63) >> 3;   // 16-byte chunk index within the 128-byte row
-          const uint32_t base = p_smem + panel * (FA_BM * 128);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, ch)), "r"(o0.x), "r"(o0.y),
-                       "r"(o0.z), "r"(o0.w) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, ch + 1)), "r"(o1.x), "r"(o1.y),
-                       "r"(o1.z), "r"(o1.w) : "memory");
         }
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);
@@ -159,10 +164,13 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
       const uint32_t to = tmem_o + lane_off;
       __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + q) * ((int64_t)p.H * p.dh) + (int64_t)h * p.dh + slice * p.DV;
 #pragma unroll 1
-      for (int c0 = 0; c0 < p.DV; c0 += 16) {
-        float v[16];
-        tmem_ld16(to + c0, v);
+      for (int cw = 0; cw < p.DV; cw += 64) {
+        float vw[64];
+        tmem_ld64(to + cw, vw);
         if (!qok) continue;
+#pragma unroll
+      for (int c0 = cw; c0 < cw + 64; c0 += 16) {
+        const float* v = vw + (c0 - cw);
         uint4 o0, o1;
         __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
         __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -173,6 +181,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         }
         reinterpret_cast<uint4*>(orow + c0)[0] = o0;
         reinterpret_cast<uint4*>(orow + c0)[1] = o1;
+      }
       }
     }
     tcgen05_fence_before();
