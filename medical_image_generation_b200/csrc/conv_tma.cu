@@ -697,25 +697,25 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   const int sms = device_info().sm_count;
   const int64_t ntiles = (b.Cdst + bn - 1) / bn;
   const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
-  // Tile / split-K plan from a small cost model (cycles): a stage costs the larger of its UMMA time and its TMA
-  // row-issue time (measured: ~3.5 cycles per 5-d box row, ~1.5 per 2-d filter row); a CTA adds prologue and
-  // epilogue; the grid runs in ceil(CTAs / SMs) waves. 256-row tiles amortise the filter stage, split-K fills
-  // the chip on the small deep levels.
+  // Tile / split-K plan from a small cost model (cycles): a stage costs the larger of its UMMA time and its operand
+  // fill time (ncu: the L2 -> SM path sustains ~60-85 B/clk/SM); a CTA adds a fixed launch / pipeline-fill / drain cost
+  // (ncu on 64-channel layers: ~15 k cycles around a 3.5 k-cycle main loop, which is why narrow layers also get
+  // 256-row tiles); the grid runs in ceil(CTAs / SMs) waves; split-K fills the chip on the small deep levels.
   int mt = 1, splits = 1;
   {
     const bool ws_ok = ws != nullptr && ws_bytes >= M * b.Cdst * 4;
     double best = 1e30;
     static const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
-    for (int m_ = 1; m_ <= (bn == 256 ? 2 : 1); ++m_) {
+    for (int m_ = 1; m_ <= 2; ++m_) {
       const int nslot_ = m_ * (TBM / b.rb);
       const int64_t mtiles_ = (b.num_boxes + nslot_ - 1) / nslot_;
-      const double t_stage = fmax(512.0 * m_ * bn / 256.0, (double)nslot_ * b.nb * 3.5 + bn * 1.5);
+      const double t_stage = fmax(512.0 * m_ * bn / 256.0, ((double)nslot_ * b.nb + bn) * 128.0 / 70.0);
       for (int s_ : cand_s) {
         if (s_ > 1 && (!ws_ok || p.num_kb / s_ < 4)) continue;
         const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
         const double kb = (double)((p.num_kb + s_ - 1) / s_);
         const double t_epi = 2500.0 + m_ * (bn / 16) * (s_ > 1 ? 160.0 : 110.0);
-        double t = waves * (kb * t_stage + t_epi + 2500.0);
+        double t = waves * (kb * t_stage + t_epi + 9000.0);
         if (s_ > 1) t += (double)M * b.Cdst * 14.0 / 3000.0 + 8000.0;   // memset + fp32 reductions + finish pass
         if (t < best) { best = t; mt = m_; splits = s_; }
       }
@@ -745,7 +745,10 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     if (make_act_map(&ym, out, b.N, rdims, b.Cdst, b.bd, b.bh, b.bw)) return 1;
     p.tma_store = 1;
   }
-  if (mt == 2) rc = launch_conv_tma<256, 2>(xm, wm, ym, p, grid, st);
+  if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2>(xm, wm, ym, p, grid, st);
+  else if (mt == 2 && bn == 128) rc = launch_conv_tma<128, 2>(xm, wm, ym, p, grid, st);
+  else if (mt == 2 && bn == 64) rc = launch_conv_tma<64, 2>(xm, wm, ym, p, grid, st);
+  else if (mt == 2) rc = launch_conv_tma<32, 2>(xm, wm, ym, p, grid, st);
   else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, ym, p, grid, st);
   else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, ym, p, grid, st);
   else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, ym, p, grid, st);
