@@ -43,16 +43,6 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
-// shared -> global box store (bulk async group); out-of-bounds elements of the box are not written
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(m), "r"(src),
-               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_commit_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;\n\tcp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-
 struct BoxGeom {
   int N, D, H, W;        // extent of the GEMM-row side (conv output for fwd, conv input for dgrad)
   int bd, bh, bw;        // box; boxes may overhang the tensor
@@ -86,39 +76,57 @@ struct ConvTmaParams {
   __nv_bfloat16* out;
   float* partial;
   int num_kb, kb_per_split;
-  int tma_store;   // epilogue stages the bf16 tile in shared memory and writes it with TMA box stores (ymap)
+  int mtiles, ntiles, splits;   // tile grid; tile index = (split * ntiles + ntile) * mtiles + mtile
 };
 
-// BN: output-channel tile; MT: number of stacked 128-row accumulators (CTA tile = MT*128 voxels x BN channels)
+// BN: output-channel tile; MT: number of stacked 128-row accumulators (tile = MT*128 voxels x BN channels).
+//
+// PERSISTENT: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... The shared-memory ring and its
+// barriers run straight through tile boundaries, so the producer prefetches the next tile's operands while the
+// current tile is still in the tensor pipe; when two accumulator sets fit in tensor memory (2*MT*BN <= 512 columns)
+// the epilogue of tile i also overlaps the main loop of tile i+1. ncu on the one-tile-per-CTA version showed ~15 k
+// cycles of launch / TMEM allocation / pipeline fill / drain around every tile: 12 % of a 256x256x6912 tile, and four
+// times the 3.5 k-cycle main loop of a 64-channel layer.
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                const __grid_constant__ CUtensorMap wmap,
-                                                               const __grid_constant__ CUtensorMap ymap,
                                                                ConvTmaParams p) {
   constexpr int A_BYTES = MT * TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = stages_of(STAGE_BYTES);
-  constexpr int TCOLS = tmem_cols(MT * BN);
+  constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;   // accumulator sets in tensor memory
+  constexpr int TCOLS = tmem_cols(NACC * MT * BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float add_s[2 * MT][BN];
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), accbar = smem_u32(&bars[2 * STAGES]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), acc_full = smem_u32(&bars[2 * STAGES]),
+                 acc_empty = smem_u32(&bars[2 * STAGES + 2]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BoxGeom& g = p.g;
   const int spt = TBM / g.rb;            // boxes per 128-row accumulator
   const int nslot = MT * spt;
-  const int64_t box0 = (int64_t)blockIdx.x * nslot;
-  const int n0 = blockIdx.y * BN;
-  const int kb_begin = blockIdx.z * p.kb_per_split;
-  const int nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+  const int64_t total_tiles = (int64_t)p.mtiles * p.ntiles * p.splits;
+
+  // tile -> (first box, first output channel, k-block range)
+  auto decode = [&](int64_t tile, int64_t& box0, int& n0, int& kb_begin, int& nkb) {
+    const int64_t rest = tile / p.mtiles;
+    box0 = (tile - rest * p.mtiles) * nslot;
+    const int sp = (int)(rest / p.ntiles);
+    n0 = (int)(rest - (int64_t)sp * p.ntiles) * BN;
+    kb_begin = sp * p.kb_per_split;
+    nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
     }
-    mbar_init(accbar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + 8 * a, 1);
+      mbar_init(acc_empty + 8 * a, 128);
+    }
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TCOLS>(smem_u32(&tmem_slot));
@@ -133,189 +141,174 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     const int row = warp * 32 + lane;
     const int r = row & (g.rb - 1), slot = row / g.rb;
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
-    // while the main loop runs: bias + per-sample channel bias of this CTA's columns, one row per box (a box lies
-    // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
-    if (!p.partial) {
-      for (int j = 0; j < nslot; ++j) {
-        int n = 0, d0, h0, w0;
-        if (box0 + j < g.num_boxes) box_origin(g, box0 + j, n, d0, h0, w0);
-        for (int c = row; c < BN; c += 128) {
-          const int col = n0 + c;
-          float a = 0.f;
-          if (col < g.Cdst) {
-            if (p.bias) a += p.bias[col];
-            if (p.chan_bias) a += p.chan_bias[(int64_t)n * g.Cdst + col];
-          }
-          add_s[j][c] = a;
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    mbar_wait(accbar, 0);
-    tcgen05_fence_after();
-#pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int64_t box = box0 + mt * spt + slot;
-      bool mok = box < g.num_boxes && r < g.nb;
-      int n = 0, d0 = 0, h0 = 0, w0 = 0;
-      if (mok) box_origin(g, box, n, d0, h0, w0);
-      mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
-      const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
-                            g.OW + (w0 + lw) * g.os[2] + g.oo[2];
-      const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + mt * BN;
-      constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load (one round trip each)
-#pragma unroll 1
-      for (int cw = 0; cw < BN; cw += LDW) {
-        if (n0 + cw >= g.Cdst) break;
-        float vw[LDW];
-        if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
-        else tmem_ld16(trow + cw, vw);
-#pragma unroll
-      for (int c0 = cw; c0 < cw + LDW; c0 += 16) {
-        if (n0 + c0 >= g.Cdst) break;
-        float* v = vw + (c0 - cw);
-        if (!mok && !p.tma_store) continue;
-        const int col0 = n0 + c0;
-        if (p.partial) {
-          red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
-          continue;
-        }
-        const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
-        const float4* ap = reinterpret_cast<const float4*>(&add_s[mt * spt + slot][c0]);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float4 b4 = ap[e];
-          v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
-        }
-        __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
-        if (p.tma_store) {
-          // stage the row in the (now idle) pipeline buffers as [box][64-channel chunk][row][128 B], 128B-swizzled like
-          // the operand tiles; one thread then stores each (box, chunk) with a TMA box store: full 128-byte lines,
-          // overhang clipped by the TMA unit, no per-thread 32-byte global stores
-          if (mok && p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
-            const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
-          }
-          uint32_t o[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            __nv_bfloat162 q = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            o[e] = *reinterpret_cast<uint32_t*>(&q);
-          }
-          const uint32_t tile = smem_base + (uint32_t)((mt * spt + slot) * (BN / 64) + (c0 >> 6)) * ((uint32_t)g.rb * 128u);
-          const int j0 = (c0 & 63) >> 3;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile + sw128_offset(r, j0)), "r"(o[0]), "r"(o[1]),
-                       "r"(o[2]), "r"(o[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(tile + sw128_offset(r, j0 + 1)), "r"(o[4]), "r"(o[5]),
-                       "r"(o[6]), "r"(o[7]) : "memory");
-          continue;
-        }
-        if (full16) {
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
-            uint4 r0 = rp[0], r1 = rp[1];
-            const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
-            const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
-          }
-          uint4 o0, o1;
-          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-            q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
-          }
-          reinterpret_cast<uint4*>(dst)[0] = o0;
-          reinterpret_cast<uint4*>(dst)[1] = o1;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (col0 + e < g.Cdst) {
-              float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
-              dst[e] = __float2bfloat16_rn(v[e] + rr);
-            }
-        }
-      }
-      }
-    }
-    if (p.tma_store) {
-      fence_proxy_async();                                 // generic-proxy smem writes -> visible to the TMA unit
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 0) {
+    int ti = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int64_t box0;
+      int n0, kb_begin, nkb;
+      decode(tile, box0, n0, kb_begin, nkb);
+      const int ab = ti % NACC;
+      // while the main loop runs: bias + per-sample channel bias of this tile's columns, one row per box (a box lies
+      // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
+      if (!p.partial) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers are done with add_s
         for (int j = 0; j < nslot; ++j) {
-          if (box0 + j >= g.num_boxes) break;
-          int n, d0, h0, w0;
-          box_origin(g, box0 + j, n, d0, h0, w0);
-          for (int c = 0; c < BN / 64; ++c) {
-            if (n0 + c * 64 >= g.Cdst) break;
-            tma_store_5d(&ymap, smem_base + (uint32_t)(j * (BN / 64) + c) * ((uint32_t)g.rb * 128u), n0 + c * 64, w0, h0, d0, n);
+          int n = 0, d0, h0, w0;
+          if (box0 + j < g.num_boxes) box_origin(g, box0 + j, n, d0, h0, w0);
+          for (int c = row; c < BN; c += 128) {
+            const int col = n0 + c;
+            float a = 0.f;
+            if (col < g.Cdst) {
+              if (p.bias) a += p.bias[col];
+              if (p.chan_bias) a += p.chan_bias[(int64_t)n * g.Cdst + col];
+            }
+            add_s[j][c] = a;
           }
         }
-        tma_store_commit_wait_read();   // shared memory may be handed to the next CTA once the TMA unit has read it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      mbar_wait(acc_full + 8 * ab, (uint32_t)(ti / NACC) & 1u);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int64_t box = box0 + mt * spt + slot;
+        bool mok = box < g.num_boxes && r < g.nb;
+        int n = 0, d0 = 0, h0 = 0, w0 = 0;
+        if (mok) box_origin(g, box, n, d0, h0, w0);
+        mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
+        const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
+                              g.OW + (w0 + lw) * g.os[2] + g.oo[2];
+        const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + ab * (MT * BN) + mt * BN;
+        constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load (one round trip each)
+#pragma unroll 1
+        for (int cw = 0; cw < BN; cw += LDW) {
+          if (n0 + cw >= g.Cdst) break;
+          float vw[LDW];
+          if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
+          else tmem_ld16(trow + cw, vw);
+          if (!mok) continue;
+#pragma unroll
+          for (int c0 = cw; c0 < cw + LDW; c0 += 16) {
+            if (n0 + c0 >= g.Cdst) break;
+            float* v = vw + (c0 - cw);
+            const int col0 = n0 + c0;
+            if (p.partial) {
+              red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
+              continue;
+            }
+            const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
+            const float4* ap = reinterpret_cast<const float4*>(&add_s[mt * spt + slot][c0]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 b4 = ap[e];
+              v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
+            }
+            __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
+            if (full16) {
+              if (p.residual) {
+                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
+                uint4 r0 = rp[0], r1 = rp[1];
+                const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
+                const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { v[e] += __bfloat162float(a0[e]); v[8 + e] += __bfloat162float(a1[e]); }
+              }
+              uint4 o0, o1;
+              __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+              __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+                q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+              }
+              reinterpret_cast<uint4*>(dst)[0] = o0;
+              reinterpret_cast<uint4*>(dst)[1] = o1;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (col0 + e < g.Cdst) {
+                  float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
+                  dst[e] = __float2bfloat16_rn(v[e] + rr);
+                }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(acc_empty + 8 * ab);   // this accumulator set may be overwritten by a later tile
     }
-    tcgen05_fence_before();
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(TBM, BN, 0, 0);
-    for (int it = 0; it < nkb; ++it) {
-      const int s = it % STAGES;
-      mbar_wait(full0 + 8 * s, (uint32_t)(it / STAGES) & 1u);
+    int s = 0, ti = 0;
+    uint32_t ph = 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      int64_t box0;
+      int n0, kb_begin, nkb;
+      decode(tile, box0, n0, kb_begin, nkb);
+      const int ab = ti % NACC;
+      mbar_wait(acc_empty + 8 * ab, ((uint32_t)(ti / NACC) & 1u) ^ 1u);   // epilogue has drained this accumulator set
       tcgen05_fence_after();
-      if (elect_one()) {
-        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
+      const uint32_t acc = tmem_acc + ab * (MT * BN);
+      for (int it = 0; it < nkb; ++it) {
+        mbar_wait(full0 + 8 * s, ph);
+        tcgen05_fence_after();
+        if (elect_one()) {
+          const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TBK / 16; ++kk) {
-          const uint64_t bd = make_smem_desc(b_smem + kk * 32, 16, 1024);
+          for (int kk = 0; kk < TBK / 16; ++kk) {
+            const uint64_t bd = make_smem_desc(b_smem + kk * 32, 16, 1024);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)
-            umma_bf16(tmem_acc + mt * BN, make_smem_desc(a_smem + mt * (TBM * 128) + kk * 32, 16, 1024), bd, idesc,
-                      (it | kk) ? 1u : 0u);
+            for (int mt = 0; mt < MT; ++mt)
+              umma_bf16(acc + mt * BN, make_smem_desc(a_smem + mt * (TBM * 128) + kk * 32, 16, 1024), bd, idesc,
+                        (it | kk) ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * s);
+          if (it == nkb - 1) umma_commit(acc_full + 8 * ab);
         }
-        umma_commit(empty0 + 8 * s);
-        if (it == nkb - 1) umma_commit(accbar);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
     }
   } else {
     // ============ TMA issuer: ONE elected thread, all address arithmetic warp-uniform ============
     // (The earlier one-lane-per-box scheme made ptxas wrap every UTMALDG in a divergence "waterfall" loop and redid the
     // tap / box index divisions every stage; this thread is the producer's critical path, so the k-block -> (tap,
-    // channel chunk) mapping is an odometer and the box origins are computed once.)
+    // channel chunk) mapping is an odometer and the box origins are computed once per tile.)
     if (elect_one()) {
-      int bn_[2 * MT], bd_[2 * MT], bh_[2 * MT], bw_[2 * MT];
-#pragma unroll
-      for (int j = 0; j < 2 * MT; ++j) {
-        bn_[j] = g.N; bd_[j] = 0; bh_[j] = 0; bw_[j] = 0;   // default: fully out of bounds -> zero rows (tile tail)
-        if (j < nslot && box0 + j < g.num_boxes) box_origin(g, box0 + j, bn_[j], bd_[j], bh_[j], bw_[j]);
-      }
       const uint32_t tx_bytes = (uint32_t)(nslot * g.nb) * 128u + B_BYTES;   // a box transfers its nb rows (zero-filled when out of bounds)
       const uint32_t slot_bytes = (uint32_t)g.rb * 128u;
-      int tap = kb_begin / g.cchunks;
-      int cch = kb_begin - tap * g.cchunks;
-      int t2 = tap % g.ks[2]; tap /= g.ks[2];
-      int t1 = tap % g.ks[1];
-      int t0 = tap / g.ks[1];
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
-        mbar_wait(empty0 + 8 * s, ((uint32_t)(it / STAGES) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(bar, tx_bytes);
-        const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
-        const int c0 = cch * 64;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int64_t box0;
+        int n0, kb_begin, nkb;
+        decode(tile, box0, n0, kb_begin, nkb);
+        int bn_[2 * MT], bd_[2 * MT], bh_[2 * MT], bw_[2 * MT];
 #pragma unroll
-        for (int j = 0; j < 2 * MT; ++j)
-          if (j < nslot) tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] + dx, bh_[j] + dy, bd_[j] + dz, bn_[j]);
-        tma_load_2d(b_smem, &wmap, bar, (kb_begin + it) * TBK, n0);
-        if (++cch == g.cchunks) {
-          cch = 0;
-          if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
+        for (int j = 0; j < 2 * MT; ++j) {
+          bn_[j] = g.N; bd_[j] = 0; bh_[j] = 0; bw_[j] = 0;   // default: fully out of bounds -> zero rows (tile tail)
+          if (j < nslot && box0 + j < g.num_boxes) box_origin(g, box0 + j, bn_[j], bd_[j], bh_[j], bw_[j]);
+        }
+        int tap = kb_begin / g.cchunks;
+        int cch = kb_begin - tap * g.cchunks;
+        int t2 = tap % g.ks[2]; tap /= g.ks[2];
+        int t1 = tap % g.ks[1];
+        int t0 = tap / g.ks[1];
+        for (int it = 0; it < nkb; ++it) {
+          const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES, bar = full0 + 8 * s;
+          mbar_wait(empty0 + 8 * s, ph ^ 1u);
+          mbar_arrive_expect_tx(bar, tx_bytes);
+          const int dz = t0 * g.sign + g.off[0], dy = t1 * g.sign + g.off[1], dx = t2 * g.sign + g.off[2];
+          const int c0 = cch * 64;
+#pragma unroll
+          for (int j = 0; j < 2 * MT; ++j)
+            if (j < nslot) tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] + dx, bh_[j] + dy, bd_[j] + dz, bn_[j]);
+          tma_load_2d(b_smem, &wmap, bar, (kb_begin + it) * TBK, n0);
+          if (++cch == g.cchunks) {
+            cch = 0;
+            if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -649,8 +642,8 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
 }
 
 template <int BN, int MT>
-static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const CUtensorMap& ym, const ConvTmaParams& p,
-                           dim3 grid, cudaStream_t st) {
+static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const ConvTmaParams& p, dim3 grid,
+                           cudaStream_t st) {
   constexpr int stage = MT * TBM * 128 + BN * 128;
   constexpr int smem = stages_of(stage) * stage + 1024;
   static bool configured = false;
@@ -659,7 +652,7 @@ static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const C
     MIG_REQUIRE(e == cudaSuccess, "conv_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
     configured = true;
   }
-  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, ym, p);
+  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, p);
   return check_launch("conv_tma_kernel");
 }
 
@@ -729,30 +722,19 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     p.partial = (float*)ws;
     cudaMemsetAsync(ws, 0, (size_t)(M * b.Cdst * 4), st);
   }
-  dim3 grid((unsigned)mtiles, (unsigned)ntiles, (unsigned)splits);
+  p.mtiles = (int)mtiles; p.ntiles = (int)ntiles; p.splits = splits;
+  int64_t nct = mtiles * ntiles * splits;
+  if (nct > sms) nct = sms;
+  dim3 grid((unsigned)nct);   // persistent: one CTA per SM walks the tiles
   int rc;
-  // TMA-store epilogue: rows map 1:1 to the output tensor, whole 64-channel chunks, no split-K partials
-  CUtensorMap ym = xm;
-  static int store_ok = -1;
-  if (store_ok < 0) {
-    const char* e = getenv("MIG_DISABLE_TMA_STORE");
-    store_ok = (e && e[0] == '1') ? 0 : 1;
-  }
-  const bool dense_rows = b.os[0] == 1 && b.os[1] == 1 && b.os[2] == 1 && b.oo[0] == 0 && b.oo[1] == 0 && b.oo[2] == 0 &&
-                          b.OD == b.D && b.OH == b.H && b.OW == b.W;
-  if (store_ok && splits == 1 && dense_rows && b.Cdst % 64 == 0 && bn >= 64) {
-    const int32_t rdims[3] = {b.D, b.H, b.W};
-    if (make_act_map(&ym, out, b.N, rdims, b.Cdst, b.bd, b.bh, b.bw)) return 1;
-    p.tma_store = 1;
-  }
-  if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2>(xm, wm, ym, p, grid, st);
-  else if (mt == 2 && bn == 128) rc = launch_conv_tma<128, 2>(xm, wm, ym, p, grid, st);
-  else if (mt == 2 && bn == 64) rc = launch_conv_tma<64, 2>(xm, wm, ym, p, grid, st);
-  else if (mt == 2) rc = launch_conv_tma<32, 2>(xm, wm, ym, p, grid, st);
-  else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, ym, p, grid, st);
-  else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, ym, p, grid, st);
-  else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, ym, p, grid, st);
-  else rc = launch_conv_tma<32, 1>(xm, wm, ym, p, grid, st);
+  if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2>(xm, wm, p, grid, st);
+  else if (mt == 2 && bn == 128) rc = launch_conv_tma<128, 2>(xm, wm, p, grid, st);
+  else if (mt == 2 && bn == 64) rc = launch_conv_tma<64, 2>(xm, wm, p, grid, st);
+  else if (mt == 2) rc = launch_conv_tma<32, 2>(xm, wm, p, grid, st);
+  else if (bn == 256) rc = launch_conv_tma<256, 1>(xm, wm, p, grid, st);
+  else if (bn == 128) rc = launch_conv_tma<128, 1>(xm, wm, p, grid, st);
+  else if (bn == 64) rc = launch_conv_tma<64, 1>(xm, wm, p, grid, st);
+  else rc = launch_conv_tma<32, 1>(xm, wm, p, grid, st);
   if (rc) return rc;
   if (splits > 1) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
