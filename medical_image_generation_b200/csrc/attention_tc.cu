@@ -3,7 +3,11 @@
 //
 //   O[b, q, h*dh + :] = softmax_k(scale * Q K^T) V        per (batch b, head h); heads live inside the channel dim.
 //
-// The L x L score matrix never goes to HBM. Two passes, both with S = Q K^T accumulated in tensor memory:
+// The L x L score matrix never goes to HBM.
+// Head dim <= 256 (pixel-space U-Nets, 128-channel heads at 32768 tokens): ONE pass with an online softmax -- running
+// row maximum / sum in registers, O accumulated in tensor memory and rescaled lazily (only when a key tile raises the
+// maximum by more than 2^8), normalised by 1/sum in the epilogue.
+// Head dim > 256: two passes, both with S = Q K^T accumulated in tensor memory:
 //   pass 0 (stats)  : per row running max / sum over all key tiles  ->  lse[row] = max + log2(sum)  (log2 domain)
 //   pass 1 (output) : P = exp2(S * scale*log2e - lse) is ALREADY normalised, so O += P V needs no rescaling of the
 //                     accumulator (no TMEM read-modify-write, no correction warps); S is double-buffered in TMEM so
@@ -127,6 +131,64 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         }
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);
+      } else if (PASS == 2) {
+        // ---- single pass, online softmax (head dim <= 256: S x2 and the whole O fit tensor memory) ----
+        // The running maximum is LAZY: the O accumulator is only rescaled when a tile raises the row maximum by more
+        // than 2^8 (P stays <= 256, harmless in bf16 / fp32); the decision is warp-uniform because tcgen05.ld/st are
+        // warp-collective. Rescaling waits for P V of the previous tile (p_empty), which every tile does anyway.
+        float v[128];
+        tmem_ld64(ts, v);
+        tmem_ld64(ts + 64, v + 64);
+        tcgen05_fence_before();
+        mbar_arrive(s_empty + 8 * buf);                // S is in registers: Q K^T of tile j+2 may overwrite it
+        float tmax = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 128; ++e) {
+          v[e] = (kbase + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
+          tmax = fmaxf(tmax, v[e]);
+        }
+        mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile is complete: P buffer free, O stable
+        tcgen05_fence_after();
+        const float m_new = fmaxf(m_run, tmax);
+        if (j == 0) {
+          m_run = m_new;
+        } else if (__any_sync(0xffffffffu, m_new > m_run + 8.f)) {
+          const float f = fast_ex2(m_run - m_new);     // 1 for rows whose maximum did not move
+          const uint32_t to = tmem_o + lane_off;
+#pragma unroll 1
+          for (int cw = 0; cw < p.DV; cw += 64) {
+            float ow[64];
+            tmem_ld64(to + cw, ow);
+#pragma unroll
+            for (int e = 0; e < 64; ++e) ow[e] *= f;
+            tmem_st64(to + cw, ow);
+          }
+          l_run *= f;
+          m_run = m_new;
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t base = p_smem + half * (FA_BM * 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int k0 = half * 64 + c * 8 + 2 * e;
+              const float p0 = fast_ex2(v[k0] - m_run), p1 = fast_ex2(v[k0 + 1] - m_run);
+              sum += p0 + p1;
+              __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
+              o[e] = *reinterpret_cast<uint32_t*>(&q2);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(base + sw128_offset(r, c)), "r"(o[0]), "r"(o[1]),
+                         "r"(o[2]), "r"(o[3]) : "memory");
+          }
+        }
+        l_run += sum;
+        tcgen05_fence_before();
+        fence_proxy_async();
+        mbar_arrive(p_full);
       } else {
         mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile has consumed the P buffer
 #pragma unroll 1
@@ -159,6 +221,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
     if (PASS == 0) {
       if (qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
     } else {
+      if (PASS == 2 && qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
+      const float inv_l = PASS == 2 ? 1.f / l_run : 1.f;
       mbar_wait(o_full, 0);
       tcgen05_fence_after();
       const uint32_t to = tmem_o + lane_off;
@@ -176,8 +240,8 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          h0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
-          h1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
+          h0[e] = __floats2bfloat162_rn(v[2 * e] * inv_l, v[2 * e + 1] * inv_l);
+          h1[e] = __floats2bfloat162_rn(v[8 + 2 * e] * inv_l, v[8 + 2 * e + 1] * inv_l);
         }
         reinterpret_cast<uint4*>(orow + c0)[0] = o0;
         reinterpret_cast<uint4*>(orow + c0)[1] = o1;
@@ -216,7 +280,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
     issue_qk(0);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) issue_qk(j + 1);
-      if (PASS == 1) {
+      if (PASS >= 1) {
         mbar_wait(p_full, (uint32_t)j & 1u);
         tcgen05_fence_after();
         for (int half = 0; half < 2; ++half) {
@@ -266,7 +330,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
     load_qk(0);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) load_qk(j + 1);
-      if (PASS == 1) load_v(j);
+      if (PASS >= 1) load_v(j);
     }
   }
   __syncthreads();
@@ -329,6 +393,7 @@ extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void*
   p.out = (__nv_bfloat16*)out;
   cudaStream_t st = as_stream(stream);
   const unsigned mt = (Lq + FA_BM - 1) / FA_BM;
+  if (dh <= 256) return launch_flash<2>(qm, km, vm, p, dim3(mt, 1, B * H), st);   // single pass, online softmax
   if (launch_flash<0>(qm, km, vm, p, dim3(mt, 1, B * H), st)) return 2;
   return launch_flash<1>(qm, km, vm, p, dim3(mt, dh / p.DV, B * H), st);
 }

@@ -146,6 +146,17 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float v[64]) {
   for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// registers -> 64 consecutive TMEM columns of this thread's lane (accumulator rescaling in the online softmax)
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const float v[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+      :
+      : "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31])), "r"(__float_as_uint(v[32])), "r"(__float_as_uint(v[33])), "r"(__float_as_uint(v[34])), "r"(__float_as_uint(v[35])), "r"(__float_as_uint(v[36])), "r"(__float_as_uint(v[37])), "r"(__float_as_uint(v[38])), "r"(__float_as_uint(v[39])), "r"(__float_as_uint(v[40])), "r"(__float_as_uint(v[41])), "r"(__float_as_uint(v[42])), "r"(__float_as_uint(v[43])), "r"(__float_as_uint(v[44])), "r"(__float_as_uint(v[45])), "r"(__float_as_uint(v[46])), "r"(__float_as_uint(v[47])), "r"(__float_as_uint(v[48])), "r"(__float_as_uint(v[49])), "r"(__float_as_uint(v[50])), "r"(__float_as_uint(v[51])), "r"(__float_as_uint(v[52])), "r"(__float_as_uint(v[53])), "r"(__float_as_uint(v[54])), "r"(__float_as_uint(v[55])), "r"(__float_as_uint(v[56])), "r"(__float_as_uint(v[57])), "r"(__float_as_uint(v[58])), "r"(__float_as_uint(v[59])), "r"(__float_as_uint(v[60])), "r"(__float_as_uint(v[61])), "r"(__float_as_uint(v[62])), "r"(__float_as_uint(v[63]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // 16-byte vector reduction into global memory (sm_90+): one L2 operation carries four fp32 addends.
 // `p` must be 16-byte aligned.
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {

@@ -420,3 +420,30 @@ def test_flash_attention_forward(B, Lq, Lk, C, heads):
     finally:
         ops.set_flash_attention(True)
     assert rel_err(got, ref2) < BF16_TOL
+
+
+@pytest.mark.parametrize("C,heads", [(128, 1), (256, 2), (512, 1)])
+def test_flash_attention_growing_logits(C, heads):
+    """Keys whose logits grow tile after tile: every key tile raises the running row maximum by far more than the lazy
+    rescale threshold (2^8), so the online-softmax kernel (head dim <= 256) must rescale its tensor-memory accumulator
+    each time; a peaked and a flat row distribution are both present. The two-pass kernel (head dim 512) sees the
+    same data."""
+    ops = _ops()
+    B, Lq, Lk = 1, 256, 1024
+    g = torch.Generator().manual_seed(7 + C)
+    q, k, v = (torch.randn(B, L, C, generator=g) for L in (Lq, Lk, Lk))
+    ramp = torch.linspace(0.2, 6.0, Lk).reshape(1, Lk, 1)          # later keys are much "louder"
+    k = k * ramp
+    q[:, ::2] *= 3.0                                               # half of the rows very peaked
+    q, k, v = bf16_round(q), bf16_round(k), bf16_round(v)
+    scale = 1 / math.sqrt(C / heads)
+
+    def split(t):
+        return t.reshape(B, -1, heads, C // heads).permute(0, 2, 1, 3)
+
+    p = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1)
+    want = (p @ split(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    qd, kd, vd = (t.to(DEV).bfloat16() for t in (q, k, v))
+    with torch.no_grad():
+        got = ops.sdpa(qd, kd, vd, heads, scale)
+    assert torch.isfinite(got).all() and rel_err(got, want) < BF16_TOL
