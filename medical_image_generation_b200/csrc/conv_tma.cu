@@ -54,7 +54,8 @@ struct BoxGeom {
   int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: +1, -pad; dgrad: -1, +pad)
   int sign;
   int Csrc, Cdst, K;     // K = taps*Csrc
-  int cchunks;           // Csrc / 64
+  int cchunks;           // ceil(Csrc / 64): the last chunk of a 96-channel source reads 32 channels past the end, which
+                         // TMA zero-fills in the activation box (so whatever the filter box holds there is multiplied by 0)
   // where a row lands in the output tensor: coordinate = row*os + oo inside an (OD,OH,OW) volume. Identity except
   // for strided dgrad, where each stride-residue class of input voxels is its own dense stride-1 problem.
   int os[3], oo[3], OD, OH, OW;
@@ -291,6 +292,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         }
         int tap = kb_begin / g.cchunks;
         int cch = kb_begin - tap * g.cchunks;
+        int kcol = tap * g.Csrc;   // filter column of (tap, channel 0)
         int t2 = tap % g.ks[2]; tap /= g.ks[2];
         int t1 = tap % g.ks[1];
         int t0 = tap / g.ks[1];
@@ -303,9 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < 2 * MT; ++j)
             if (j < nslot) tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] + dx, bh_[j] + dy, bd_[j] + dz, bn_[j]);
-          tma_load_2d(b_smem, &wmap, bar, (kb_begin + it) * TBK, n0);
+          tma_load_2d(b_smem, &wmap, bar, kcol + c0, n0);
           if (++cch == g.cchunks) {
             cch = 0;
+            kcol += g.Csrc;
             if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -591,7 +594,7 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   for (int i = 0; i < 3; ++i)
     if (g->stride[i] != 1) return false;
   const int csrc = which == 1 ? g->Cout : g->Cin;
-  if (csrc % 64 != 0) return false;
+  if (which == 2 ? csrc % 64 != 0 : (csrc % 8 != 0 || csrc < 48)) return false;   // wgrad panels must not straddle taps
   if (which == 2 && g->Cout % 8 != 0) return false;
   const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
   int bd, bh, bw, rb;
@@ -635,7 +638,7 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   b.Csrc = which == 1 ? g->Cout : g->Cin;
   b.Cdst = which == 1 ? g->Cin : g->Cout;
   b.K = taps * b.Csrc;
-  b.cchunks = b.Csrc / 64;
+  b.cchunks = (b.Csrc + 63) / 64;
   for (int i = 0; i < 3; ++i) { b.os[i] = 1; b.oo[i] = 0; }
   b.OD = b.D; b.OH = b.H; b.OW = b.W;
   return b;
@@ -686,7 +689,7 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   p.bias = bias; p.chan_bias = chan_bias;
   p.residual = (const __nv_bfloat16*)residual;
   p.out = (__nv_bfloat16*)out;
-  p.num_kb = b.K / TBK;
+  p.num_kb = (b.K / b.Csrc) * b.cchunks;   // taps x channel chunks
   const int sms = device_info().sm_count;
   const int64_t ntiles = (b.Cdst + bn - 1) / bn;
   const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
@@ -860,7 +863,7 @@ int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w
         b.sign = -1;
         b.Csrc = g->Cout; b.Cdst = g->Cin;
         b.K = nt * b.Csrc;
-        b.cchunks = b.Csrc / 64;
+        b.cchunks = (b.Csrc + 63) / 64;
         b.OD = g->in_dims[0]; b.OH = g->in_dims[1]; b.OW = g->in_dims[2];
         int rc = launch_box_conv(b, g->N, g->out_dims, dy, wp, nullptr, nullptr, nullptr, dx, nullptr, 0, stream);
         if (rc) return rc;

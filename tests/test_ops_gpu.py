@@ -49,6 +49,9 @@ CONV_CASES = [
     (3, 64, 64, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),      # 6^3: 3x6x6 boxes in 128-row slots (108 valid rows), odd box count
     (2, 64, 128, (5, 5, 5), (3, 3, 3), (1, 1, 1), (1, 1, 1)),     # 5^3: one 125-row box per sample
     (1, 64, 3, (8, 8, 8), (3, 3, 3), (1, 1, 1), (1, 1, 1)),       # out conv of the LDM U-Net: 3 output channels on the TMA kernel
+    (1, 96, 32, (16, 16, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # 96 source channels: second 64-channel chunk half out of bounds
+    (2, 96, 64, (8, 8, 8), (1, 1, 1), (1, 1, 1), (0, 0, 0)),      # ... 1x1x1 skip conv over a concat input
+    (1, 80, 48, (8, 8, 16), (3, 3, 3), (1, 1, 1), (1, 1, 1)),     # 80 -> 48: both directions use partial chunks
     # strided Downsample convs: dgrad runs as stride-residue classes on the TMA kernel
     (2, 64, 64, (16, 16, 16), (3, 3, 3), (2, 2, 2), (1, 1, 1)),
     (1, 128, 64, (8, 16, 16), (3, 3, 3), (1, 2, 2), (1, 1, 1)),   # anisotropic stride
