@@ -53,6 +53,8 @@ struct BoxGeom {
   int ks[3];             // kernel
   int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: +1, -pad; dgrad: -1, +pad)
   int sign;
+  int ss[3];             // source stride: source coordinate = row*ss + tap*sign + off (2 for a stride-2 forward conv /
+                         // wgrad, where the TMA tensor map walks the source with the same element stride)
   int Csrc, Cdst, K;     // K = taps*Csrc
   int cchunks;           // ceil(Csrc / 64): the last chunk of a 96-channel source reads 32 channels past the end, which
                          // TMA zero-fills in the activation box (so whatever the filter box holds there is multiplied by 0)
@@ -304,7 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           const int c0 = cch * 64;
 #pragma unroll
           for (int j = 0; j < 2 * MT; ++j)
-            if (j < nslot) tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] + dx, bh_[j] + dy, bd_[j] + dz, bn_[j]);
+            if (j < nslot)
+              tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] * g.ss[2] + dx, bh_[j] * g.ss[1] + dy,
+                          bd_[j] * g.ss[0] + dz, bn_[j]);
           tma_load_2d(b_smem, &wmap, bar, kcol + c0, n0);
           if (++cch == g.cchunks) {
             cch = 0;
@@ -494,7 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
         for (int a = 0; a < APAN; ++a) tma_load_5d(a_smem + a * PANEL, &dymap, bar, co0 + a * 64, w0, h0, d0, n);
 #pragma unroll
         for (int q = 0; q < NPAN; ++q) {
-          if (cc[q] >= 0) tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc[q], w0 + dx[q], h0 + dy[q], d0 + dz[q], n);
+          if (cc[q] >= 0)
+            tma_load_5d(b_smem + q * PANEL, &xmap, bar, cc[q], w0 * g.ss[2] + dx[q], h0 * g.ss[1] + dy[q], d0 * g.ss[0] + dz[q], n);
           // a panel past the end of K is loaded fully out of bounds (n = N) -> zeros, keeps the byte count fixed
           else tma_load_5d(b_smem + q * PANEL, &xmap, bar, 0, 0, 0, 0, g.N);
         }
@@ -591,10 +596,16 @@ static bool pick_box_rows(int D, int H, int W, int* bd, int* bh, int* bw, int* r
 
 // which: 0 fwd, 1 dgrad, 2 wgrad
 bool tma_conv_eligible(const mig_conv_geom* g, int which) {
-  for (int i = 0; i < 3; ++i)
-    if (g->stride[i] != 1) return false;
+  bool strided = false;
+  for (int i = 0; i < 3; ++i) {
+    if (g->stride[i] < 1 || g->stride[i] > 2) return false;
+    strided = strided || g->stride[i] != 1;
+  }
+  if (strided && which == 1) return false;   // strided dgrad: stride-residue classes (tma_conv_dgrad_strided)
   const int csrc = which == 1 ? g->Cout : g->Cin;
-  if (which == 2 ? csrc % 64 != 0 : (csrc % 8 != 0 || csrc < 48)) return false;   // wgrad panels must not straddle taps
+  // wgrad panels must not straddle taps; a strided forward conv takes 32 channels too (half-empty chunk, still far
+  // ahead of the gather kernel)
+  if (which == 2 ? csrc % 64 != 0 : (csrc % 8 != 0 || csrc < (strided ? 32 : 48))) return false;
   if (which == 2 && g->Cout % 8 != 0) return false;
   const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
   int bd, bh, bw, rb;
@@ -602,15 +613,20 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   return pick_box_k(dims[0], dims[1], dims[2], &bd, &bh, &bw);
 }
 
-static int make_act_map(CUtensorMap* m, const void* base, int N, const int32_t dims[3], int C, int bd, int bh, int bw) {
+static int make_act_map(CUtensorMap* m, const void* base, int N, const int32_t dims[3], int C, int bd, int bh, int bw,
+                        const int* estride = nullptr) {
   // 5-d (C, W, H, D, N) with a 64-channel x box window
   EncodeTiledFn enc = get_encode();
   MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
   cuuint64_t gd[5] = {(cuuint64_t)C, (cuuint64_t)dims[2], (cuuint64_t)dims[1], (cuuint64_t)dims[0], (cuuint64_t)N};
   cuuint64_t gs[4] = {(cuuint64_t)C * 2, (cuuint64_t)dims[2] * C * 2, (cuuint64_t)dims[1] * dims[2] * C * 2,
                       (cuuint64_t)dims[0] * dims[1] * dims[2] * C * 2};
-  cuuint32_t bx[5] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, 1};
-  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  // With an element stride s the box SPANS bw*s tensor elements and delivers every s-th one: bw voxels reach shared
+  // memory, exactly the source voxels of bw consecutive outputs of a stride-s convolution.
+  const int sd = estride ? estride[0] : 1, sh = estride ? estride[1] : 1, sw = estride ? estride[2] : 1;
+  cuuint32_t bx[5] = {64, (cuuint32_t)(bw * sw), (cuuint32_t)(bh * sh), (cuuint32_t)(bd * sd), 1};
+  cuuint32_t es[5] = {1, (cuuint32_t)sw, (cuuint32_t)sh, (cuuint32_t)sd, 1};
+  MIG_REQUIRE(bx[1] <= 256 && bx[2] <= 256 && bx[3] <= 256, "conv_tma: strided box exceeds the TMA box limit");
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -635,6 +651,7 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
     taps *= g->ksize[i];
   }
   b.sign = which == 1 ? -1 : 1;
+  for (int i = 0; i < 3; ++i) b.ss[i] = which == 1 ? 1 : g->stride[i];
   b.Csrc = which == 1 ? g->Cout : g->Cin;
   b.Cdst = which == 1 ? g->Cin : g->Cout;
   b.K = taps * b.Csrc;
@@ -678,7 +695,7 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
                            int64_t ws_bytes, void* stream) {
   cudaStream_t st = as_stream(stream);
   CUtensorMap xm, wm;
-  if (make_act_map(&xm, src, N, sdims, b.Csrc, b.bd, b.bh, b.bw)) return 1;
+  if (make_act_map(&xm, src, N, sdims, b.Csrc, b.bd, b.bh, b.bw, b.ss)) return 1;
   const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
   uint64_t dims[2] = {(uint64_t)b.K, (uint64_t)b.Cdst};
   uint64_t strides[1] = {(uint64_t)b.K * 2};
@@ -861,6 +878,7 @@ int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w
           b.oo[i] = a[i].o;
         }
         b.sign = -1;
+        for (int i = 0; i < 3; ++i) b.ss[i] = 1;
         b.Csrc = g->Cout; b.Cdst = g->Cin;
         b.K = nt * b.Csrc;
         b.cchunks = (b.Csrc + 63) / 64;
@@ -892,7 +910,7 @@ int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float*
   cudaStream_t st = as_stream(stream);
   CUtensorMap dym, xm;
   if (make_act_map(&dym, dy, g->N, g->out_dims, g->Cout, b.bd, b.bh, b.bw)) return 1;
-  if (make_act_map(&xm, x, g->N, g->in_dims, g->Cin, b.bd, b.bh, b.bw)) return 1;
+  if (make_act_map(&xm, x, g->N, g->in_dims, g->Cin, b.bd, b.bh, b.bw, b.ss)) return 1;
   // Tile / split plan from the same kind of cost model as the forward kernel: stage = max(UMMA, TMA row issue),
   // CTA = stages + prologue + fp32 reduction epilogue (16-byte red ops), grid = ceil(CTAs / SMs) waves.
   int bn = 64, mt = 1;
