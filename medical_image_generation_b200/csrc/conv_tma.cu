@@ -744,7 +744,12 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   }
   p.mtiles = (int)mtiles; p.ntiles = (int)ntiles; p.splits = splits;
   int64_t nct = mtiles * ntiles * splits;
-  if (nct > sms) nct = sms;
+  static int one_tile_per_cta = -1;   // A/B switch: static round-robin persistence vs. hardware CTA scheduling
+  if (one_tile_per_cta < 0) {
+    const char* e = getenv("MIG_CONV_NONPERSISTENT");
+    one_tile_per_cta = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (nct > sms && !one_tile_per_cta) nct = sms;
   dim3 grid((unsigned)nct);   // persistent: one CTA per SM walks the tiles
   int rc;
   if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2>(xm, wm, p, grid, st);
