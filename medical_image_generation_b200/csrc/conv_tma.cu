@@ -1,18 +1,21 @@
-// tcgen05 engine, part 3: all-TMA implicit-GEMM convolution (stride 1, channel counts that are multiples of 64).
+// tcgen05 engine, part 3: all-TMA implicit-GEMM convolution (fwd / dgrad: source channels >= 48, multiple of 8; wgrad:
+// multiple of 64; stride 1, or stride 2 through tensor-map element strides / stride-residue classes).
 //
 // The im2col matrix is never gathered by threads. The NDHWC activation tensor is described to the TMA unit as a
-// 5-d tensor (C, W, H, D, N); a GEMM row tile is a BOX of voxels (bw x bh x bd = 64 voxels, two boxes per 128-row
-// UMMA tile) and the K loop walks (filter tap, 64-channel chunk). For tap (tz,ty,tx) the A tile is simply the same
-// box shifted by the tap offset; coordinates that fall outside the tensor are filled with zeros by the TMA unit,
-// which IS the convolution's zero padding (the halo). A few elected lanes issue the TMA loads, one thread issues
-// the UMMAs, four warps only run the epilogue -- there is no address arithmetic and no load instruction in the
-// main loop at all, and up to STAGES-1 whole stages (~130 KB) are in flight per SM.
+// 5-d tensor (C, W, H, D, N); a GEMM row tile is a BOX of voxels (bw x bh x bd voxels in a 64- or 128-row slot) and
+// the K loop walks (filter tap, 64-channel chunk). For tap (tz,ty,tx) the A tile is simply the same box shifted by the
+// tap offset; coordinates that fall outside the tensor are filled with zeros by the TMA unit, which IS the
+// convolution's zero padding (the halo). ONE elected thread issues the TMA loads (odometer indexing, warp-uniform
+// arithmetic), one thread issues the UMMAs, four warps only run the epilogue -- there is no address arithmetic and no
+// load instruction in the main loop at all, and up to STAGES-1 whole stages (~130 KB) are in flight per SM.
 //
-// Measured (profiles/): the limiter of these kernels is the TMA unit's row rate (each 128-byte box row costs a few
-// cycles), not L2 or HBM bandwidth, so the CTA tile is made as large as TMEM allows: MT = 2 stacks two 128-row
-// UMMA accumulators (2 x 256 TMEM columns = all 512) that share every B stage, i.e. a 256 x 256 tile per CTA.
+// The CTA tile is made as large as TMEM allows: MT = 2 stacks two 128-row UMMA accumulators that share every B stage
+// (256 x 256 per tile = all 512 TMEM columns); narrower layers keep two accumulator sets so that the epilogue of one
+// tile overlaps the main loop of the next. What was learnt from ncu on the way: the producer
+// THREAD, not the TMA unit, limited the first versions (one lane per box, divisions per stage); the 24^3-level layers
+// now run at the same rate as cuBLAS bf16 GEMMs on this pool.
 //
-//   conv_tma_kernel   fwd and dgrad (dgrad = same kernel on dY with mirrored taps and the transposed filter)
+//   conv_tma_kernel   persistent; fwd and dgrad (dgrad = same kernel on dY with mirrored taps and the transposed filter)
 //   wgrad_tma_kernel  dW[Cout][tap*Cin] += dY^T * im2col(X): both operands MN-major, voxel reduction walks boxes,
 //                     split across CTAs, fp32 red.global.add into the gradient.
 #include <cuda.h>
