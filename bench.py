@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--engine", type=int, default=0, help="0 auto (tcgen05 where eligible), 1 SIMT only")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient all-reduce bucket size (multi-GPU)")
     return ap.parse_args()
 
 
@@ -201,7 +202,7 @@ def run_b200(args):
     n_params = sum(p.numel() for p in model.parameters())
     sched = mig.DDPMScheduler(**planner.LDM_SCHEDULER_KWARGS)
     # whole-step CUDA graph: two eager steps, capture on the third untimed step, replay afterwards
-    trainer = LDMTrainer(model, sched, lr=2e-5, grad_clip_max_norm=1.0, cuda_graph=not args.no_graph,
+    trainer = LDMTrainer(model, sched, lr=2e-5, grad_clip_max_norm=1.0, cuda_graph=not args.no_graph, bucket_mb=args.bucket_mb,
                          graph_warmup_steps=2)
     B = args.batch
     gen = torch.Generator().manual_seed(1000 + rank)
