@@ -16,7 +16,7 @@ torch.manual_seed(42)
 kw = planner.ddpm_kwargs([64, 64], latent_channels=1)
 unet = bench.rerandomize_zero_init(mig.DiffusionModelUNet(**kw)).cuda().train()
 print(f"2-D U-Net: {sum(p.numel() for p in unet.parameters()) / 1e6:.1f} M parameters")
-tr = LDMTrainer(unet, mig.DDPMScheduler(**planner.LDM_SCHEDULER_KWARGS), lr=2e-5, grad_clip_max_norm=1.0)
+tr = LDMTrainer(unet, mig.DDPMScheduler(**planner.LDM_SCHEDULER_KWARGS), lr=2e-5, grad_clip_max_norm=1.0, cuda_graph=True)
 x = torch.rand(2, 1, 64, 64, device="cuda")
 losses = []
 torch.cuda.synchronize()
