@@ -30,7 +30,11 @@ namespace mig {
 
 using namespace tc;
 
-constexpr int FA_THREADS = 192;
+constexpr int FA_MAX_THREADS = 320;
+// softmax warps: 4 (thread = query row) in the two-pass kernels; 8 in the online kernel, where warps w and w+4 share
+// the rows of TMEM lane quadrant w and each takes 64 of the 128 keys of a tile -- the softmax, not the tensor pipe, is
+// the critical path at head dim 128 (128 exp2 + packing per row and tile against 1024 cycles of UMMA)
+__host__ __device__ constexpr int fa_softmax_warps(int pass) { return pass == 2 ? 8 : 4; }
 constexpr int FA_BM = 128, FA_BN = 128;         // query rows / keys per tile
 constexpr int FA_QK_STAGES = 3, FA_V_STAGES = 2;
 constexpr int FA_QK_STAGE_BYTES = 2 * FA_BM * 128;   // Q chunk + K chunk, 64 channels each
@@ -45,27 +49,33 @@ __device__ __forceinline__ float fast_ex2(float x) {
 
 struct FlashParams {
   int B, H, Lq, Lk, dh, DV;   // DV = value/output columns handled by one CTA (<= 256)
+  int qk_stages;              // (Q chunk, K chunk) ring depth: 3, or 2 when 256-wide V stages leave no room
   float scale_log2;           // softmax scale * log2(e)
   float* lse;                 // [B*H][Lq], log2 domain
   __nv_bfloat16* out;         // (B, Lq, H*dh)
 };
 
-// bars: qk_full[3] qk_empty[3] v_full[2] v_empty[2] s_full[2] s_empty[2] p_full p_empty o_full
+// bars: qk_full[3] qk_empty[3] v_full[2] v_empty[2] s_full[2] s_empty[2] p_full[2] p_empty[2] o_full
+// The P tile is DOUBLE-buffered: the softmax of key tile j+1 writes P[(j+1)&1] while P V of tile j still reads P[j&1];
+// with a single buffer the exp2 work and the P V MMAs of consecutive tiles were serialised (3150 cycles per tile for
+// 1024 cycles of UMMA).
 template <int PASS>
-__global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_constant__ CUtensorMap qmap,
+__global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __grid_constant__ CUtensorMap qmap,
                                                                   const __grid_constant__ CUtensorMap kmap,
                                                                   const __grid_constant__ CUtensorMap vmap,
                                                                   FlashParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t qk_smem = smem_base;
-  const uint32_t p_smem = qk_smem + FA_QK_STAGES * FA_QK_STAGE_BYTES;
-  const uint32_t v_smem = p_smem + FA_P_BYTES;
-  __shared__ __align__(8) uint64_t bars[17];
+  const uint32_t p_smem = qk_smem + p.qk_stages * FA_QK_STAGE_BYTES;
+  const uint32_t v_smem = p_smem + 2 * FA_P_BYTES;
+  constexpr int SW = fa_softmax_warps(PASS);
+  __shared__ __align__(8) uint64_t bars[19];
   __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][2][FA_BM];   // online kernel: row max / row sum exchange between the two key halves
   const uint32_t b0 = smem_u32(&bars[0]);
   const uint32_t qk_full = b0, qk_empty = b0 + 8 * 3, v_full = b0 + 8 * 6, v_empty = b0 + 8 * 8, s_full = b0 + 8 * 10,
-                 s_empty = b0 + 8 * 12, p_full = b0 + 8 * 14, p_empty = b0 + 8 * 15, o_full = b0 + 8 * 16;
+                 s_empty = b0 + 8 * 12, p_full = b0 + 8 * 14, p_empty = b0 + 8 * 16, o_full = b0 + 8 * 18;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * FA_BM;
   const int slice = blockIdx.y;
@@ -78,25 +88,27 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
     for (int i = 0; i < 3; ++i) { mbar_init(qk_full + 8 * i, 1); mbar_init(qk_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
-      mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, 128);
+      mbar_init(s_full + 8 * i, 1); mbar_init(s_empty + 8 * i, SW * 32);
     }
-    mbar_init(p_full, 128); mbar_init(p_empty, 1); mbar_init(o_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(p_full + 8 * i, SW * 32); mbar_init(p_empty + 8 * i, 1); }
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<512>(smem_u32(&tmem_slot));
-  if (warp == 5 && lane == 0) { tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
+  if (warp == SW) tmem_alloc<512>(smem_u32(&tmem_slot));
+  if (warp == SW + 1 && lane == 0) { tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = tmem_slot;
   const uint32_t tmem_o = tmem_base + 256;   // S buffers at columns [0,128) and [128,256)
 
-  if (warp < 4) {
-    // ============================ softmax / epilogue: one thread per query row ============================
-    const int r = warp * 32 + lane;
+  if (warp < SW) {
+    // ============================ softmax / epilogue: thread = query row (x key half in the online kernel) ===========
+    const int r = (warp & 3) * 32 + lane;
+    const int hs = warp >> 2;   // key half of this thread (always 0 in the two-pass kernels)
     const int q = q0 + r;
     const bool qok = q < p.Lq;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     float lse_r = 0.f;
     if (PASS == 1) lse_r = qok ? p.lse[(int64_t)blockIdx.z * p.Lq + q] : 0.f;
@@ -136,46 +148,54 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         // The running maximum is LAZY: the O accumulator is only rescaled when a tile raises the row maximum by more
         // than 2^8 (P stays <= 256, harmless in bf16 / fp32); the decision is warp-uniform because tcgen05.ld/st are
         // warp-collective. Rescaling waits for P V of the previous tile (p_empty), which every tile does anyway.
-        float v[128];
-        tmem_ld64(ts, v);
-        tmem_ld64(ts + 64, v + 64);
+        float v[64];
+        tmem_ld64(ts + hs * 64, v);                    // this thread's 64 keys of the tile
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);                // S is in registers: Q K^T of tile j+2 may overwrite it
+        const int kb = kbase + hs * 64;
         float tmax = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 128; ++e) {
-          v[e] = (kbase + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
+        for (int e = 0; e < 64; ++e) {
+          v[e] = (kb + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
           tmax = fmaxf(tmax, v[e]);
         }
-        mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile is complete: P buffer free, O stable
-        tcgen05_fence_after();
-        const float m_new = fmaxf(m_run, tmax);
+        // row maximum over both key halves: exchange through shared memory (double-buffered by tile parity)
+        xch[j & 1][hs][r] = tmax;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        tmax = fmaxf(tmax, xch[j & 1][hs ^ 1][r]);
+        const int pb = j & 1;
+        const float m_new = fmaxf(m_run, tmax);        // identical in both threads of a row
         if (j == 0) {
           m_run = m_new;
         } else if (__any_sync(0xffffffffu, m_new > m_run + 8.f)) {
+          // O must be stable: P V of tile j-1 (the latest user of P[(j-1)&1]) has to be complete
+          mbar_wait(p_empty + 8 * ((j - 1) & 1), (uint32_t)((j - 1) >> 1) & 1u);
+          tcgen05_fence_after();
           const float f = fast_ex2(m_run - m_new);     // 1 for rows whose maximum did not move
           const uint32_t to = tmem_o + lane_off;
+          // the two threads of a row split the O columns (whole 64-column loads; a 64-wide O stays with half 0)
+          const int ncw = p.DV / 64, cbeg = ncw >= 2 ? hs * (ncw / 2) : 0, cend = ncw >= 2 ? (hs ? ncw : ncw / 2) : (hs ? 0 : 1);
 #pragma unroll 1
-          for (int cw = 0; cw < p.DV; cw += 64) {
+          for (int cw = cbeg; cw < cend; ++cw) {
             float ow[64];
-            tmem_ld64(to + cw, ow);
+            tmem_ld64(to + cw * 64, ow);
 #pragma unroll
             for (int e = 0; e < 64; ++e) ow[e] *= f;
-            tmem_st64(to + cw, ow);
+            tmem_st64(to + cw * 64, ow);
           }
           l_run *= f;
           m_run = m_new;
         }
         float sum = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const uint32_t base = p_smem + half * (FA_BM * 128);
+        mbar_wait(p_empty + 8 * pb, ((uint32_t)(j >> 1) & 1u) ^ 1u);   // P V of tile j-2 has consumed this P buffer
+        {
+          const uint32_t base = p_smem + pb * FA_P_BYTES + hs * (FA_BM * 128);   // P panel of this key half
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const int k0 = half * 64 + c * 8 + 2 * e;
+              const int k0 = c * 8 + 2 * e;
               const float p0 = fast_ex2(v[k0] - m_run), p1 = fast_ex2(v[k0 + 1] - m_run);
               sum += p0 + p1;
               __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
@@ -185,18 +205,19 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
                          "r"(o[2]), "r"(o[3]) : "memory");
           }
         }
-        l_run += sum;
+        l_run += sum;                                  // partial sum of this key half; combined in the epilogue
         tcgen05_fence_before();
         fence_proxy_async();
-        mbar_arrive(p_full);
+        mbar_arrive(p_full + 8 * pb);
       } else {
-        mbar_wait(p_empty, ((uint32_t)j & 1u) ^ 1u);   // P V of the previous tile has consumed the P buffer
+        const int pb = j & 1;
+        mbar_wait(p_empty + 8 * pb, ((uint32_t)(j >> 1) & 1u) ^ 1u);   // P V of tile j-2 has consumed this P buffer
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           float v[64];
           tmem_ld64(ts + half * 64, v);
           const int kb = kbase + half * 64;
-          const uint32_t base = p_smem + half * (FA_BM * 128);   // one 64-key panel per half
+          const uint32_t base = p_smem + pb * FA_P_BYTES + half * (FA_BM * 128);   // one 64-key panel per half
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                          // 16-byte chunks of the 128-byte row
             uint32_t o[4];
@@ -215,20 +236,31 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);
         fence_proxy_async();          // generic-proxy smem writes -> visible to the UMMA (async proxy)
-        mbar_arrive(p_full);
+        mbar_arrive(p_full + 8 * pb);
       }
     }
     if (PASS == 0) {
       if (qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
     } else {
-      if (PASS == 2 && qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
-      const float inv_l = PASS == 2 ? 1.f / l_run : 1.f;
+      float inv_l = 1.f;
+      int cw_beg = 0, cw_end = p.DV;
+      if (PASS == 2) {
+        // both key halves hold a partial row sum under the same running maximum: combine, then split the O columns
+        xch[0][hs][r] = l_run;
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        l_run += xch[0][hs ^ 1][r];
+        inv_l = 1.f / l_run;
+        if (qok && hs == 0) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
+        const int ncw = p.DV / 64;
+        cw_beg = (ncw >= 2 ? hs * (ncw / 2) : 0) * 64;
+        cw_end = (ncw >= 2 ? (hs ? ncw : ncw / 2) : (hs ? 0 : 1)) * 64;
+      }
       mbar_wait(o_full, 0);
       tcgen05_fence_after();
       const uint32_t to = tmem_o + lane_off;
       __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + q) * ((int64_t)p.H * p.dh) + (int64_t)h * p.dh + slice * p.DV;
 #pragma unroll 1
-      for (int cw = 0; cw < p.DV; cw += 64) {
+      for (int cw = cw_beg; cw < cw_end; cw += 64) {
         float vw[64];
         tmem_ld64(to + cw, vw);
         if (!qok) continue;
@@ -249,7 +281,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
       }
     }
     tcgen05_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == SW) {
     // ============================ UMMA issuer ============================
     const uint32_t idesc_s = make_idesc(FA_BM, FA_BN, 0, 0);
     const uint32_t idesc_o = make_idesc(FA_BM, p.DV, 0, 1);
@@ -274,27 +306,27 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
           if (c == nkc - 1) umma_commit(s_full + 8 * buf);
         }
         __syncwarp();
-        if (++qs == FA_QK_STAGES) { qs = 0; qph ^= 1u; }
+        if (++qs == p.qk_stages) { qs = 0; qph ^= 1u; }
       }
     };
     issue_qk(0);
     for (int j = 0; j < nkv; ++j) {
       if (j + 1 < nkv) issue_qk(j + 1);
       if (PASS >= 1) {
-        mbar_wait(p_full, (uint32_t)j & 1u);
+        mbar_wait(p_full + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
         tcgen05_fence_after();
         for (int half = 0; half < 2; ++half) {
           mbar_wait(v_full + 8 * vs, vph);
           tcgen05_fence_after();
           if (elect_one()) {
-            const uint32_t a = p_smem + half * (FA_BM * 128), bsm = v_smem + vs * v_stage_bytes;
+            const uint32_t a = p_smem + (j & 1) * FA_P_BYTES + half * (FA_BM * 128), bsm = v_smem + vs * v_stage_bytes;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma_bf16(tmem_o, make_smem_desc(a + kk * 32, 16, 1024), make_smem_desc(bsm + kk * 2048, FA_PANEL, 1024),
                         idesc_o, (j | half | kk) ? 1u : 0u);
             umma_commit(v_empty + 8 * vs);
             if (half == 1) {
-              umma_commit(p_empty);
+              umma_commit(p_empty + 8 * (j & 1));
               if (j == nkv - 1) umma_commit(o_full);
             }
           }
@@ -314,7 +346,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
         mbar_arrive_expect_tx(bar, FA_QK_STAGE_BYTES);
         tma_load_4d(a, &qmap, bar, c * 64, h, q0, b);
         tma_load_4d(a + FA_BM * 128, &kmap, bar, c * 64, h, j * FA_BN, b);
-        if (++qs == FA_QK_STAGES) { qs = 0; qph ^= 1u; }
+        if (++qs == p.qk_stages) { qs = 0; qph ^= 1u; }
       }
     };
     auto load_v = [&](int j) {
@@ -334,7 +366,7 @@ __global__ void __launch_bounds__(FA_THREADS, 1) flash_fwd_kernel(const __grid_c
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == SW) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
@@ -356,16 +388,20 @@ bool flash_eligible(int H, int dh) {
 }
 
 template <int PASS>
-static int launch_flash(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, const FlashParams& p,
+static int launch_flash(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, FlashParams p,
                         dim3 grid, cudaStream_t st) {
-  const int smem = FA_QK_STAGES * FA_QK_STAGE_BYTES + FA_P_BYTES + FA_V_STAGES * 4 * FA_PANEL + 1024;
-  static bool configured = false;
-  if (!configured) {
+  auto bytes = [&](int qk_stages) {
+    return qk_stages * FA_QK_STAGE_BYTES + 2 * FA_P_BYTES + FA_V_STAGES * (p.DV / 64) * FA_PANEL + 1024;
+  };
+  p.qk_stages = bytes(FA_QK_STAGES) <= 227 * 1024 - 4096 ? FA_QK_STAGES : 2;   // 4 KB left for static shared memory
+  const int smem = bytes(p.qk_stages);
+  static int configured = 0;
+  if (configured < smem) {
     cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     MIG_REQUIRE(e == cudaSuccess, "flash_attention: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
+    configured = smem;
   }
-  flash_fwd_kernel<PASS><<<grid, FA_THREADS, smem, st>>>(qm, km, vm, p);
+  flash_fwd_kernel<PASS><<<grid, (fa_softmax_warps(PASS) + 2) * 32, smem, st>>>(qm, km, vm, p);
   return check_launch("flash_fwd_kernel");
 }
 
