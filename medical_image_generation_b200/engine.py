@@ -130,6 +130,7 @@ class FlatAdamW:
         # ---- gradient buckets (contiguous slices of the used region) ----
         self.buckets = None
         self._index_of = {}
+        self._sync_enabled = True
         if _dist_on():
             self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
             self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
@@ -137,9 +138,16 @@ class FlatAdamW:
 
     # called from the backward kernels' wrappers once a parameter's gradient is complete in `main_grad`
     def _grad_ready(self, p) -> None:
+        if not self._sync_enabled:   # gradient accumulation: only the last micro-step's backward reduces
+            return
         i = self._index_of.get(id(p))
         if i is not None:
             self.buckets.ready(i)
+
+    def set_grad_sync(self, enabled: bool) -> None:
+        """Gradient accumulation (train_ldm.py:173): micro-steps before the last one add into the flat gradient
+        buffer without firing the bucket all-reduce; the last micro-step's backward reduces the accumulated sums."""
+        self._sync_enabled = bool(enabled)
 
     def zero_grad(self) -> None:
         self.grad.zero_()
@@ -188,8 +196,12 @@ class LDMTrainer:
 
     def __init__(self, unet, scheduler, lr: float = 2e-5, grad_clip_max_norm: Optional[float] = 1.0,
                  weight_decay: float = 1e-2, bucket_mb: float = 64.0, cuda_graph: bool = False,
-                 graph_warmup_steps: int = 3):
+                 graph_warmup_steps: int = 3, grad_accumulate_step: int = 1):
         self.unet, self.scheduler = unet, scheduler
+        # config['grad_accumulate_step'] (train_ldm.py:173): the optimiser steps every k-th call of step(); gradients
+        # of the micro-steps are SUMMED (the reference does not rescale the loss)
+        self.grad_accumulate_step = max(1, int(grad_accumulate_step))
+        self._micro = 0
         self.opt = FlatAdamW(unet, lr=lr, weight_decay=weight_decay, max_grad_norm=grad_clip_max_norm,
                              bucket_mb=bucket_mb)
         if _dist_on():  # identical replicas: broadcast rank 0's parameters (flat: one collective)
@@ -199,7 +211,7 @@ class LDMTrainer:
         # CUDA graph of the whole step (add_noise -> U-Net fwd -> MSE -> bwd -> all-reduce -> clip -> AdamW): the
         # step is ~1300 kernel launches, so replaying one graph removes the launch gaps. The first
         # `graph_warmup_steps` calls run eagerly (they are real optimiser steps), the next call is captured.
-        self.cuda_graph = cuda_graph
+        self.cuda_graph = cuda_graph and self.grad_accumulate_step == 1
         self._eager_calls = 0
         self._warm = graph_warmup_steps
         self._graph = None
@@ -248,14 +260,29 @@ class LDMTrainer:
             timesteps = torch.randint(0, s.num_train_timesteps, (x0.shape[0],), device=x0.device).long()
         if noise is None:      # train_ldm.py:159
             noise = torch.randn_like(x0)
-        self.opt.zero_grad()
+        last = self._micro + 1 >= self.grad_accumulate_step
+        if self._micro == 0:
+            self.opt.zero_grad()
+        self.opt.set_grad_sync(last)
         noisy = s.add_noise(original_samples=x0, noise=noise, timesteps=timesteps)
         pred = self.unet(x=noisy, timesteps=timesteps)
         target = s.get_velocity(x0, noise, timesteps) if s.prediction_type == "v_prediction" else noise
         loss = ops.mse_loss(pred, target)
         loss.backward()
-        self.opt.step()
+        if last:
+            self.opt.step()
+            self._micro = 0
+        else:
+            self._micro += 1
         return loss
+
+    def flush(self) -> None:
+        """Optimiser step on a partial accumulation group (the reference also steps on the last batch of an epoch,
+        train_ldm.py:173: `or (step + 1) == len(train_loader)`)."""
+        if self._micro > 0:
+            self.opt.set_grad_sync(True)
+            self.opt.step()
+            self._micro = 0
 
 
 class AETrainer:

@@ -246,6 +246,38 @@ def test_flat_engine_matches_torch_optimizer(golden):
     tr.opt.close()
 
 
+def test_gradient_accumulation_matches_torch(golden):
+    """config['grad_accumulate_step'] = 2 (train_ldm.py:173): two backward passes sum their gradients, clip + AdamW run
+    on the sum; a trailing partial group is stepped by flush()."""
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200.engine import LDMTrainer
+    g = golden("unet3d_small")
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    ma, _ = _build(g, torch.float32)
+    mb, _ = _build(g, torch.float32)
+    s = mig.DDPMScheduler(**kw)
+    tr = LDMTrainer(ma, s, lr=1e-3, grad_clip_max_norm=1.0, grad_accumulate_step=2)
+    opt = torch.optim.AdamW(mb.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(5)
+    opt.zero_grad(set_to_none=True)
+    for step in range(5):   # 2 full groups + 1 trailing micro-step
+        x0 = torch.randn(2, 3, 8, 8, 8, generator=gen).to(DEV)
+        noise = torch.randn(2, 3, 8, 8, 8, generator=gen).to(DEV)
+        t = torch.randint(0, 1000, (2,), generator=gen).to(DEV)
+        tr.step(x0, noise=noise, timesteps=t)
+        mig.ops.mse_loss(mb(s.add_noise(x0, noise, t), t), noise).backward()
+        if (step + 1) % 2 == 0 or step == 4:
+            if step == 4:
+                tr.flush()
+            torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+    pa, pb = dict(ma.named_parameters()), dict(mb.named_parameters())
+    worst = max(rel_err(pa[k], pb[k]) for k in pa)
+    assert worst < 2e-4, worst
+    tr.opt.close()
+
+
 def test_cuda_graph_step_replays_correctly(golden):
     """The whole training step captured in a CUDA graph: step counter lives on the device, every replay is a real
     optimiser step (parameters move, loss stays finite and comparable to the eager steps)."""
