@@ -291,8 +291,10 @@ class AETrainer:
     412-414). Perceptual and adversarial terms are out of scope. Data-parallel like LDMTrainer."""
 
     def __init__(self, autoencoder, lr: float = 5e-5, kl_weight: float = 1e-7,
-                 grad_clip_max_norm: Optional[float] = 1.0, bucket_mb: float = 64.0):
+                 grad_clip_max_norm: Optional[float] = 1.0, bucket_mb: float = 64.0, grad_accumulate_step: int = 1):
         self.ae, self.kl_weight = autoencoder, kl_weight
+        self.grad_accumulate_step = max(1, int(grad_accumulate_step))   # train_autoencoder.py:427
+        self._micro = 0
         # the reference uses torch.optim.Adam (no weight decay) for the generator (train_autoencoder.py:470)
         self.opt = FlatAdamW(autoencoder, lr=lr, weight_decay=0.0, max_grad_norm=grad_clip_max_norm,
                              bucket_mb=bucket_mb, unused=("proj_attn",))
@@ -302,14 +304,28 @@ class AETrainer:
                  ops._stream())
 
     def step(self, images: torch.Tensor, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
-        self.opt.zero_grad()
+        last = self._micro + 1 >= self.grad_accumulate_step
+        if self._micro == 0:
+            self.opt.zero_grad()
+        self.opt.set_grad_sync(last)
         z_mu, z_sigma = self.ae.encode(images)
         z = ops.vae_reparam(z_mu, z_sigma, eps) if eps is not None else self.ae.sampling(z_mu, z_sigma)
         recon = self.ae.decode(z)
         loss = ops.l1_loss(recon, images) + self.kl_weight * ops.kl_loss(z_mu, z_sigma)
         loss.backward()
-        self.opt.step()
+        if last:
+            self.opt.step()
+            self._micro = 0
+        else:
+            self._micro += 1
         return loss
+
+    def flush(self) -> None:
+        """Optimiser step on a trailing partial accumulation group (train_autoencoder.py:427)."""
+        if self._micro > 0:
+            self.opt.set_grad_sync(True)
+            self.opt.step()
+            self._micro = 0
 
 
 @torch.no_grad()
