@@ -89,6 +89,7 @@ class FlatAdamW:
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not named:
             raise ValueError("module has no trainable parameters")
+        self._torch_order = [p for _, p in named]   # torch.optim indexes parameters in registration order
         dev = named[0][1].device
         if dev.type != "cuda":
             raise RuntimeError("FlatAdamW needs the module on a CUDA device")
@@ -184,6 +185,48 @@ class FlatAdamW:
 
     def state_dict(self) -> dict:
         return dict(step=self.step_count, m=self.m, v=self.v, lr=self.lr)
+
+    # ---- checkpoint interchange with the reference: ckpt['optimizer_state_dict'] (train_ldm.py:472-477, 496-499) ----
+    def torch_state_dict(self) -> dict:
+        """The optimiser state in torch.optim.AdamW's own state_dict() layout (parameters indexed in registration
+        order, per-parameter `step` / `exp_avg` / `exp_avg_sq`; parameters that never received a gradient have no
+        entry, as in torch), so a checkpoint written here resumes in the reference trainer and vice versa."""
+        state = {}
+        for i, p in enumerate(self._torch_order):
+            off, k = p._mig_slot
+            if off >= self.used_numel or self.step_count == 0:
+                continue
+            view = lambda buf: buf[off:off + k].as_strided(p.shape, p.stride()).detach().clone()  # noqa: E731
+            state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": view(self.m), "exp_avg_sq": view(self.v)}
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     params=list(range(len(self._torch_order))))
+        return {"state": state, "param_groups": [group]}
+
+    def load_torch_state_dict(self, sd: dict) -> None:
+        """Inverse of torch_state_dict(): accepts torch.optim.AdamW / Adam state dicts of the same module."""
+        group = sd["param_groups"][0]
+        if len(group["params"]) != len(self._torch_order):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, the module has {len(self._torch_order)}")
+        self.lr, self.betas, self.eps = float(group["lr"]), tuple(group["betas"]), float(group["eps"])
+        self.weight_decay = float(group.get("weight_decay", 0.0))
+        self.m.zero_()
+        self.v.zero_()
+        step = 0
+        for j, idx in enumerate(group["params"]):
+            st = sd["state"].get(idx)
+            if st is None:
+                continue
+            p = self._torch_order[j]
+            off, k = p._mig_slot
+            if off >= self.used_numel:
+                continue
+            with torch.no_grad():
+                self.m[off:off + k].as_strided(p.shape, p.stride()).copy_(st["exp_avg"])
+                self.v[off:off + k].as_strided(p.shape, p.stride()).copy_(st["exp_avg_sq"])
+            step = max(step, int(float(st["step"])))
+        self.step_count = step
+        self.step_dev.fill_(step)
 
     def close(self) -> None:
         ops.set_grad_ready_hook(None)

@@ -278,6 +278,50 @@ def test_gradient_accumulation_matches_torch(golden):
     tr.opt.close()
 
 
+def test_optimizer_state_interchange_with_torch(golden):
+    """ckpt['optimizer_state_dict'] interchange (train_ldm.py:472-477): the flat optimiser exports torch.optim.AdamW's
+    state_dict layout; loading it into a real torch AdamW (and back into a fresh flat optimiser) continues the same
+    trajectory."""
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200.engine import LDMTrainer
+    g = golden("unet3d_small")
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    s = mig.DDPMScheduler(**kw)
+    ma, _ = _build(g, torch.float32)
+    tr = LDMTrainer(ma, s, lr=1e-3, grad_clip_max_norm=1.0)
+    gen = torch.Generator().manual_seed(11)
+
+    def batch():
+        return (torch.randn(2, 3, 8, 8, 8, generator=gen).to(DEV), torch.randn(2, 3, 8, 8, 8, generator=gen).to(DEV),
+                torch.randint(0, 1000, (2,), generator=gen).to(DEV))
+
+    for _ in range(2):
+        tr.step(*batch())
+    sd = tr.opt.torch_state_dict()
+    # (1) resume in torch
+    mb, _ = _build(g, torch.float32)
+    mb.load_state_dict(ma.state_dict())
+    opt = torch.optim.AdamW(mb.parameters(), lr=1e-3)
+    opt.load_state_dict(sd)
+    # (2) resume in a fresh flat optimiser
+    mc, _ = _build(g, torch.float32)
+    mc.load_state_dict(ma.state_dict())
+    tr.opt.close()
+    tr2 = LDMTrainer(mc, s, lr=5e-4, grad_clip_max_norm=1.0)
+    tr2.opt.load_torch_state_dict(opt.state_dict())
+    assert tr2.opt.step_count == 2 and abs(tr2.opt.lr - 1e-3) < 1e-12
+    x0, noise, t = batch()
+    tr2.step(x0, noise=noise, timesteps=t)
+    opt.zero_grad(set_to_none=True)
+    mig.ops.mse_loss(mb(s.add_noise(x0, noise, t), t), noise).backward()
+    torch.nn.utils.clip_grad_norm_(mb.parameters(), 1.0)
+    opt.step()
+    pb, pc = dict(mb.named_parameters()), dict(mc.named_parameters())
+    worst = max(rel_err(pc[k], pb[k]) for k in pb)
+    assert worst < 2e-4, worst
+    tr2.opt.close()
+
+
 def test_cuda_graph_step_replays_correctly(golden):
     """The whole training step captured in a CUDA graph: step counter lives on the device, every replay is a real
     optimiser step (parameters move, loss stays finite and comparable to the eager steps)."""
