@@ -131,6 +131,9 @@ int mig_nhwc_to_nchw(int src_dtype, int dst_dtype, const void* x, void* y, int32
                      void* stream);
 /* column sums of a [rows][C] matrix into fp32 out[C] (bias gradients); out += when accumulate */
 int mig_colsum(int dtype, const void* x, float* out, int64_t rows, int32_t C, int accumulate, void* stream);
+/* y[r][c] = x[r][c] + bias[c] (channels-last rows; in place allowed). Bias of nn.ConvTranspose{2,3}d inside monai
+ * Convolution(is_transposed=True), ae:66-76: the transposed convolution itself runs as mig_conv_dgrad. */
+int mig_add_channel_bias(int dtype, const void* x, const float* bias, void* y, int64_t rows, int32_t C, void* stream);
 /* per-(n,c) broadcast add over S positions: y[n,s,c] = x[n,s,c] + b[n,c] and its reduction backward */
 int mig_chan_bias_bwd(int dtype, const void* dy, float* db, int32_t N, int64_t S, int32_t C, void* stream);
 

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "mig_nchw_to_nhwc": [_i, _i, _p, _p, _i, _i, _l, _p],
     "mig_nhwc_to_nchw": [_i, _i, _p, _p, _i, _i, _l, _p],
     "mig_colsum": [_i, _p, _p, _l, _i, _i, _p],
+    "mig_add_channel_bias": [_i, _p, _p, _p, _l, _i, _p],
     "mig_chan_bias_bwd": [_i, _p, _p, _i, _l, _i, _p],
     "mig_softmax_fwd": [_i, _i, _p, _p, _l, _i, _f, _p],
     "mig_softmax_bwd": [_i, _i, _p, _p, _p, _l, _i, _f, _p],

@@ -29,13 +29,16 @@ class Upsample(nn.Module):
     def __init__(self, spatial_dims, in_channels, use_convtranspose, stride=2, kernel_size=4, padding=1):
         super().__init__()
         self.stride = stride
-        if use_convtranspose:
-            raise NotImplementedError("use_convtranspose=True is not on the B200 hot path yet (SURVEY.md K13); the "
-                                      "planner always emits use_convtranspose=False (configuration.py:843)")
-        self.conv = ConvBlock(spatial_dims, in_channels, in_channels, strides=1, kernel_size=3, padding=1)
+        if use_convtranspose:   # ae:66-76
+            self.conv = ConvBlock(spatial_dims, in_channels, in_channels, strides=stride, kernel_size=kernel_size,
+                                  padding=padding, is_transposed=True)
+        else:
+            self.conv = ConvBlock(spatial_dims, in_channels, in_channels, strides=1, kernel_size=3, padding=1)
         self.use_convtranspose = use_convtranspose
 
     def forward(self, x):
+        if self.use_convtranspose:
+            return self.conv(_entry(x))
         x = ops.upsample_nearest(_entry(x), _tup(self.stride, x.ndim - 2))
         return self.conv(x)
 

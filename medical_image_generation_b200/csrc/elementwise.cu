@@ -54,6 +54,46 @@ struct AddcmulF { __device__ float operator()(float a, float b, float c) const {
 
 using namespace mig;
 
+namespace mig {
+// y[r][c] = x[r][c] + bias[c] over channels-last rows (bias of the transposed convolution, whose forward runs on the
+// dgrad kernels and therefore has no fused epilogue)
+template <typename T>
+__global__ void __launch_bounds__(256) add_channel_bias_kernel(const T* __restrict__ x, const float* __restrict__ bias,
+                                                               T* __restrict__ y, int64_t rows, int C) {
+  const int64_t total = rows * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(to_f(x[i]) + bias[(int)(i % C)]);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) add_channel_bias_vec_kernel(const T* __restrict__ x, const float* __restrict__ bias,
+                                                                   T* __restrict__ y, int64_t rows, int C) {
+  constexpr int V = Vec16<T>::N;
+  const int cv = C / V;
+  const int64_t total = rows * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * V;
+    Vec16<T> v = ld16(x + i * V), o;
+#pragma unroll
+    for (int j = 0; j < V; ++j) o.set(j, v.get(j) + bias[c0 + j]);
+    st16(y + i * V, o);
+  }
+}
+}  // namespace mig
+
+extern "C" int mig_add_channel_bias(int dtype, const void* x, const float* bias, void* y, int64_t rows, int32_t C,
+                                    void* stream) {
+  MIG_REQUIRE(x && bias && y && rows >= 0 && C > 0, "add_channel_bias: bad argument");
+  if (rows == 0) return 0;
+  MIG_DISPATCH_DTYPE(dtype, T, {
+    if (C % Vec16<T>::N == 0 && aligned16(x) && aligned16(y))
+      add_channel_bias_vec_kernel<T><<<bw_grid(rows * C / Vec16<T>::N, 256), 256, 0, as_stream(stream)>>>(
+          (const T*)x, bias, (T*)y, rows, C);
+    else
+      add_channel_bias_kernel<T><<<bw_grid(rows * C, 256), 256, 0, as_stream(stream)>>>((const T*)x, bias, (T*)y, rows, C);
+  });
+  return check_launch("add_channel_bias");
+}
+
 extern "C" int mig_silu_fwd(int dtype, const void* x, void* y, int64_t n, void* stream) {
   MIG_DISPATCH_DTYPE(dtype, T, return (launch_map<T, 1>(x, nullptr, nullptr, y, n, stream, SiluF{}, "silu_fwd")));
 }

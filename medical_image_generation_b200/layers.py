@@ -57,15 +57,52 @@ class ConvNd(nn.Module):
                 f"padding={self.padding}")
 
 
+class ConvTransposeNd(nn.Module):
+    """nn.ConvTranspose{2,3}d replacement (weight (Cin, Cout, *k), torch's default initialisation); the kernels are the
+    convolution data-gradient kernels (ops.conv_transpose_nd)."""
+
+    def __init__(self, spatial_dims: int, in_channels: int, out_channels: int, kernel_size, stride, padding,
+                 output_padding):
+        super().__init__()
+        if spatial_dims not in (2, 3):
+            raise ValueError("only 2-D and 3-D convolutions are supported")
+        self.spatial_dims = spatial_dims
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = _tup(kernel_size, spatial_dims)
+        self.stride = _tup(stride, spatial_dims)
+        self.padding = _tup(padding, spatial_dims)
+        self.output_padding = _tup(output_padding, spatial_dims)
+        w = torch.empty(in_channels, out_channels, *self.kernel_size)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        bound = 1 / math.sqrt(out_channels * math.prod(self.kernel_size))   # torch: fan_in of the transposed filter
+        self.weight = nn.Parameter(w.contiguous(memory_format=_cl_format(spatial_dims)))
+        self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
+
+    def forward(self, x, chan_bias=None, residual=None):
+        if chan_bias is not None or residual is not None:
+            raise RuntimeError("transposed convolutions have no fused epilogue inputs")
+        return ops.conv_transpose_nd(x, self.weight, self.bias, self.stride, self.padding, self.output_padding)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, output_padding={self.output_padding}")
+
+
 class ConvBlock(nn.Module):
     """Stand-in for monai.networks.blocks.Convolution(conv_only=True): single child named `conv`.
-    padding=None means same-padding (k-1)//2."""
+    padding=None means same-padding (k-1)//2; is_transposed=True builds a ConvTranspose with MONAI's default
+    output_padding = stride - 1."""
 
-    def __init__(self, spatial_dims, in_channels, out_channels, strides=1, kernel_size=3, padding=None):
+    def __init__(self, spatial_dims, in_channels, out_channels, strides=1, kernel_size=3, padding=None,
+                 is_transposed=False):
         super().__init__()
         k = _tup(kernel_size, spatial_dims)
         p = tuple((ki - 1) // 2 for ki in k) if padding is None else _tup(padding, spatial_dims)
-        self.conv = ConvNd(spatial_dims, in_channels, out_channels, k, _tup(strides, spatial_dims), p)
+        s = _tup(strides, spatial_dims)
+        if is_transposed:
+            self.conv = ConvTransposeNd(spatial_dims, in_channels, out_channels, k, s, p, tuple(si - 1 for si in s))
+        else:
+            self.conv = ConvNd(spatial_dims, in_channels, out_channels, k, s, p)
 
     def forward(self, x, chan_bias=None, residual=None):
         return self.conv(x, chan_bias=chan_bias, residual=residual)

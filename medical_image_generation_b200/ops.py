@@ -341,6 +341,87 @@ def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=
     return _ConvFn.apply(x, weight, bias, chan_bias, residual, s, p)
 
 
+class _ConvTransposeFn(Function):
+    """nn.ConvTranspose{2,3}d (monai Convolution(is_transposed=True), ae:66-76) on the convolution kernels: a transposed
+    convolution IS the data gradient of the strided convolution with the same filter, so
+        forward  = mig_conv_dgrad   (stride-residue classes on the tcgen05 kernels, no zero-insertion),
+        d/dx     = mig_conv_fwd     (the strided convolution itself),
+        d/dw     = mig_conv_wgrad   with the roles of input and output gradient exchanged.
+    weight: (Cin, Cout, *k) like torch's ConvTranspose, channels-last memory = [Cin][tap][Cout] = the [Cout'][tap][Cin']
+    filter of the underlying convolution (Cout' = Cin, Cin' = Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, output_padding):
+        N, Cin = x.shape[0], x.shape[1]
+        nd = x.ndim - 2
+        if weight.shape[0] != Cin:
+            raise RuntimeError(f"conv_transpose: input has {Cin} channels but the filter expects {weight.shape[0]}")
+        Cout = weight.shape[1]
+        k = tuple(weight.shape[2:])
+        out_sp = tuple((x.shape[2 + i] - 1) * stride[i] - 2 * padding[i] + k[i] + output_padding[i] for i in range(nd))
+        # geometry of the underlying convolution: it maps the transposed conv's OUTPUT to its INPUT
+        geom, back3 = _geom(N, out_sp, Cout, Cin, k, stride, padding)
+        if tuple(back3[3 - nd:]) != tuple(x.shape[2:]):
+            raise RuntimeError(f"conv_transpose: output_padding {output_padding} is inconsistent with stride {stride}")
+        wk = _filter_for(weight, x.dtype)
+        y = empty_cl((N, Cout, *out_sp), x.dtype, x.device)
+        dt = _dt(x)
+        need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 1, _ENGINE)
+        ws = _workspace(need, x.device)
+        _conv_call("dgrad", geom, "mig_conv_dgrad", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(y), _ENGINE, _ptr(ws),
+                   ws.numel(), _stream())
+        if bias is not None:
+            call("mig_add_channel_bias", dt, _ptr(y), _ptr(bias), _ptr(y), y.numel() // Cout, Cout, _stream())
+        ctx.geom = geom
+        ctx.bias_ref, ctx.weight_ref = bias, weight
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, _ = ctx.saved_tensors
+        weight, bias, geom = ctx.weight_ref, ctx.bias_ref, ctx.geom
+        dy = as_cl(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dt = _dt(x)
+        lib = _lib.load()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wk = _filter_for(weight, x.dtype)
+            dx = torch.empty_like(x)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+            ws = _workspace(need, x.device)
+            _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(dy), _ptr(wk), None, None, None, _ptr(dx),
+                       _ENGINE, _ptr(ws), ws.numel(), _stream())
+        if ctx.needs_input_grad[1]:
+            w_main = getattr(weight, "main_grad", None)
+            dw_buf = w_main if w_main is not None else empty_cl(weight.shape, torch.float32, x.device).zero_()
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
+            ws = _workspace(need, x.device)
+            # underlying convolution: input = dy (of this op), output gradient = x (of this op)
+            _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(dy), _ptr(x), _ptr(dw_buf), None, _ENGINE,
+                       _ptr(ws), ws.numel(), _stream())
+            dw = _deliver(weight, None) if w_main is not None else dw_buf
+        if bias is not None and ctx.needs_input_grad[2]:
+            b_main = getattr(bias, "main_grad", None)
+            Cout = dy.shape[1]
+            db_buf = b_main if b_main is not None else torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            call("mig_colsum", dt, _ptr(dy), _ptr(db_buf), dy.numel() // Cout, Cout, 1, _stream())
+            db = _deliver(bias, None) if b_main is not None else db_buf
+        return dx, dw, db, None, None, None
+
+
+def conv_transpose_nd(x, weight, bias=None, stride=1, padding=0, output_padding=0):
+    """ConvTranspose{2,3}d; x channels-last compute dtype, weight (Cin, Cout, *k)."""
+    _require_cuda(x, "conv_transpose_nd")
+    nd = x.ndim - 2
+    tup = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * nd  # noqa: E731
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    return _ConvTransposeFn.apply(x, weight, bias, tup(stride), tup(padding), tup(output_padding))
+
+
 class _LinearFn(Function):
     """y[r, o] = sum_i x[r, i] w[o, i] + b[o]  -- a 1x1x1 conv over `rows` voxels (unet:436-438,1832-1834)."""
 

@@ -48,6 +48,13 @@ CASES = {
         with_encoder_nonlocal_attn=True, with_decoder_nonlocal_attn=True,
         downsample_parameters=[[[1, 1, 1], [3, 3, 1], [1, 1, 0]], [[2, 2, 1], [3, 3, 1], [1, 1, 0]]],
         upsample_parameters=[[[2, 2, 1], [3, 3, 1], [1, 1, 0]]])),
+    # transposed-convolution upsampling (ae:66-76; never emitted by the planner, configuration.py:843)
+    "ae3d_convtranspose": dict(kind="ae", batch=1, in_shape=(1, 16, 16, 8), cfg=dict(
+        spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=[16, 32],
+        attention_levels=[False, False], latent_channels=3, norm_num_groups=8,
+        with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False, use_convtranspose=True,
+        downsample_parameters=[[[1, 1, 1], [3, 3, 3], [1, 1, 1]], [[2, 2, 1], [3, 3, 3], [1, 1, 1]]],
+        upsample_parameters=[[[2, 2, 1], [3, 3, 3], [1, 1, 1]]])),
     "ae2d_small": dict(kind="ae", batch=2, in_shape=(1, 32, 32), cfg=dict(
         spatial_dims=2, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=[32, 64],
         attention_levels=[False, False], latent_channels=3, norm_num_groups=16,

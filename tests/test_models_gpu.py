@@ -21,7 +21,7 @@ def _build(g, dtype):
 
 
 UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond"]
-AES = ["ae3d_small", "ae3d_attn_aniso", "ae2d_small"]
+AES = ["ae3d_small", "ae3d_attn_aniso", "ae2d_small", "ae3d_convtranspose"]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

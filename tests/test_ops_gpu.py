@@ -425,6 +425,48 @@ def test_flash_attention_forward(B, Lq, Lk, C, heads):
     assert rel_err(got, ref2) < BF16_TOL
 
 
+CONVT_CASES = [
+    (2, 16, 16, (6, 6, 6), (3, 3, 3), (2, 2, 2), (1, 1, 1)),     # MONAI default output_padding = stride - 1
+    (1, 64, 64, (8, 8, 8), (3, 3, 3), (2, 2, 2), (1, 1, 1)),     # tcgen05 stride-residue classes
+    (1, 32, 32, (16, 16, 16), (3, 3, 3), (2, 2, 1), (1, 1, 1)),  # anisotropic stride, halo-kernel classes
+    (2, 24, 40, (9, 7), (4, 4), (2, 2), (1, 1)),                 # 2-D, kernel 4, different channel counts
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", CONVT_CASES)
+def test_conv_transpose_fwd_bwd(case, dtype):
+    """nn.ConvTranspose{2,3}d (ae:66-76) on the convolution data-gradient / forward / wgrad kernels."""
+    ops = _ops()
+    N, Cin, Cout, sp, k, s, p = case
+    op = tuple(si - 1 for si in s)
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = torch.randn((N, Cin, *sp), generator=g)
+    w = torch.randn((Cin, Cout, *k), generator=g) / math.sqrt(Cin * math.prod(k))
+    b = torch.randn(Cout, generator=g) * 0.1
+    if dtype == torch.bfloat16:
+        x, w = bf16_round(x), bf16_round(w)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    fn = F.conv_transpose3d if len(sp) == 3 else F.conv_transpose2d
+    y_ref = fn(xr, wr, br, stride=s, padding=p, output_padding=op)
+    dy = torch.randn(y_ref.shape, generator=g)
+    if dtype == torch.bfloat16:
+        dy = bf16_round(dy)
+    y_ref.backward(dy)
+    fmt = torch.channels_last_3d if len(sp) == 3 else torch.channels_last
+    xd = x.to(DEV).to(dtype).contiguous(memory_format=fmt).requires_grad_(True)
+    wd = w.to(DEV).contiguous(memory_format=fmt).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True)
+    y = ops.conv_transpose_nd(xd, wd, bd, s, p, op)
+    y.backward(dy.to(DEV).to(dtype))
+    tol = 1e-4 if dtype == torch.float32 else BF16_TOL
+    assert y.shape == y_ref.shape
+    assert rel_err(y, y_ref) < tol
+    assert rel_err(xd.grad, xr.grad) < tol
+    assert rel_err(wd.grad, wr.grad) < tol
+    assert rel_err(bd.grad, br.grad) < tol
+
+
 @pytest.mark.parametrize("C,heads", [(128, 1), (256, 2), (512, 1)])
 def test_flash_attention_growing_logits(C, heads):
     """Keys whose logits grow tile after tile: every key tile raises the running row maximum by far more than the lazy
