@@ -124,6 +124,12 @@ int mig_upsample_nearest_fwd(int dtype, const void* x, void* y, int32_t N, const
                              const int32_t factors[3], int32_t C, void* stream);
 int mig_upsample_nearest_bwd(int dtype, const void* dy, void* dx, int32_t N, const int32_t in_dims[3],
                              const int32_t factors[3], int32_t C, void* stream);
+/* nn.AvgPool{2,3}d(kernel, stride) without padding: Downsample(use_conv=False) of ResnetBlock(down=True), unet:513-518,
+ * 641-644 (resblock_updown=True). in_dims = pooled tensor's INPUT extent; out = (in - k) / s + 1 per axis. */
+int mig_avgpool_fwd(int dtype, const void* x, void* y, int32_t N, const int32_t in_dims[3], const int32_t ksize[3],
+                    const int32_t stride[3], int32_t C, void* stream);
+int mig_avgpool_bwd(int dtype, const void* dy, void* dx, int32_t N, const int32_t in_dims[3], const int32_t ksize[3],
+                    const int32_t stride[3], int32_t C, void* stream);
 /* NCDHW <-> NDHWC with optional dtype change (module boundary) */
 int mig_nchw_to_nhwc(int src_dtype, int dst_dtype, const void* x, void* y, int32_t N, int32_t C, int64_t S,
                      void* stream);

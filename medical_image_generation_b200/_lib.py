@@ -63,6 +63,8 @@ _SIGNATURES = {
     "mig_split_channels": [_i, _p, _p, _p, _l, _i, _i, _p],
     "mig_upsample_nearest_fwd": [_i, _p, _p, _i, _I3, _I3, _i, _p],
     "mig_upsample_nearest_bwd": [_i, _p, _p, _i, _I3, _I3, _i, _p],
+    "mig_avgpool_fwd": [_i, _p, _p, _i, _I3, _I3, _I3, _i, _p],
+    "mig_avgpool_bwd": [_i, _p, _p, _i, _I3, _I3, _I3, _i, _p],
     "mig_nchw_to_nhwc": [_i, _i, _p, _p, _i, _i, _l, _p],
     "mig_nhwc_to_nchw": [_i, _i, _p, _p, _i, _i, _l, _p],
     "mig_colsum": [_i, _p, _p, _l, _i, _i, _p],

@@ -322,6 +322,123 @@ static int launch_upsample(const void* src, void* dst, int N, const int32_t* in_
 }
 }  // namespace mig
 
+// ------------------------------------------------------------------------------------------------
+// nn.AvgPool{2,3}d(kernel, stride), no padding -- Downsample(use_conv=False) inside ResnetBlock(down=True),
+// unet:513-518,641-644 (resblock_updown). Channels-last, one thread per (voxel, 16-byte channel vector).
+// ------------------------------------------------------------------------------------------------
+namespace mig {
+struct PoolGeom { int N, D, H, W, OD, OH, OW, kd, kh, kw, sd, sh, sw, C; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, PoolGeom g, int cw) {
+  const int cpr = g.C / cw;
+  const int64_t total = (int64_t)g.N * g.OD * g.OH * g.OW * cpr;
+  const float inv = 1.f / (float)(g.kd * g.kh * g.kw);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpr);
+    int64_t v = i / cpr;
+    const int ow = (int)(v % g.OW); v /= g.OW;
+    const int oh = (int)(v % g.OH); v /= g.OH;
+    const int od = (int)(v % g.OD);
+    const int n = (int)(v / g.OD);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < g.kd; ++a)
+      for (int b = 0; b < g.kh; ++b)
+        for (int e = 0; e < g.kw; ++e) {
+          const int64_t src = ((((int64_t)n * g.D + od * g.sd + a) * g.H + oh * g.sh + b) * g.W + ow * g.sw + e) * g.C +
+                              (int64_t)c * cw;
+          if (cw > 1) {
+            const Vec16<T> t = ld16(x + src);
+#pragma unroll
+            for (int j = 0; j < Vec16<T>::N; ++j) acc[j] += t.get(j);
+          } else {
+            acc[0] += to_f(x[src]);
+          }
+        }
+    const int64_t dst = (i / cpr) * g.C + (int64_t)c * cw;
+    if (cw > 1) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < Vec16<T>::N; ++j) o.set(j, acc[j] * inv);
+      st16(y + dst, o);
+    } else {
+      y[dst] = from_f<T>(acc[0] * inv);
+    }
+  }
+}
+// dx[i] = (1 / window) * sum of dy[o] over the output positions whose window contains i (gather: no atomics, windows
+// may overlap when kernel > stride)
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, PoolGeom g, int cw) {
+  const int cpr = g.C / cw;
+  const int64_t total = (int64_t)g.N * g.D * g.H * g.W * cpr;
+  const float inv = 1.f / (float)(g.kd * g.kh * g.kw);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cpr);
+    int64_t v = i / cpr;
+    const int w = (int)(v % g.W); v /= g.W;
+    const int h = (int)(v % g.H); v /= g.H;
+    const int d = (int)(v % g.D);
+    const int n = (int)(v / g.D);
+    auto lo = [](int p, int k, int s) { const int t = p - k + 1; return t <= 0 ? 0 : (t + s - 1) / s; };
+    auto hi = [](int p, int s, int on) { const int t = p / s; return t < on - 1 ? t : on - 1; };
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int od = lo(d, g.kd, g.sd); od <= hi(d, g.sd, g.OD); ++od)
+      for (int oh = lo(h, g.kh, g.sh); oh <= hi(h, g.sh, g.OH); ++oh)
+        for (int ow = lo(w, g.kw, g.sw); ow <= hi(w, g.sw, g.OW); ++ow) {
+          const int64_t src = ((((int64_t)n * g.OD + od) * g.OH + oh) * g.OW + ow) * g.C + (int64_t)c * cw;
+          if (cw > 1) {
+            const Vec16<T> t = ld16(dy + src);
+#pragma unroll
+            for (int j = 0; j < Vec16<T>::N; ++j) acc[j] += t.get(j);
+          } else {
+            acc[0] += to_f(dy[src]);
+          }
+        }
+    const int64_t dst = (i / cpr) * g.C + (int64_t)c * cw;
+    if (cw > 1) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < Vec16<T>::N; ++j) o.set(j, acc[j] * inv);
+      st16(dx + dst, o);
+    } else {
+      dx[dst] = from_f<T>(acc[0] * inv);
+    }
+  }
+}
+
+template <typename T>
+static int launch_avgpool(bool bwd, const void* a, void* b, int N, const int32_t* in_dims, const int32_t* ksize,
+                          const int32_t* stride, int C, void* stream) {
+  PoolGeom g;
+  g.N = N; g.D = in_dims[0]; g.H = in_dims[1]; g.W = in_dims[2];
+  g.kd = ksize[0]; g.kh = ksize[1]; g.kw = ksize[2];
+  g.sd = stride[0]; g.sh = stride[1]; g.sw = stride[2];
+  g.C = C;
+  MIG_REQUIRE(g.kd >= 1 && g.kh >= 1 && g.kw >= 1 && g.sd >= 1 && g.sh >= 1 && g.sw >= 1, "avgpool: bad kernel / stride");
+  MIG_REQUIRE(g.D >= g.kd && g.H >= g.kh && g.W >= g.kw, "avgpool: kernel larger than the input");
+  g.OD = (g.D - g.kd) / g.sd + 1; g.OH = (g.H - g.kh) / g.sh + 1; g.OW = (g.W - g.kw) / g.sw + 1;
+  const int V = Vec16<T>::N;
+  const int cw = (C % V == 0 && aligned16(a) && aligned16(b)) ? V : 1;
+  const int64_t items = (int64_t)N * (bwd ? (int64_t)g.D * g.H * g.W : (int64_t)g.OD * g.OH * g.OW) * (C / cw);
+  if (items == 0) return 0;
+  if (bwd) avgpool_bwd_kernel<T><<<bw_grid(items, 256), 256, 0, as_stream(stream)>>>((const T*)a, (T*)b, g, cw);
+  else avgpool_fwd_kernel<T><<<bw_grid(items, 256), 256, 0, as_stream(stream)>>>((const T*)a, (T*)b, g, cw);
+  return check_launch(bwd ? "avgpool_bwd" : "avgpool_fwd");
+}
+}  // namespace mig
+
+extern "C" int mig_avgpool_fwd(int dtype, const void* x, void* y, int32_t N, const int32_t in_dims[3],
+                               const int32_t ksize[3], const int32_t stride[3], int32_t C, void* stream) {
+  MIG_REQUIRE(x && y && in_dims && ksize && stride, "avgpool_fwd: null argument");
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_avgpool<T>(false, x, y, N, in_dims, ksize, stride, C, stream)));
+}
+extern "C" int mig_avgpool_bwd(int dtype, const void* dy, void* dx, int32_t N, const int32_t in_dims[3],
+                               const int32_t ksize[3], const int32_t stride[3], int32_t C, void* stream) {
+  MIG_REQUIRE(dy && dx && in_dims && ksize && stride, "avgpool_bwd: null argument");
+  MIG_DISPATCH_DTYPE(dtype, T, return (launch_avgpool<T>(true, dy, dx, N, in_dims, ksize, stride, C, stream)));
+}
+
 extern "C" int mig_upsample_nearest_fwd(int dtype, const void* x, void* y, int32_t N, const int32_t in_dims[3],
                                         const int32_t factors[3], int32_t C, void* stream) {
   MIG_DISPATCH_DTYPE(dtype, T, return (launch_upsample<T, false>(x, y, N, in_dims, factors, C, stream)));

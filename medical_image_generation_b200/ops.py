@@ -728,6 +728,41 @@ class _UpsampleFn(Function):
         return dx, None
 
 
+class _AvgPoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, ksize, stride):
+        N, Cc = x.shape[0], x.shape[1]
+        nd = x.ndim - 2
+        in3, k3, s3 = _sp3(x.shape[2:]), (1,) * (3 - nd) + tuple(ksize), (1,) * (3 - nd) + tuple(stride)
+        if any(x.shape[2 + i] < ksize[i] for i in range(nd)):
+            raise RuntimeError(f"avg_pool: kernel {tuple(ksize)} is larger than the input {tuple(x.shape[2:])}")
+        out_sp = tuple((x.shape[2 + i] - ksize[i]) // stride[i] + 1 for i in range(nd))
+        y = empty_cl((N, Cc, *out_sp), x.dtype, x.device)
+        I3 = C.c_int32 * 3
+        call("mig_avgpool_fwd", _dt(x), _ptr(x), _ptr(y), N, I3(*in3), I3(*k3), I3(*s3), Cc, _stream())
+        ctx.cfg = (in3, k3, s3, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        in3, k3, s3, shape = ctx.cfg
+        dy = as_cl(dy)
+        dx = empty_cl(shape, dy.dtype, dy.device)
+        I3 = C.c_int32 * 3
+        call("mig_avgpool_bwd", _dt(dy), _ptr(dy), _ptr(dx), shape[0], I3(*in3), I3(*k3), I3(*s3), shape[1], _stream())
+        return dx, None, None
+
+
+def avg_pool(x, kernel_size, stride):
+    """nn.AvgPool{2,3}d(kernel_size, stride), no padding (unet:517-518)."""
+    _require_cuda(x, "avg_pool")
+    nd = x.ndim - 2
+    tup = lambda v: tuple(int(a) for a in v) if isinstance(v, (list, tuple)) else (int(v),) * nd  # noqa: E731
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    return _AvgPoolFn.apply(x, tup(kernel_size), tup(stride))
+
+
 def upsample_nearest(x, factors):
     """F.interpolate(x, scale_factor=factors, mode='nearest') for integer per-axis factors (unet:580, ae:99)."""
     nd = x.ndim - 2

@@ -135,13 +135,17 @@ class Downsample(nn.Module):
         else:
             if self.num_channels != self.out_channels:
                 raise ValueError("num_channels and out_channels must be equal when use_conv=False")
-            raise NotImplementedError("AvgPool down-sampling (resblock_updown=True) is not on the B200 hot path yet")
+            nd = spatial_dims
+            self.op = None   # nn.AvgPool{nd}d(kernel_size, stride): no parameters, no state_dict entries
+            self.pool_kernel, self.pool_stride = _tup(kernel_size, nd), _tup(stride, nd)
 
     def forward(self, x, emb=None):
         del emb
         if x.shape[1] != self.num_channels:
             raise ValueError(f"Input number of channels ({x.shape[1]}) is not equal to expected number of channels "
                              f"({self.num_channels})")
+        if self.op is None:
+            return ops.avg_pool(_entry(x), self.pool_kernel, self.pool_stride)
         return self.op(_entry(x))
 
 
@@ -177,12 +181,15 @@ class ResnetBlock(nn.Module):
         self.emb_channels = temb_channels
         self.out_channels = out_channels or in_channels
         self.up, self.down = up, down
-        if up or down:
-            raise NotImplementedError("resblock_updown=True is not on the B200 hot path yet (SURVEY.md K12)")
         self.norm1 = GroupNorm(norm_num_groups, in_channels, norm_eps)
         self.nonlinearity = SiLU()
         self.conv1 = ConvBlock(spatial_dims, in_channels, self.out_channels, strides=1, kernel_size=3, padding=1)
         self.upsample = self.downsample = None
+        if up:       # unet:641-642 (resblock_updown): parameter-free nearest up-sampling of both branches
+            self.upsample = Upsample(spatial_dims, in_channels, use_conv=False, stride=stride, padding=padding)
+        elif down:   # unet:643-644: parameter-free average pooling of both branches
+            self.downsample = Downsample(spatial_dims, in_channels, use_conv=False, kernel_size=kernel_size,
+                                         stride=stride, padding=padding)
         self.time_emb_proj = Linear(temb_channels, self.out_channels)
         self.norm2 = GroupNorm(norm_num_groups, self.out_channels, norm_eps)
         self.conv2 = zero_module(ConvBlock(spatial_dims, self.out_channels, self.out_channels, strides=1,
@@ -196,6 +203,10 @@ class ResnetBlock(nn.Module):
     def forward(self, x, emb):
         x = _entry(x)
         h = self.norm1(x, silu=True)
+        if self.upsample is not None:      # unet:672-679
+            x, h = self.upsample(x), self.upsample(h)
+        elif self.downsample is not None:
+            x, h = self.downsample(x), self.downsample(h)
         # the (B, 4*C0) embedding path stays in fp32: it is tiny and feeds the conv epilogue as an fp32 bias
         temb = self.time_emb_proj(self.nonlinearity(emb if emb.dtype == torch.float32 else emb.float()))
         h = self.conv1(h, chan_bias=temb)

@@ -33,6 +33,12 @@ CASES = {
         attention_levels=[False, True], num_head_channels=[0, 16], norm_num_groups=16,
         with_conditioning=True, cross_attention_dim=24, num_class_embeds=5, transformer_num_layers=1,
         strides=[[1, 1, 1], [2, 2, 2]], kernel_sizes=[[3, 3, 3]] * 2, paddings=[[1, 1, 1]] * 2)),
+    # resblock_updown=True (unet:641-644,757-768,1231-1242): AvgPool / nearest ResnetBlocks instead of strided convs.
+    # Only consistent when the level's kernel equals its stride (the pool has no padding); hand-written, never planned.
+    "unet3d_updown": dict(kind="unet", batch=2, in_shape=(2, 8, 8, 4), cfg=dict(
+        spatial_dims=3, in_channels=2, out_channels=2, num_res_blocks=1, num_channels=[16, 32],
+        attention_levels=[False, True], num_head_channels=[0, 16], norm_num_groups=8, resblock_updown=True,
+        strides=[[1, 1, 1], [2, 2, 1]], kernel_sizes=[[3, 3, 3], [2, 2, 1]], paddings=[[1, 1, 1], [0, 0, 0]])),
     # AE-default structure at reduced width (create_autoencoder_dict, configuration.py:821-862)
     "ae3d_small": dict(kind="ae", batch=2, in_shape=(1, 16, 16, 16), cfg=dict(
         spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=2, num_channels=[16, 32, 64],

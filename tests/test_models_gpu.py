@@ -20,7 +20,7 @@ def _build(g, dtype):
     return m.to(DEV).train(), params
 
 
-UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond"]
+UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond", "unet3d_updown"]
 AES = ["ae3d_small", "ae3d_attn_aniso", "ae2d_small", "ae3d_convtranspose"]
 
 

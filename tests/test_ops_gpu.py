@@ -425,6 +425,30 @@ def test_flash_attention_forward(B, Lq, Lk, C, heads):
     assert rel_err(got, ref2) < BF16_TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape,k,s", [((2, 16, 8, 8, 4), (2, 2, 1), (2, 2, 1)), ((1, 8, 9, 7, 6), (3, 3, 3), (2, 2, 2)),
+                                       ((3, 24, 10, 12), (2, 2), (2, 2)), ((1, 5, 7, 7), (3, 2), (1, 2))])
+def test_avg_pool_fwd_bwd(shape, k, s, dtype):
+    """nn.AvgPool{2,3}d(kernel, stride) of ResnetBlock(down=True) (unet:517-518), overlapping windows included."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g)
+    if dtype == torch.bfloat16:
+        x = bf16_round(x)
+    xr = x.clone().requires_grad_(True)
+    pool = F.avg_pool3d if len(shape) == 5 else F.avg_pool2d
+    y_ref = pool(xr, kernel_size=k, stride=s)
+    dy = torch.randn(y_ref.shape, generator=g)
+    if dtype == torch.bfloat16:
+        dy = bf16_round(dy)
+    y_ref.backward(dy)
+    xd = x.to(DEV).to(dtype).requires_grad_(True)
+    y = ops.avg_pool(xd, k, s)
+    y.backward(dy.to(DEV).to(dtype))
+    tol = 1e-5 if dtype == torch.float32 else BF16_TOL
+    assert y.shape == y_ref.shape and rel_err(y, y_ref) < tol and rel_err(xd.grad, xr.grad) < tol
+
+
 CONVT_CASES = [
     (2, 16, 16, (6, 6, 6), (3, 3, 3), (2, 2, 2), (1, 1, 1)),     # MONAI default output_padding = stride - 1
     (1, 64, 64, (8, 8, 8), (3, 3, 3), (2, 2, 2), (1, 1, 1)),     # tcgen05 stride-residue classes
