@@ -16,7 +16,7 @@ class DiffusionInferer:
             raise NotImplementedError(f"{mode} condition is not supported")
         noisy = self.scheduler.add_noise(original_samples=inputs, noise=noise, timesteps=timesteps)
         if mode == "concat":
-            noisy = torch.cat([noisy, condition], dim=1)
+            noisy = ops.cat_channels(noisy, condition)
             condition = None
         return diffusion_model(x=noisy, timesteps=timesteps, context=condition)
 
@@ -34,7 +34,7 @@ class DiffusionInferer:
         for i, t in enumerate(scheduler.timesteps):
             tt = torch.Tensor((t,)).to(input_noise.device)
             if mode == "concat":
-                out = diffusion_model(torch.cat([image, conditioning], dim=1), timesteps=tt, context=None)
+                out = diffusion_model(ops.cat_channels(image, conditioning), timesteps=tt, context=None)
             else:
                 out = diffusion_model(image, timesteps=tt, context=conditioning)
             z = None if step_noises is None else step_noises[i]

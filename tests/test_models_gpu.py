@@ -175,6 +175,28 @@ def test_inferer_sampling_loop_matches_oracle(golden):
     assert rel_err(got, want) < 5e-4
 
 
+def test_inferer_concat_conditioning(golden):
+    """mode='concat' (upstream DiffusionInferer): the condition is concatenated to the noisy input along channels and
+    no cross-attention context is passed; __call__ and sample() against the oracle U-Net on the same tensors."""
+    import medical_image_generation_b200 as mig
+    from oracle import torch_oracle as O
+    from oracle.ddpm_oracle import OracleDDPMScheduler
+    g = golden("unet3d_updown")          # in_channels = 2: one image channel + one condition channel
+    m, params = _build(g, torch.float32)
+    m.eval()
+    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    s, o = mig.DDPMScheduler(**kw), OracleDDPMScheduler(**kw)
+    gen = torch.Generator().manual_seed(123)
+    x0, noise, cond = (torch.randn(2, 1, 8, 8, 4, generator=gen) for _ in range(3))
+    t = torch.randint(0, 1000, (2,), generator=gen)
+    with torch.no_grad():
+        got = mig.DiffusionInferer(s)(x0.to(DEV), m, noise.to(DEV), t.to(DEV), condition=cond.to(DEV), mode="concat")
+        want = O.unet_forward(params, g["cfg"], torch.cat([o.add_noise(x0, noise, t), cond], dim=1), t)
+    assert got.shape == want.shape and rel_err(got, want) < 5e-4
+    with pytest.raises(NotImplementedError):
+        mig.DiffusionInferer(s)(x0.to(DEV), m, noise.to(DEV), t.to(DEV), condition=cond.to(DEV), mode="film")
+
+
 def test_train_step_loss_curve_tracks_oracle(golden):
     """20 AdamW steps of epsilon-prediction training (train_ldm.py:143-183 semantics) on the small 3-D U-Net:
     fp32 CUDA path vs the oracle driven by torch.optim.AdamW on CPU, same data/noise/timesteps."""
