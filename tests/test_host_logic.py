@@ -178,3 +178,50 @@ def test_planner_shapes_for_baseline_configs():
     assert O.compute_output_size([160, 160, 128], p) == [40, 40, 32]
     p = O.compute_downsample_parameters([32, 32, 16], 3)   # thin axis: kernel 1 / pad 0 (the Upsample defect case)
     assert p[0][1] == [3, 3, 1] and p[0][2] == [1, 1, 0]
+
+
+def test_compat_install_rebinds_trainer_imports():
+    """compat.install(): the names the medimgen trainers import resolve to the B200 classes, in the
+    defining modules and in an already imported trainer module; uninstall() restores them. Dummy modules stand in for
+    medimgen / generative, which are not installed here."""
+    import sys
+    import types
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200 import compat
+
+    class Old:  # noqa: D401
+        pass
+
+    fakes = {}
+    for name in ("medimgen", "generative", "generative.networks"):
+        fakes[name] = types.ModuleType(name)
+        fakes[name].__path__ = []
+    for name, attrs in (("medimgen.diffusion_model_unet_with_strides", ["DiffusionModelUNet"]),
+                        ("medimgen.autoencoderkl_with_strides", ["AutoencoderKL"]),
+                        ("generative.networks.schedulers", ["DDPMScheduler"]),
+                        ("generative.inferers", ["DiffusionInferer", "LatentDiffusionInferer"])):
+        m = types.ModuleType(name)
+        for a in attrs:
+            setattr(m, a, Old)
+        fakes[name] = m
+    trainer = types.ModuleType("medimgen.train_ldm")
+    trainer.DiffusionModelUNet = Old      # `from ... import DiffusionModelUNet` done before install()
+    trainer.VQVAE = Old                   # untouched
+    fakes["medimgen.train_ldm"] = trainer
+    saved = {k: sys.modules.get(k) for k in fakes}
+    sys.modules.update(fakes)
+    try:
+        patched = compat.install()
+        assert "generative.inferers.LatentDiffusionInferer" in patched and "medimgen.train_ldm.DiffusionModelUNet" in patched
+        assert fakes["medimgen.diffusion_model_unet_with_strides"].DiffusionModelUNet is mig.DiffusionModelUNet
+        assert fakes["generative.networks.schedulers"].DDPMScheduler is mig.DDPMScheduler
+        assert trainer.DiffusionModelUNet is mig.DiffusionModelUNet and trainer.VQVAE is Old
+        compat.uninstall()
+        assert fakes["generative.inferers"].DiffusionInferer is Old and trainer.DiffusionModelUNet is Old
+    finally:
+        compat.uninstall()
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
