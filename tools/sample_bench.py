@@ -41,5 +41,17 @@ with torch.no_grad():
     e1.record()
     torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
+eager_ms = ms
+# the same loop through the public API with the model forward replayed from a CUDA graph (no gain here: the kernels
+# of a reverse step are long enough to keep the launch queue full)
+s.timesteps = s.timesteps[:steps + 3]            # DiffusionInferer.sample walks scheduler.timesteps
+with torch.no_grad():
+    torch.cuda.synchronize()
+    e0.record()
+    img = inf.sample(x, m, s, verbose=False, cuda_graph=True)
+    e1.record()
+    torch.cuda.synchronize()
+print(f"(CUDA-graph forward, incl. warm-up + capture) {e0.elapsed_time(e1) / (steps + 3):.2f} ms per reverse step")
+ms = eager_ms
 print(f"DDPM sampling widths {widths}: {ms:.2f} ms per reverse step -> {1000 * ms / 1e3:.1f} s per 1000-step volume -> "
       f"{60.0 / (1000 * ms / 1e3):.2f} volumes/min/GPU (extrapolated from {steps} timed steps); finite={bool(torch.isfinite(img).all())}")
