@@ -15,6 +15,8 @@ SHAPES = [  # (N, Cin, Cout, spatial) 3x3x3 stride 1 pad 1 -- the LDM-default U-
     (8, 768, 768, 12), (8, 768, 768, 6), (8, 1536, 768, 6)]
 if which == "big":
     SHAPES = SHAPES[:2]
+elif which == "deep":
+    SHAPES = SHAPES[3:]
 elif which == "mid":   # 64/128-channel layers of the AE / pixel-space U-Nets
     SHAPES = [(1, 64, 64, 64), (2, 64, 64, 48), (1, 128, 128, 32), (1, 64, 32, 96)]
 print(torch.cuda.get_device_name(0))
