@@ -227,6 +227,100 @@ __global__ void __launch_bounds__(256, CS == 1 ? 2 : 1) thin_wgrad_kernel(const 
   }
 }
 
+// The common case -- 3x3x3 filter on a 4x8x8 tile -- with everything known at compile time: the halo is 6x10x10, every
+// tap is an IMMEDIATE shared-memory offset, there is no per-tap branch, and the thread's 16 wide-tensor values of a tile
+// are requested before the first FMA (ncu on the generic kernel: 64 % of the executed instructions were address
+// arithmetic and per-tap branches, and 35 % of the stall samples waited on the wide-tensor load).
+template <int CD, int CS>
+__global__ void __launch_bounds__(256, CS == 1 ? 2 : 1) thin_wgrad_k3_kernel(const __nv_bfloat16* __restrict__ wide,
+                                                                            const __nv_bfloat16* __restrict__ thin,
+                                                                            float* __restrict__ dw, int out_mode,
+                                                                            ThinGeom g) {
+  constexpr int PAIRS = CD / 2, VL = 256 / PAIRS, NV = 256 / VL;   // channel pairs, voxel lanes, voxels per thread
+  constexpr int HY = 10, HX = 10;
+  extern __shared__ __align__(16) float sm[];
+  float* dw_s = sm;                      // [27][CS][CD]
+  float* halo = sm + 27 * CS * CD;       // [6][10][10][CS]
+  for (int i = threadIdx.x; i < 27 * CS * CD; i += 256) dw_s[i] = 0.f;
+  const int cp = threadIdx.x % PAIRS, vl = threadIdx.x / PAIRS;
+  const bool mirror = g.sign < 0;        // dgrad-style tap order (halo offset 2 - t)
+  float acc[27][CS][2];
+#pragma unroll
+  for (int a = 0; a < 27; ++a)
+#pragma unroll
+    for (int b = 0; b < CS; ++b) acc[a][b][0] = acc[a][b][1] = 0.f;
+  for (int64_t t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    int n, z0, y0, x0;
+    thin_tile_origin(g, t, n, z0, y0, x0);
+    // wide-tensor values of this thread's voxels first (up to 16 independent 4-byte loads), then the halo
+    constexpr int PF = NV > 16 ? 16 : NV;
+    __nv_bfloat162 wv[PF];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        const int v = vl + (k0 + k) * VL;
+        const int z = z0 + (v >> 6), y = y0 + ((v >> 3) & 7), x = x0 + (v & 7);
+        wv[k] = __floats2bfloat162_rn(0.f, 0.f);
+        if (z < g.od[0] && y < g.od[1] && x < g.od[2]) {
+          const int64_t m = (((int64_t)n * g.od[0] + z) * g.od[1] + y) * g.od[2] + x;
+          wv[k] = *reinterpret_cast<const __nv_bfloat162*>(wide + m * CD + 2 * cp);
+        }
+      }
+    };
+    fetch(0);
+    __syncthreads();
+    thin_load_halo(g, thin, halo, n, z0, y0, x0);
+    __syncthreads();
+#pragma unroll 1
+    for (int k0 = 0; k0 < NV; k0 += PF) {
+      if (k0 > 0) fetch(k0);
+#pragma unroll
+      for (int k = 0; k < PF; ++k) {
+        const int v = vl + (k0 + k) * VL;
+        const float* hb = halo + (((v >> 6) * HY + ((v >> 3) & 7)) * HX + (v & 7)) * CS;
+        const float w0 = __low2float(wv[k]), w1 = __high2float(wv[k]);
+        if (!mirror) {
+#pragma unroll
+          for (int a = 0; a < 27; ++a) {
+            const int off = (((a / 9) * HY + (a / 3) % 3) * HX + a % 3) * CS;
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+              const float s_ = hb[off + cs];
+              acc[a][cs][0] = fmaf(s_, w0, acc[a][cs][0]);
+              acc[a][cs][1] = fmaf(s_, w1, acc[a][cs][1]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < 27; ++a) {
+            const int off = (((2 - a / 9) * HY + (2 - (a / 3) % 3)) * HX + (2 - a % 3)) * CS;
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+              const float s_ = hb[off + cs];
+              acc[a][cs][0] = fmaf(s_, w0, acc[a][cs][0]);
+              acc[a][cs][1] = fmaf(s_, w1, acc[a][cs][1]);
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 27; ++a)
+#pragma unroll
+    for (int cs = 0; cs < CS; ++cs) {
+      atomicAdd(&dw_s[(a * CS + cs) * CD + 2 * cp], acc[a][cs][0]);
+      atomicAdd(&dw_s[(a * CS + cs) * CD + 2 * cp + 1], acc[a][cs][1]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 27 * CS * CD; i += 256) {
+    const int c = i % CD, cs = (i / CD) % CS, tap = i / (CD * CS);
+    const int64_t dst = out_mode == 0 ? ((int64_t)c * 27 + tap) * CS + cs : ((int64_t)cs * 27 + tap) * CD + c;
+    atomicAdd(dw + dst, dw_s[i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
@@ -293,8 +387,12 @@ static int launch_thin_wgrad(const ThinGeom& t, const void* wide, const void* th
   const int smem = (27 * CS * CD + thin_halo_floats(t)) * 4;
   int64_t grid = (int64_t)device_info().sm_count * 2;
   if (grid > t.num_tiles) grid = t.num_tiles;
-  thin_wgrad_kernel<CD, CS><<<(unsigned)grid, 256, smem, st>>>((const __nv_bfloat16*)wide, (const __nv_bfloat16*)thin, dw,
-                                                               out_mode, t);
+  if (t.ks[0] == 3 && t.ks[1] == 3 && t.ks[2] == 3 && t.tz == 4 && t.ty == 8 && t.tx == 8)
+    thin_wgrad_k3_kernel<CD, CS><<<(unsigned)grid, 256, smem, st>>>((const __nv_bfloat16*)wide, (const __nv_bfloat16*)thin,
+                                                                    dw, out_mode, t);
+  else
+    thin_wgrad_kernel<CD, CS><<<(unsigned)grid, 256, smem, st>>>((const __nv_bfloat16*)wide, (const __nv_bfloat16*)thin, dw,
+                                                                 out_mode, t);
   return check_launch("thin_wgrad_kernel");
 }
 
