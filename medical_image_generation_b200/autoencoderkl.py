@@ -265,8 +265,8 @@ class AutoencoderKL(nn.Module):
     @staticmethod
     def initialize(module):
         """ae:836-838 (InitWeights_He, ae:41-49): kaiming-normal filters, zero biases; applied with .apply()."""
-        from .layers import ConvNd
-        if isinstance(module, ConvNd):
+        from .layers import ConvNd, ConvTransposeNd
+        if isinstance(module, (ConvNd, ConvTransposeNd)):   # ae:46 also covers ConvTranspose{2,3}d
             with torch.no_grad():
                 w = torch.empty(module.weight.shape)
                 nn.init.kaiming_normal_(w, a=1e-2)

@@ -395,12 +395,8 @@ static int launch_flash(const CUtensorMap& qm, const CUtensorMap& km, const CUte
   };
   p.qk_stages = bytes(FA_QK_STAGES) <= 227 * 1024 - 4096 ? FA_QK_STAGES : 2;   // 4 KB left for static shared memory
   const int smem = bytes(p.qk_stages);
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(flash_fwd_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "flash_attention: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(flash_fwd_kernel<PASS>, smem, optin, "flash_attention")) return rc;
   flash_fwd_kernel<PASS><<<grid, (fa_softmax_warps(PASS) + 2) * 32, smem, st>>>(qm, km, vm, p);
   return check_launch("flash_fwd_kernel");
 }

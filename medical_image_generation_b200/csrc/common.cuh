@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -31,6 +32,27 @@ struct DeviceInfo {
 const DeviceInfo& device_info();
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Opt-in to > 48 KB of dynamic shared memory. cudaFuncSetAttribute is PER DEVICE, so the "already done" state is kept per
+// device (one process may drive several GPUs); atomics make concurrent first calls from several host threads benign (the
+// attribute call is idempotent).
+struct SmemOptIn {
+  std::atomic<int> bytes[16];
+};
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int smem, SmemOptIn& state, const char* what) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  if (state.bytes[dev].load(std::memory_order_acquire) >= smem) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot opt in to %d bytes of shared memory: %s", what, smem, cudaGetErrorString(e));
+    return 1;
+  }
+  state.bytes[dev].store(smem, std::memory_order_release);
+  return 0;
+}
 
 // ---- dtype helpers ------------------------------------------------------------------------------
 template <typename T>

@@ -351,12 +351,8 @@ static int launch_halo(const HaloProblem& h, const void* src, const void* wk, co
   const int nvox = p.hz * p.hy * p.hx;
   const int nstg = p.Npad > 32 ? 1 : 2;
   const int smem = T * 4 * p.Npad * 16 + nstg * (nvox * 64 + 128) + 2 * (nvox * 64 + 512 + 128) + 512;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "conv_halo: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(conv_halo_kernel, smem, optin, "conv_halo")) return rc;
   int64_t grid = device_info().sm_count;
   if (grid > p.num_tiles) grid = p.num_tiles;
   conv_halo_kernel<<<(unsigned)grid, H_THREADS, smem, as_stream(stream)>>>(xm, p);
@@ -688,12 +684,8 @@ int halo_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float
   if (halo_map(&dym, dy, p.N, p.OD, p.OH, p.OW, p.Cout, HT_X, HT_Y, 1)) return 1;
   const int nvox = p.hz * p.hy * p.hx;
   const int smem = (nvox * 64 + 128) + (128 * p.Cout * 2 + 128) + 2 * (nvox * 64 + 512 + 128) + 2 * 8 * (128 * 16 + 16) + 512;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "wgrad_halo: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = smem;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(wgrad_halo_kernel, smem, optin, "wgrad_halo")) return rc;
   int64_t pairs = device_info().sm_count / 2;
   if (pairs > p.num_tiles) pairs = p.num_tiles;
   if (pairs < 1) pairs = 1;

@@ -669,12 +669,8 @@ static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const C
                            cudaStream_t st) {
   constexpr int stage = MT * TBM * 128 + BN * 128;
   constexpr int smem = stages_of(stage) * stage + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "conv_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(conv_tma_kernel<BN, MT>, smem, optin, "conv_tma")) return rc;
   conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, p);
   return check_launch("conv_tma_kernel");
 }
@@ -903,12 +899,8 @@ static int launch_wgrad_tma(const CUtensorMap& dym, const CUtensorMap& xm, const
                             cudaStream_t st) {
   constexpr int stage = (2 * MT + BN / 64) * PANEL;
   constexpr int smem = stages_of(stage) * stage + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "wgrad_tma: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(wgrad_tma_kernel<BN, MT>, smem, optin, "wgrad_tma")) return rc;
   wgrad_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(dym, xm, p);
   return check_launch("wgrad_tma_kernel");
 }

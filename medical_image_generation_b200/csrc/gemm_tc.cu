@@ -279,12 +279,8 @@ static int pick_bn(int cdst) { return cdst > 128 ? 256 : (cdst > 64 ? 128 : (cds
 template <int BN>
 static int launch_conv_tc(const CUtensorMap& wmap, const ConvTcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = stages_for(BN) * (TBM * 128 + BN * 128) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "conv_tc: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(conv_tc_kernel<BN>, smem, optin, "conv_tc")) return rc;
   conv_tc_kernel<BN><<<grid, kThreads, smem, st>>>(wmap, p);
   return check_launch("conv_tc_kernel");
 }

@@ -197,12 +197,8 @@ bool tc_wgrad_eligible(const mig_conv_geom* g) {
 template <int BN>
 static int launch_wgrad(const CUtensorMap& map, const WgradParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = stages2_for(BN) * (2 * PANEL + (BN / 64) * PANEL) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "wgrad_tc: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(wgrad_tc_kernel<BN>, smem, optin, "wgrad_tc")) return rc;
   wgrad_tc_kernel<BN><<<grid, kThreads, smem, st>>>(map, p);
   return check_launch("wgrad_tc_kernel");
 }
@@ -446,12 +442,8 @@ bool tc_gemm_eligible(const mig_gemm_desc* d, int dtype_ab, int dtype_c) {
 template <int BN>
 static int launch_gemm(const CUtensorMap& am, const CUtensorMap& bm, const GemmTcParams& p, dim3 grid, cudaStream_t st) {
   constexpr int smem = stages2_for(BN) * (TBM * 128 + BN * 128) + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    MIG_REQUIRE(e == cudaSuccess, "gemm_tc: cannot opt in to %d bytes of shared memory: %s", smem, cudaGetErrorString(e));
-    configured = true;
-  }
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(gemm_tc_kernel<BN>, smem, optin, "gemm_tc")) return rc;
   gemm_tc_kernel<BN><<<grid, kThreads, smem, st>>>(am, bm, p);
   return check_launch("gemm_tc_kernel");
 }

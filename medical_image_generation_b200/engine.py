@@ -124,6 +124,7 @@ class FlatAdamW:
                 p.data = view
             p.main_grad = self.grad[off:off + k].as_strided(p.shape, p.stride())
             p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
+            p._mig_shadow_version = p._version   # ops._filter_for re-casts the slot when the master changed in place
             p._mig_slot = (off, k)
             self.params.append((n, p))
             off += pad(k)
@@ -135,11 +136,13 @@ class FlatAdamW:
         if _dist_on():
             self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
             self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
-            ops.set_grad_ready_hook(self._grad_ready)
+        # every owned parameter carries the callback of ITS optimiser (several FlatAdamW instances can coexist)
+        for _, p in self.params:
+            p._mig_grad_ready = self._grad_ready
 
     # called from the backward kernels' wrappers once a parameter's gradient is complete in `main_grad`
     def _grad_ready(self, p) -> None:
-        if not self._sync_enabled:   # gradient accumulation: only the last micro-step's backward reduces
+        if self.buckets is None or not self._sync_enabled:   # accumulation: only the last micro-step reduces
             return
         i = self._index_of.get(id(p))
         if i is not None:
@@ -178,6 +181,14 @@ class FlatAdamW:
              self.used_numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
              float(self.weight_decay), int(self.step_count), sumsq_ptr, max_norm, ops._ptr(self.shadow),
              ops._ptr(self.step_dev), st)
+
+    def refresh_shadow(self) -> None:
+        """Re-derive the whole bf16 shadow from the fp32 master (one cast launch). Needed only after writing to
+        `self.master` directly; in-place changes through the nn.Parameters (load_state_dict, copy_, initialize) are
+        detected per parameter by ops._filter_for via the autograd version counter."""
+        call("mig_cast", 0, 1, ops._ptr(self.master), ops._ptr(self.shadow), self.master.numel(), ops._stream())
+        for _, p in self.params:
+            p._mig_shadow_version = p._version
 
     def grad_norm(self) -> torch.Tensor:
         """Global gradient norm of the last step() (device scalar; no sync)."""
@@ -229,7 +240,9 @@ class FlatAdamW:
         self.step_dev.fill_(step)
 
     def close(self) -> None:
-        ops.set_grad_ready_hook(None)
+        for _, p in self.params:
+            if getattr(p, "_mig_grad_ready", None) == self._grad_ready:
+                p._mig_grad_ready = None
 
 
 class LDMTrainer:
@@ -249,8 +262,7 @@ class LDMTrainer:
                              bucket_mb=bucket_mb)
         if _dist_on():  # identical replicas: broadcast rank 0's parameters (flat: one collective)
             dist.broadcast(self.opt.master, src=0)
-            call("mig_cast", 0, 1, ops._ptr(self.opt.master), ops._ptr(self.opt.shadow), self.opt.master.numel(),
-                 ops._stream())
+            self.opt.refresh_shadow()
         # CUDA graph of the whole step (add_noise -> U-Net fwd -> MSE -> bwd -> all-reduce -> clip -> AdamW): the
         # step is ~1300 kernel launches, so replaying one graph removes the launch gaps. The first
         # `graph_warmup_steps` calls run eagerly (they are real optimiser steps), the next call is captured.
@@ -278,11 +290,15 @@ class LDMTrainer:
             self._static_x = x0.clone()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            saved = (self.opt.step_count, self._micro)   # host state the captured (never executed) step advances
             try:
                 with torch.cuda.graph(graph):
                     self._static_loss = self._eager_step(self._static_x, None, None)
             except Exception as e:  # noqa: BLE001 -- fall back loudly, never silently change numerics
                 self.cuda_graph = False
+                self.opt.step_count, self._micro = saved
+                if self.opt.buckets is not None:
+                    self.opt.buckets.reset()
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the training step failed ({e}); continuing eagerly")
                 torch.cuda.synchronize()
@@ -343,8 +359,7 @@ class AETrainer:
                              bucket_mb=bucket_mb, unused=("proj_attn",))
         if _dist_on():
             dist.broadcast(self.opt.master, src=0)
-            call("mig_cast", 0, 1, ops._ptr(self.opt.master), ops._ptr(self.opt.shadow), self.opt.master.numel(),
-                 ops._stream())
+            self.opt.refresh_shadow()
 
     def step(self, images: torch.Tensor, eps: Optional[torch.Tensor] = None) -> torch.Tensor:
         last = self._micro + 1 >= self.grad_accumulate_step

@@ -188,15 +188,6 @@ def _conv_call(kind, geom, name, *args):
     _PROFILE.append((kind, flops, (geom.Cin, geom.Cout, od, ks), e0, e1))
 
 
-_grad_ready_hook = None
-
-
-def set_grad_ready_hook(fn) -> None:
-    """engine.FlatAdamW registers a callback fired when a parameter's gradient is complete in `param.main_grad`."""
-    global _grad_ready_hook
-    _grad_ready_hook = fn
-
-
 def _deliver(param, grad):
     """Route a parameter gradient: into `param.main_grad` (flat-buffer view owned by engine.FlatAdamW) when present --
     returning None to autograd -- else hand it to autograd unchanged. `grad=None` means the kernel already accumulated
@@ -208,8 +199,9 @@ def _deliver(param, grad):
         return grad
     if grad is not None:
         mg.add_(grad)
-    if _grad_ready_hook is not None:
-        _grad_ready_hook(param)
+    hook = getattr(param, "_mig_grad_ready", None)   # set per parameter by the engine.FlatAdamW that owns it
+    if hook is not None:
+        hook(param)
     return None
 
 
@@ -217,6 +209,12 @@ def _filter_for(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     if dtype == torch.bfloat16:
         shadow = getattr(weight, "_mig_shadow", None)  # bf16 copy kept current by the fused AdamW kernel
         if shadow is not None:
+            # The fused AdamW kernel writes master + shadow together and never bumps the autograd version counter, so
+            # a version that differs from the one recorded at the last refresh means somebody ELSE changed the fp32
+            # master in place (load_state_dict after the trainer was built -- the reference's resume order,
+            # train_ldm.py:522-525 --, AutoencoderKL.initialize, zero_module, copy_): re-cast this parameter's slot.
+            if weight._version != weight._mig_shadow_version:
+                refresh_shadow(weight)
             return shadow
     w = weight.detach()
     if not _is_cl(w):
@@ -234,6 +232,14 @@ def _filter_for(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     call("mig_cast", _dt(w), _dt(wk), _ptr(w), _ptr(wk), w.numel(), _stream())
     cache[dtype] = (stamp, wk)
     return wk
+
+
+def refresh_shadow(weight) -> None:
+    """Re-cast one parameter's fp32 master slot into its bf16 shadow slot (both are the same strided view of a
+    contiguous, 64-element aligned slot of the flat buffers owned by engine.FlatAdamW)."""
+    shadow = weight._mig_shadow
+    call("mig_cast", F32, BF16, _ptr(weight), _ptr(shadow), weight.numel(), _stream())
+    weight._mig_shadow_version = weight._version
 
 
 def clear_caches() -> None:

@@ -75,12 +75,17 @@ def run_case(name: str, case: dict) -> dict:
 
 def main():
     os.makedirs(OUT, exist_ok=True)
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]   # python -m oracle.gen_golden [case ...]
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         g = run_case(name, case)
         path = os.path.join(OUT, name + ".pt")
         torch.save(g, path)
         print(f"{name}: out {tuple(g['out'].shape)} |out|max {float(g['out'].abs().max()):.4f} "
               f"params {sum(torch.Size(s).numel() for s in g['shapes'].values())} -> {os.path.getsize(path)/1e3:.0f} kB")
+    if only and "planner" not in only:
+        return
     # planner goldens: the four pure functions of configuration.py:751-902
     pf = ref.planner_functions()
     sizes = [[96, 96, 96], [24, 24, 24], [128, 128, 64], [160, 160, 128], [64, 64], [32, 32, 16], [40, 40, 32],

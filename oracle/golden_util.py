@@ -17,6 +17,13 @@ CASES = {
         spatial_dims=3, in_channels=3, out_channels=3, num_res_blocks=2, num_channels=[32, 64, 96],
         attention_levels=[False, True, True], num_head_channels=[0, 64, 96], norm_num_groups=16,
         strides=[[1, 1, 1], [2, 2, 2], [2, 2, 2]], kernel_sizes=[[3, 3, 3]] * 3, paddings=[[1, 1, 1]] * 3)),
+    # BASELINE config 3 at FULL width (create_ddpm_dict: 256/512/768, one 512-/768-channel head per attention level,
+    # 441 M parameters; K up to 41 472, 1536-channel skip-concat inputs) on a small latent so the CPU reference finishes
+    # in seconds. Parameters are re-drawn from the seed (never stored), so the golden stays ~1.5 MB.
+    "unet3d_ldm_width": dict(kind="unet", batch=2, in_shape=(3, 8, 8, 8), cfg=dict(
+        spatial_dims=3, in_channels=3, out_channels=3, num_res_blocks=2, num_channels=[256, 512, 768],
+        attention_levels=[False, True, True], num_head_channels=[0, 512, 768], norm_num_groups=32,
+        strides=[[1, 1, 1], [2, 2, 2], [2, 2, 2]], kernel_sizes=[[3, 3, 3]] * 3, paddings=[[1, 1, 1]] * 3)),
     # anisotropic strides, multi-head attention, odd spatial sizes (BASELINE config 4 shape class)
     "unet3d_aniso": dict(kind="unet", batch=1, in_shape=(1, 12, 12, 6), cfg=dict(
         spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=[16, 32, 64],

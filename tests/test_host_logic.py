@@ -180,6 +180,63 @@ def test_planner_shapes_for_baseline_configs():
     assert p[0][1] == [3, 3, 1] and p[0][2] == [1, 1, 0]
 
 
+def test_package_planner_matches_reference_golden(golden):
+    """The PACKAGE planner (medical_image_generation_b200/planner.py, what bench.py and users call) against the values the
+    unmodified reference functions produced (tests/golden/planner.pt, configuration.py:751-818)."""
+    from medical_image_generation_b200 import planner
+    plan = golden("planner")
+    assert len(plan["params"]) >= 27
+    for (size, n), want in plan["params"].items():
+        got = planner.compute_downsample_parameters(list(size), n)
+        assert got == want, (size, n)
+        assert planner.compute_output_size(list(size), got) == plan["out"][(size, n)]
+
+
+def test_package_planner_kwargs_match_reference_dicts():
+    """create_autoencoder_dict / create_ddpm_dict (configuration.py:821-902) run live from the reference when it is
+    present: the constructor kwargs the package planner emits must equal the reference's `vae_params` / `ddpm_params`."""
+    from oracle import reference_loader as ref
+    from medical_image_generation_b200 import planner
+    if not ref.available():
+        pytest.skip("reference checkout not present on this box")
+    pf = ref.planner_functions()
+    for patch, in_ch in (([96, 96, 96], 1), ([160, 160, 128], 2), ([448, 512, 512], 1), ([64, 64], 1)):
+        nd = len(patch)
+        ds_cfg = {"median_shape": patch, "max_shape": patch if nd == 3 else [1] + patch}
+        vae = pf["create_autoencoder_dict"](ds_cfg, list(range(in_ch)), nd)
+        mine = planner.autoencoder_kwargs(patch, in_channels=in_ch)
+        assert set(vae) == set(mine)
+        for k, v in vae.items():
+            assert mine[k] == v, (patch, k, mine[k], v)
+        ddpm = pf["create_ddpm_dict"](ds_cfg, nd)
+        latent = planner.compute_output_size(patch, mine["downsample_parameters"])
+        got = planner.ddpm_kwargs(latent, latent_channels=8)
+        assert set(ddpm) == set(got)
+        for k, v in ddpm.items():
+            assert got[k] == v, (patch, k, got[k], v)
+
+
+def test_autoencoder_initialize_covers_transposed_convs():
+    """InitWeights_He (ae:41-49) re-initialises Conv AND ConvTranspose filters (kaiming normal, a=1e-2) and zeroes biases."""
+    from medical_image_generation_b200.layers import ConvNd, ConvTransposeNd
+    cfg = dict(CASES["ae3d_convtranspose"]["cfg"])
+    m = mig.AutoencoderKL(**cfg)
+    before = {n: p.detach().clone() for n, p in m.named_parameters()}
+    torch.manual_seed(0)
+    m.apply(m.initialize)
+    seen_t = 0
+    for name, mod in m.named_modules():
+        if isinstance(mod, (ConvNd, ConvTransposeNd)):
+            seen_t += isinstance(mod, ConvTransposeNd)
+            assert float(mod.bias.abs().max()) == 0.0, name
+            assert not torch.equal(mod.weight, before[name + ".weight"]), name
+            fan_in = mod.weight.shape[1] * int(np.prod(mod.weight.shape[2:]))
+            want_std = (2.0 / (1 + 1e-2 ** 2)) ** 0.5 / fan_in ** 0.5
+            if mod.weight.numel() >= 2048:
+                assert abs(float(mod.weight.std()) / want_std - 1) < 0.15, name
+    assert seen_t >= 1
+
+
 def test_compat_install_rebinds_trainer_imports():
     """compat.install(): the names the medimgen trainers import resolve to the B200 classes, in the
     defining modules and in an already imported trainer module; uninstall() restores them. Dummy modules stand in for

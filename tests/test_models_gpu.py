@@ -20,7 +20,8 @@ def _build(g, dtype):
     return m.to(DEV).train(), params
 
 
-UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond", "unet3d_updown"]
+# unet3d_ldm_width: BASELINE config 3 at FULL width (256/512/768, 441 M parameters, single 512-/768-channel heads) on 2x3x8^3
+UNETS = ["unet3d_small", "unet3d_aniso", "unet2d_small", "unet3d_cond", "unet3d_updown", "unet3d_ldm_width"]
 AES = ["ae3d_small", "ae3d_attn_aniso", "ae2d_small", "ae3d_convtranspose"]
 
 
@@ -215,37 +216,145 @@ def test_inferer_concat_conditioning(golden):
         mig.DiffusionInferer(s)(x0.to(DEV), m, noise.to(DEV), t.to(DEV), condition=cond.to(DEV), mode="film")
 
 
-def test_train_step_loss_curve_tracks_oracle(golden):
-    """20 AdamW steps of epsilon-prediction training (train_ldm.py:143-183 semantics) on the small 3-D U-Net:
-    fp32 CUDA path vs the oracle driven by torch.optim.AdamW on CPU, same data/noise/timesteps."""
-    import medical_image_generation_b200 as mig
+_CURVE_CACHE = {}
+
+
+def _oracle_loss_curve(g, steps, lr):
+    """`steps` AdamW steps of epsilon-prediction training (train_ldm.py:143-183 semantics) of the oracle U-Net driven
+    by torch.optim.AdamW + clip_grad_norm_ on CPU fp32. Returns (losses, batches) so the CUDA path sees the same data."""
     from oracle import torch_oracle as O
     from oracle.ddpm_oracle import OracleDDPMScheduler
     from oracle.golden_util import golden_params
-    g = golden("unet3d_aniso")
-    m, _ = _build(g, torch.float32)
+    key = (g["name"], steps, lr)
+    if key in _CURVE_CACHE:
+        return _CURVE_CACHE[key]
     ref_params = {k: v.clone().requires_grad_(True) for k, v in golden_params(g["shapes"], g["seed"]).items()}
-    used = [k for k in ref_params if "proj_attn" not in k]
-    opt_ref = torch.optim.AdamW([ref_params[k] for k in used], lr=1e-4)
-    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
-    kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
-    s, o = mig.DDPMScheduler(**kw), OracleDDPMScheduler(**kw)
+    used = [ref_params[k] for k in ref_params if "proj_attn" not in k]
+    opt_ref = torch.optim.AdamW(used, lr=lr)
+    o = OracleDDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
     gen = torch.Generator().manual_seed(5)
-    curve, curve_ref = [], []
-    for step in range(20):
-        x0 = torch.randn(2, 1, 12, 12, 6, generator=gen)
+    B = g["batch"]
+    shape = tuple(g["inputs"]["x"].shape[1:])
+    curve, batches = [], []
+    for _ in range(steps):
+        x0 = torch.randn((B, *shape), generator=gen)
         noise = torch.randn(x0.shape, generator=gen)
-        t = torch.randint(0, 1000, (2,), generator=gen)
-        loss_ref = torch.nn.functional.mse_loss(O.unet_forward(ref_params, g["cfg"], o.add_noise(x0, noise, t), t), noise)
-        opt_ref.zero_grad(); loss_ref.backward()
-        torch.nn.utils.clip_grad_norm_([ref_params[k] for k in used], 1.0); opt_ref.step()
+        t = torch.randint(0, 1000, (B,), generator=gen)
+        loss = torch.nn.functional.mse_loss(O.unet_forward(ref_params, g["cfg"], o.add_noise(x0, noise, t), t), noise)
+        opt_ref.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(used, 1.0)
+        opt_ref.step()
+        curve.append(float(loss))
+        batches.append((x0, noise, t))
+    _CURVE_CACHE[key] = (curve, batches)
+    return curve, batches
+
+
+CURVE_STEPS = 200          # north_star: "200-step loss curves tracking"
+CURVE_TOL_FP32 = 1e-2      # every one of the 200 losses within 1 % of the oracle's (fp32 CUDA-core path, torch AdamW)
+CURVE_TOL_BF16_STEP = 0.10  # bf16 production path (flat fused AdamW, bf16 shadow weights): every loss within 10 % ...
+CURVE_TOL_BF16_MEAN = 0.02  # ... and the mean |relative deviation| over the 200 steps within 2 %
+
+
+def test_train_step_loss_curve_tracks_oracle_fp32(golden):
+    """200 AdamW steps on the small anisotropic 3-D U-Net: fp32 CUDA path + torch.optim.AdamW vs the oracle on CPU, same
+    data / noise / timesteps every step."""
+    import medical_image_generation_b200 as mig
+    g = golden("unet3d_aniso")
+    curve_ref, batches = _oracle_loss_curve(g, CURVE_STEPS, 1e-4)
+    m, _ = _build(g, torch.float32)
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4)
+    s = mig.DDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    curve = []
+    for x0, noise, t in batches:
         pred = m(s.add_noise(x0.to(DEV), noise.to(DEV), t.to(DEV)), t.to(DEV))
         loss = mig.ops.mse_loss(pred, noise.to(DEV))
-        opt.zero_grad(set_to_none=True); loss.backward()
-        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0); opt.step()
-        curve.append(float(loss)); curve_ref.append(float(loss_ref))
-    assert max(abs(a - b) / abs(b) for a, b in zip(curve, curve_ref)) < 2e-3, (curve, curve_ref)
-    assert curve[-1] < curve[0]
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        opt.step()
+        curve.append(float(loss))
+    dev = [abs(a - b) / abs(b) for a, b in zip(curve, curve_ref)]
+    print(f"fp32 loss curve: max rel dev {max(dev):.3e} (first 20: {max(dev[:20]):.3e}), loss {curve_ref[0]:.4f} -> {curve_ref[-1]:.4f}")
+    assert max(dev[:20]) < 2e-3, dev[:20]
+    assert max(dev) < CURVE_TOL_FP32, max(dev)
+    assert sum(curve[-20:]) < sum(curve[:20])
+
+
+def test_train_step_loss_curve_tracks_oracle_bf16(golden):
+    """The PRODUCTION path over the same 200 steps: bf16 tensor-core kernels, engine.LDMTrainer (flat fused clip + AdamW,
+    bf16 shadow weights) against the fp32 oracle + torch.optim.AdamW. bf16 rounding makes single losses wobble, so the
+    bar is per-step <= 10 % and mean |deviation| <= 2 % (stated tolerances; fp32 bar is 1 %)."""
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200.engine import LDMTrainer
+    g = golden("unet3d_aniso")
+    curve_ref, batches = _oracle_loss_curve(g, CURVE_STEPS, 1e-4)
+    m, _ = _build(g, torch.bfloat16)
+    s = mig.DDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    tr = LDMTrainer(m, s, lr=1e-4, grad_clip_max_norm=1.0)
+    curve = [float(tr.step(x0.to(DEV), noise=noise.to(DEV), timesteps=t.to(DEV))) for x0, noise, t in batches]
+    tr.opt.close()
+    dev = [abs(a - b) / abs(b) for a, b in zip(curve, curve_ref)]
+    print(f"bf16 loss curve: max rel dev {max(dev):.3e}, mean {sum(dev) / len(dev):.3e}")
+    assert max(dev) < CURVE_TOL_BF16_STEP, max(dev)
+    assert sum(dev) / len(dev) < CURVE_TOL_BF16_MEAN
+    assert sum(curve[-20:]) < sum(curve[:20])
+
+
+def test_shadow_follows_in_place_parameter_changes(golden):
+    """Reference resume order (train_ldm.py:522-525): the optimiser exists BEFORE load_model() copies the checkpoint into
+    the parameters. The bf16 shadow the tensor-core kernels read must follow such in-place changes of the fp32 master."""
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200.engine import LDMTrainer
+    from oracle.golden_util import golden_params
+    g = golden("unet3d_small")
+    s = mig.DDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    m = mig.DiffusionModelUNet(**g["cfg"], compute_dtype=torch.bfloat16).to(DEV)     # random init ...
+    tr = LDMTrainer(m, s)                                                               # ... shadow = random init
+    m.load_state_dict(golden_params(g["shapes"], g["seed"]))                            # checkpoint arrives afterwards
+    fresh, _ = _build(g, torch.bfloat16)
+    x = g["inputs"]["x"].to(DEV)
+    t = g["inputs"]["timesteps"].to(DEV)
+    with torch.no_grad():
+        got, want = m.eval()(x, t), fresh.eval()(x, t)
+    assert rel_err(got, want) < 1e-6 and rel_err(got, g["out"]) < BF16_TOL
+    with torch.no_grad():   # a later manual edit of one filter is picked up as well
+        m.conv_in.conv.weight.mul_(0.5)
+        fresh.conv_in.conv.weight.mul_(0.5)
+        assert rel_err(m(x, t), fresh(x, t)) < 1e-6
+    tr.opt.close()
+
+
+def test_graph_capture_failure_leaves_clean_state(golden, monkeypatch):
+    """A failed CUDA-graph capture falls back to eager steps without leaving the host step counter ahead of the
+    device counter (the captured-but-never-executed step must not count)."""
+    import medical_image_generation_b200 as mig
+    from medical_image_generation_b200.engine import LDMTrainer
+    g = golden("unet3d_small")
+    m, _ = _build(g, torch.bfloat16)
+    s = mig.DDPMScheduler(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+    tr = LDMTrainer(m, s, cuda_graph=True, graph_warmup_steps=1)
+    x = torch.randn(2, 3, 8, 8, 8, device=DEV)
+    tr.step(x)
+    real = tr._eager_step
+    calls = {"n": 0}
+
+    def flaky(*a, **k):
+        calls["n"] += 1
+        out = real(*a, **k)
+        if calls["n"] == 1:     # inside the capture: the step body ran on the host, then capture "fails"
+            raise RuntimeError("injected capture failure")
+        return out
+
+    monkeypatch.setattr(tr, "_eager_step", flaky)
+    with pytest.warns(UserWarning, match="capture of the training step failed"):
+        tr.step(x)
+    tr.step(x)
+    torch.cuda.synchronize()
+    assert tr.cuda_graph is False
+    assert tr.opt.step_count == int(tr.opt.step_dev) == 3
+    tr.opt.close()
 
 
 def test_flat_engine_matches_torch_optimizer(golden):

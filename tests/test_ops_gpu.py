@@ -130,6 +130,39 @@ def test_conv_fwd_bwd(case, dtype, engine):
     assert wd.grad.dtype == torch.float32
 
 
+# BASELINE config 3 layer shapes at FULL size (production engine only; the CPU reference of each takes seconds)
+WIDE_CONV_CASES = [
+    (2, 1536, 768, (6, 6, 6), (3, 3, 3), (1, 1, 1), (1, 1, 1)),    # first up-block resnet: K = 41 472 over a skip concat
+    (2, 1024, 512, (12, 12, 12), (3, 3, 3), (1, 1, 1), (1, 1, 1)),  # 512+512 concat input at the 12^3 level
+    (8, 512, 512, (24, 24, 24), (3, 3, 3), (1, 1, 1), (1, 1, 1)),   # the Upsample conv: the single largest layer
+    (8, 512, 512, (12, 12, 12), (3, 3, 3), (2, 2, 2), (1, 1, 1)),   # Downsample 12^3 -> 6^3
+    (8, 1536, 768, (6, 6, 6), (1, 1, 1), (1, 1, 1), (0, 0, 0)),     # 1x1x1 skip connection over the widest concat
+]
+
+
+@pytest.mark.parametrize("case", WIDE_CONV_CASES)
+def test_conv_fwd_bwd_baseline_width(case):
+    ops = _ops()
+    N, Cin, Cout, sp, k, s, p = case
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = bf16_round(torch.randn((N, Cin, *sp), generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, *k), generator=g) / math.sqrt(Cin * math.prod(k)))
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y_ref = _conv_ref(xr, wr, br, s, p)
+    probe = torch.randn(y_ref.shape, generator=g)
+    (y_ref * probe).sum().backward()
+    xd = _cl(x.to(DEV).to(torch.bfloat16)).requires_grad_(True)
+    wd = _cl(w.to(DEV)).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True)
+    y = ops.conv_nd(xd, wd, bd, s, p)
+    (y.float() * probe.to(DEV)).sum().backward()
+    assert rel_err(y, y_ref) < BF16_TOL
+    assert rel_err(xd.grad, xr.grad) < BF16_TOL
+    assert rel_err(wd.grad, wr.grad) < BF16_TOL
+    assert rel_err(bd.grad, br.grad) < BF16_TOL
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("rows,K,O,bias", [(5, 32, 48, True), (300, 64, 64, True), (7, 24, 16, False),
                                             (1000, 256, 512, True), (2, 1024, 768, True)])
