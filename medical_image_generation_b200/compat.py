@@ -17,12 +17,23 @@ imported them -- to the B200 implementations, so an unmodified trainer builds an
 
 Nothing else of `generative` / `medimgen` is touched (VQVAE, discriminators, losses, metrics, data loading stay the
 reference's). `uninstall()` restores the original bindings.
+
+Where `monai-generative` is not installed at all, `install()` puts the package's own minimal `generative` on sys.path
+(`medical_image_generation_b200/shims/generative`: scheduler + inferers = the B200 classes, placeholders for what the
+step never executes). Where the reference's two model files cannot be imported (they need MONAI), modules of the same
+names exposing the B200 classes are registered instead, so `from medimgen.diffusion_model_unet_with_strides import
+DiffusionModelUNet` in an unmodified trainer still resolves.
 """
 from __future__ import annotations
 
 import importlib
+import importlib.util
+import os
 import sys
+import types
 from typing import Dict, List, Tuple
+
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
 
 _DEFINING = {
     "medimgen.diffusion_model_unet_with_strides": ("DiffusionModelUNet",),
@@ -46,13 +57,29 @@ def install(strict: bool = False) -> List[str]:
     repl = _replacements()
     patched: List[str] = []
     originals = {}
+    try:
+        have_generative = importlib.util.find_spec("generative") is not None
+    except (ImportError, ValueError):
+        have_generative = "generative" in sys.modules
+    if not have_generative and _SHIMS not in sys.path:
+        sys.path.append(_SHIMS)          # appended: a real monai-generative always wins
+        patched.append("sys.path+=shims/generative")
     for modname, names in _DEFINING.items():
         try:
             mod = importlib.import_module(modname)
         except ImportError:
-            if strict:
-                raise
-            continue
+            parent = modname.rsplit(".", 1)[0]
+            try:
+                importlib.import_module(parent)
+            except ImportError:
+                if strict:
+                    raise
+                continue
+            # the package exists but this module's own imports fail (MONAI missing): stand-in module of the same name
+            mod = types.ModuleType(modname)
+            mod.__doc__ = f"registered by medical_image_generation_b200.compat: B200 classes under {modname}"
+            sys.modules[modname] = mod
+            _saved.append((sys.modules, modname, None))
         for name in names:
             if hasattr(mod, name):
                 originals[name] = getattr(mod, name)
@@ -77,4 +104,12 @@ def uninstall() -> None:
     """Undo install()."""
     while _saved:
         mod, name, old = _saved.pop()
-        setattr(mod, name, old)
+        if mod is sys.modules:
+            sys.modules.pop(name, None)
+        else:
+            setattr(mod, name, old)
+    if _SHIMS in sys.path:
+        sys.path.remove(_SHIMS)
+        for k in [k for k in sys.modules if k == "generative" or k.startswith("generative.")]:
+            if getattr(sys.modules[k], "__file__", None) and sys.modules[k].__file__.startswith(_SHIMS):
+                del sys.modules[k]

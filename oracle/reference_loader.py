@@ -1,6 +1,7 @@
-"""Import the UNMODIFIED reference model files from /root/reference under the MONAI shim.
+"""Import the UNMODIFIED reference model files from /root/reference (build container) or from the byte-for-byte copies
+staged into the git-ignored baseline/_ref/ (GPU box; oracle/stage_reference.py) under the MONAI shim.
 
-Only usable in the build container (the GPU box has no /root/reference). Used by
+TEST / BENCH-BASELINE INFRASTRUCTURE. Used by
 oracle/gen_golden.py to produce tests/golden/*.pt and by CPU tests (skipped when absent) that
 pin oracle/torch_oracle.py against the real thing.
 """
@@ -11,7 +12,11 @@ import importlib.util
 import os
 import sys
 
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 REFERENCE_ROOT = os.environ.get("MEDIMGEN_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "medimgen", "diffusion_model_unet_with_strides.py")):
+    # the GPU box has no /root/reference: use the byte-for-byte copies staged by oracle/stage_reference.py (git-ignored)
+    REFERENCE_ROOT = _STAGED
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
 _cache: dict = {}
 
