@@ -129,7 +129,8 @@ def test_unmodified_train_ldm_runs_on_b200_modules(trainer_env, tmp_path):
     t = torch.tensor([5], device="cuda")
     with torch.no_grad():
         a, b = ldm.ddpm.eval()(x, t), ldm2.ddpm.eval()(x, t)
-    assert torch.equal(a, b)
+    # same weights -> same output up to the bf16 noise of atomically reduced GroupNorm statistics (random weights: ~1)
+    assert float((a - b).norm() / b.norm()) < 2e-2
     # sampling through the reference's sample_images (train_ldm.py:332-366): full reverse process of T = 12 steps + decode
     imgs = ldm.sample_images(z_shape, inferer, verbose=False, seed=42)
     assert tuple(imgs.shape) == (2, 1, 16, 16, 16) and torch.isfinite(imgs).all()
