@@ -28,7 +28,7 @@ extern "C" {
 #define MIG_F32 0
 #define MIG_BF16 1
 
-#define MIG_ABI_VERSION 1
+#define MIG_ABI_VERSION 2
 
 /* Geometry of one N-d convolution (1 <= nd <= 3 handled by setting leading dims to 1). */
 typedef struct {
@@ -43,6 +43,16 @@ const char* mig_last_error(void);
 int mig_abi_version(void);
 /* 1 when the running device is sm_100 and the tcgen05 kernels are usable */
 int mig_has_tcgen05(void);
+
+/* mig_conv_fwd that ALSO delivers the GroupNorm statistics of its output (north_star: "GroupNorm statistics ... fused
+ * into the ... epilogue"): gn_sums[n][g][2] (fp64) = (sum y, sum y^2) per (sample, group) of the bf16-rounded result,
+ * consumed by mig_groupnorm_apply for the GroupNorm that follows the convolution (unet:648 after conv1, unet:628 of the
+ * next block after conv2, ae:167). Accumulated by the tcgen05 kernel's epilogue (warp-shuffle reduction of the fp32
+ * tile, fp64 red.global per (CTA, group)); plans whose epilogue only sees partial sums (split-K) and the other engines
+ * run one statistics pass over y instead. Needs mig_groupnorm_can_split(dtype, N, out voxels, Cout, gn_groups). */
+int mig_conv_fwd_stats(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+                       const float* chan_bias, const void* residual, void* y, double* gn_sums, int32_t gn_groups,
+                       int engine, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- K1/K2/K3: Conv{2,3}d as implicit GEMM -------------------------------------------------------
  * replaces nn.Conv{2,3}d inside monai Convolution: unet:510-518,557-565,630-659,664,1820,1935;
@@ -89,11 +99,23 @@ int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* o
 int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y,
                       float* mean, float* rstd, int32_t N, int64_t S, int32_t C, int32_t G, float eps,
                       int fuse_silu, void* workspace, int64_t workspace_bytes, void* stream);
+/* dx_colsum (optional, [N][C] fp32): receives sum_s dx[n,s,c] -- the bias / time-embedding gradient of the convolution
+ * that produced x (unet:691-695), so that convolution's backward needs no column-sum pass over dy. */
 int mig_groupnorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* beta,
-                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                      const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
                       int32_t N, int64_t S, int32_t C, int32_t G, int fuse_silu,
                       void* workspace, int64_t workspace_bytes, void* stream);
 int64_t mig_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t G);
+/* The two halves of the forward as separate entry points (bf16, C a multiple of 32: mig_groupnorm_can_split() == 1).
+ * sums: double [N][G][2] = (sum x, sum x^2) per (sample, group) -- written by mig_groupnorm_stats, or accumulated by
+ * the epilogue of the convolution that produced x (mig_conv_fwd_stats), which removes the statistics pass over x.
+ * mig_groupnorm_apply derives mean / rstd from the sums itself and stores them ([N][G] fp32) for the backward pass. */
+int mig_groupnorm_can_split(int dtype, int32_t N, int64_t S, int32_t C, int32_t G);
+int mig_groupnorm_stats(int dtype, const void* x, double* sums, int32_t N, int64_t S, int32_t C, int32_t G,
+                        void* stream);
+int mig_groupnorm_apply(int dtype, const void* x, const float* gamma, const float* beta, const double* sums, void* y,
+                        float* mean, float* rstd, int32_t N, int64_t S, int32_t C, int32_t G, float eps,
+                        int fuse_silu, void* stream);
 
 /* LayerNorm over the last dim (BasicTransformerBlock norm1-3, unet:225-227) */
 int mig_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,

@@ -40,13 +40,17 @@ _SIGNATURES = {
     "mig_abi_version": [],
     "mig_has_tcgen05": [],
     "mig_conv_fwd": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _p, _p, _i, _p, _l, _p],
+    "mig_conv_fwd_stats": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _l, _p],
     "mig_conv_dgrad": [C.POINTER(ConvGeom), _i, _p, _p, _p, _i, _p, _l, _p],
     "mig_conv_wgrad": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _i, _p, _l, _p],
     "mig_conv_workspace_bytes": [C.POINTER(ConvGeom), _i, _i, _i],
     "mig_gemm_strided": [C.POINTER(GemmDesc), _i, _i, _p, _p, _p, _i, _p],
     "mig_flash_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mig_groupnorm_fwd": [_i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p, _l, _p],
-    "mig_groupnorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _l, _p],
+    "mig_groupnorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _l, _p],
+    "mig_groupnorm_can_split": [_i, _i, _l, _i, _i],
+    "mig_groupnorm_stats": [_i, _p, _p, _i, _l, _i, _i, _p],
+    "mig_groupnorm_apply": [_i, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p],
     "mig_groupnorm_workspace_bytes": [_i, _l, _i, _i],
     "mig_layernorm_fwd": [_i, _p, _p, _p, _p, _p, _p, _l, _i, _f, _p],
     "mig_layernorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _l, _i, _p],
@@ -111,7 +115,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.mig_abi_version() != 1:
+    if lib.mig_abi_version() != 2:
         raise RuntimeError("libmedimgen_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -74,10 +74,11 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         x = _entry(x)
-        h = self.conv1(self.norm1(x, silu=True))
+        h = self.conv1(self.norm1(x, silu=True), gn_groups=self.norm2.num_groups)
+        h._mig_sole_consumer_gn = True   # norm2 is conv1's only consumer: its backward hands conv1 the column sums of dy
         h = self.norm2(h, silu=True)
         skip = x if self.in_channels == self.out_channels else self.nin_shortcut(x)
-        return self.conv2(h, residual=skip)
+        return self.conv2(h, residual=skip, gn_groups=self.norm2.num_groups)
 
 
 class AttentionBlock(SelfAttentionBlock):

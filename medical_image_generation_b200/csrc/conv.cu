@@ -32,7 +32,11 @@ int tc_gemm_strided(const mig_gemm_desc* d, int dtype_c, const void* A, const vo
 // conv_tma.cu
 bool tma_conv_eligible(const mig_conv_geom* g, int which);
 int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
-                 const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream);
+                 const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream, double* gn_sums = nullptr,
+                 int gn_groups = 0, int* stats_done = nullptr);
+// groupnorm_tma.cu
+bool gt_eligible(int N, int64_t S, int C, int G);
+int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* stream);
 int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
                    void* stream);
 int tma_conv_wgrad(const mig_conv_geom* g, const void* x, const void* dy, float* dw, void* stream);
@@ -113,13 +117,14 @@ static bool halo_enabled() {
 }
 
 static int run_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
-                   const void* residual, void* y, void* ws, int64_t wsb, void* stream) {
+                   const void* residual, void* y, void* ws, int64_t wsb, void* stream, double* gn_sums = nullptr,
+                   int gn_groups = 0, int* stats_done = nullptr) {
   if (halo_enabled() && halo_conv_eligible(g, 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
       (!residual || aligned16(residual)))
     return halo_conv_fwd(g, x, w, bias, chan_bias, residual, y, stream);
   if (tma_enabled() && tma_conv_eligible(g, 0) && aligned16(x) && aligned16(w) && aligned16(y) &&
       (!residual || aligned16(residual)))
-    return tma_conv_fwd(g, x, w, bias, chan_bias, residual, y, ws, wsb, stream);
+    return tma_conv_fwd(g, x, w, bias, chan_bias, residual, y, ws, wsb, stream, gn_sums, gn_groups, stats_done);
   return tc_conv_fwd(g, x, w, bias, chan_bias, residual, y, ws, wsb, stream);
 }
 static int run_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t wsb,
@@ -171,14 +176,47 @@ extern "C" int64_t mig_conv_workspace_bytes(const mig_conv_geom* g, int dtype, i
   return simt > tc ? simt : tc;
 }
 
+static int conv_fwd_impl(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+                         const float* chan_bias, const void* residual, void* y, int engine, void* workspace,
+                         int64_t workspace_bytes, void* stream, double* gn_sums, int gn_groups, int* stats_done);
+
 extern "C" int mig_conv_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
                             const float* chan_bias, const void* residual, void* y, int engine, void* workspace,
                             int64_t workspace_bytes, void* stream) {
+  return conv_fwd_impl(g, dtype, x, w, bias, chan_bias, residual, y, engine, workspace, workspace_bytes, stream, nullptr,
+                       0, nullptr);
+}
+
+// mig_conv_fwd that ALSO delivers the GroupNorm statistics of its output: gn_sums[n][g][2] (fp64) = (sum y, sum y^2) per
+// (sample, group) of the bf16-rounded result, for the GroupNorm that consumes it (unet:648,698; ae:167): from the
+// epilogue of the tcgen05 kernel where the plan allows it, otherwise by one statistics pass over y. Requires
+// mig_groupnorm_can_split(dtype, N, out voxels, Cout, gn_groups).
+extern "C" int mig_conv_fwd_stats(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+                                  const float* chan_bias, const void* residual, void* y, double* gn_sums,
+                                  int32_t gn_groups, int engine, void* workspace, int64_t workspace_bytes,
+                                  void* stream) {
+  MIG_REQUIRE(g && gn_sums && gn_groups > 0, "conv_fwd_stats: null argument");
+  const int64_t S = (int64_t)g->out_dims[0] * g->out_dims[1] * g->out_dims[2];
+  MIG_REQUIRE(dtype == MIG_BF16 && gt_eligible(g->N, S, g->Cout, gn_groups),
+              "conv_fwd_stats: output is not eligible for split GroupNorm (bf16, Cout a multiple of 32)");
+  cudaMemsetAsync(gn_sums, 0, sizeof(double) * (size_t)g->N * gn_groups * 2, as_stream(stream));
+  int done = 0;
+  if (int rc = conv_fwd_impl(g, dtype, x, w, bias, chan_bias, residual, y, engine, workspace, workspace_bytes, stream,
+                             gn_sums, gn_groups, &done))
+    return rc;
+  if (done) return 0;
+  return gt_stats(y, gn_sums, g->N, S, g->Cout, gn_groups, stream);
+}
+
+static int conv_fwd_impl(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
+                         const float* chan_bias, const void* residual, void* y, int engine, void* workspace,
+                         int64_t workspace_bytes, void* stream, double* gn_sums, int gn_groups, int* stats_done) {
   MIG_REQUIRE(g && x && w && y, "conv_fwd: null argument");
   if (skinny_eligible(g) && !chan_bias && !residual) return skinny_fwd(g, dtype, x, w, bias, nullptr, nullptr, y, stream);
   if (thin_ok(g, dtype, 0, engine) && aligned16(y) && (!residual || aligned16(residual)))
     return thin_conv(g, 0, x, w, bias, chan_bias, residual, y, stream);
-  if (use_tc(g, dtype, 0, engine)) return run_fwd(g, x, w, bias, chan_bias, residual, y, workspace, workspace_bytes, stream);
+  if (use_tc(g, dtype, 0, engine))
+    return run_fwd(g, x, w, bias, chan_bias, residual, y, workspace, workspace_bytes, stream, gn_sums, gn_groups, stats_done);
   if (want_pad(g, dtype, 0, engine) && workspace && workspace_bytes >= mig_conv_workspace_bytes(g, dtype, 0, engine)) {
     // pad the input channels of x and of the filter to a multiple of 8 (zeros), then the normal tensor-core path
     const int cp = pad8(g->Cin), T = taps(g);

@@ -83,7 +83,36 @@ struct ConvTmaParams {
   float* partial;
   int num_kb, kb_per_split;
   int mtiles, ntiles, splits;   // tile grid; tile index = (split * ntiles + ntile) * mtiles + mtile
+  // GroupNorm statistics of the OUTPUT, accumulated by the epilogue (forward, no split-K): sums[n][g][2] (fp64) +=
+  // (sum y, sum y^2) of the bf16-rounded values, for the GroupNorm that consumes this convolution (unet:648,698 / ae:167)
+  double* gn_sums;
+  int gn_cpg, gn_G;
 };
+
+// Sum eight per-thread values over the 32 lanes of a warp with 7 + 2 shuffles (recursive halving: after step k every
+// lane keeps 8 / 2^k values). Returns, in every lane, the warp total of value index ((lane>>4)&1)*4 + ((lane>>3)&1)*2 +
+// ((lane>>2)&1).
+__device__ __forceinline__ float warp_sum8(const float v[8], int lane) {
+  float a[4], b[2], c;
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = h16 ? v[i + 4] : v[i], send = h16 ? v[i] : v[i + 4];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = h8 ? a[i + 2] : a[i], send = h8 ? a[i] : a[i + 2];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  {
+    const float keep = h4 ? b[1] : b[0], send = h4 ? b[0] : b[1];
+    c = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;
+}
 
 // BN: output-channel tile; MT: number of stacked 128-row accumulators (tile = MT*128 voxels x BN channels).
 //
@@ -93,7 +122,9 @@ struct ConvTmaParams {
 // the epilogue of tile i also overlaps the main loop of tile i+1. ncu on the one-tile-per-CTA version showed ~15 k
 // cycles of launch / TMEM allocation / pipeline fill / drain around every tile: 12 % of a 256x256x6912 tile, and four
 // times the 3.5 k-cycle main loop of a 64-channel layer.
-template <int BN, int MT>
+// BMN: the B operand (filter) is MN-major -- the UNTRANSPOSED filter [Csrc][tap][Cdst] read through a 3-d tensor map as
+// 64 x 64 panels. This is how dgrad runs on the forward filter layout without a per-step transposed copy.
+template <int BN, int MT, bool BMN = false>
 __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                const __grid_constant__ CUtensorMap wmap,
                                                                ConvTmaParams p) {
@@ -177,10 +208,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int64_t box = box0 + mt * spt + slot;
-        bool mok = box < g.num_boxes && r < g.nb;
+        const bool bok = box < g.num_boxes;        // warp-uniform: a warp's 32 rows lie in one box
         int n = 0, d0 = 0, h0 = 0, w0 = 0;
-        if (mok) box_origin(g, box, n, d0, h0, w0);
-        mok = mok && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang the tensor
+        if (bok) box_origin(g, box, n, d0, h0, w0);
+        const bool mok = bok && r < g.nb && (d0 + ld < g.D) && (h0 + lh < g.H) && (w0 + lw < g.W);   // boxes may overhang
+        const bool st = p.gn_sums != nullptr && bok;
         const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
                               g.OW + (w0 + lw) * g.os[2] + g.oo[2];
         const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + ab * (MT * BN) + mt * BN;
@@ -191,14 +223,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           float vw[LDW];
           if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
           else tmem_ld16(trow + cw, vw);
-          if (!mok) continue;
+          if (!mok && !st) continue;
+          float us[LDW / 8], uq[LDW / 8];   // GroupNorm partials per 8-column unit of this row
+#pragma unroll
+          for (int u = 0; u < LDW / 8; ++u) us[u] = uq[u] = 0.f;
 #pragma unroll
           for (int c0 = cw; c0 < cw + LDW; c0 += 16) {
             if (n0 + c0 >= g.Cdst) break;
             float* v = vw + (c0 - cw);
             const int col0 = n0 + c0;
             if (p.partial) {
-              red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
+              if (mok) red_add_16(p.partial + m * g.Cdst + col0, v, g.Cdst - col0);
               continue;
             }
             const bool full16 = (col0 + 16 <= g.Cdst) && ((g.Cdst & 7) == 0);
@@ -210,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             }
             __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
             if (full16) {
-              if (p.residual) {
+              if (p.residual && mok) {
                 const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
                 uint4 r0 = rp[0], r1 = rp[1];
                 const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
@@ -226,15 +261,55 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
                 q0[e] = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
                 q1[e] = __floats2bfloat162_rn(v[8 + 2 * e], v[8 + 2 * e + 1]);
               }
-              reinterpret_cast<uint4*>(dst)[0] = o0;
-              reinterpret_cast<uint4*>(dst)[1] = o1;
-            } else {
+              if (mok) {
+                reinterpret_cast<uint4*>(dst)[0] = o0;
+                reinterpret_cast<uint4*>(dst)[1] = o1;
+              }
+              if (st && mok) {   // statistics of what the consumer will read: the ROUNDED values
+                const int u = (c0 - cw) >> 3;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f0 = __bfloat1622float2(q0[e]), f1 = __bfloat1622float2(q1[e]);
+                  us[u] += f0.x + f0.y;
+                  uq[u] = fmaf(f0.x, f0.x, fmaf(f0.y, f0.y, uq[u]));
+                  us[u + 1] += f1.x + f1.y;
+                  uq[u + 1] = fmaf(f1.x, f1.x, fmaf(f1.y, f1.y, uq[u + 1]));
+                }
+              }
+            } else if (mok) {
 #pragma unroll
               for (int e = 0; e < 16; ++e)
                 if (col0 + e < g.Cdst) {
                   float rr = p.residual ? __bfloat162float(p.residual[m * g.Cdst + col0 + e]) : 0.f;
                   dst[e] = __float2bfloat16_rn(v[e] + rr);
                 }
+            }
+          }
+          if constexpr (LDW == 64) {
+            if (st) {
+              // 32 columns at a time: at most four groups (cpg >= 8) -> one 8-value warp reduction, 8 fp64 atomics
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const int cbase = n0 + cw + 32 * hf;
+                if (cbase >= g.Cdst) break;
+                const int gfirst = cbase / p.gn_cpg;
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int slot = (cbase + 8 * u) / p.gn_cpg - gfirst;
+#pragma unroll
+                  for (int sl = 0; sl < 4; ++sl)
+                    if (slot == sl) { acc[2 * sl] += us[4 * hf + u]; acc[2 * sl + 1] += uq[4 * hf + u]; }
+                }
+                const float tot = warp_sum8(acc, lane);
+                const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int grp = gfirst + (idx >> 1);
+                const int cend = cbase + 32 < g.Cdst ? cbase + 32 : g.Cdst;
+                if ((lane & 3) == 0 && grp < p.gn_G && grp * p.gn_cpg < cend)
+                  atomicAdd(p.gn_sums + ((int64_t)n * p.gn_G + grp) * 2 + (idx & 1), (double)tot);
+              }
             }
           }
         }
@@ -244,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(TBM, BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc(TBM, BN, 0, BMN ? 1 : 0);
     int s = 0, ti = 0;
     uint32_t ph = 0;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -262,7 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
           const uint32_t a_smem = smem_base + s * STAGE_BYTES, b_smem = a_smem + A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < TBK / 16; ++kk) {
-            const uint64_t bd = make_smem_desc(b_smem + kk * 32, 16, 1024);
+            const uint64_t bd = BMN ? make_smem_desc(b_smem + kk * 2048, PANEL, 1024)   // 16 K rows of every 64-column panel
+                                    : make_smem_desc(b_smem + kk * 32, 16, 1024);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
               umma_bf16(acc + mt * BN, make_smem_desc(a_smem + mt * (TBM * 128) + kk * 32, 16, 1024), bd, idesc,
@@ -298,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         int tap = kb_begin / g.cchunks;
         int cch = kb_begin - tap * g.cchunks;
         int kcol = tap * g.Csrc;   // filter column of (tap, channel 0)
+        int tapi = tap;            // linear tap index (BMN: coordinate 1 of the 3-d filter map)
         int t2 = tap % g.ks[2]; tap /= g.ks[2];
         int t1 = tap % g.ks[1];
         int t0 = tap / g.ks[1];
@@ -312,10 +389,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             if (j < nslot)
               tma_load_5d(a_smem + j * slot_bytes, &xmap, bar, c0, bw_[j] * g.ss[2] + dx, bh_[j] * g.ss[1] + dy,
                           bd_[j] * g.ss[0] + dz, bn_[j]);
-          tma_load_2d(b_smem, &wmap, bar, kcol + c0, n0);
+          if constexpr (BMN) {
+#pragma unroll
+            for (int q = 0; q < BN / 64; ++q)   // panels past Cdst are out of bounds -> zero-filled, byte count unchanged
+              tma_load_3d(b_smem + q * PANEL, &wmap, bar, n0 + q * 64, tapi, c0);
+          } else {
+            tma_load_2d(b_smem, &wmap, bar, kcol + c0, n0);
+          }
           if (++cch == g.cchunks) {
             cch = 0;
             kcol += g.Csrc;
+            ++tapi;
             if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -664,42 +748,62 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   return b;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool BMN = false>
 static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const ConvTmaParams& p, dim3 grid,
                            cudaStream_t st) {
   constexpr int stage = MT * TBM * 128 + BN * 128;
   constexpr int smem = stages_of(stage) * stage + 1024;
   static SmemOptIn optin;
-  if (int rc = ensure_dynamic_smem(conv_tma_kernel<BN, MT>, smem, optin, "conv_tma")) return rc;
-  conv_tma_kernel<BN, MT><<<grid, kThreads, smem, st>>>(xm, wm, p);
+  if (int rc = ensure_dynamic_smem(conv_tma_kernel<BN, MT, BMN>, smem, optin, "conv_tma")) return rc;
+  conv_tma_kernel<BN, MT, BMN><<<grid, kThreads, smem, st>>>(xm, wm, p);
   return check_launch("conv_tma_kernel");
 }
 
+// Optional extras of a launch: GroupNorm statistics of the output (forward) and the MN-major filter operand (dgrad on
+// the untransposed filter).
+struct BoxExtras {
+  double* gn_sums = nullptr;   // [N][G][2], accumulated into (caller zeroes)
+  int gn_groups = 0;
+  bool stats_done = false;     // out: the epilogue produced the statistics (false: split-K plan, caller falls back)
+  bool bmn = false;            // filter is [Csrc][taps][Cdst] (the forward layout seen from dgrad)
+};
+
 static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const void* src, const void* wk,
                            const float* bias, const float* chan_bias, const void* residual, void* out, void* ws,
-                           int64_t ws_bytes, void* stream);
+                           int64_t ws_bytes, void* stream, BoxExtras* ex = nullptr);
 
-// src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc]
+// src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc] (or, with ex->bmn, as
+// [Csrc][taps][Cdst])
 static int run_conv_tma(const mig_conv_geom* g, int which, const void* src, const void* wk, const float* bias,
                         const float* chan_bias, const void* residual, void* out, void* ws, int64_t ws_bytes,
-                        void* stream) {
+                        void* stream, BoxExtras* ex = nullptr) {
   BoxGeom b = make_box_geom(g, which);
   const int32_t* sdims = which == 1 ? g->out_dims : g->in_dims;   // extent of the SOURCE tensor
-  return launch_box_conv(b, g->N, sdims, src, wk, bias, chan_bias, residual, out, ws, ws_bytes, stream);
+  return launch_box_conv(b, g->N, sdims, src, wk, bias, chan_bias, residual, out, ws, ws_bytes, stream, ex);
 }
 
 // Launch the kernel for a prepared geometry. Split-K (needs `ws`) is only legal when rows map 1:1 to the output.
 static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const void* src, const void* wk,
                            const float* bias, const float* chan_bias, const void* residual, void* out, void* ws,
-                           int64_t ws_bytes, void* stream) {
+                           int64_t ws_bytes, void* stream, BoxExtras* ex) {
   cudaStream_t st = as_stream(stream);
   CUtensorMap xm, wm;
   if (make_act_map(&xm, src, N, sdims, b.Csrc, b.bd, b.bh, b.bw, b.ss)) return 1;
   const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
-  uint64_t dims[2] = {(uint64_t)b.K, (uint64_t)b.Cdst};
-  uint64_t strides[1] = {(uint64_t)b.K * 2};
-  uint32_t box[2] = {TBK, (uint32_t)bn};
-  if (make_map(&wm, wk, 2, dims, strides, box)) return 1;
+  const bool bmn = ex && ex->bmn;
+  if (bmn) {
+    MIG_REQUIRE(bn >= 64, "conv_tma: the MN-major filter operand needs at least 64 output channels");
+    const int T = b.K / b.Csrc;
+    uint64_t dims[3] = {(uint64_t)b.Cdst, (uint64_t)T, (uint64_t)b.Csrc};
+    uint64_t strides[2] = {(uint64_t)b.Cdst * 2, (uint64_t)T * b.Cdst * 2};
+    uint32_t box[3] = {64, 1, 64};
+    if (make_map(&wm, wk, 3, dims, strides, box)) return 1;
+  } else {
+    uint64_t dims[2] = {(uint64_t)b.K, (uint64_t)b.Cdst};
+    uint64_t strides[1] = {(uint64_t)b.K * 2};
+    uint32_t box[2] = {TBK, (uint32_t)bn};
+    if (make_map(&wm, wk, 2, dims, strides, box)) return 1;
+  }
   ConvTmaParams p{};
   p.g = b;
   p.bias = bias; p.chan_bias = chan_bias;
@@ -741,6 +845,13 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     p.partial = (float*)ws;
     cudaMemsetAsync(ws, 0, (size_t)(M * b.Cdst * 4), st);
   }
+  if (ex && ex->gn_sums && splits == 1 && bn >= 64 && b.Cdst % 16 == 0 && ex->gn_groups > 0 &&
+      b.Cdst % ex->gn_groups == 0 && (b.Cdst / ex->gn_groups) % 8 == 0) {
+    p.gn_sums = ex->gn_sums;
+    p.gn_G = ex->gn_groups;
+    p.gn_cpg = b.Cdst / ex->gn_groups;
+    ex->stats_done = true;
+  }
   p.mtiles = (int)mtiles; p.ntiles = (int)ntiles; p.splits = splits;
   int64_t nct = mtiles * ntiles * splits;
   static int one_tile_per_cta = -1;   // A/B switch: static round-robin persistence vs. hardware CTA scheduling
@@ -751,6 +862,14 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   if (nct > sms && !one_tile_per_cta) nct = sms;
   dim3 grid((unsigned)nct);   // persistent: one CTA per SM walks the tiles
   int rc;
+  if (bmn) {
+    if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2, true>(xm, wm, p, grid, st);
+    else if (mt == 2 && bn == 128) rc = launch_conv_tma<128, 2, true>(xm, wm, p, grid, st);
+    else if (mt == 2) rc = launch_conv_tma<64, 2, true>(xm, wm, p, grid, st);
+    else if (bn == 256) rc = launch_conv_tma<256, 1, true>(xm, wm, p, grid, st);
+    else if (bn == 128) rc = launch_conv_tma<128, 1, true>(xm, wm, p, grid, st);
+    else rc = launch_conv_tma<64, 1, true>(xm, wm, p, grid, st);
+  } else
   if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2>(xm, wm, p, grid, st);
   else if (mt == 2 && bn == 128) rc = launch_conv_tma<128, 2>(xm, wm, p, grid, st);
   else if (mt == 2 && bn == 64) rc = launch_conv_tma<64, 2>(xm, wm, p, grid, st);
@@ -776,13 +895,32 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   return 0;
 }
 
+// gn_sums / gn_groups (optional): GroupNorm statistics of y from the epilogue; *stats_done tells whether they were
+// produced (a split-K plan cannot: its epilogue only sees partial sums).
 int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
-                 const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream) {
-  return run_conv_tma(g, 0, x, w, bias, chan_bias, residual, y, ws, ws_bytes, stream);
+                 const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream, double* gn_sums,
+                 int gn_groups, int* stats_done) {
+  BoxExtras ex;
+  ex.gn_sums = gn_sums;
+  ex.gn_groups = gn_groups;
+  int rc = run_conv_tma(g, 0, x, w, bias, chan_bias, residual, y, ws, ws_bytes, stream, &ex);
+  if (stats_done) *stats_done = ex.stats_done ? 1 : 0;
+  return rc;
 }
 
 int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,
                    void* stream) {
+  static int bmn_ok = -1;   // A/B switch: MIG_DGRAD_TRANSPOSE=1 restores the per-call transposed filter copy
+  if (bmn_ok < 0) {
+    const char* e = getenv("MIG_DGRAD_TRANSPOSE");
+    bmn_ok = (e && e[0] == '1') ? 0 : 1;
+  }
+  if (bmn_ok && g->Cin % 64 == 0) {
+    // the forward filter [Cout][taps][Cin] IS an MN-major B operand for dX = dY * W: no transposed copy, no workspace
+    BoxExtras ex;
+    ex.bmn = true;
+    return run_conv_tma(g, 1, dy, w, nullptr, nullptr, nullptr, dx, ws, ws_bytes, stream, &ex);
+  }
   const int T = g->ksize[0] * g->ksize[1] * g->ksize[2];
   int64_t wt_bytes = ((int64_t)g->Cin * T * g->Cout * 2 + 255) / 256 * 256;
   MIG_REQUIRE(ws && ws_bytes >= wt_bytes, "conv_dgrad(tma): workspace too small");

@@ -13,6 +13,27 @@
 
 namespace mig {
 
+// bf16 production path: TMA-staged streaming kernels (groupnorm_tma.cu)
+bool gt_eligible(int N, int64_t S, int C, int G);
+int64_t gt_bwd_workspace_bytes(int N, int64_t S, int C, int G);
+int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* stream);
+int gt_apply(const void* x, const float* gamma, const float* beta, const double* sums, void* y, float* mean, float* rstd,
+             int N, int64_t S, int C, int G, float eps, int silu, void* stream);
+int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean, const float* rstd,
+           void* dx, float* dgamma, float* dbeta, float* dx_colsum, int N, int64_t S, int C, int G, int silu, void* ws,
+           int64_t ws_bytes, void* stream);
+
+static bool gt_use(int dtype_bytes, const void* a, const void* b, int N, int64_t S, int C, int G) {
+  static int disabled = -1;   // A/B switch for profiling: MIG_GN_LEGACY=1 keeps the register-streaming kernels
+  if (disabled < 0) {
+    const char* e = getenv("MIG_GN_LEGACY");
+    disabled = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (disabled || dtype_bytes != 2 || device_info().cc_major < 9) return false;
+  if (((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) != 0) return false;
+  return gt_eligible(N, S, C, G);
+}
+
 struct GnGeom {
   int N, C, G, cpg;
   int64_t S;
@@ -343,6 +364,10 @@ static int gn_fwd(const void* x, const float* gamma, const float* beta, void* y,
                   int64_t S, int C, int G, float eps, int silu, void* ws, int64_t ws_bytes, void* stream) {
   if (gn_check<T>(x, N, S, C, G)) return 1;
   MIG_REQUIRE(ws_bytes >= (int64_t)N * G * 2 * (int64_t)sizeof(double), "groupnorm_fwd: workspace too small");
+  if (gt_use((int)sizeof(T), x, y, N, S, C, G)) {
+    if (int rc = gt_stats(x, (double*)ws, N, S, C, G, stream)) return rc;
+    return gt_apply(x, gamma, beta, (const double*)ws, y, mean, rstd, N, S, C, G, eps, silu, stream);
+  }
   cudaStream_t st = as_stream(stream);
   GnGeom g = make_geom<T>(N, S, C, G, (int64_t)device_info().sm_count * 4);
   int chunks = (int)((S + g.rows_per_cta - 1) / g.rows_per_cta);
@@ -359,9 +384,11 @@ static int gn_fwd(const void* x, const float* gamma, const float* beta, void* y,
 
 template <typename T>
 static int gn_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean,
-                  const float* rstd, void* dx, float* dgamma, float* dbeta, int N, int64_t S, int C, int G, int silu,
-                  void* ws, int64_t ws_bytes, void* stream) {
+                  const float* rstd, void* dx, float* dgamma, float* dbeta, float* dx_colsum, int N, int64_t S, int C,
+                  int G, int silu, void* ws, int64_t ws_bytes, void* stream) {
   if (gn_check<T>(x, N, S, C, G)) return 1;
+  if (gt_use((int)sizeof(T), x, dy, N, S, C, G) && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)
+    return gt_bwd(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, N, S, C, G, silu, ws, ws_bytes, stream);
   int64_t need = ((int64_t)N * C * 2 + (int64_t)N * G * 2) * (int64_t)sizeof(float);
   MIG_REQUIRE(ws_bytes >= need, "groupnorm_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -388,7 +415,10 @@ static int gn_bwd(const void* x, const void* dy, const float* gamma, const float
   float inv = 1.f / ((float)S * (float)g.cpg);
   if (silu) gn_bwd_apply_kernel<T, true><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsg, (T*)dx, g, inv);
   else gn_bwd_apply_kernel<T, false><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsg, (T*)dx, g, inv);
-  return check_launch("groupnorm_bwd");
+  if (int rc = check_launch("groupnorm_bwd")) return rc;
+  if (dx_colsum)   // per-(n, c) sums of dx for the producing convolution's bias / time-embedding gradient
+    return mig_chan_bias_bwd(sizeof(T) == 2 ? MIG_BF16 : MIG_F32, dx, dx_colsum, N, S, C, stream);
+  return 0;
 }
 
 // ---- LayerNorm over the last dim: one warp per row --------------------------------------------------
@@ -464,10 +494,11 @@ __global__ void __launch_bounds__(256) ln_bwd_param_kernel(const T* __restrict__
 using namespace mig;
 
 extern "C" int64_t mig_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t G) {
-  (void)S;
   int64_t fwd = (int64_t)N * G * 2 * 8;
   int64_t bwd = ((int64_t)N * C * 2 + (int64_t)N * G * 2) * 4;
-  return fwd > bwd ? fwd : bwd;
+  int64_t tma = gt_bwd_workspace_bytes(N, S, C, G);
+  int64_t need = fwd > bwd ? fwd : bwd;
+  return need > tma ? need : tma;
 }
 
 extern "C" int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,
@@ -477,11 +508,29 @@ extern "C" int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, c
                                                  workspace_bytes, stream)));
 }
 extern "C" int mig_groupnorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* beta,
-                                 const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, int32_t N,
-                                 int64_t S, int32_t C, int32_t G, int fuse_silu, void* workspace,
-                                 int64_t workspace_bytes, void* stream) {
-  MIG_DISPATCH_DTYPE(dtype, T, return (gn_bwd<T>(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, N, S, C, G,
-                                                 fuse_silu, workspace, workspace_bytes, stream)));
+                                 const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                                 float* dx_colsum, int32_t N, int64_t S, int32_t C, int32_t G, int fuse_silu,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (gn_bwd<T>(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, N, S, C,
+                                                 G, fuse_silu, workspace, workspace_bytes, stream)));
+}
+
+// Statistics and apply as separate entry points: a convolution epilogue (mig_conv_fwd_stats) can stand in for the first.
+extern "C" int mig_groupnorm_stats(int dtype, const void* x, double* sums, int32_t N, int64_t S, int32_t C, int32_t G,
+                                   void* stream) {
+  MIG_REQUIRE(dtype == MIG_BF16 && gt_use(2, x, x, N, S, C, G),
+              "groupnorm_stats: needs a bf16 tensor with C a multiple of 32 (use mig_groupnorm_fwd otherwise)");
+  return gt_stats(x, sums, N, S, C, G, stream);
+}
+extern "C" int mig_groupnorm_apply(int dtype, const void* x, const float* gamma, const float* beta, const double* sums,
+                                   void* y, float* mean, float* rstd, int32_t N, int64_t S, int32_t C, int32_t G,
+                                   float eps, int fuse_silu, void* stream) {
+  MIG_REQUIRE(dtype == MIG_BF16 && gt_use(2, x, y, N, S, C, G),
+              "groupnorm_apply: needs a bf16 tensor with C a multiple of 32 (use mig_groupnorm_fwd otherwise)");
+  return gt_apply(x, gamma, beta, sums, y, mean, rstd, N, S, C, G, eps, fuse_silu, stream);
+}
+extern "C" int mig_groupnorm_can_split(int dtype, int32_t N, int64_t S, int32_t C, int32_t G) {
+  return dtype == MIG_BF16 && gt_use(2, nullptr, nullptr, N, S, C, G) ? 1 : 0;
 }
 
 extern "C" int mig_layernorm_fwd(int dtype, const void* x, const float* gamma, const float* beta, void* y, float* mean,

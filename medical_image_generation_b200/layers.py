@@ -49,8 +49,9 @@ class ConvNd(nn.Module):
         self.weight = nn.Parameter(w.contiguous(memory_format=_cl_format(spatial_dims)))
         self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
 
-    def forward(self, x, chan_bias=None, residual=None):
-        return ops.conv_nd(x, self.weight, self.bias, self.stride, self.padding, chan_bias=chan_bias, residual=residual)
+    def forward(self, x, chan_bias=None, residual=None, gn_groups=0):
+        return ops.conv_nd(x, self.weight, self.bias, self.stride, self.padding, chan_bias=chan_bias, residual=residual,
+                           gn_groups=gn_groups)
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
@@ -78,7 +79,7 @@ class ConvTransposeNd(nn.Module):
         self.weight = nn.Parameter(w.contiguous(memory_format=_cl_format(spatial_dims)))
         self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound))
 
-    def forward(self, x, chan_bias=None, residual=None):
+    def forward(self, x, chan_bias=None, residual=None, gn_groups=0):
         if chan_bias is not None or residual is not None:
             raise RuntimeError("transposed convolutions have no fused epilogue inputs")
         return ops.conv_transpose_nd(x, self.weight, self.bias, self.stride, self.padding, self.output_padding)
@@ -104,8 +105,8 @@ class ConvBlock(nn.Module):
         else:
             self.conv = ConvNd(spatial_dims, in_channels, out_channels, k, s, p)
 
-    def forward(self, x, chan_bias=None, residual=None):
-        return self.conv(x, chan_bias=chan_bias, residual=residual)
+    def forward(self, x, chan_bias=None, residual=None, gn_groups=0):
+        return self.conv(x, chan_bias=chan_bias, residual=residual, gn_groups=gn_groups)
 
 
 class GroupNorm(nn.Module):

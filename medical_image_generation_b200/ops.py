@@ -258,9 +258,18 @@ def _geom(N, in_sp, Cin, Cout, ksize, stride, pad):
     return _lib.conv_geom(N, in3, out3, Cin, Cout, k3, s3, p3), out3
 
 
+_LAST_GN_SUMS = []   # hand-over of the epilogue statistics from _ConvFn.forward to conv_nd (which tags the output)
+
+
+def _gn_split_ok(x_dtype, N, S, Cc, groups) -> bool:
+    if x_dtype != torch.bfloat16 or _ENGINE == _lib.ENGINE_SIMT or not groups:
+        return False
+    return bool(_lib.load().mig_groupnorm_can_split(BF16, int(N), int(S), int(Cc), int(groups)))
+
+
 class _ConvFn(Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, chan_bias, residual, stride, padding):
+    def forward(ctx, x, weight, bias, chan_bias, residual, stride, padding, gn_groups=0):
         N, Cin = x.shape[0], x.shape[1]
         nd = x.ndim - 2
         Cout = weight.shape[0]
@@ -275,8 +284,15 @@ class _ConvFn(Function):
         dt = _dt(x)
         need = _lib.load().mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
         ws = _workspace(need, x.device)
-        _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias), _ptr(residual),
-             _ptr(y), _ENGINE, _ptr(ws), ws.numel(), _stream())
+        if gn_groups and _gn_split_ok(x.dtype, N, out3[0] * out3[1] * out3[2], Cout, gn_groups):
+            # the epilogue also accumulates the GroupNorm statistics of y for the norm that consumes it
+            sums = torch.empty((N, gn_groups, 2), dtype=torch.float64, device=x.device)
+            _conv_call("fwd", geom, "mig_conv_fwd_stats", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias),
+                       _ptr(residual), _ptr(y), _ptr(sums), int(gn_groups), _ENGINE, _ptr(ws), ws.numel(), _stream())
+            _LAST_GN_SUMS.append((sums, int(gn_groups)))
+        else:
+            _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), _ptr(wk), _ptr(bias), _ptr(chan_bias), _ptr(residual),
+                 _ptr(y), _ENGINE, _ptr(ws), ws.numel(), _stream())
         ctx.geom = geom
         ctx.has = (bias is not None, chan_bias is not None, residual is not None)
         ctx.bias_ref, ctx.weight_ref = bias, weight  # the Parameter objects (carry main_grad / shadow attributes)
@@ -288,6 +304,11 @@ class _ConvFn(Function):
         x, _ = ctx.saved_tensors
         weight = ctx.weight_ref
         geom = ctx.geom
+        # per-(n, c) column sums of dy, when the GroupNorm that consumed this conv's output computed them in its own
+        # backward (ops._GroupNormFn): they ARE the time-embedding gradient, and summed over n the bias gradient
+        colsum = getattr(dy, "_mig_colsum", None)
+        if colsum is not None and tuple(colsum.shape) != (dy.shape[0], dy.shape[1]):
+            colsum = None
         dy = as_cl(dy)
         if dy.dtype != x.dtype:
             dy = dy.to(x.dtype)
@@ -316,24 +337,34 @@ class _ConvFn(Function):
             need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
             ws = _workspace(need, x.device)
             # the kernels ACCUMULATE: straight into the flat gradient buffer when the engine owns the parameter
-            _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw_buf), _ptr(db_buf), _ENGINE, _ptr(ws),
-                 ws.numel(), _stream())
+            db_arg = db_buf
+            if want_b and colsum is not None:   # bias gradient = sum over samples of the ready-made column sums
+                call("mig_colsum", F32, _ptr(colsum), _ptr(db_buf), colsum.shape[0], colsum.shape[1], 1, _stream())
+                db_arg = None
+            if want_w or db_arg is not None:
+                _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(x), _ptr(dy), _ptr(dw_buf), _ptr(db_arg),
+                           _ENGINE, _ptr(ws), ws.numel(), _stream())
             if want_w:
                 dw = _deliver(weight, None) if w_main is not None else dw_buf
             if want_b:
                 db = _deliver(bias, None) if b_main is not None else db_buf
         if ctx.has[1] and ctx.needs_input_grad[3]:
             N, Cout = dy.shape[0], dy.shape[1]
-            dcb = torch.empty((N, Cout), dtype=torch.float32, device=dy.device)
-            call("mig_chan_bias_bwd", dt, _ptr(dy), _ptr(dcb), N, dy.numel() // (N * Cout), Cout, _stream())
+            if colsum is not None:
+                dcb = colsum
+            else:
+                dcb = torch.empty((N, Cout), dtype=torch.float32, device=dy.device)
+                call("mig_chan_bias_bwd", dt, _ptr(dy), _ptr(dcb), N, dy.numel() // (N * Cout), Cout, _stream())
         if ctx.has[2] and ctx.needs_input_grad[4]:
             dres = dy
-        return dx, dw, db, dcb, dres, None, None
+        return dx, dw, db, dcb, dres, None, None, None
 
 
-def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=None):
+def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=None, gn_groups=0):
     """Conv{2,3}d with fused epilogue: + bias[c] + chan_bias[n,c] (time embedding, unet:691-695)
-    + residual (skip add, unet:701 / ae:204). x, residual: channels-last compute dtype."""
+    + residual (skip add, unet:701 / ae:204). x, residual: channels-last compute dtype.
+    gn_groups > 0: the epilogue also accumulates the statistics of a GroupNorm(gn_groups) over the output; they ride on
+    the returned tensor (`_mig_gn_sums`) and ops.group_norm on that tensor skips its statistics pass."""
     _require_cuda(x, "conv_nd")
     nd = x.ndim - 2
     s = tuple(stride) if isinstance(stride, (list, tuple)) else (stride,) * nd
@@ -344,7 +375,11 @@ def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=
         chan_bias = chan_bias.float().contiguous()
     if residual is not None and (not _is_cl(residual) or residual.dtype != x.dtype):
         residual = to_channels_last(residual, x.dtype)
-    return _ConvFn.apply(x, weight, bias, chan_bias, residual, s, p)
+    del _LAST_GN_SUMS[:]
+    y = _ConvFn.apply(x, weight, bias, chan_bias, residual, s, p, int(gn_groups or 0))
+    if _LAST_GN_SUMS:
+        y._mig_gn_sums = _LAST_GN_SUMS.pop()
+    return y
 
 
 class _ConvTransposeFn(Function):
@@ -515,13 +550,20 @@ class _GroupNormFn(Function):
         y = torch.empty_like(x)
         mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
         rstd = torch.empty_like(mean)
-        need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
-        ws = _workspace(need, x.device)
-        call("mig_groupnorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), N, S, Cc,
-             groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
+        pre = getattr(x, "_mig_gn_sums", None)   # statistics accumulated by the producing convolution's epilogue
+        if pre is not None and pre[1] == groups and tuple(pre[0].shape) == (N, groups, 2) and \
+                _gn_split_ok(x.dtype, N, S, Cc, groups):
+            call("mig_groupnorm_apply", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(pre[0]), _ptr(y), _ptr(mean),
+                 _ptr(rstd), N, S, Cc, groups, float(eps), int(silu), _stream())
+        else:
+            need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
+            ws = _workspace(need, x.device)
+            call("mig_groupnorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), N, S, Cc,
+                 groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
         ctx.save_for_backward(x, gamma, beta, mean, rstd)
         ctx.cfg = (groups, silu)
         ctx.refs = (gamma, beta)
+        ctx.want_colsum = bool(getattr(x, "_mig_sole_consumer_gn", False))
         return y
 
     @staticmethod
@@ -538,8 +580,14 @@ class _GroupNormFn(Function):
         dbeta = torch.empty_like(beta)
         need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
         ws = _workspace(need, x.device)
+        colsum = torch.empty((N, Cc), dtype=torch.float32, device=x.device) if ctx.want_colsum else None
         call("mig_groupnorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx),
-             _ptr(dgamma), _ptr(dbeta), N, S, Cc, groups, int(silu), _ptr(ws), ws.numel(), _stream())
+             _ptr(dgamma), _ptr(dbeta), _ptr(colsum), N, S, Cc, groups, int(silu), _ptr(ws), ws.numel(), _stream())
+        if colsum is not None:
+            # rides on the gradient tensor to the backward of the convolution that produced x (its bias and
+            # time-embedding gradients are these column sums); if autograd hands that node a different tensor
+            # (several consumers -> accumulated gradient) the attribute is simply absent and the conv sums dy itself
+            dx._mig_colsum = colsum
         return dx, _deliver(ctx.refs[0], dgamma), _deliver(ctx.refs[1], dbeta), None, None, None
 
 

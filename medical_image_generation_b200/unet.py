@@ -209,10 +209,12 @@ class ResnetBlock(nn.Module):
             x, h = self.downsample(x), self.downsample(h)
         # the (B, 4*C0) embedding path stays in fp32: it is tiny and feeds the conv epilogue as an fp32 bias
         temb = self.time_emb_proj(self.nonlinearity(emb if emb.dtype == torch.float32 else emb.float()))
-        h = self.conv1(h, chan_bias=temb)
+        # conv1's epilogue accumulates norm2's statistics; conv2's those of whichever GroupNorm reads the block output
+        h = self.conv1(h, chan_bias=temb, gn_groups=self.norm2.num_groups)
+        h._mig_sole_consumer_gn = True   # norm2 is conv1's only consumer: its backward hands conv1 the column sums of dy
         h = self.norm2(h, silu=True)
         skip = x if isinstance(self.skip_connection, nn.Identity) else self.skip_connection(x)
-        return self.conv2(h, residual=skip)
+        return self.conv2(h, residual=skip, gn_groups=self.norm2.num_groups)
 
 
 class _LevelBlock(nn.Module):

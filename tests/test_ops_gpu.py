@@ -191,7 +191,11 @@ def test_linear(rows, K, O, bias, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("silu", [False, True])
 @pytest.mark.parametrize("N,C,G,sp", [(2, 32, 16, (6, 6, 6)), (1, 256, 32, (5, 4, 3)), (2, 16, 16, (9, 9)),
-                                      (1, 1536, 32, (3, 3, 3)), (2, 64, 8, (17, 5, 3)), (1, 32, 32, (24, 24, 24))])
+                                      (1, 1536, 32, (3, 3, 3)), (2, 64, 8, (17, 5, 3)), (1, 32, 32, (24, 24, 24)),
+                                      # TMA-staged bf16 kernels: groups straddling 256-channel slabs (cpg 24 / 40), groups
+                                      # straddling 16-byte vectors (cpg 6), many row chunks, 256-row stages
+                                      (8, 768, 32, (6, 6, 6)), (2, 1280, 32, (4, 4, 4)), (2, 96, 16, (8, 8, 8)),
+                                      (2, 256, 32, (24, 24, 24)), (1, 32, 16, (40, 40, 40)), (3, 512, 32, (12, 12, 12))])
 def test_group_norm(N, C, G, sp, silu, dtype):
     ops = _ops()
     g = torch.Generator().manual_seed(C + G)
@@ -219,6 +223,132 @@ def test_group_norm(N, C, G, sp, silu, dtype):
     assert rel_err(y, y_ref) < tol
     assert rel_err(xd.grad, xr.grad) < tol
     assert rel_err(gd.grad, gr.grad) < tol and rel_err(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("C,G,sp", [(64, 16, (8, 8, 8)), (256, 32, (6, 6, 6)), (96, 16, (5, 6, 7))])
+def test_group_norm_split_and_colsum(C, G, sp):
+    """The two halves of the bf16 forward through their own entry points (statistics as raw fp64 sums -- what a
+    convolution epilogue accumulates -- then apply), and the per-(n, c) column sums of dx the backward hands to the
+    producing convolution."""
+    import ctypes as Cc
+    ops = _ops()
+    from medical_image_generation_b200 import _lib
+    N = 2
+    S = math.prod(sp)
+    g = torch.Generator().manual_seed(C)
+    x = bf16_round(torch.randn((N, C, *sp), generator=g) * 1.5 - 0.3)
+    gamma, beta = 1 + 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    xd = _cl(x.to(DEV).to(torch.bfloat16))
+    assert _lib.load().mig_groupnorm_can_split(1, N, S, C, G) == 1
+    sums = torch.empty(N, G, 2, dtype=torch.float64, device=DEV)
+    _lib.call("mig_groupnorm_stats", 1, ops._ptr(xd), ops._ptr(sums), N, S, C, G, ops._stream())
+    xg = x.reshape(N, G, C // G, -1).double()
+    want = torch.stack([xg.sum(dim=(2, 3)), (xg * xg).sum(dim=(2, 3))], dim=-1)
+    assert rel_err(sums, want) < 1e-5
+    y = torch.empty_like(xd)
+    mean, rstd = torch.empty(N, G, device=DEV), torch.empty(N, G, device=DEV)
+    _lib.call("mig_groupnorm_apply", 1, ops._ptr(xd), ops._ptr(gamma.to(DEV)), ops._ptr(beta.to(DEV)), ops._ptr(sums),
+              ops._ptr(y), ops._ptr(mean), ops._ptr(rstd), N, S, C, G, 1e-6, 1, ops._stream())
+    assert rel_err(y, F.silu(F.group_norm(x, G, gamma, beta, 1e-6))) < BF16_TOL
+    assert rel_err(mean, xg.mean(dim=(2, 3))) < 1e-5
+    # backward with the column sums requested
+    dy = bf16_round(torch.randn(x.shape, generator=g))
+    dyd = _cl(dy.to(DEV).to(torch.bfloat16))
+    dx = torch.empty_like(xd)
+    dgam, dbet = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    colsum = torch.empty(N, C, device=DEV)
+    need = _lib.load().mig_groupnorm_workspace_bytes(N, S, C, G)
+    ws = torch.empty(int(need), dtype=torch.uint8, device=DEV)
+    _lib.call("mig_groupnorm_bwd", 1, ops._ptr(xd), ops._ptr(dyd), ops._ptr(gamma.to(DEV)), ops._ptr(beta.to(DEV)),
+              ops._ptr(mean), ops._ptr(rstd), ops._ptr(dx), ops._ptr(dgam), ops._ptr(dbet), ops._ptr(colsum), N, S, C, G, 1,
+              ops._ptr(ws), ws.numel(), ops._stream())
+    xr = x.clone().requires_grad_(True)
+    F.silu(F.group_norm(xr, G, gamma, beta, 1e-6)).backward(dy)
+    assert rel_err(dx, xr.grad) < BF16_TOL
+    # the column sums are computed analytically from the statistics pass (fp32), not from the rounded dx
+    assert rel_err(colsum, xr.grad.sum(dim=tuple(range(2, x.ndim)))) < 5e-3
+
+
+@pytest.mark.parametrize("case", [
+    (2, 64, 256, (16, 16, 16), 32, True),     # tcgen05 epilogue statistics, 8 channels per group, residual + time embedding
+    (1, 128, 768, (8, 8, 8), 32, False),      # 24 channels per group: groups straddle the 32-column reduction units
+    (1, 64, 128, (12, 12, 12), 16, True),     # one 128-column tile, 8 channels per group
+    (2, 128, 512, (12, 12, 12), 32, False),   # 16 channels per group, two N tiles
+    (3, 256, 1280, (4, 4, 4), 32, False),     # 40 channels per group, N-tile tail (1280 = 5 x 256)
+    (2, 128, 256, (6, 6, 6), 32, True),       # split-K plan: statistics fall back to one pass over y
+    (1, 32, 32, (32, 32, 32), 16, False),     # halo kernel (2 channels per group): statistics pass fallback
+])
+def test_conv_epilogue_groupnorm_statistics(case):
+    """mig_conv_fwd_stats: the convolution also delivers (sum y, sum y^2) per (sample, group) of its bf16 output, and
+    ops.group_norm on that tensor (apply only) equals GroupNorm computed from scratch."""
+    ops = _ops()
+    N, Cin, Cout, sp, G, extras = case
+    g = torch.Generator().manual_seed(Cout + sp[0])
+    x = bf16_round(torch.randn((N, Cin, *sp), generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, 3, 3, 3), generator=g) / math.sqrt(Cin * 27))
+    b = torch.randn(Cout, generator=g) * 0.1
+    xd, wd, bd = _cl(x.to(DEV).to(torch.bfloat16)), _cl(w.to(DEV)), b.to(DEV)
+    cb = res = None
+    if extras:
+        cb = (torch.randn((N, Cout), generator=g) * 0.3).to(DEV)
+        res = _cl(bf16_round(torch.randn((N, Cout, *sp), generator=g)).to(DEV).to(torch.bfloat16))
+    with torch.no_grad():
+        y = ops.conv_nd(xd, wd, bd, 1, 1, chan_bias=cb, residual=res, gn_groups=G)
+        y_plain = ops.conv_nd(xd, wd, bd, 1, 1, chan_bias=cb, residual=res)
+    assert torch.equal(y, y_plain)                       # the statistics epilogue must not change the output
+    sums, groups = y._mig_gn_sums
+    assert groups == G and tuple(sums.shape) == (N, G, 2)
+    yg = y.float().cpu().reshape(N, G, Cout // G, -1).double()
+    want = torch.stack([yg.sum(dim=(2, 3)), (yg * yg).sum(dim=(2, 3))], dim=-1)
+    assert rel_err(sums[..., 1], want[..., 1]) < 1e-5
+    assert float((sums[..., 0].cpu() - want[..., 0]).abs().max()) < 1e-4 * float(want[..., 1].sqrt().max()) + 1e-3
+    gamma, beta = (1 + 0.2 * torch.randn(Cout, generator=g)).to(DEV), (0.2 * torch.randn(Cout, generator=g)).to(DEV)
+    seen = []
+    real = ops.call
+    ops.call = lambda name, *a: (seen.append(name), real(name, *a))[1]
+    try:
+        with torch.no_grad():
+            z = ops.group_norm(y, gamma, beta, G, 1e-6, silu=True)
+    finally:
+        ops.call = real
+    assert seen == ["mig_groupnorm_apply"], seen
+    z_ref = F.silu(F.group_norm(y.float().cpu(), G, gamma.cpu(), beta.cpu(), 1e-6))
+    assert rel_err(z, z_ref) < BF16_TOL
+
+
+def test_resnet_block_backward_uses_groupnorm_column_sums():
+    """conv1's bias / time-embedding gradients come from norm2's backward (no mig_chan_bias_bwd / bias column-sum pass
+    over dy for conv1) and still match the oracle."""
+    from medical_image_generation_b200 import unet as U
+    from oracle import torch_oracle as O
+    ops = _ops()
+    g = torch.Generator().manual_seed(4)
+    rb = U.ResnetBlock(3, 64, 32, 64, norm_num_groups=16)
+    with torch.no_grad():
+        for p in rb.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.1 if p.ndim > 1 else 0.3))
+    rb = rb.to(DEV)
+    x = torch.randn(2, 64, 8, 8, 8, generator=g)
+    emb = torch.randn(2, 32, generator=g)
+    sd = {"blk." + k: v.detach().cpu().clone().requires_grad_(True) for k, v in rb.state_dict().items()}
+    probe = torch.randn(2, 64, 8, 8, 8, generator=g)
+    embr = emb.clone().requires_grad_(True)
+    (O.unet_resnet_block(sd, "blk", x, embr, 16, 1e-6) * probe).sum().backward()
+    seen = []
+    real = ops.call
+    ops.call = lambda name, *a: (seen.append(name), real(name, *a))[1]
+    try:
+        embd = emb.to(DEV).requires_grad_(True)
+        y = rb(x.to(DEV).to(torch.bfloat16), embd)
+        (y.float() * probe.to(DEV)).sum().backward()
+    finally:
+        ops.call = real
+    assert seen.count("mig_chan_bias_bwd") == 0, seen
+    named = dict(rb.named_parameters())
+    assert rel_err(named["conv1.conv.bias"].grad, sd["blk.conv1.conv.bias"].grad) < 3e-2
+    assert rel_err(named["time_emb_proj.weight"].grad, sd["blk.time_emb_proj.weight"].grad) < 3e-2
+    assert rel_err(embd.grad, embr.grad) < 3e-2
+    assert rel_err(named["conv1.conv.weight"].grad, sd["blk.conv1.conv.weight"].grad) < 3e-2
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
