@@ -53,6 +53,10 @@ int mig_has_tcgen05(void);
 int mig_conv_fwd_stats(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,
                        const float* chan_bias, const void* residual, void* y, double* gn_sums, int32_t gn_groups,
                        int engine, void* workspace, int64_t workspace_bytes, void* stream);
+/* 1 when mig_conv_fwd_stats takes the statistics from the tcgen05 epilogue for this geometry and workspace size
+ * (0: it runs the statistics pass over y) */
+int mig_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int dtype, int32_t gn_groups, int engine,
+                                   int64_t workspace_bytes);
 
 /* ---- K1/K2/K3: Conv{2,3}d as implicit GEMM -------------------------------------------------------
  * replaces nn.Conv{2,3}d inside monai Convolution: unet:510-518,557-565,630-659,664,1820,1935;

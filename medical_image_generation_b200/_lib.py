@@ -41,6 +41,7 @@ _SIGNATURES = {
     "mig_has_tcgen05": [],
     "mig_conv_fwd": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _p, _p, _i, _p, _l, _p],
     "mig_conv_fwd_stats": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _p, _l, _p],
+    "mig_conv_fwd_stats_in_epilogue": [C.POINTER(ConvGeom), _i, _i, _i, _l],
     "mig_conv_dgrad": [C.POINTER(ConvGeom), _i, _p, _p, _p, _i, _p, _l, _p],
     "mig_conv_wgrad": [C.POINTER(ConvGeom), _i, _p, _p, _p, _p, _i, _p, _l, _p],
     "mig_conv_workspace_bytes": [C.POINTER(ConvGeom), _i, _i, _i],

@@ -34,6 +34,7 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which);
 int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const float* bias, const float* chan_bias,
                  const void* residual, void* y, void* ws, int64_t ws_bytes, void* stream, double* gn_sums = nullptr,
                  int gn_groups = 0, int* stats_done = nullptr);
+bool tma_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int gn_groups, int64_t ws_bytes);
 // groupnorm_tma.cu
 bool gt_eligible(int N, int64_t S, int C, int G);
 int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* stream);
@@ -206,6 +207,15 @@ extern "C" int mig_conv_fwd_stats(const mig_conv_geom* g, int dtype, const void*
     return rc;
   if (done) return 0;
   return gt_stats(y, gn_sums, g->N, S, g->Cout, gn_groups, stream);
+}
+
+// 1 when mig_conv_fwd_stats takes the statistics from the tcgen05 epilogue for this geometry (0: statistics pass over y)
+extern "C" int mig_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int dtype, int32_t gn_groups, int engine,
+                                              int64_t workspace_bytes) {
+  if (!g || !use_tc(g, dtype, 0, engine) || !tma_enabled() || !tma_conv_eligible(g, 0)) return 0;
+  if (halo_enabled() && halo_conv_eligible(g, 0)) return 0;
+  if (skinny_eligible(g) || thin_ok(g, dtype, 0, engine)) return 0;
+  return tma_conv_fwd_stats_in_epilogue(g, gn_groups, workspace_bytes) ? 1 : 0;
 }
 
 static int conv_fwd_impl(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,

@@ -31,6 +31,11 @@ using namespace tc;
 int filter_transpose(int dtype, const void* w, void* wt, int Cout, int Tn, int Cin, void* stream);
 
 constexpr int TBM = 128, TBK = 64, kThreads = 192, PANEL = 64 * 128;
+// conv_tma_kernel: warps 0-3 and 6-9 are TWO epilogue groups (a warp reads the TMEM lane quadrant warp % 4; the groups
+// split the accumulator columns in 64-column chunks), warp 4 issues the UMMAs, warp 5 the TMA loads. With one group the
+// epilogue of a 256 x 256 tile (all 512 TMEM columns, so nothing to overlap it with) cost ~6 k cycles next to a ~55 k
+// cycle main loop; the second group halves that and pays for the GroupNorm statistics the epilogue now also produces.
+constexpr int kConvThreads = 320;
 constexpr int kSmemBudget = 200 * 1024;
 __host__ __device__ constexpr int stages_of(int stage_bytes) {
   return kSmemBudget / stage_bytes > 8 ? 8 : kSmemBudget / stage_bytes;
@@ -125,7 +130,7 @@ __device__ __forceinline__ float warp_sum8(const float v[8], int lane) {
 // BMN: the B operand (filter) is MN-major -- the UNTRANSPOSED filter [Csrc][tap][Cdst] read through a 3-d tensor map as
 // 64 x 64 panels. This is how dgrad runs on the forward filter layout without a per-step transposed copy.
 template <int BN, int MT, bool BMN = false>
-__global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                const __grid_constant__ CUtensorMap wmap,
                                                                ConvTmaParams p) {
   constexpr int A_BYTES = MT * TBM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + 8 * a, 1);
-      mbar_init(acc_empty + 8 * a, 128);
+      mbar_init(acc_empty + 8 * a, 256);
     }
     fence_barrier_init();
   }
@@ -173,9 +178,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_acc = tmem_slot;
 
-  if (warp < 4) {
-    // ===================== epilogue =====================
-    const int row = warp * 32 + lane;
+  if (warp < 4 || warp >= 6) {
+    // ===================== epilogue: two groups of four warps =====================
+    const int eg = warp >= 6 ? 1 : 0;          // column group
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read (warps 6..9 -> 2,3,0,1)
+    const int row = quad * 32 + lane;
+    const int etid = eg * 128 + row;
     const int r = row & (g.rb - 1), slot = row / g.rb;
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
     int ti = 0;
@@ -187,11 +195,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
       // while the main loop runs: bias + per-sample channel bias of this tile's columns, one row per box (a box lies
       // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
       if (!p.partial) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's readers are done with add_s
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the previous tile's readers are done with add_s
         for (int j = 0; j < nslot; ++j) {
           int n = 0, d0, h0, w0;
           if (box0 + j < g.num_boxes) box_origin(g, box0 + j, n, d0, h0, w0);
-          for (int c = row; c < BN; c += 128) {
+          for (int c = etid; c < BN; c += 256) {
             const int col = n0 + c;
             float a = 0.f;
             if (col < g.Cdst) {
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
             add_s[j][c] = a;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       mbar_wait(acc_full + 8 * ab, (uint32_t)(ti / NACC) & 1u);
       tcgen05_fence_after();
@@ -215,10 +223,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tma_kernel(const __grid_cons
         const bool st = p.gn_sums != nullptr && bok;
         const int64_t m = (((int64_t)n * g.OD + (d0 + ld) * g.os[0] + g.oo[0]) * g.OH + (h0 + lh) * g.os[1] + g.oo[1]) *
                               g.OW + (w0 + lw) * g.os[2] + g.oo[2];
-        const uint32_t trow = tmem_acc + ((uint32_t)(warp * 32) << 16) + ab * (MT * BN) + mt * BN;
+        const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16) + ab * (MT * BN) + mt * BN;
         constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load (one round trip each)
 #pragma unroll 1
-        for (int cw = 0; cw < BN; cw += LDW) {
+        for (int cw = eg * LDW; cw < BN; cw += 2 * LDW) {
           if (n0 + cw >= g.Cdst) break;
           float vw[LDW];
           if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
@@ -755,7 +763,7 @@ static int launch_conv_tma(const CUtensorMap& xm, const CUtensorMap& wm, const C
   constexpr int smem = stages_of(stage) * stage + 1024;
   static SmemOptIn optin;
   if (int rc = ensure_dynamic_smem(conv_tma_kernel<BN, MT, BMN>, smem, optin, "conv_tma")) return rc;
-  conv_tma_kernel<BN, MT, BMN><<<grid, kThreads, smem, st>>>(xm, wm, p);
+  conv_tma_kernel<BN, MT, BMN><<<grid, kConvThreads, smem, st>>>(xm, wm, p);
   return check_launch("conv_tma_kernel");
 }
 
@@ -771,6 +779,37 @@ struct BoxExtras {
 static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const void* src, const void* wk,
                            const float* bias, const float* chan_bias, const void* residual, void* out, void* ws,
                            int64_t ws_bytes, void* stream, BoxExtras* ex = nullptr);
+
+// Tile / split-K plan from a small cost model (cycles): a stage costs the larger of its UMMA time and its operand
+// fill time (ncu: the L2 -> SM path sustains ~60-85 B/clk/SM); a CTA adds a fixed launch / pipeline-fill / drain cost
+// (ncu on 64-channel layers: ~15 k cycles around a 3.5 k-cycle main loop, which is why narrow layers also get
+// 256-row tiles); the grid runs in ceil(CTAs / SMs) waves; split-K fills the chip on the small deep levels.
+static void plan_box_conv(const BoxGeom& b, int bn, int num_kb, bool ws_ok, int* mt, int* splits) {
+  const int sms = device_info().sm_count;
+  const int64_t ntiles = (b.Cdst + bn - 1) / bn;
+  const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
+  double best = 1e30;
+  static const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
+  *mt = 1; *splits = 1;
+  for (int m_ = 1; m_ <= 2; ++m_) {
+    const int nslot_ = m_ * (TBM / b.rb);
+    const int64_t mtiles_ = (b.num_boxes + nslot_ - 1) / nslot_;
+    const double t_stage = fmax(512.0 * m_ * bn / 256.0, ((double)nslot_ * b.nb + bn) * 128.0 / 70.0);
+    for (int s_ : cand_s) {
+      if (s_ > 1 && (!ws_ok || num_kb / s_ < 4)) continue;
+      const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
+      const double kb = (double)((num_kb + s_ - 1) / s_);
+      const double t_epi = 2500.0 + m_ * (bn / 32) * (s_ > 1 ? 160.0 : 110.0);   // two epilogue groups share the columns
+      double t = waves * (kb * t_stage + t_epi + 9000.0);
+      if (s_ > 1) t += (double)M * b.Cdst * 14.0 / 3000.0 + 8000.0;   // memset + fp32 reductions + finish pass
+      if (t < best) { best = t; *mt = m_; *splits = s_; }
+    }
+  }
+}
+
+static bool epilogue_stats_ok(const BoxGeom& b, int bn, int splits, int groups) {
+  return splits == 1 && bn >= 64 && b.Cdst % 16 == 0 && groups > 0 && b.Cdst % groups == 0 && (b.Cdst / groups) % 8 == 0;
+}
 
 // src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc] (or, with ex->bmn, as
 // [Csrc][taps][Cdst])
@@ -813,30 +852,8 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
   const int sms = device_info().sm_count;
   const int64_t ntiles = (b.Cdst + bn - 1) / bn;
   const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
-  // Tile / split-K plan from a small cost model (cycles): a stage costs the larger of its UMMA time and its operand
-  // fill time (ncu: the L2 -> SM path sustains ~60-85 B/clk/SM); a CTA adds a fixed launch / pipeline-fill / drain cost
-  // (ncu on 64-channel layers: ~15 k cycles around a 3.5 k-cycle main loop, which is why narrow layers also get
-  // 256-row tiles); the grid runs in ceil(CTAs / SMs) waves; split-K fills the chip on the small deep levels.
   int mt = 1, splits = 1;
-  {
-    const bool ws_ok = ws != nullptr && ws_bytes >= M * b.Cdst * 4;
-    double best = 1e30;
-    static const int cand_s[] = {1, 2, 3, 4, 6, 8, 12, 16};
-    for (int m_ = 1; m_ <= 2; ++m_) {
-      const int nslot_ = m_ * (TBM / b.rb);
-      const int64_t mtiles_ = (b.num_boxes + nslot_ - 1) / nslot_;
-      const double t_stage = fmax(512.0 * m_ * bn / 256.0, ((double)nslot_ * b.nb + bn) * 128.0 / 70.0);
-      for (int s_ : cand_s) {
-        if (s_ > 1 && (!ws_ok || p.num_kb / s_ < 4)) continue;
-        const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
-        const double kb = (double)((p.num_kb + s_ - 1) / s_);
-        const double t_epi = 2500.0 + m_ * (bn / 16) * (s_ > 1 ? 160.0 : 110.0);
-        double t = waves * (kb * t_stage + t_epi + 9000.0);
-        if (s_ > 1) t += (double)M * b.Cdst * 14.0 / 3000.0 + 8000.0;   // memset + fp32 reductions + finish pass
-        if (t < best) { best = t; mt = m_; splits = s_; }
-      }
-    }
-  }
+  plan_box_conv(b, bn, p.num_kb, ws != nullptr && ws_bytes >= M * b.Cdst * 4, &mt, &splits);
   const int nslot = mt * (TBM / b.rb);
   const int64_t mtiles = (b.num_boxes + nslot - 1) / nslot;
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
@@ -845,8 +862,7 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     p.partial = (float*)ws;
     cudaMemsetAsync(ws, 0, (size_t)(M * b.Cdst * 4), st);
   }
-  if (ex && ex->gn_sums && splits == 1 && bn >= 64 && b.Cdst % 16 == 0 && ex->gn_groups > 0 &&
-      b.Cdst % ex->gn_groups == 0 && (b.Cdst / ex->gn_groups) % 8 == 0) {
+  if (ex && ex->gn_sums && epilogue_stats_ok(b, bn, splits, ex->gn_groups)) {
     p.gn_sums = ex->gn_sums;
     p.gn_G = ex->gn_groups;
     p.gn_cpg = b.Cdst / ex->gn_groups;
@@ -906,6 +922,19 @@ int tma_conv_fwd(const mig_conv_geom* g, const void* x, const void* w, const flo
   int rc = run_conv_tma(g, 0, x, w, bias, chan_bias, residual, y, ws, ws_bytes, stream, &ex);
   if (stats_done) *stats_done = ex.stats_done ? 1 : 0;
   return rc;
+}
+
+// would tma_conv_fwd's epilogue produce the GroupNorm statistics for this geometry / workspace?
+bool tma_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int gn_groups, int64_t ws_bytes) {
+  BoxGeom b = make_box_geom(g, 0);
+  const int bn = b.Cdst > 128 ? 256 : (b.Cdst > 64 ? 128 : (b.Cdst > 32 ? 64 : 32));
+  const int num_kb = (b.K / b.Csrc) * b.cchunks;
+  const int64_t M = (int64_t)b.N * b.D * b.H * b.W;
+  int mt, splits;
+  plan_box_conv(b, bn, num_kb, ws_bytes >= M * b.Cdst * 4, &mt, &splits);
+  const int kbs = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kbs - 1) / kbs;
+  return epilogue_stats_ok(b, bn, splits, gn_groups);
 }
 
 int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,

@@ -11,9 +11,10 @@
 //     by TMA (cp.async.bulk.tensor, one elected thread): 48-64 KB per CTA are in flight regardless of registers;
 //   * the grid is exactly one wave (2 CTAs per SM x SM count), sized on the host;
 //   * every thread keeps a fixed 16-byte channel vector, so per-channel coefficients / partial sums live in registers;
-//   * backward statistics are written as per-CTA partials (no atomics, deterministic) and summed by a finalize kernel,
-//     which also emits the per-(sample, channel) column sums of dx -- the bias / time-embedding gradient of the
-//     convolution that produced x (saves that conv's colsum passes over dy).
+//   * backward statistics are written as per-CTA partials (no atomics, deterministic) and summed by one small kernel;
+//     the apply kernel derives the group sums from the totals itself and also emits the per-(sample, channel) column
+//     sums of dx -- the bias / time-embedding gradient of the convolution that produced x (saves that conv's colsum
+//     passes over dy).
 // Forward statistics arrive either from the producing convolution's epilogue (conv_tma.cu, mig_conv_fwd_stats) or from
 // gt_stats_kernel; the apply kernel turns the raw fp64 sums into mean / rstd itself (no finalize launch).
 #include <cuda.h>
@@ -308,52 +309,33 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_stats_kernel(const __gri
   }
 }
 
-// totals[n][c][3] = sum over chunks of the partials
-__global__ void __launch_bounds__(256) gt_bwd_total_kernel(const float* __restrict__ part, float* __restrict__ tot, int N,
+// One thread per (channel, moment): totals[n][c][m] = sum over chunks of the partials, and dgamma / dbeta = sum over n.
+// (The group sums A, B and the column sums of dx are derived from the totals by the apply kernel itself, so the
+// backward is statistics -> this kernel -> apply: no separate finalize launch.)
+__global__ void __launch_bounds__(128) gt_bwd_total_kernel(const float* __restrict__ part, float* __restrict__ tot,
+                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
                                                            int C, int chunks) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)N * C * 3) return;
-  const int64_t n = i / ((int64_t)C * 3), rem = i - n * (int64_t)C * 3;
-  float s = 0.f;
-  for (int k = 0; k < chunks; ++k) s += part[(n * chunks + k) * (int64_t)C * 3 + rem];
-  tot[i] = s;
-}
-
-// one thread per channel: dgamma / dbeta; one thread per (n, g): A, B and the per-(n, c) column sums of dx
-__global__ void __launch_bounds__(128) gt_bwd_finalize_kernel(const float* __restrict__ tot, const float* __restrict__ gamma,
-                                                              const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, float* __restrict__ dgamma,
-                                                              float* __restrict__ dbeta, float* __restrict__ grp,
-                                                              float* __restrict__ dxsum, int N, int C, int G, float S) {
-  const int cpg = C / G;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < C) {
-    float a = 0.f, b = 0.f;
-    for (int n = 0; n < N; ++n) {
-      a += tot[((int64_t)n * C + i) * 3];
-      b += tot[((int64_t)n * C + i) * 3 + 1];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // = c * 3 + moment
+  if (i >= C * 3) return;
+  float all = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* p = part + ((int64_t)n * chunks) * C * 3 + i;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < chunks; k += 4) {
+      s0 += p[(int64_t)k * C * 3];
+      s1 += p[(int64_t)(k + 1) * C * 3];
+      s2 += p[(int64_t)(k + 2) * C * 3];
+      s3 += p[(int64_t)(k + 3) * C * 3];
     }
-    if (dgamma) dgamma[i] = a;
-    if (dbeta) dbeta[i] = b;
+    for (; k < chunks; ++k) s0 += p[(int64_t)k * C * 3];
+    const float s = (s0 + s1) + (s2 + s3);
+    tot[(int64_t)n * C * 3 + i] = s;
+    all += s;
   }
-  if (i < N * G) {
-    const int n = i / G, gi = i - n * G;
-    float a = 0.f, b = 0.f;
-    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-      a = fmaf(gamma[c], tot[((int64_t)n * C + c) * 3], a);
-      b = fmaf(gamma[c], tot[((int64_t)n * C + c) * 3 + 1], b);
-    }
-    grp[2 * i] = a;
-    grp[2 * i + 1] = b;
-    if (dxsum) {
-      // sum_s dx[n,s,c] = rstd * (gamma_c * sum dz - (A * sum xhat + B * S) / cnt),  sum xhat = rstd * (sum x - S mean)
-      const float r = rstd[i], m = mean[i], inv = 1.f / (S * (float)cpg);
-      for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
-        const float sxh = r * (tot[((int64_t)n * C + c) * 3 + 2] - S * m);
-        dxsum[(int64_t)n * C + c] = r * (gamma[c] * tot[((int64_t)n * C + c) * 3 + 1] - (a * sxh + b * S) * inv);
-      }
-    }
-  }
+  const int c = i / 3, m = i - 3 * c;
+  if (m == 0 && dgamma) dgamma[c] = all;
+  if (m == 1 && dbeta) dbeta[c] = all;
 }
 
 // ---- backward apply: dx = rstd * (dz*gamma - (xhat*A + B) / cnt) ------------------------------------------------------
@@ -364,8 +346,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
                                                                      const float* __restrict__ beta,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd,
-                                                                     const float* __restrict__ grp,
-                                                                     __nv_bfloat16* __restrict__ dx, GtGeom g,
+                                                                     const float* __restrict__ tot,
+                                                                     __nv_bfloat16* __restrict__ dx,
+                                                                     float* __restrict__ dxsum, GtGeom g,
                                                                      float inv_count) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -376,16 +359,34 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
   const int c0 = slab * g.cb + tcol * 8;
   // dx = k1*dz - k2*xhat - k3 with xhat = x*rs + m2, z = xhat*ga + be
   float rs[8], m2[8], ga[8], be[8], k1[8], k2[8], k3[8];
+  const float* tn = tot + (int64_t)n * g.C * 3;
+  float A = 0.f, B = 0.f;
+  int gprev = -1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int gi = n * g.G + (c0 + j) / g.cpg;
+    const int grp = (c0 + j) / g.cpg, gi = n * g.G + grp;
+    if (grp != gprev) {   // group sums A = sum_c gamma_c * (sum dz xhat), B = sum_c gamma_c * (sum dz): a few dozen L2 hits
+      A = B = 0.f;
+      for (int c = grp * g.cpg; c < (grp + 1) * g.cpg; ++c) {
+        const float gc = gamma[c];
+        A = fmaf(gc, tn[c * 3], A);
+        B = fmaf(gc, tn[c * 3 + 1], B);
+      }
+      gprev = grp;
+    }
     rs[j] = rstd[gi];
     m2[j] = -mean[gi] * rs[j];
     ga[j] = gamma[c0 + j];
     be[j] = beta[c0 + j];
     k1[j] = rs[j] * ga[j];
-    k2[j] = rs[j] * grp[2 * gi] * inv_count;
-    k3[j] = rs[j] * grp[2 * gi + 1] * inv_count;
+    k2[j] = rs[j] * A * inv_count;
+    k3[j] = rs[j] * B * inv_count;
+    if (dxsum && chunk == 0 && threadIdx.x < g.cvb) {
+      // sum_s dx[n,s,c] = rstd * (gamma_c * sum dz - (A * sum xhat + B * S) / cnt),  sum xhat = rstd * (sum x - S mean)
+      const float S = (float)g.S;
+      const float sxh = rs[j] * (tn[(c0 + j) * 3 + 2] - S * mean[gi]);
+      dxsum[(int64_t)n * g.C + c0 + j] = rs[j] * (ga[j] * tn[(c0 + j) * 3 + 1] - (A * sxh + B * S) * inv_count);
+    }
   }
   __nv_bfloat16* obase = dx + ((int64_t)n * g.S) * g.C + c0;
   gt_stream<2, 3>(&xm, &dym, g, smem, smem_u32(&bars[0]), n, slab, chunk, [&](int64_t r, uint32_t a0, uint32_t a1) {
@@ -416,7 +417,7 @@ static int gt_optin(K kernel, int smem, SmemOptIn& st, const char* what) {
 int64_t gt_bwd_workspace_bytes(int N, int64_t S, int C, int G) {
   if (!gt_eligible(N, S, C, G)) return 0;
   GtGeom g = gt_geom(N, S, C, G);
-  return ((int64_t)N * g.chunks * C * 3 + (int64_t)N * C * 3 + (int64_t)N * G * 2) * 4 + 256;
+  return ((int64_t)N * g.chunks * C * 3 + (int64_t)N * C * 3) * 4 + 256;
 }
 
 int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* stream) {
@@ -465,7 +466,6 @@ int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
   if (gt_map(&xm, x, g) || gt_map(&dym, dy, g)) return 1;
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* tot = part + (int64_t)N * g.chunks * C * 3;
-  float* grp = tot + (int64_t)N * C * 3;
   constexpr int smem = 3 * 2 * GT_TENSOR_STAGE + 128;
   dim3 grid(g.chunks, g.slabs, N);
   if (silu) {
@@ -477,20 +477,18 @@ int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
     if (int rc = gt_optin(gt_bwd_stats_kernel<false>, smem, o, "groupnorm_bwd")) return rc;
     gt_bwd_stats_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, part, g);
   }
-  const int64_t nt = (int64_t)N * C * 3;
-  gt_bwd_total_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(part, tot, N, C, g.chunks);
-  const int fin = C > N * G ? C : N * G;
-  gt_bwd_finalize_kernel<<<(fin + 127) / 128, 128, 0, st>>>(tot, gamma, mean, rstd, dgamma, dbeta, grp, dx_colsum, N, C, G,
-                                                            (float)S);
+  gt_bwd_total_kernel<<<(C * 3 + 127) / 128, 128, 0, st>>>(part, tot, dgamma, dbeta, N, C, g.chunks);
   const float inv = 1.f / ((float)S * (float)g.cpg);
   if (silu) {
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<true>, smem, o, "groupnorm_bwd")) return rc;
-    gt_bwd_apply_kernel<true><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, (__nv_bfloat16*)dx, g, inv);
+    gt_bwd_apply_kernel<true><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, tot, (__nv_bfloat16*)dx,
+                                                              dx_colsum, g, inv);
   } else {
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<false>, smem, o, "groupnorm_bwd")) return rc;
-    gt_bwd_apply_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, (__nv_bfloat16*)dx, g, inv);
+    gt_bwd_apply_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, tot, (__nv_bfloat16*)dx,
+                                                               dx_colsum, g, inv);
   }
   return check_launch("groupnorm_bwd");
 }
