@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--engine", type=int, default=0, help="0 auto (tcgen05 where eligible), 1 SIMT only")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient all-reduce bucket size (multi-GPU)")
+    ap.add_argument("--no-shard", action="store_true",
+                    help="multi-GPU: replicated AdamW + gradient all-reduce instead of the sharded optimiser")
     ap.add_argument("--sample-steps", type=int, default=1000,
                     help="reverse steps timed in the sampling block (1000 = one whole volume, no extrapolation)")
     ap.add_argument("--no-sampling", action="store_true")
@@ -436,7 +438,7 @@ def run_b200(args):
     sched = mig.DDPMScheduler(**planner.LDM_SCHEDULER_KWARGS)
     # whole-step CUDA graph: two eager steps, capture on the third untimed step, replay afterwards
     trainer = LDMTrainer(model, sched, lr=2e-5, grad_clip_max_norm=1.0, cuda_graph=not args.no_graph, bucket_mb=args.bucket_mb,
-                         graph_warmup_steps=2)
+                         graph_warmup_steps=2, shard_optimizer=False if args.no_shard else None)
     B = args.batch
     gen = torch.Generator().manual_seed(1000 + rank)
     host = [torch.randn((B, *LATENT), generator=gen).pin_memory() for _ in range(4)]   # rank-offset seeds
@@ -575,6 +577,7 @@ def run_b200(args):
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": train_config(world, B, n_params), "final_loss": final_loss,
+                "optimizer_sharded": bool(trainer.opt.sharded),
                 "e2e": {"value": world * B * args.steps / e2e_s, "unit": "samples/s",
                         "h2d_bytes_per_step": B * 4 * LATENT[0] * LATENT[1] * LATENT[2] * LATENT[3],
                         "d2h_bytes_per_step": 4},

@@ -219,6 +219,15 @@ int mig_sumsq(const float* g, float* out, float* partials, int64_t n, void* stre
 int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int32_t step, const float* sumsq, float max_norm,
                    void* bf16_shadow, const int32_t* step_device, void* stream);
+/* Sharded optimiser (data parallel; ZeRO-1 style): the same two kernels over `count` pieces of `piece`
+ * elements lying `stride` elements apart -- the slice ONE rank owns of every reduce-scattered gradient bucket. All
+ * pointers are passed at the rank's first owned element; piece and stride are multiples of 4. */
+int mig_sumsq_strided(const float* g, float* out, float* partials, int64_t piece, int64_t stride, int64_t count,
+                      void* stream);
+int mig_adamw_step_strided(float* p, const float* g, float* m, float* v, int64_t piece, int64_t stride, int64_t count,
+                           float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                           const float* sumsq, float max_norm, void* bf16_shadow, const int32_t* step_device,
+                           void* stream);
 
 #ifdef __cplusplus
 }

@@ -88,6 +88,8 @@ _SIGNATURES = {
     "mig_vae_sample_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _l, _p],
     "mig_sumsq": [_p, _p, _p, _l, _p],
     "mig_adamw_step": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _f, _p, _p, _p],
+    "mig_sumsq_strided": [_p, _p, _p, _l, _l, _l, _p],
+    "mig_adamw_step_strided": [_p, _p, _p, _p, _l, _l, _l, _f, _f, _f, _f, _f, _i, _p, _f, _p, _p, _p],
 }
 _RESTYPES = {"mig_last_error": C.c_char_p, "mig_conv_workspace_bytes": C.c_int64,
              "mig_groupnorm_workspace_bytes": C.c_int64}

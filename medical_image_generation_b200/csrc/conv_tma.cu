@@ -807,8 +807,18 @@ static void plan_box_conv(const BoxGeom& b, int bn, int num_kb, bool ws_ok, int*
   }
 }
 
-static bool epilogue_stats_ok(const BoxGeom& b, int bn, int splits, int groups) {
-  return splits == 1 && bn >= 64 && b.Cdst % 16 == 0 && groups > 0 && b.Cdst % groups == 0 && (b.Cdst / groups) % 8 == 0;
+// The epilogue can only deliver the statistics when it sees final values (no split-K) and whole 8-channel units of one
+// group. It is USED when it is free: with two accumulator sets in tensor memory (2*MT*BN <= 512 columns) the epilogue of
+// tile i overlaps the main loop of tile i+1. For the 256 x 256 tile the epilogue is exposed, and measured on the
+// config-3 step the extra reduction work cost 0.8 ms of convolution time per step to save 0.16 ms of (L2-resident)
+// statistics passes -- there the separate pass is the faster design. MIG_GN_EPILOGUE=always / never overrides (tests).
+static bool epilogue_stats_ok(const BoxGeom& b, int bn, int mt, int splits, int groups) {
+  if (!(splits == 1 && bn >= 64 && b.Cdst % 16 == 0 && groups > 0 && b.Cdst % groups == 0 && (b.Cdst / groups) % 8 == 0))
+    return false;
+  const char* e = getenv("MIG_GN_EPILOGUE");
+  if (e && e[0] == 'a') return true;
+  if (e && e[0] == 'n') return false;
+  return 2 * mt * bn <= 512;
 }
 
 // src: activation being convolved (x for fwd, dy for dgrad); wk: filter as [Cdst][taps][Csrc] (or, with ex->bmn, as
@@ -862,7 +872,7 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     p.partial = (float*)ws;
     cudaMemsetAsync(ws, 0, (size_t)(M * b.Cdst * 4), st);
   }
-  if (ex && ex->gn_sums && epilogue_stats_ok(b, bn, splits, ex->gn_groups)) {
+  if (ex && ex->gn_sums && epilogue_stats_ok(b, bn, mt, splits, ex->gn_groups)) {
     p.gn_sums = ex->gn_sums;
     p.gn_G = ex->gn_groups;
     p.gn_cpg = b.Cdst / ex->gn_groups;
@@ -934,7 +944,7 @@ bool tma_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int gn_groups, int64
   plan_box_conv(b, bn, num_kb, ws_bytes >= M * b.Cdst * 4, &mt, &splits);
   const int kbs = (num_kb + splits - 1) / splits;
   splits = (num_kb + kbs - 1) / kbs;
-  return epilogue_stats_ok(b, bn, splits, gn_groups);
+  return epilogue_stats_ok(b, bn, mt, splits, gn_groups);
 }
 
 int tma_conv_dgrad(const mig_conv_geom* g, const void* dy, const void* w, void* dx, void* ws, int64_t ws_bytes,

@@ -1017,13 +1017,22 @@ extern "C" int mig_vae_sample_bwd(int dtype, const void* logvar, const void* eps
 // optimizer: sum of squares + fused clip/AdamW over flat fp32 buffers
 // ------------------------------------------------------------------------------------------------
 namespace mig {
+// Strided view used by the sharded optimiser: `count` pieces of `piece4` float4s, `stride4` float4s apart (the slice a
+// rank owns of every gradient bucket). piece4 == 0: one contiguous range.
+struct Pieces { int64_t piece4, stride4; };
+__device__ __forceinline__ int64_t piece_index(const Pieces& s, int64_t i) {
+  if (s.piece4 == 0) return i;
+  const int64_t b = i / s.piece4;
+  return b * s.stride4 + (i - b * s.piece4);
+}
+
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, float* __restrict__ out, int64_t n,
-                                                    int vec) {
+                                                    int vec, Pieces ps) {
   __shared__ float red[33];
   float acc = 0.f;
   const int64_t nvec = vec ? n / 4 : 0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(g)[i];
+    float4 v = reinterpret_cast<const float4*>(g)[piece_index(ps, i)];
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   for (int64_t i = nvec * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -1038,7 +1047,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                                                     float* __restrict__ m, float* __restrict__ v, int64_t n,
                                                     AdamArgs a, const float* __restrict__ sumsq,
                                                     __nv_bfloat16* __restrict__ shadow,
-                                                    const int* __restrict__ step_dev) {
+                                                    const int* __restrict__ step_dev, Pieces ps) {
   if (step_dev) {   // step counter lives on the device (CUDA-graph replay): bias corrections computed here
     const double t = (double)step_dev[0];
     a.bc1 = (float)(1.0 - pow((double)a.b1, t));
@@ -1063,7 +1072,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const
                    ((reinterpret_cast<uintptr_t>(shadow) & 7) == 0);
   if (vec) {   // 128-bit streaming accesses: 7 fp32 streams + the bf16 shadow, one pass over the flat buffers
     const int64_t n4 = n / 4;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t ii = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ii < n4; ii += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t i = piece_index(ps, ii);
       float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<const float4*>(g)[i];
       float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
       upd(P.x, G.x, M.x, V.x); upd(P.y, G.y, M.y, V.y); upd(P.z, G.z, M.z, V.z); upd(P.w, G.w, M.w, V.w);
@@ -1095,9 +1105,22 @@ extern "C" int mig_sumsq(const float* g, float* out, float* partials, int64_t n,
   // must compute bit-identical clip coefficients or they drift apart.
   int grid = bw_grid((n + 3) / 4, 256, 4);
   if (grid > kLossBlocks) grid = kLossBlocks;
-  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, partials, n, aligned16(g));
+  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, partials, n, aligned16(g), Pieces{0, 0});
   loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, out, 1.0);
   return check_launch("sumsq");
+}
+// the same over `count` pieces of `piece` elements, `stride` elements apart, starting at g (sharded optimiser: the
+// slice this rank owns of every gradient bucket). piece, stride: multiples of 4; g 16-byte aligned.
+extern "C" int mig_sumsq_strided(const float* g, float* out, float* partials, int64_t piece, int64_t stride,
+                                 int64_t count, void* stream) {
+  MIG_REQUIRE(piece > 0 && count > 0 && partials != nullptr, "sumsq_strided: empty input or missing partials buffer");
+  MIG_REQUIRE(piece % 4 == 0 && stride % 4 == 0 && aligned16(g), "sumsq_strided: pieces must be 16-byte aligned");
+  const int64_t n = piece * count;
+  int grid = bw_grid((n + 3) / 4, 256, 4);
+  if (grid > kLossBlocks) grid = kLossBlocks;
+  sumsq_kernel<<<grid, 256, 0, as_stream(stream)>>>(g, partials, n, 1, Pieces{piece / 4, stride / 4});
+  loss_final_kernel<<<1, 256, 0, as_stream(stream)>>>(partials, grid, out, 1.0);
+  return check_launch("sumsq_strided");
 }
 extern "C" int mig_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                               float beta2, float eps, float weight_decay, int32_t step, const float* sumsq,
@@ -1108,6 +1131,25 @@ extern "C" int mig_adamw_step(float* p, const float* g, float* m, float* v, int6
   AdamArgs a{lr, beta1, beta2, eps, weight_decay, (float)(1.0 - pow((double)beta1, (double)s)),
              (float)sqrt(1.0 - pow((double)beta2, (double)s)), max_norm};
   adamw_kernel<<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, sumsq, (__nv_bfloat16*)bf16_shadow,
-                                                               step_device);
+                                                               step_device, Pieces{0, 0});
   return check_launch("adamw");
+}
+// mig_adamw_step over `count` pieces of `piece` elements, `stride` elements apart (all buffers share the layout and are
+// passed at the first owned element): the update of the slices ONE data-parallel rank owns (ZeRO-1 style sharding).
+extern "C" int mig_adamw_step_strided(float* p, const float* g, float* m, float* v, int64_t piece, int64_t stride,
+                                      int64_t count, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                      int32_t step, const float* sumsq, float max_norm, void* bf16_shadow,
+                                      const int32_t* step_device, void* stream) {
+  if (piece <= 0 || count <= 0) return 0;
+  MIG_REQUIRE(step >= 1 || step_device != nullptr, "adamw: step counts from 1");
+  MIG_REQUIRE(piece % 4 == 0 && stride % 4 == 0 && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v) &&
+                  (reinterpret_cast<uintptr_t>(bf16_shadow) & 7) == 0,
+              "adamw_strided: pieces must be 16-byte aligned");
+  const int s = step >= 1 ? step : 1;
+  AdamArgs a{lr, beta1, beta2, eps, weight_decay, (float)(1.0 - pow((double)beta1, (double)s)),
+             (float)sqrt(1.0 - pow((double)beta2, (double)s)), max_norm};
+  const int64_t n = piece * count;
+  adamw_kernel<<<bw_grid(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, sumsq, (__nv_bfloat16*)bf16_shadow,
+                                                               step_device, Pieces{piece / 4, stride / 4});
+  return check_launch("adamw_strided");
 }

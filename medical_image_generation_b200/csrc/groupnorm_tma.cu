@@ -11,9 +11,8 @@
 //     by TMA (cp.async.bulk.tensor, one elected thread): 48-64 KB per CTA are in flight regardless of registers;
 //   * the grid is exactly one wave (2 CTAs per SM x SM count), sized on the host;
 //   * every thread keeps a fixed 16-byte channel vector, so per-channel coefficients / partial sums live in registers;
-//   * backward statistics are written as per-CTA partials (no atomics, deterministic) and summed by one small kernel;
-//     the apply kernel derives the group sums from the totals itself and also emits the per-(sample, channel) column
-//     sums of dx -- the bias / time-embedding gradient of the convolution that produced x (saves that conv's colsum
+//   * backward statistics are written as per-CTA partials (no atomics, deterministic) and summed by one small kernel
+//     that also forms the group sums and the per-(sample, channel) column sums of dx -- the bias / time-embedding gradient of the convolution that produced x (saves that conv's colsum
 //     passes over dy).
 // Forward statistics arrive either from the producing convolution's epilogue (conv_tma.cu, mig_conv_fwd_stats) or from
 // gt_stats_kernel; the apply kernel turns the raw fp64 sums into mean / rstd itself (no finalize launch).
@@ -309,33 +308,55 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_stats_kernel(const __gri
   }
 }
 
-// One thread per (channel, moment): totals[n][c][m] = sum over chunks of the partials, and dgamma / dbeta = sum over n.
-// (The group sums A, B and the column sums of dx are derived from the totals by the apply kernel itself, so the
-// backward is statistics -> this kernel -> apply: no separate finalize launch.)
-__global__ void __launch_bounds__(128) gt_bwd_total_kernel(const float* __restrict__ part, float* __restrict__ tot,
-                                                           float* __restrict__ dgamma, float* __restrict__ dbeta, int N,
-                                                           int C, int chunks) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // = c * 3 + moment
-  if (i >= C * 3) return;
-  float all = 0.f;
-  for (int n = 0; n < N; ++n) {
-    const float* p = part + ((int64_t)n * chunks) * C * 3 + i;
+// Totals and group sums in ONE small launch. Block (q, n) owns a quarter of the groups of sample n: its threads add the
+// per-CTA partials of the block's channels (coalesced: consecutive threads, consecutive (channel, moment) items), keep
+// the totals in shared memory, then one thread per group forms A = sum_c gamma_c * (sum dz xhat), B = sum_c gamma_c *
+// (sum dz) and the column sums of dx. tot[n][c][3] goes to global memory for dgamma / dbeta (summed over n by the
+// apply kernel's first CTAs).
+__global__ void __launch_bounds__(256) gt_bwd_reduce_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ tot,
+                                                            float* __restrict__ grp, float* __restrict__ dxsum, int N,
+                                                            int C, int G, int chunks, float S) {
+  extern __shared__ float tl[];   // [(c1 - c0) * 3]
+  const int n = blockIdx.y, cpg = C / G;
+  const int gq = (G + gridDim.x - 1) / gridDim.x;
+  const int g0 = blockIdx.x * gq, g1 = min(G, g0 + gq);
+  if (g0 >= g1) return;
+  const int c0 = g0 * cpg, nitem = (g1 - g0) * cpg * 3;
+  const float* p = part + ((int64_t)n * chunks) * C * 3 + (int64_t)c0 * 3;
+  for (int i = threadIdx.x; i < nitem; i += blockDim.x) {
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int k = 0;
     for (; k + 3 < chunks; k += 4) {
-      s0 += p[(int64_t)k * C * 3];
-      s1 += p[(int64_t)(k + 1) * C * 3];
-      s2 += p[(int64_t)(k + 2) * C * 3];
-      s3 += p[(int64_t)(k + 3) * C * 3];
+      s0 += p[(int64_t)k * C * 3 + i];
+      s1 += p[(int64_t)(k + 1) * C * 3 + i];
+      s2 += p[(int64_t)(k + 2) * C * 3 + i];
+      s3 += p[(int64_t)(k + 3) * C * 3 + i];
     }
-    for (; k < chunks; ++k) s0 += p[(int64_t)k * C * 3];
+    for (; k < chunks; ++k) s0 += p[(int64_t)k * C * 3 + i];
     const float s = (s0 + s1) + (s2 + s3);
-    tot[(int64_t)n * C * 3 + i] = s;
-    all += s;
+    tl[i] = s;
+    tot[((int64_t)n * C + c0) * 3 + i] = s;
   }
-  const int c = i / 3, m = i - 3 * c;
-  if (m == 0 && dgamma) dgamma[c] = all;
-  if (m == 1 && dbeta) dbeta[c] = all;
+  __syncthreads();
+  for (int gi = g0 + threadIdx.x; gi < g1; gi += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+      a = fmaf(gamma[c], tl[(c - c0) * 3], a);
+      b = fmaf(gamma[c], tl[(c - c0) * 3 + 1], b);
+    }
+    grp[2 * (n * G + gi)] = a;
+    grp[2 * (n * G + gi) + 1] = b;
+    if (dxsum) {
+      // sum_s dx[n,s,c] = rstd * (gamma_c * sum dz - (A * sum xhat + B * S) / cnt),  sum xhat = rstd * (sum x - S mean)
+      const float r = rstd[n * G + gi], m = mean[n * G + gi], inv = 1.f / (S * (float)cpg);
+      for (int c = gi * cpg; c < (gi + 1) * cpg; ++c) {
+        const float sxh = r * (tl[(c - c0) * 3 + 2] - S * m);
+        dxsum[(int64_t)n * C + c] = r * (gamma[c] * tl[(c - c0) * 3 + 1] - (a * sxh + b * S) * inv);
+      }
+    }
+  }
 }
 
 // ---- backward apply: dx = rstd * (dz*gamma - (xhat*A + B) / cnt) ------------------------------------------------------
@@ -346,9 +367,11 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
                                                                      const float* __restrict__ beta,
                                                                      const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd,
+                                                                     const float* __restrict__ grp,
                                                                      const float* __restrict__ tot,
                                                                      __nv_bfloat16* __restrict__ dx,
-                                                                     float* __restrict__ dxsum, GtGeom g,
+                                                                     float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, GtGeom g,
                                                                      float inv_count) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -359,33 +382,27 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
   const int c0 = slab * g.cb + tcol * 8;
   // dx = k1*dz - k2*xhat - k3 with xhat = x*rs + m2, z = xhat*ga + be
   float rs[8], m2[8], ga[8], be[8], k1[8], k2[8], k3[8];
-  const float* tn = tot + (int64_t)n * g.C * 3;
-  float A = 0.f, B = 0.f;
-  int gprev = -1;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int grp = (c0 + j) / g.cpg, gi = n * g.G + grp;
-    if (grp != gprev) {   // group sums A = sum_c gamma_c * (sum dz xhat), B = sum_c gamma_c * (sum dz): a few dozen L2 hits
-      A = B = 0.f;
-      for (int c = grp * g.cpg; c < (grp + 1) * g.cpg; ++c) {
-        const float gc = gamma[c];
-        A = fmaf(gc, tn[c * 3], A);
-        B = fmaf(gc, tn[c * 3 + 1], B);
-      }
-      gprev = grp;
-    }
+    const int gi = n * g.G + (c0 + j) / g.cpg;
     rs[j] = rstd[gi];
     m2[j] = -mean[gi] * rs[j];
     ga[j] = gamma[c0 + j];
     be[j] = beta[c0 + j];
     k1[j] = rs[j] * ga[j];
-    k2[j] = rs[j] * A * inv_count;
-    k3[j] = rs[j] * B * inv_count;
-    if (dxsum && chunk == 0 && threadIdx.x < g.cvb) {
-      // sum_s dx[n,s,c] = rstd * (gamma_c * sum dz - (A * sum xhat + B * S) / cnt),  sum xhat = rstd * (sum x - S mean)
-      const float S = (float)g.S;
-      const float sxh = rs[j] * (tn[(c0 + j) * 3 + 2] - S * mean[gi]);
-      dxsum[(int64_t)n * g.C + c0 + j] = rs[j] * (ga[j] * tn[(c0 + j) * 3 + 1] - (A * sxh + B * S) * inv_count);
+    k2[j] = rs[j] * grp[2 * gi] * inv_count;
+    k3[j] = rs[j] * grp[2 * gi + 1] * inv_count;
+  }
+  if (n == 0 && chunk == 0 && threadIdx.x < g.cvb) {   // dgamma / dbeta = totals summed over the samples
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = 0.f, b = 0.f;
+      for (int nn = 0; nn < g.N; ++nn) {
+        a += tot[((int64_t)nn * g.C + c0 + j) * 3];
+        b += tot[((int64_t)nn * g.C + c0 + j) * 3 + 1];
+      }
+      if (dgamma) dgamma[c0 + j] = a;
+      if (dbeta) dbeta[c0 + j] = b;
     }
   }
   __nv_bfloat16* obase = dx + ((int64_t)n * g.S) * g.C + c0;
@@ -417,7 +434,7 @@ static int gt_optin(K kernel, int smem, SmemOptIn& st, const char* what) {
 int64_t gt_bwd_workspace_bytes(int N, int64_t S, int C, int G) {
   if (!gt_eligible(N, S, C, G)) return 0;
   GtGeom g = gt_geom(N, S, C, G);
-  return ((int64_t)N * g.chunks * C * 3 + (int64_t)N * C * 3) * 4 + 256;
+  return ((int64_t)N * g.chunks * C * 3 + (int64_t)N * C * 3 + (int64_t)N * G * 2) * 4 + 256;
 }
 
 int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* stream) {
@@ -466,6 +483,7 @@ int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
   if (gt_map(&xm, x, g) || gt_map(&dym, dy, g)) return 1;
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   float* tot = part + (int64_t)N * g.chunks * C * 3;
+  float* grp = tot + (int64_t)N * C * 3;
   constexpr int smem = 3 * 2 * GT_TENSOR_STAGE + 128;
   dim3 grid(g.chunks, g.slabs, N);
   if (silu) {
@@ -477,18 +495,22 @@ int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
     if (int rc = gt_optin(gt_bwd_stats_kernel<false>, smem, o, "groupnorm_bwd")) return rc;
     gt_bwd_stats_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, part, g);
   }
-  gt_bwd_total_kernel<<<(C * 3 + 127) / 128, 128, 0, st>>>(part, tot, dgamma, dbeta, N, C, g.chunks);
+  {
+    const int pb = G >= 4 ? 4 : 1, gq = (G + pb - 1) / pb;
+    gt_bwd_reduce_kernel<<<dim3(pb, N), 256, (size_t)gq * g.cpg * 3 * sizeof(float), st>>>(
+        part, gamma, mean, rstd, tot, grp, dx_colsum, N, C, G, g.chunks, (float)S);
+  }
   const float inv = 1.f / ((float)S * (float)g.cpg);
   if (silu) {
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<true>, smem, o, "groupnorm_bwd")) return rc;
-    gt_bwd_apply_kernel<true><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, tot, (__nv_bfloat16*)dx,
-                                                              dx_colsum, g, inv);
+    gt_bwd_apply_kernel<true><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, tot,
+                                                              (__nv_bfloat16*)dx, dgamma, dbeta, g, inv);
   } else {
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<false>, smem, o, "groupnorm_bwd")) return rc;
-    gt_bwd_apply_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, tot, (__nv_bfloat16*)dx,
-                                                               dx_colsum, g, inv);
+    gt_bwd_apply_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, tot,
+                                                               (__nv_bfloat16*)dx, dgamma, dbeta, g, inv);
   }
   return check_launch("groupnorm_bwd");
 }

@@ -80,12 +80,108 @@ class GradBuckets:
                 self.flat[bk["lo"]:bk["hi"]].div_(self.world)
 
 
+class ShardedBuckets:
+    """Gradient exchange of the SHARDED optimiser (ZeRO-1 style; SURVEY.md section 8e asks for one exchange step -- this is
+    the same step with half the wire bytes and 1/world of the optimiser work per rank).
+
+    The flat buffer is [ sharded region | replicated region | ... ]:
+      * sharded region = the bf16-consumed parameters (conv filters, attention projections): `nb` UNIFORM buckets of
+        `bucket` elements; bucket b is reduce-scattered (mean) as soon as every parameter overlapping it has its
+        gradient, so rank r ends up with the reduced slice [b*bucket + r*piece, +piece) of every bucket (piece =
+        bucket / world). A parameter may span several buckets.
+      * replicated region = the few parameters the kernels read in fp32 (biases, norm gains, the time-embedding MLP):
+        ONE all-reduce; every rank updates them redundantly, so no parameter gather is needed for them.
+    After the optimiser step `gather(buf)` all-gathers the owned slices of `buf` (the bf16 shadow every step; the fp32
+    master / Adam moments only for checkpoints). gloo (CPU tests) has neither AVG nor reduce_scatter_tensor: it falls back
+    to all_reduce + divide, which leaves the same values in the owned slices."""
+
+    def __init__(self, flat: torch.Tensor, spans, shard_numel: int, bucket: int, repl_lo: int, repl_hi: int,
+                 repl_members, group=None):
+        self.flat, self.group = flat, group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        if bucket % self.world or shard_numel % bucket:
+            raise ValueError("bucket size must divide the sharded region and be a multiple of the world size")
+        self.bucket, self.piece, self.nb = bucket, bucket // self.world, shard_numel // bucket
+        self.shard_numel = shard_numel
+        self.buckets = [dict(lo=b * bucket, hi=(b + 1) * bucket, kind="rs", n=0, pending=0, work=None)
+                        for b in range(self.nb)]
+        self.member_buckets = []                      # member index -> bucket indices it overlaps
+        for lo, hi in spans:                          # sharded members, buffer order
+            bs = list(range(lo // bucket, (hi - 1) // bucket + 1)) if hi > lo else []
+            for b in bs:
+                self.buckets[b]["n"] += 1
+            self.member_buckets.append(bs)
+        self.repl = None
+        if repl_hi > repl_lo:
+            self.repl = dict(lo=repl_lo, hi=repl_hi, kind="ar", n=len(repl_members), pending=0, work=None)
+            self.buckets.append(self.repl)
+            for _ in repl_members:
+                self.member_buckets.append([len(self.buckets) - 1])
+        self.seen = set()
+        self.reset()
+
+    def _launch(self, bk) -> None:
+        buf = self.flat[bk["lo"]:bk["hi"]]
+        if bk["kind"] == "rs" and self.nccl:
+            mine = buf[self.rank * self.piece:(self.rank + 1) * self.piece]     # in place: output = own slice of input
+            bk["work"] = dist.reduce_scatter_tensor(mine, buf, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            op = dist.ReduceOp.AVG if self.nccl else dist.ReduceOp.SUM
+            bk["work"] = dist.all_reduce(buf, op=op, group=self.group, async_op=True)
+
+    def ready(self, index: int) -> None:
+        if index in self.seen:
+            return
+        self.seen.add(index)
+        for b in self.member_buckets[index]:
+            bk = self.buckets[b]
+            bk["pending"] -= 1
+            if bk["pending"] == 0:
+                self._launch(bk)
+
+    def reset(self) -> None:
+        self.seen.clear()
+        for bk in self.buckets:
+            bk["pending"], bk["work"] = bk["n"], None
+
+    def finish(self) -> None:
+        for bk in self.buckets:
+            if bk["work"] is None:
+                self._launch(bk)
+        for bk in self.buckets:
+            bk["work"].wait()
+            if not self.nccl:
+                self.flat[bk["lo"]:bk["hi"]].div_(self.world)
+
+    def owned(self, buf: torch.Tensor, b: int) -> torch.Tensor:
+        lo = b * self.bucket + self.rank * self.piece
+        return buf[lo:lo + self.piece]
+
+    def gather(self, buf: torch.Tensor) -> None:
+        """All-gather the owned slices of `buf` (same layout as the gradient buffer) in place, bucket by bucket."""
+        works = []
+        for b in range(self.nb):
+            whole = buf[b * self.bucket:(b + 1) * self.bucket]
+            if self.nccl:
+                works.append(dist.all_gather_into_tensor(whole, self.owned(buf, b), group=self.group, async_op=True))
+            else:
+                parts = [torch.empty_like(self.owned(buf, b)) for _ in range(self.world)]
+                dist.all_gather(parts, self.owned(buf, b).clone(), group=self.group)
+                for r, part in enumerate(parts):
+                    whole[r * self.piece:(r + 1) * self.piece].copy_(part)
+        for w in works:
+            w.wait()
+
+
 class FlatAdamW:
     """AdamW + global-norm clipping over flat buffers; numerics follow torch.optim.AdamW / clip_grad_norm_."""
 
+    FP32_CONSUMED = ("time_embed", "time_emb_proj", "class_embedding")   # Linear weights the kernels read in fp32
+
     def __init__(self, module: torch.nn.Module, lr: float = 2e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2, max_grad_norm: Optional[float] = 1.0, bucket_mb: float = 64.0,
-                 unused: Iterable[str] = ("proj_attn",)):
+                 unused: Iterable[str] = ("proj_attn",), shard: Optional[bool] = None):
         named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not named:
             raise ValueError("module has no trainable parameters")
@@ -94,17 +190,38 @@ class FlatAdamW:
         if dev.type != "cuda":
             raise RuntimeError("FlatAdamW needs the module on a CUDA device")
         is_unused = lambda n: any(tag in n for tag in unused)  # noqa: E731
+        world = dist.get_world_size() if _dist_on() else 1
+        # Sharded update (ZeRO-1 style) when data parallel: only meaningful in bf16 mode, where every large parameter
+        # is consumed through its bf16 shadow (the fp32 parity mode reads the masters themselves on every rank).
+        bf16_mode = getattr(module, "compute_dtype", torch.bfloat16) == torch.bfloat16
+        self.sharded = world > 1 and bf16_mode and (True if shard is None else bool(shard))
         # backward produces gradients roughly in reverse registration order: lay the buffer out in that order so a
         # bucket (contiguous slice) completes early and can be reduced while the rest of backward still runs
         used = [(n, p) for n, p in reversed(named) if not is_unused(n)]
         tail = [(n, p) for n, p in named if is_unused(n)]
+        # fp32-consumed parameters (1-D: biases / norm gains; the time-embedding MLP) form the replicated region
+        fp32_used = lambda n, p: p.ndim <= 1 or any(tag in n for tag in self.FP32_CONSUMED)  # noqa: E731
+        if self.sharded:
+            shard_part = [(n, p) for n, p in used if not fp32_used(n, p)]
+            repl_part = [(n, p) for n, p in used if fp32_used(n, p)]
+        else:
+            shard_part, repl_part = [], used
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
         # every parameter starts on a 64-element boundary (256 B fp32 / 128 B bf16): TMA and the 16-byte vector paths
         # need aligned bases. Padding elements stay exactly zero (zero grad, zero master) through AdamW.
         pad = lambda k: (k + 63) // 64 * 64  # noqa: E731
-        self.used_numel = sum(pad(p.numel()) for _, p in used)
+        shard_raw = sum(pad(p.numel()) for _, p in shard_part)
+        self.bucket_elems = 0
+        self.shard_numel = 0
+        if self.sharded and shard_raw:
+            unit = world * 64
+            self.bucket_elems = max(unit, (int(bucket_mb * (1 << 20) / 4) + unit - 1) // unit * unit)
+            self.shard_numel = (shard_raw + self.bucket_elems - 1) // self.bucket_elems * self.bucket_elems
+        repl_numel = sum(pad(p.numel()) for _, p in repl_part)
+        self.repl_lo = self.shard_numel
+        self.used_numel = self.shard_numel + repl_numel
         total = self.used_numel + sum(pad(p.numel()) for _, p in tail)
         self.master = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -112,30 +229,44 @@ class FlatAdamW:
         self.v = torch.zeros(self.used_numel, dtype=torch.float32, device=dev)
         self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._ss = torch.zeros(2, dtype=torch.float32, device=dev)     # sharded: [own slices, replicated region]
         self._partials = torch.zeros(2048, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.params = []
-        off = 0
-        for n, p in used + tail:
-            k = p.numel()
-            with torch.no_grad():
-                view = self.master[off:off + k].as_strided(p.shape, p.stride())
-                view.copy_(p)
-                p.data = view
-            p.main_grad = self.grad[off:off + k].as_strided(p.shape, p.stride())
-            p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
-            p._mig_shadow_version = p._version   # ops._filter_for re-casts the slot when the master changed in place
-            p._mig_slot = (off, k)
-            self.params.append((n, p))
-            off += pad(k)
+
+        def place(group, off):
+            spans = []
+            for n, p in group:
+                k = p.numel()
+                with torch.no_grad():
+                    view = self.master[off:off + k].as_strided(p.shape, p.stride())
+                    view.copy_(p)
+                    p.data = view
+                p.main_grad = self.grad[off:off + k].as_strided(p.shape, p.stride())
+                p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
+                p._mig_shadow_version = p._version   # ops._filter_for re-casts the slot when the master changed in place
+                p._mig_slot = (off, k)
+                self.params.append((n, p))
+                spans.append((off, off + pad(k)))
+                off += pad(k)
+            return spans, off
+
+        shard_spans, _ = place(shard_part, 0)
+        _, off = place(repl_part, self.repl_lo)
+        place(tail, off)
         call("mig_cast", 0, 1, ops._ptr(self.master), ops._ptr(self.shadow), total, ops._stream())
         # ---- gradient buckets (contiguous slices of the used region) ----
         self.buckets = None
         self._index_of = {}
         self._sync_enabled = True
         if _dist_on():
-            self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
-            self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
+            if self.sharded:
+                self.buckets = ShardedBuckets(self.grad, shard_spans, self.shard_numel, self.bucket_elems or world * 64,
+                                              self.repl_lo, self.used_numel, repl_part)
+                self._index_of = {id(p): i for i, (_, p) in enumerate(shard_part + repl_part)}
+            else:
+                self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
+                self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
         # every owned parameter carries the callback of ITS optimiser (several FlatAdamW instances can coexist)
         for _, p in self.params:
             p._mig_grad_ready = self._grad_ready
@@ -172,15 +303,51 @@ class FlatAdamW:
         self.step_count += 1          # host mirror; the kernel reads the device counter (valid under graph replay)
         self.step_dev.add_(1)
         st = ops._stream()
+        hp = (float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
+              int(self.step_count))
         sumsq_ptr = None
         max_norm = 0.0
+        if not (self.sharded and self.shard_numel):
+            if self.max_grad_norm:
+                call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), ops._ptr(self._partials), self.used_numel, st)
+                sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
+            call("mig_adamw_step", ops._ptr(self.master), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
+                 self.used_numel, *hp, sumsq_ptr, max_norm, ops._ptr(self.shadow), ops._ptr(self.step_dev), st)
+            return
+        # ---- sharded: this rank owns slice `rank` of every bucket of the sharded region ----
+        bk = self.buckets
+        first = bk.rank * bk.piece
+        own = lambda buf: ops._ptr(buf[first:])  # noqa: E731   (first owned element; pieces lie `bucket` apart)
+        n_repl = self.used_numel - self.repl_lo
         if self.max_grad_norm:
-            call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), ops._ptr(self._partials), self.used_numel, st)
+            # ||g||^2 = sum over ranks of the owned slices (one scalar all-reduce; the same value on every rank, so the
+            # clip coefficient and with it the replicas stay bit-identical) + the replicated region
+            call("mig_sumsq_strided", own(self.grad), ops._ptr(self._ss[0:1]), ops._ptr(self._partials), bk.piece,
+                 bk.bucket, bk.nb, st)
+            dist.all_reduce(self._ss[0:1], op=dist.ReduceOp.SUM, group=bk.group)
+            if n_repl:
+                call("mig_sumsq", ops._ptr(self.grad[self.repl_lo:]), ops._ptr(self._ss[1:2]), ops._ptr(self._partials),
+                     n_repl, st)
+            else:
+                self._ss[1:2].zero_()
+            call("mig_add", 0, ops._ptr(self._ss[0:1]), ops._ptr(self._ss[1:2]), ops._ptr(self.sumsq), 1, st)
             sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
-        call("mig_adamw_step", ops._ptr(self.master), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
-             self.used_numel, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
-             float(self.weight_decay), int(self.step_count), sumsq_ptr, max_norm, ops._ptr(self.shadow),
-             ops._ptr(self.step_dev), st)
+        call("mig_adamw_step_strided", own(self.master), own(self.grad), own(self.m), own(self.v), bk.piece, bk.bucket,
+             bk.nb, *hp, sumsq_ptr, max_norm, own(self.shadow), ops._ptr(self.step_dev), st)
+        if n_repl:
+            lo = self.repl_lo
+            call("mig_adamw_step", ops._ptr(self.master[lo:]), ops._ptr(self.grad[lo:]), ops._ptr(self.m[lo:]),
+                 ops._ptr(self.v[lo:]), n_repl, *hp, sumsq_ptr, max_norm, ops._ptr(self.shadow[lo:]),
+                 ops._ptr(self.step_dev), st)
+        bk.gather(self.shadow)      # every rank needs all bf16 weights for the next forward: 2 bytes per parameter
+
+    def consolidate(self) -> None:
+        """COLLECTIVE. With the sharded update a rank holds current fp32 masters / Adam moments only for the slices it
+        owns (the bf16 shadows are always complete). Call this on every rank before `module.state_dict()` /
+        `torch_state_dict()` (checkpoints, train_ldm.py:466-491): it all-gathers master, m and v."""
+        if self.sharded and self.shard_numel:
+            for buf in (self.master, self.m, self.v):
+                self.buckets.gather(buf)
 
     def refresh_shadow(self) -> None:
         """Re-derive the whole bf16 shadow from the fp32 master (one cast launch). Needed only after writing to
@@ -252,14 +419,16 @@ class LDMTrainer:
 
     def __init__(self, unet, scheduler, lr: float = 2e-5, grad_clip_max_norm: Optional[float] = 1.0,
                  weight_decay: float = 1e-2, bucket_mb: float = 64.0, cuda_graph: bool = False,
-                 graph_warmup_steps: int = 3, grad_accumulate_step: int = 1):
+                 graph_warmup_steps: int = 3, grad_accumulate_step: int = 1, shard_optimizer: Optional[bool] = None):
         self.unet, self.scheduler = unet, scheduler
         # config['grad_accumulate_step'] (train_ldm.py:173): the optimiser steps every k-th call of step(); gradients
         # of the micro-steps are SUMMED (the reference does not rescale the loss)
         self.grad_accumulate_step = max(1, int(grad_accumulate_step))
         self._micro = 0
+        # data parallel + bf16: the optimiser is sharded by default (reduce-scatter, 1/world of AdamW per rank,
+        # all-gather of the bf16 weights); shard_optimizer=False keeps the replicated all-reduce scheme
         self.opt = FlatAdamW(unet, lr=lr, weight_decay=weight_decay, max_grad_norm=grad_clip_max_norm,
-                             bucket_mb=bucket_mb)
+                             bucket_mb=bucket_mb, shard=shard_optimizer)
         if _dist_on():  # identical replicas: broadcast rank 0's parameters (flat: one collective)
             dist.broadcast(self.opt.master, src=0)
             self.opt.refresh_shadow()
@@ -342,6 +511,30 @@ class LDMTrainer:
             self.opt.set_grad_sync(True)
             self.opt.step()
             self._micro = 0
+
+    def checkpoint(self, epoch: int, validation_loss: float) -> dict:
+        """COLLECTIVE (call on every rank; save on one). The reference's checkpoint dict (train_ldm.py:472-477):
+        `network_state_dict` = the module's state_dict, `optimizer_state_dict` in torch.optim.AdamW's own layout. With
+        the sharded optimiser the fp32 masters / moments are gathered from their owners first."""
+        self.opt.consolidate()
+        return {"epoch": epoch, "network_state_dict": self.unet.state_dict(),
+                "optimizer_state_dict": self.opt.torch_state_dict(), "validation_loss": validation_loss}
+
+
+@torch.no_grad()
+def latent_scale_factor(autoencoder, images: torch.Tensor, src: int = 0) -> torch.Tensor:
+    """`scale_factor = 1 / std(z)` of the FIRST batch (train_ldm.py:98-118), computed ONCE on rank `src` and broadcast:
+    it is data dependent, and every data-parallel rank must scale its latents by the same number.
+    Returns a 0-d tensor on the autoencoder's device."""
+    dev = next(autoencoder.parameters()).device
+    sf = torch.zeros((), dtype=torch.float32, device=dev)
+    rank = dist.get_rank() if _dist_on() else src
+    if rank == src:
+        z = autoencoder.encode_stage_2_inputs(images.to(dev))
+        sf = (1.0 / torch.std(z.float())).reshape(())
+    if _dist_on():
+        dist.broadcast(sf, src=src)
+    return sf
 
 
 class AETrainer:

@@ -280,13 +280,16 @@ def test_group_norm_split_and_colsum(C, G, sp):
     (2, 128, 256, (6, 6, 6), 32, True, False),      # split-K plan: statistics fall back to one pass over y
     (1, 32, 32, (32, 32, 32), 16, False, False),    # halo kernel (2 channels per group): statistics pass
 ])
-def test_conv_epilogue_groupnorm_statistics(case):
+def test_conv_epilogue_groupnorm_statistics(case, monkeypatch):
     """mig_conv_fwd_stats: the convolution also delivers (sum y, sum y^2) per (sample, group) of its bf16 output, and
     ops.group_norm on that tensor (apply only) equals GroupNorm computed from scratch."""
     ops = _ops()
     import ctypes as Cc
     from medical_image_generation_b200 import _lib
     N, Cin, Cout, sp, G, extras, in_epilogue = case
+    # by default the epilogue delivers the statistics only where it is hidden behind the next tile (narrow layers);
+    # "always" exercises it for every group width
+    monkeypatch.setenv("MIG_GN_EPILOGUE", "always")
     geom = _lib.conv_geom(N, sp, sp, Cin, Cout, (3, 3, 3), (1, 1, 1), (1, 1, 1))
     need = _lib.load().mig_conv_workspace_bytes(Cc.byref(geom), 1, 0, 0)
     assert bool(_lib.load().mig_conv_fwd_stats_in_epilogue(Cc.byref(geom), 1, G, 0, max(int(need), 1 << 20))) == in_epilogue

@@ -61,7 +61,41 @@ if rank == 0:
     worst = max(float((pa[k] - pb[k]).norm() / pb[k].norm().clamp_min(1e-12)) for k in pa)
     ok_global = worst < 5e-4
     print(f"dp{world}: replicas identical={same}; vs single-process global batch worst rel diff {worst:.2e}", flush=True)
-flag = torch.tensor([int(same and ok_global)], device="cuda")
+# ---- bf16 production mode: SHARDED optimiser (reduce-scatter / owned-slice AdamW / all-gather of the bf16 weights) must
+# follow the replicated all-reduce scheme, keep the bf16 weights identical on every rank, and consolidate() must restore
+# complete fp32 masters everywhere
+def run_bf16(shard):
+    m = mig.DiffusionModelUNet(**g["cfg"], compute_dtype=torch.bfloat16)
+    m.load_state_dict(params)
+    m = m.cuda().train()
+    t_ = LDMTrainer(m, mig.DDPMScheduler(**kw), lr=1e-3, bucket_mb=0.25, shard_optimizer=shard)
+    assert t_.opt.sharded == shard
+    losses = []
+    for x0, nz, t in data:
+        sl = slice(rank * B, (rank + 1) * B)
+        losses.append(float(t_.step(x0[sl].cuda(), noise=nz[sl].cuda(), timesteps=t[sl].cuda())))
+    t_.opt.consolidate()
+    out = (t_.opt.master.clone(), t_.opt.shadow.clone(), dict((k, v.detach().clone()) for k, v in m.state_dict().items()),
+           losses, t_.opt.buckets.nb if shard else 0)
+    t_.opt.close()
+    return out
+
+
+master_s, shadow_s, sd_s, loss_s, nb = run_bf16(True)
+master_r, shadow_r, sd_r, loss_r, _ = run_bf16(False)
+chk = shadow_s.float().clone()
+dist.broadcast(chk, src=0)
+same_shadow = bool(torch.equal(chk, shadow_s.float()))
+chk = master_s.clone()
+dist.broadcast(chk, src=0)
+same_master = bool(torch.equal(chk, master_s))
+worst_sd = max(float((sd_s[k].float() - sd_r[k].float()).norm() / sd_r[k].float().norm().clamp_min(1e-12)) for k in sd_r)
+ok_shard = same_shadow and same_master and worst_sd < 5e-3 and nb > 1
+if rank == 0:
+    print(f"dp{world} bf16 sharded ({nb} buckets): bf16 weights identical on all ranks={same_shadow}; consolidated fp32 masters "
+          f"identical={same_master}; sharded vs replicated state_dict worst rel diff {worst_sd:.2e}; losses {loss_s} vs {loss_r}",
+          flush=True)
+flag = torch.tensor([int(same and ok_global and ok_shard)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()
 sys.exit(0 if int(flag) == 1 else 1)
