@@ -97,6 +97,13 @@ int mig_gemm_strided(const mig_gemm_desc* d, int dtype_ab, int dtype_c, const vo
  * (receives the log2-domain log-sum-exp). dh must be a multiple of 64 (above 256: a multiple of 256). */
 int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B, int32_t H,
                             int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream);
+/* Backward of the above without any L x L tensor (training path of unet:396-416): P is recomputed per tile from q, k and
+ * the forward's `lse`; o / d_o are the forward output and its gradient; `delta` is a workspace of B*H*Lq floats
+ * (receives rowsum(d_o * o)). dq (B,Lq,H*dh), dk / dv (B,Lk,H*dh): bf16, fully written. dh: a multiple of 64. Heads wider
+ * than the tensor-memory accumulators (the LDM's 512 / 768-channel single heads) are processed in column slices. */
+int mig_flash_attention_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                            const float* lse, float* delta, void* dq, void* dk, void* dv, int32_t B, int32_t H,
+                            int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream);
 
 /* ---- K4/K5: GroupNorm (+SiLU), nn.GroupNorm at unet:628,648,275,377,1932; ae:157,167,238,451,604 ----
  * x,y: [N][S][C] channels-last, S = D*H*W. mean/rstd: [N][G] fp32 (saved for backward). */

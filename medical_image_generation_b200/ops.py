@@ -908,24 +908,30 @@ def sdpa(q, k, v, heads: int, scale_: float):
     _require_cuda(q, "sdpa")
     q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
     if flash_attention_usable(q, k, v, heads):
+        if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+            return _FlashSdpaFn.apply(q, k, v, int(heads), float(scale_))
         return flash_attention(q, k, v, int(heads), float(scale_))
     return _SdpaFn.apply(q, k, v, int(heads), float(scale_))
 
 
 _FLASH = True
+_FLASH_TRAIN = True
 
 
-def set_flash_attention(enabled: bool) -> None:
-    global _FLASH
+def set_flash_attention(enabled: bool, training: Optional[bool] = None) -> None:
+    """enabled: use the fused tcgen05 attention kernels at all; training: also for calls that need gradients (fused
+    forward + fused backward, no L x L tensor). `training=False` keeps the unfused GEMM + softmax chain for training."""
+    global _FLASH, _FLASH_TRAIN
     _FLASH = bool(enabled)
+    if training is not None:
+        _FLASH_TRAIN = bool(training)
 
 
 def flash_attention_usable(q, k, v, heads: int) -> bool:
-    """The fused tcgen05 kernel is forward-only: used when no gradient is needed (sampling, validation, the frozen
-    autoencoder) and the head dim fits (multiple of 64; above 256 a multiple of 256)."""
+    """The fused tcgen05 kernels need bf16 and a head dim that is a multiple of 64 (above 256: a multiple of 256)."""
     if not _FLASH or _ENGINE == _lib.ENGINE_SIMT or q.dtype != torch.bfloat16:
         return False
-    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+    if not _FLASH_TRAIN and torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
         return False
     dh = q.shape[-1] // heads
     if dh % 64 != 0 or (dh > 256 and dh % 256 != 0) or q.shape[0] * heads >= 65536:
@@ -933,15 +939,46 @@ def flash_attention_usable(q, k, v, heads: int) -> bool:
     return bool(_lib.load().mig_has_tcgen05())
 
 
-def flash_attention(q, k, v, heads: int, scale_: float):
-    """softmax(scale * q k^T) v without materialising the score matrix (unet:128-135 / 406-416). No autograd."""
+def _flash_fwd(q, k, v, heads: int, scale_: float):
     B, Lq, Cc = q.shape
     Lk = k.shape[1]
     out = torch.empty_like(q)
     lse = torch.empty((B * heads, Lq), dtype=torch.float32, device=q.device)
     call("mig_flash_attention_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, Lq, Lk, Cc // heads,
          float(scale_), _stream())
-    return out
+    return out, lse
+
+
+def flash_attention(q, k, v, heads: int, scale_: float):
+    """softmax(scale * q k^T) v without materialising the score matrix (unet:128-135 / 406-416). No autograd."""
+    return _flash_fwd(q, k, v, heads, scale_)[0]
+
+
+class _FlashSdpaFn(Function):
+    """Training attention on the fused kernels: forward saves only O and the per-row log-sum-exp; backward recomputes P
+    tile by tile (mig_flash_attention_bwd). No L x L tensor is ever allocated."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads, scale_):
+        out, lse = _flash_fwd(q, k, v, heads, scale_)
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.cfg = (heads, scale_)
+        return out
+
+    @staticmethod
+    def backward(ctx, dO):
+        q, k, v, out, lse = ctx.saved_tensors
+        heads, scale_ = ctx.cfg
+        B, Lq, Cc = q.shape
+        Lk = k.shape[1]
+        dO = dO.contiguous()
+        if dO.dtype != q.dtype:
+            dO = dO.to(q.dtype)
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        delta = torch.empty((B * heads, Lq), dtype=torch.float32, device=q.device)
+        call("mig_flash_attention_bwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(dO), _ptr(lse), _ptr(delta), _ptr(dq),
+             _ptr(dk), _ptr(dv), B, heads, Lq, Lk, Cc // heads, float(scale_), _stream())
+        return dq, dk, dv, None, None
 
 
 # ----------------------------------------------------------------------------------------------

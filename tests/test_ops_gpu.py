@@ -601,6 +601,50 @@ def test_flash_attention_forward(B, Lq, Lk, C, heads):
     assert rel_err(got, ref2) < BF16_TOL
 
 
+@pytest.mark.parametrize("B,Lq,Lk,C,heads", [(2, 256, 256, 128, 1), (1, 200, 333, 128, 2), (2, 216, 216, 768, 1),
+                                              (1, 1728, 1728, 512, 1), (1, 130, 70, 64, 1), (1, 5, 3, 256, 4),
+                                              (1, 700, 300, 256, 1), (2, 384, 384, 192, 1)])
+def test_flash_attention_backward(B, Lq, Lk, C, heads):
+    """Training attention through the fused kernels (no L x L tensor): dQ, dK, dV of mig_flash_attention_bwd against fp32
+    autograd of softmax attention on the CPU -- ragged tails, cross-attention lengths, multi-head, and the 512 / 768-channel
+    single heads of the LDM default (column-sliced accumulators)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(Lq * 3 + Lk + C)
+    q, k, v = (bf16_round(torch.randn(B, L, C, generator=g)) for L in (Lq, Lk, Lk))
+    probe = bf16_round(torch.randn(B, Lq, C, generator=g))
+    scale = 1 / math.sqrt(C / heads)
+
+    def split(t):
+        return t.reshape(B, -1, heads, C // heads).permute(0, 2, 1, 3)
+
+    qr, kr, vr = (t.clone().requires_grad_(True) for t in (q, k, v))
+    p = torch.softmax(split(qr) @ split(kr).transpose(-1, -2) * scale, dim=-1)
+    want = (p @ split(vr)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    (want * probe).sum().backward()
+    qd, kd, vd = (t.to(DEV).bfloat16().requires_grad_(True) for t in (q, k, v))
+    seen = []
+    real = ops.call
+    ops.call = lambda name, *a: (seen.append(name), real(name, *a))[1]
+    try:
+        got = ops.sdpa(qd, kd, vd, heads, scale)
+        (got.float() * probe.to(DEV)).sum().backward()
+    finally:
+        ops.call = real
+    assert seen == ["mig_flash_attention_fwd", "mig_flash_attention_bwd"], seen
+    assert rel_err(got, want) < BF16_TOL
+    assert rel_err(qd.grad, qr.grad) < BF16_TOL
+    assert rel_err(kd.grad, kr.grad) < BF16_TOL
+    assert rel_err(vd.grad, vr.grad) < BF16_TOL
+    # and against the unfused GEMM + softmax training chain on the same bf16 inputs
+    ops.set_flash_attention(True, training=False)
+    try:
+        q2, k2, v2 = (t.to(DEV).bfloat16().requires_grad_(True) for t in (q, k, v))
+        (ops.sdpa(q2, k2, v2, heads, scale).float() * probe.to(DEV)).sum().backward()
+    finally:
+        ops.set_flash_attention(True, training=True)
+    assert rel_err(qd.grad, q2.grad) < BF16_TOL and rel_err(kd.grad, k2.grad) < BF16_TOL
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("shape,k,s", [((2, 16, 8, 8, 4), (2, 2, 1), (2, 2, 1)), ((1, 8, 9, 7, 6), (3, 3, 3), (2, 2, 2)),
                                        ((3, 24, 10, 12), (2, 2), (2, 2)), ((1, 5, 7, 7), (3, 2), (1, 2))])

@@ -89,11 +89,16 @@ same_shadow = bool(torch.equal(chk, shadow_s.float()))
 chk = master_s.clone()
 dist.broadcast(chk, src=0)
 same_master = bool(torch.equal(chk, master_s))
-worst_sd = max(float((sd_s[k].float() - sd_r[k].float()).norm() / sd_r[k].float().norm().clamp_min(1e-12)) for k in sd_r)
-ok_shard = same_shadow and same_master and worst_sd < 5e-3 and nb > 1
+# global (norm-weighted) difference: single tensors whose true gradient is zero (to_k.bias, ...) take sign-random Adam
+# steps of size lr in BOTH runs, so a per-tensor maximum measures noise, not the optimiser
+num = sum(float((sd_s[k].float() - sd_r[k].float()).pow(2).sum()) for k in sd_r)
+den = sum(float(sd_r[k].float().pow(2).sum()) for k in sd_r)
+worst_sd = (num / den) ** 0.5
+loss_dev = max(abs(a - b) / abs(b) for a, b in zip(loss_s, loss_r))
+ok_shard = same_shadow and same_master and worst_sd < 2e-3 and loss_dev < 2e-3 and nb > 1
 if rank == 0:
     print(f"dp{world} bf16 sharded ({nb} buckets): bf16 weights identical on all ranks={same_shadow}; consolidated fp32 masters "
-          f"identical={same_master}; sharded vs replicated state_dict worst rel diff {worst_sd:.2e}; losses {loss_s} vs {loss_r}",
+          f"identical={same_master}; sharded vs replicated state_dict global rel diff {worst_sd:.2e}; losses {loss_s} vs {loss_r}",
           flush=True)
 flag = torch.tensor([int(same and ok_global and ok_shard)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
