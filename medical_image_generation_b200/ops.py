@@ -915,27 +915,40 @@ def sdpa(q, k, v, heads: int, scale_: float):
 
 
 _FLASH = True
-_FLASH_TRAIN = True
+_FLASH_TRAIN = "auto"
+_FLASH_TRAIN_BYTES = 2 << 30   # "auto": L x L buffers of the unfused chain above this size -> fused kernels regardless
 
 
-def set_flash_attention(enabled: bool, training: Optional[bool] = None) -> None:
-    """enabled: use the fused tcgen05 attention kernels at all; training: also for calls that need gradients (fused
-    forward + fused backward, no L x L tensor). `training=False` keeps the unfused GEMM + softmax chain for training."""
+def set_flash_attention(enabled: bool, training=None) -> None:
+    """enabled: use the fused tcgen05 attention kernels at all. training (calls that need gradients): True = always the
+    fused forward + backward (no L x L tensor), False = always the unfused GEMM + softmax chain, "auto" (default) = the
+    faster of the two as measured on B200 (profiles/r02_attention_training.log):
+      * head dim <= 256: fused (one pass, the accumulators of a whole head fit tensor memory: 3.6x faster at d = 128,
+        L = 32768, and 8.6 GB of score buffers disappear);
+      * head dim 512 / 768 (the LDM's single heads): the accumulators must be column-sliced and every slice recomputes
+        Q K^T and dO V^T, which triples the tensor work -- the unfused chain is 2x faster at L = 1728..6400; the fused
+        path is taken for short sequences (L <= 256, launch-bound: 9 kernels vs 3) and when the unfused chain's L x L
+        buffers (12 bytes per score) would exceed 2 GiB."""
     global _FLASH, _FLASH_TRAIN
     _FLASH = bool(enabled)
     if training is not None:
-        _FLASH_TRAIN = bool(training)
+        _FLASH_TRAIN = training if training == "auto" else bool(training)
 
 
 def flash_attention_usable(q, k, v, heads: int) -> bool:
     """The fused tcgen05 kernels need bf16 and a head dim that is a multiple of 64 (above 256: a multiple of 256)."""
     if not _FLASH or _ENGINE == _lib.ENGINE_SIMT or q.dtype != torch.bfloat16:
         return False
-    if not _FLASH_TRAIN and torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
-        return False
     dh = q.shape[-1] // heads
     if dh % 64 != 0 or (dh > 256 and dh % 256 != 0) or q.shape[0] * heads >= 65536:
         return False
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+        if _FLASH_TRAIN is False:
+            return False
+        if _FLASH_TRAIN == "auto" and dh > 256:
+            Lq, Lk = q.shape[1], k.shape[1]
+            if Lq > 256 and q.shape[0] * heads * Lq * Lk * 12 <= _FLASH_TRAIN_BYTES:
+                return False
     return bool(_lib.load().mig_has_tcgen05())
 
 

@@ -625,11 +625,13 @@ def test_flash_attention_backward(B, Lq, Lk, C, heads):
     seen = []
     real = ops.call
     ops.call = lambda name, *a: (seen.append(name), real(name, *a))[1]
+    ops.set_flash_attention(True, training=True)     # ("auto" would pick the unfused chain for d = 512 at L = 1728)
     try:
         got = ops.sdpa(qd, kd, vd, heads, scale)
         (got.float() * probe.to(DEV)).sum().backward()
     finally:
         ops.call = real
+        ops.set_flash_attention(True, training="auto")
     assert seen == ["mig_flash_attention_fwd", "mig_flash_attention_bwd"], seen
     assert rel_err(got, want) < BF16_TOL
     assert rel_err(qd.grad, qr.grad) < BF16_TOL
@@ -641,7 +643,7 @@ def test_flash_attention_backward(B, Lq, Lk, C, heads):
         q2, k2, v2 = (t.to(DEV).bfloat16().requires_grad_(True) for t in (q, k, v))
         (ops.sdpa(q2, k2, v2, heads, scale).float() * probe.to(DEV)).sum().backward()
     finally:
-        ops.set_flash_attention(True, training=True)
+        ops.set_flash_attention(True, training="auto")
     assert rel_err(qd.grad, q2.grad) < BF16_TOL and rel_err(kd.grad, k2.grad) < BF16_TOL
 
 

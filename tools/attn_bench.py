@@ -33,7 +33,7 @@ for (B, L, C, heads) in ((8, 1728, 512, 1), (8, 216, 768, 1), (2, 6400, 512, 1),
         torch.cuda.synchronize()
         row.append(e0.elapsed_time(e1) / 5)
         row.append((torch.cuda.max_memory_allocated() - base) / 1e6)
-    ops.set_flash_attention(True, training=True)
+    ops.set_flash_attention(True, training="auto")
     fl = 4.0 * B * L * L * C * 3.5   # fwd 2 GEMMs + bwd 5 GEMMs
     print(f"B={B} L={L} d={C // heads}: flash fwd+bwd {row[0]:.3f} ms ({fl / row[0] / 1e9:.0f} TFLOP/s algorithmic, peak extra memory "
           f"{row[1]:.0f} MB) | unfused {row[2] if len(row) > 2 else float('nan'):.3f} ms (peak extra memory {row[3] if len(row) > 3 else float('nan'):.0f} MB)",
