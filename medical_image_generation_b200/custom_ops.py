@@ -40,7 +40,7 @@ class _Ctx:
 
 
 def _cl_shape_like(x, shape):
-    return x.new_empty(tuple(shape), memory_format=ops._mf(len(shape)))
+    return torch.empty(tuple(shape), dtype=x.dtype, device=x.device, memory_format=ops._mf(len(shape)))
 
 
 # ---- conv_nd ----------------------------------------------------------------------------------------------------------
