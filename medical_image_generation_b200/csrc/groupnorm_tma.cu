@@ -32,9 +32,7 @@ constexpr int GT_MAX_STAGES = 4;
 
 struct GtGeom {
   int N, C, G, cpg;
-  int64_t S;                    // rows per sample of the (possibly folded) 2-d view
-  int ldc;                      // elements per row of the view: C, or 256 when folded
-  int nv;                       // distinct 8-channel vectors per row (C / 8, also when folded)
+  int64_t S;
   int slabs, cb, cvb, rpp, R;   // channel slabs, channels / 16-byte vectors per slab row, rows per pass, rows per stage
   int chunks;                   // row chunks per (sample, slab)
   int64_t rows_per_chunk;       // multiple of R
@@ -57,18 +55,8 @@ bool gt_eligible(int N, int64_t S, int C, int G) {
 static GtGeom gt_geom(int N, int64_t S, int C, int G) {
   GtGeom g;
   g.N = N; g.C = C; g.G = G; g.cpg = C / G; g.S = S;
-  g.ldc = C;
-  g.nv = C / 8;
   g.cb = slab_channels(C);
-  // Narrow tensors (C = 32 / 64 / 128: the AE and the pixel-space U-Net at full resolution) are FOLDED: [S][C] is
-  // contiguous, so a sample is also a [S*C/256][256] matrix whose column j holds channel j % C. TMA rows become 512 bytes
-  // instead of 64-256, and a warp still owns whole 512-byte rows.
-  if (C < 256 && 256 % C == 0 && (S * C) % 256 == 0) {
-    g.S = S * C / 256;
-    g.ldc = 256;
-    g.cb = 256;
-  }
-  g.slabs = g.ldc / g.cb;
+  g.slabs = C / g.cb;
   g.cvb = g.cb / 8;
   g.rpp = GT_THREADS / g.cvb;
   g.R = GT_TENSOR_STAGE / (g.cb * 2);
@@ -85,8 +73,8 @@ static GtGeom gt_geom(int N, int64_t S, int C, int G) {
 static int gt_map(CUtensorMap* m, const void* base, const GtGeom& g) {
   EncodeTiledFn enc = get_encode();
   MIG_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable (driver too old?)");
-  cuuint64_t gd[2] = {(cuuint64_t)g.ldc, (cuuint64_t)((int64_t)g.N * g.S)};
-  cuuint64_t gs[1] = {(cuuint64_t)g.ldc * 2};
+  cuuint64_t gd[2] = {(cuuint64_t)g.C, (cuuint64_t)((int64_t)g.N * g.S)};
+  cuuint64_t gs[1] = {(cuuint64_t)g.C * 2};
   cuuint32_t bx[2] = {(cuuint32_t)g.cb, (cuuint32_t)g.R};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gd, gs, bx, es,
@@ -186,7 +174,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_stats_kernel(const __grid_co
   for (int i = threadIdx.x; i < 2 * 256; i += GT_THREADS) gacc[i] = 0.f;
   __syncthreads();
   const int tcol = threadIdx.x % g.cvb;
-  const int c0 = (slab * g.cb + tcol * 8) % g.C, g0 = g.ldc == g.C ? (slab * g.cb) / g.cpg : 0;
+  const int c0 = slab * g.cb + tcol * 8, g0 = (slab * g.cb) / g.cpg;
   int j = 0;
   while (j < 8) {   // merge the channels of this vector that share a group before touching shared memory
     const int grp = (c0 + j) / g.cpg;
@@ -196,7 +184,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_stats_kernel(const __grid_co
     atomicAdd(&gacc[2 * (grp - g0) + 1], b);
   }
   __syncthreads();
-  const int ng = g.ldc == g.C ? (g.cb + g.cpg - 1) / g.cpg + 1 : g.G;
+  const int ng = (g.cb + g.cpg - 1) / g.cpg + 1;
   for (int i = threadIdx.x; i < 2 * ng && i < 2 * 256; i += GT_THREADS) {
     const int grp = g0 + (i >> 1);
     const float v = gacc[i];
@@ -236,7 +224,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_apply_kernel(const __grid_co
       rstd[n * g.G + grp] = r;
     }
   const int tcol = threadIdx.x % g.cvb;
-  const int col = slab * g.cb + tcol * 8, c0 = col % g.C;   // memory column of the view / channel
+  const int c0 = slab * g.cb + tcol * 8;
   float a[8], b[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -245,7 +233,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_apply_kernel(const __grid_co
     a[j] = r * gamma[c0 + j];
     b[j] = fmaf(-m, a[j], beta[c0 + j]);
   }
-  __nv_bfloat16* ybase = y + ((int64_t)n * g.S) * g.ldc + col;
+  __nv_bfloat16* ybase = y + ((int64_t)n * g.S) * g.C + c0;
   gt_stream<1, 4>(&xm, &xm, g, smem, smem_u32(&bars[0]), n, slab, chunk, [&](int64_t r, uint32_t a0, uint32_t) {
     float f[8];
     unpack8(lds16(a0), f);
@@ -254,7 +242,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_apply_kernel(const __grid_co
       const float z = fmaf(f[j], a[j], b[j]);
       f[j] = SILU ? z * sigmoid_tanh_f(z) : z;
     }
-    *reinterpret_cast<uint4*>(ybase + r * g.ldc) = pack8(f);
+    *reinterpret_cast<uint4*>(ybase + r * g.C) = pack8(f);
   });
 }
 
@@ -273,7 +261,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_stats_kernel(const __gri
   gt_init_bars(bars, 3);
   const int n = blockIdx.z, slab = blockIdx.y, chunk = blockIdx.x;
   const int tcol = threadIdx.x % g.cvb;
-  const int c0 = (slab * g.cb + tcol * 8) % g.C;
+  const int c0 = slab * g.cb + tcol * 8;
   float rs[8], m2[8], ga[8], be[8], p1[8], p2[8], p3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -311,15 +299,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_stats_kernel(const __gri
     red[(3 * j + 2) * GT_THREADS + threadIdx.x] = p3[j];
   }
   __syncthreads();
-  // distinct channel vectors of this CTA: the slab's cvb, or (folded view) the C / 8 vectors that repeat along the row
-  const bool folded = g.ldc != g.C;
-  const int nvec = folded ? g.nv : g.cvb;
-  float* dst = part + (((int64_t)n * g.chunks + chunk) * g.C + (folded ? 0 : slab * g.cb)) * 3;
-  for (int e = threadIdx.x; e < nvec * 24; e += GT_THREADS) {
-    const int q = e / nvec, cv = e - q * nvec;
+  float* dst = part + (((int64_t)n * g.chunks + chunk) * g.C + slab * g.cb) * 3;
+  for (int e = threadIdx.x; e < g.cvb * 24; e += GT_THREADS) {
+    const int q = e / g.cvb, tc = e - q * g.cvb;
     float sum = 0.f;
-    for (int t = cv; t < GT_THREADS; t += nvec) sum += red[q * GT_THREADS + t];   // all threads with this channel vector
-    dst[(cv * 8 + q / 3) * 3 + (q % 3)] = sum;
+    for (int rr = 0; rr < g.rpp; ++rr) sum += red[q * GT_THREADS + rr * g.cvb + tc];
+    dst[(tc * 8 + q / 3) * 3 + (q % 3)] = sum;
   }
 }
 
@@ -394,7 +379,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
   gt_init_bars(bars, 3);
   const int n = blockIdx.z, slab = blockIdx.y, chunk = blockIdx.x;
   const int tcol = threadIdx.x % g.cvb;
-  const int col = slab * g.cb + tcol * 8, c0 = col % g.C;
+  const int c0 = slab * g.cb + tcol * 8;
   // dx = k1*dz - k2*xhat - k3 with xhat = x*rs + m2, z = xhat*ga + be
   float rs[8], m2[8], ga[8], be[8], k1[8], k2[8], k3[8];
 #pragma unroll
@@ -408,7 +393,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
     k2[j] = rs[j] * grp[2 * gi] * inv_count;
     k3[j] = rs[j] * grp[2 * gi + 1] * inv_count;
   }
-  if (n == 0 && chunk == 0 && threadIdx.x < (g.ldc != g.C ? g.nv : g.cvb)) {   // dgamma / dbeta = totals summed over n
+  if (n == 0 && chunk == 0 && threadIdx.x < g.cvb) {   // dgamma / dbeta = totals summed over the samples
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float a = 0.f, b = 0.f;
@@ -420,7 +405,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
       if (dbeta) dbeta[c0 + j] = b;
     }
   }
-  __nv_bfloat16* obase = dx + ((int64_t)n * g.S) * g.ldc + col;
+  __nv_bfloat16* obase = dx + ((int64_t)n * g.S) * g.C + c0;
   gt_stream<2, 3>(&xm, &dym, g, smem, smem_u32(&bars[0]), n, slab, chunk, [&](int64_t r, uint32_t a0, uint32_t a1) {
     float x[8], d[8];
     unpack8(lds16(a0), x);
@@ -436,7 +421,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
       }
       x[j] = fmaf(k1[j], dz, -fmaf(k2[j], xh, k3[j]));
     }
-    *reinterpret_cast<uint4*>(obase + r * g.ldc) = pack8(x);
+    *reinterpret_cast<uint4*>(obase + r * g.C) = pack8(x);
   });
 }
 
