@@ -201,11 +201,10 @@ class FlatAdamW:
         tail = [(n, p) for n, p in named if is_unused(n)]
         # fp32-consumed parameters (1-D: biases / norm gains; the time-embedding MLP) form the replicated region
         fp32_used = lambda n, p: p.ndim <= 1 or any(tag in n for tag in self.FP32_CONSUMED)  # noqa: E731
-        if self.sharded:
-            shard_part = [(n, p) for n, p in used if not fp32_used(n, p)]
-            repl_part = [(n, p) for n, p in used if fp32_used(n, p)]
-        else:
-            shard_part, repl_part = [], used
+        # (the split is kept without sharding too: it puts to_q / to_k / to_v weights -- and their biases -- next to each
+        #  other, which is what lets an attention block run ONE fused QKV projection, ops.fuse_linears)
+        shard_part = [(n, p) for n, p in used if not fp32_used(n, p)]
+        repl_part = [(n, p) for n, p in used if fp32_used(n, p)]
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
@@ -214,7 +213,7 @@ class FlatAdamW:
         pad = lambda k: (k + 63) // 64 * 64  # noqa: E731
         shard_raw = sum(pad(p.numel()) for _, p in shard_part)
         self.bucket_elems = 0
-        self.shard_numel = 0
+        self.shard_numel = shard_raw
         if self.sharded and shard_raw:
             unit = world * 64
             self.bucket_elems = max(unit, (int(bucket_mb * (1 << 20) / 4) + unit - 1) // unit * unit)
@@ -246,6 +245,7 @@ class FlatAdamW:
                 p._mig_shadow = self.shadow[off:off + k].as_strided(p.shape, p.stride())
                 p._mig_shadow_version = p._version   # ops._filter_for re-casts the slot when the master changed in place
                 p._mig_slot = (off, k)
+                p._mig_flat = self
                 self.params.append((n, p))
                 spans.append((off, off + pad(k)))
                 off += pad(k)
@@ -265,8 +265,9 @@ class FlatAdamW:
                                               self.repl_lo, self.used_numel, repl_part)
                 self._index_of = {id(p): i for i, (_, p) in enumerate(shard_part + repl_part)}
             else:
-                self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in used], int(bucket_mb * (1 << 20) / 4))
-                self._index_of = {id(p): i for i, (_, p) in enumerate(used)}
+                order = shard_part + repl_part
+                self.buckets = GradBuckets(self.grad, [pad(p.numel()) for _, p in order], int(bucket_mb * (1 << 20) / 4))
+                self._index_of = {id(p): i for i, (_, p) in enumerate(order)}
         # every owned parameter carries the callback of ITS optimiser (several FlatAdamW instances can coexist)
         for _, p in self.params:
             p._mig_grad_ready = self._grad_ready
@@ -307,7 +308,7 @@ class FlatAdamW:
               int(self.step_count))
         sumsq_ptr = None
         max_norm = 0.0
-        if not (self.sharded and self.shard_numel):
+        if not (self.sharded and self.buckets is not None and self.buckets.nb):
             if self.max_grad_norm:
                 call("mig_sumsq", ops._ptr(self.grad), ops._ptr(self.sumsq), ops._ptr(self._partials), self.used_numel, st)
                 sumsq_ptr, max_norm = ops._ptr(self.sumsq), float(self.max_grad_norm)
@@ -345,7 +346,7 @@ class FlatAdamW:
         """COLLECTIVE. With the sharded update a rank holds current fp32 masters / Adam moments only for the slices it
         owns (the bf16 shadows are always complete). Call this on every rank before `module.state_dict()` /
         `torch_state_dict()` (checkpoints, train_ldm.py:466-491): it all-gathers master, m and v."""
-        if self.sharded and self.shard_numel:
+        if self.sharded and self.buckets is not None and self.buckets.nb:
             for buf in (self.master, self.m, self.v):
                 self.buckets.gather(buf)
 

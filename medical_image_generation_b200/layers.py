@@ -187,13 +187,33 @@ class SelfAttentionBlock(nn.Module):
         self.to_v = Linear(num_channels, num_channels)
         self.proj_attn = Linear(num_channels, num_channels)
 
+    def _fused_qkv(self):
+        """ops.FusedLinearParams of to_q/to_k/to_v when a FlatAdamW owns them (cached per storage), else None."""
+        wq = self.to_q.weight
+        if getattr(wq, "_mig_flat", None) is None:
+            return None
+        key = (wq.data_ptr(), self.to_k.weight.data_ptr(), self.to_v.weight.data_ptr(), id(wq._mig_flat))
+        cache = self.__dict__.get("_mig_qkv")
+        if cache is None or cache[0] != key:
+            cache = (key, ops.fuse_linears([("q", self.to_q), ("k", self.to_k), ("v", self.to_v)]))
+            self.__dict__["_mig_qkv"] = cache
+        return cache[1]
+
     def forward(self, x):
         x = ops.to_channels_last(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
         B, Cc = x.shape[0], x.shape[1]
         h = self.norm(x)
         # channels-last memory IS the (B, L, C) token matrix in the reference's d,h,w order (unet:428-434)
         tokens = h.permute(0, *range(2, h.ndim), 1).reshape(B, -1, Cc)
-        q, k, v = self.to_q(tokens), self.to_k(tokens), self.to_v(tokens)
-        o = ops.sdpa(q, k, v, self.num_heads, self.scale)
+        fused = self._fused_qkv()
+        if fused is not None:
+            # to_q / to_k / to_v (unet:436-438) as ONE projection GEMM: the flat optimiser keeps the three weight matrices
+            # side by side; attention reads the column slices in place and returns ONE gradient tensor
+            fused.refresh()
+            qkv = ops.linear(tokens, fused.weight, fused.bias)
+            o = ops.sdpa_qkv(qkv, self.num_heads, self.scale, order=fused.order)
+        else:
+            q, k, v = self.to_q(tokens), self.to_k(tokens), self.to_v(tokens)
+            o = ops.sdpa(q, k, v, self.num_heads, self.scale)
         o = o.reshape(B, *x.shape[2:], Cc).permute(0, x.ndim - 1, *range(1, x.ndim - 1))
         return ops.add(o, x)

@@ -242,6 +242,69 @@ def refresh_shadow(weight) -> None:
     weight._mig_shadow_version = weight._version
 
 
+class FusedLinearParams:
+    """Several nn.Linear layers that read the same input, presented as ONE (sum of out_features, in_features) weight and
+    one bias: possible when engine.FlatAdamW laid their parameters out next to each other in its flat buffers (it does
+    for to_q / to_k / to_v of every attention block). `weight` / `bias` are leaf views of the fp32 master buffer that
+    carry the same attributes the kernels' wrappers look for on real parameters (main_grad, bf16 shadow, grad-ready
+    callback), `order` is the order of the layers' rows in the fused matrix."""
+
+    def __init__(self, weight, bias, order, members):
+        self.weight, self.bias, self.order, self.members = weight, bias, order, members
+
+    def refresh(self):
+        for m in self.members:   # a member changed in place behind the optimiser's back (load_state_dict, copy_)
+            if getattr(m, "_mig_shadow", None) is not None and m._version != m._mig_shadow_version:
+                refresh_shadow(m)
+
+
+def fuse_linears(named_linears):
+    """[(name, Linear-like module with .weight/.bias)] -> FusedLinearParams or None (parameters not flat-owned or not
+    adjacent)."""
+    ws = [(n, m.weight) for n, m in named_linears]
+    bs = [(n, m.bias) for n, m in named_linears]
+    opt = getattr(ws[0][1], "_mig_flat", None)
+    if opt is None or any(getattr(w, "_mig_flat", None) is not opt for _, w in ws):
+        return None
+    if any(b is None or getattr(b, "_mig_flat", None) is not opt for _, b in bs):
+        return None
+    ws.sort(key=lambda t: t[1]._mig_slot[0])
+    order = tuple(n for n, _ in ws)
+    bs.sort(key=lambda t: order.index(t[0]))
+    out_f, in_f = ws[0][1].shape
+
+    def adjacent(ps):
+        off = ps[0][1]._mig_slot[0]
+        for _, p in ps:
+            o, k = p._mig_slot
+            if o != off or k % 64 != 0 or not p.is_contiguous():
+                return None
+            off += k
+        return ps[0][1]._mig_slot[0]
+
+    if any(tuple(w.shape) != (out_f, in_f) for _, w in ws):
+        return None
+    wo, bo = adjacent(ws), adjacent(bs)
+    if wo is None or bo is None:
+        return None
+    n = len(ws)
+    members = [w for _, w in ws] + [b for _, b in bs]
+
+    def ready(_p):
+        for m in members:
+            opt._grad_ready(m)
+
+    W = opt.master[wo:wo + n * out_f * in_f].view(n * out_f, in_f).requires_grad_(True)
+    W.main_grad = opt.grad[wo:wo + n * out_f * in_f].view(n * out_f, in_f)
+    W._mig_shadow = opt.shadow[wo:wo + n * out_f * in_f].view(n * out_f, in_f)
+    W._mig_shadow_version = W._version
+    W._mig_grad_ready = ready
+    Bv = opt.master[bo:bo + n * out_f].requires_grad_(True)
+    Bv.main_grad = opt.grad[bo:bo + n * out_f]
+    Bv._mig_grad_ready = lambda _p: None      # the weight's callback reports all members
+    return FusedLinearParams(W, Bv, order, members)
+
+
 def clear_caches() -> None:
     _workspaces.clear()
 
@@ -844,23 +907,52 @@ def _gemm(A, B, Cm, M, N, K, bo, bi, a, b, c, alpha=1.0, accumulate=False):
     call("mig_gemm_strided", C.byref(d), _dt(A), _dt(Cm), _ptr(A), _ptr(B), _ptr(Cm), _ENGINE, _stream())
 
 
+def _sdpa_fwd_unfused(q, k, v, B, Lq, Lk, Cc, heads, scale_, ld):
+    """softmax(scale q k^T) v with q/k/v given as (B, L, Cc) views whose rows lie `ld` elements apart (ld = Cc for
+    contiguous tensors, 3*Cc for the column slices of a fused QKV projection). Returns (O contiguous, P)."""
+    dh = Cc // heads
+    dev = q.device
+    # scores in fp32 (softmax statistics in fp32 as under autocast), probabilities in the compute dtype
+    S = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
+    _gemm(q, k, S, Lq, Lk, dh, B, heads, (ld, 1, Lq * ld, dh), (1, ld, Lk * ld, dh), (Lk, 1, heads * Lq * Lk, Lq * Lk))
+    P = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
+    call("mig_softmax_fwd", F32, _dt(P), _ptr(S), _ptr(P), B * heads * Lq, Lk, float(scale_), _stream())
+    del S
+    O = torch.empty((B, Lq, Cc), dtype=q.dtype, device=dev)
+    _gemm(P, v, O, Lq, dh, Lk, B, heads, (Lk, 1, heads * Lq * Lk, Lq * Lk), (ld, 1, Lk * ld, dh), (Cc, 1, Lq * Cc, dh))
+    return O, P
+
+
+def _sdpa_bwd_unfused(q, k, v, P, dO, dQ, dK, dV, B, Lq, Lk, Cc, heads, scale_, ld, ldg):
+    """Gradients of the above into dQ / dK / dV, (B, L, Cc) views with row stride `ldg`."""
+    dh = Cc // heads
+    dev = q.device
+    sP = (Lk, 1, heads * Lq * Lk, Lq * Lk)
+    # dV[key, d] = sum_q P[q, key] dO[q, d]
+    _gemm(P, dO, dV, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lq * Cc, dh), (ldg, 1, Lk * ldg, dh))
+    # dP[q, key] = sum_d dO[q, d] V[key, d]
+    dP = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
+    _gemm(dO, v, dP, Lq, Lk, dh, B, heads, (Cc, 1, Lq * Cc, dh), (1, ld, Lk * ld, dh), sP)
+    # dS = scale * P * (dP - rowsum(dP * P))   (gradient w.r.t. the UNscaled scores)
+    dS = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
+    if q.dtype == torch.float32:
+        call("mig_softmax_bwd", F32, F32, _ptr(P), _ptr(dP), _ptr(dS), B * heads * Lq, Lk, float(scale_), _stream())
+    else:
+        dS32 = dP  # in place on the fp32 buffer, then narrowed
+        call("mig_softmax_bwd", BF16, F32, _ptr(P), _ptr(dP), _ptr(dS32), B * heads * Lq, Lk, float(scale_), _stream())
+        call("mig_cast", F32, BF16, _ptr(dS32), _ptr(dS), dS.numel(), _stream())
+    del dP
+    # dQ[q, d] = sum_key dS[q, key] K[key, d] ; dK[key, d] = sum_q dS[q, key] Q[q, d]
+    _gemm(dS, k, dQ, Lq, dh, Lk, B, heads, sP, (ld, 1, Lk * ld, dh), (ldg, 1, Lq * ldg, dh))
+    _gemm(dS, q, dK, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (ld, 1, Lq * ld, dh), (ldg, 1, Lk * ldg, dh))
+
+
 class _SdpaFn(Function):
     @staticmethod
     def forward(ctx, q, k, v, heads, scale_):
         B, Lq, Cc = q.shape
         Lk = k.shape[1]
-        dh = Cc // heads
-        dev = q.device
-        # scores in fp32 (softmax statistics in fp32 as under autocast), probabilities in the compute dtype
-        S = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
-        _gemm(q, k, S, Lq, Lk, dh, B, heads, (Cc, 1, Lq * Cc, dh), (1, Cc, Lk * Cc, dh),
-              (Lk, 1, heads * Lq * Lk, Lq * Lk))
-        P = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
-        call("mig_softmax_fwd", F32, _dt(P), _ptr(S), _ptr(P), B * heads * Lq, Lk, float(scale_), _stream())
-        del S
-        O = torch.empty((B, Lq, Cc), dtype=q.dtype, device=dev)
-        _gemm(P, v, O, Lq, dh, Lk, B, heads, (Lk, 1, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lk * Cc, dh),
-              (Cc, 1, Lq * Cc, dh))
+        O, P = _sdpa_fwd_unfused(q, k, v, B, Lq, Lk, Cc, heads, scale_, Cc)
         ctx.save_for_backward(q, k, v, P)
         ctx.cfg = (heads, scale_)
         return O
@@ -871,36 +963,73 @@ class _SdpaFn(Function):
         heads, scale_ = ctx.cfg
         B, Lq, Cc = q.shape
         Lk = k.shape[1]
-        dh = Cc // heads
-        dev = q.device
         dO = dO.contiguous()
         if dO.dtype != q.dtype:
             dO = dO.to(q.dtype)
-        sP = (Lk, 1, heads * Lq * Lk, Lq * Lk)
-        # dV[key, d] = sum_q P[q, key] dO[q, d]
-        dV = torch.empty_like(v)
-        _gemm(P, dO, dV, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lq * Cc, dh),
-              (Cc, 1, Lk * Cc, dh))
-        # dP[q, key] = sum_d dO[q, d] V[key, d]
-        dP = torch.empty((B * heads, Lq, Lk), dtype=torch.float32, device=dev)
-        _gemm(dO, v, dP, Lq, Lk, dh, B, heads, (Cc, 1, Lq * Cc, dh), (1, Cc, Lk * Cc, dh), sP)
-        # dS = scale * P * (dP - rowsum(dP * P))   (gradient w.r.t. the UNscaled scores)
-        dS = torch.empty((B * heads, Lq, Lk), dtype=q.dtype, device=dev)
-        if q.dtype == torch.float32:
-            call("mig_softmax_bwd", F32, F32, _ptr(P), _ptr(dP), _ptr(dS), B * heads * Lq, Lk, float(scale_), _stream())
-        else:
-            dS32 = dP  # in place on the fp32 buffer, then narrowed
-            call("mig_softmax_bwd", BF16, F32, _ptr(P), _ptr(dP), _ptr(dS32), B * heads * Lq, Lk, float(scale_),
-                 _stream())
-            call("mig_cast", F32, BF16, _ptr(dS32), _ptr(dS), dS.numel(), _stream())
-        del dP
-        # dQ[q, d] = sum_key dS[q, key] K[key, d] ; dK[key, d] = sum_q dS[q, key] Q[q, d]
-        dQ = torch.empty_like(q)
-        _gemm(dS, k, dQ, Lq, dh, Lk, B, heads, sP, (Cc, 1, Lk * Cc, dh), (Cc, 1, Lq * Cc, dh))
-        dK = torch.empty_like(k)
-        _gemm(dS, q, dK, Lk, dh, Lq, B, heads, (1, Lk, heads * Lq * Lk, Lq * Lk), (Cc, 1, Lq * Cc, dh),
-              (Cc, 1, Lk * Cc, dh))
+        dQ, dK, dV = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        _sdpa_bwd_unfused(q, k, v, P, dO, dQ, dK, dV, B, Lq, Lk, Cc, heads, scale_, Cc, Cc)
         return dQ, dK, dV, None, None
+
+
+class _QkvSdpaFn(Function):
+    """Self-attention on the output of ONE fused QKV projection: qkv (B, L, 3C) holds the three projections side by side
+    (`order`, e.g. ("v", "k", "q") -- the order the flat optimiser lays the three weight matrices out). The unfused GEMMs
+    read the column slices in place (row stride 3C) and the backward writes dq / dk / dv straight into the slices of
+    ONE gradient tensor, so the projection's dgrad and wgrad are single GEMMs as well (unet:436-438 as one Linear)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale_, order):
+        B, L, C3 = qkv.shape
+        Cc = C3 // 3
+        sl = {name: qkv[:, :, i * Cc:(i + 1) * Cc] for i, name in enumerate(order)}
+        q, k, v = sl["q"], sl["k"], sl["v"]
+        use_flash = flash_attention_usable(qkv[:, :, :Cc], qkv[:, :, :Cc], qkv[:, :, :Cc], heads, needs_grad=bool(ctx.needs_input_grad[0]))
+        if use_flash:
+            qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+            O, lse = _flash_fwd(qc, kc, vc, heads, scale_)
+            ctx.save_for_backward(qc, kc, vc, O, lse)
+        else:
+            O, P = _sdpa_fwd_unfused(q, k, v, B, L, L, Cc, heads, scale_, C3)
+            ctx.save_for_backward(qkv, P)
+        ctx.cfg = (heads, scale_, tuple(order), use_flash, (B, L, Cc))
+        return O
+
+    @staticmethod
+    def backward(ctx, dO):
+        heads, scale_, order, use_flash, (B, L, Cc) = ctx.cfg
+        dO = dO.contiguous()
+        C3 = 3 * Cc
+        if use_flash:
+            qc, kc, vc, O, lse = ctx.saved_tensors
+            if dO.dtype != qc.dtype:
+                dO = dO.to(qc.dtype)
+            dqkv = torch.empty((B, L, C3), dtype=qc.dtype, device=qc.device)
+            dq, dk, dv = torch.empty_like(qc), torch.empty_like(kc), torch.empty_like(vc)
+            delta = torch.empty((B * heads, L), dtype=torch.float32, device=qc.device)
+            call("mig_flash_attention_bwd", _ptr(qc), _ptr(kc), _ptr(vc), _ptr(O), _ptr(dO), _ptr(lse), _ptr(delta), _ptr(dq),
+                 _ptr(dk), _ptr(dv), B, heads, L, L, Cc // heads, float(scale_), _stream())
+            parts = {"q": dq, "k": dk, "v": dv}
+            rows = B * L
+            a, b_, c = (parts[n] for n in order)
+            # three column blocks -> one (rows, 3C) matrix: concat(concat(a, b), c) with the channel-concat kernel
+            ab = torch.empty((rows, 2 * Cc), dtype=qc.dtype, device=qc.device)
+            call("mig_concat_channels", _dt(a), _ptr(a), _ptr(b_), _ptr(ab), rows, Cc, Cc, _stream())
+            call("mig_concat_channels", _dt(a), _ptr(ab), _ptr(c), _ptr(dqkv), rows, 2 * Cc, Cc, _stream())
+            return dqkv, None, None, None
+        qkv, P = ctx.saved_tensors
+        if dO.dtype != qkv.dtype:
+            dO = dO.to(qkv.dtype)
+        dqkv = torch.empty_like(qkv)
+        sl = {name: qkv[:, :, i * Cc:(i + 1) * Cc] for i, name in enumerate(order)}
+        dsl = {name: dqkv[:, :, i * Cc:(i + 1) * Cc] for i, name in enumerate(order)}
+        _sdpa_bwd_unfused(sl["q"], sl["k"], sl["v"], P, dO, dsl["q"], dsl["k"], dsl["v"], B, L, L, Cc, heads, scale_, C3, C3)
+        return dqkv, None, None, None
+
+
+def sdpa_qkv(qkv, heads: int, scale_: float, order=("q", "k", "v")):
+    """Self-attention over a fused projection output qkv (B, L, 3C); see _QkvSdpaFn."""
+    _require_cuda(qkv, "sdpa_qkv")
+    return _QkvSdpaFn.apply(qkv.contiguous(), int(heads), float(scale_), tuple(order))
 
 
 def sdpa(q, k, v, heads: int, scale_: float):
@@ -935,14 +1064,16 @@ def set_flash_attention(enabled: bool, training=None) -> None:
         _FLASH_TRAIN = training if training == "auto" else bool(training)
 
 
-def flash_attention_usable(q, k, v, heads: int) -> bool:
+def flash_attention_usable(q, k, v, heads: int, needs_grad=None) -> bool:
     """The fused tcgen05 kernels need bf16 and a head dim that is a multiple of 64 (above 256: a multiple of 256)."""
     if not _FLASH or _ENGINE == _lib.ENGINE_SIMT or q.dtype != torch.bfloat16:
         return False
     dh = q.shape[-1] // heads
     if dh % 64 != 0 or (dh > 256 and dh % 256 != 0) or q.shape[0] * heads >= 65536:
         return False
-    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+    if needs_grad is None:
+        needs_grad = torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad)
+    if needs_grad:
         if _FLASH_TRAIN is False:
             return False
         if _FLASH_TRAIN == "auto" and dh > 256:
