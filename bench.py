@@ -371,7 +371,7 @@ def hbm_block(dev, pk):
                                              ptr(rstd), N, S, Cc, G, 1e-6, 1, ptr(ws), ws.numel(), ops._stream()),
         2 * numel * 2, "GroupNorm+SiLU forward, 8x256x24^3 bf16: read x + write y")
     run("groupnorm_silu_bwd", lambda i: call("mig_groupnorm_bwd", 1, ptr(xs[i]), ptr(dys[i]), ptr(gamma), ptr(beta), ptr(mean),
-                                             ptr(rstd), ptr(ys[i]), ptr(dgam), ptr(dbet), None, N, S, Cc, G, 1, ptr(ws), ws.numel(),
+                                             ptr(rstd), ptr(ys[i]), ptr(dgam), ptr(dbet), None, None, 0, N, S, Cc, G, 1, ptr(ws), ws.numel(),
                                              ops._stream()),
         3 * numel * 2, "GroupNorm+SiLU backward: read x, dy + write dx")
     del xs, dys, ys

@@ -28,7 +28,7 @@ extern "C" {
 #define MIG_F32 0
 #define MIG_BF16 1
 
-#define MIG_ABI_VERSION 2
+#define MIG_ABI_VERSION 3
 
 /* Geometry of one N-d convolution (1 <= nd <= 3 handled by setting leading dims to 1). */
 typedef struct {
@@ -111,11 +111,14 @@ int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, const float*
                       float* mean, float* rstd, int32_t N, int64_t S, int32_t C, int32_t G, float eps,
                       int fuse_silu, void* workspace, int64_t workspace_bytes, void* stream);
 /* dx_colsum (optional, [N][C] fp32): receives sum_s dx[n,s,c] -- the bias / time-embedding gradient of the convolution
- * that produced x (unet:691-695), so that convolution's backward needs no column-sum pass over dy. */
+ * that produced x (unet:691-695), so that convolution's backward needs no column-sum pass over dy.
+ * dx_addend (optional, same shape/dtype as dx): dx = GroupNorm gradient + dx_addend -- the gradient that reaches x through
+ * the block's skip path (unet:701: x also feeds the residual add), fused instead of a separate accumulation pass.
+ * accumulate_dparams != 0: dgamma / dbeta are ADDED to (they point into the optimiser's flat gradient buffer). */
 int mig_groupnorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* beta,
                       const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta, float* dx_colsum,
-                      int32_t N, int64_t S, int32_t C, int32_t G, int fuse_silu,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      const void* dx_addend, int accumulate_dparams, int32_t N, int64_t S, int32_t C, int32_t G,
+                      int fuse_silu, void* workspace, int64_t workspace_bytes, void* stream);
 int64_t mig_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t G);
 /* The two halves of the forward as separate entry points (bf16, C a multiple of 32: mig_groupnorm_can_split() == 1).
  * sums: double [N][G][2] = (sum x, sum x^2) per (sample, group) -- written by mig_groupnorm_stats, or accumulated by

@@ -49,7 +49,7 @@ _SIGNATURES = {
     "mig_flash_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mig_flash_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mig_groupnorm_fwd": [_i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p, _l, _p],
-    "mig_groupnorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _i, _p, _l, _p],
+    "mig_groupnorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p],
     "mig_groupnorm_can_split": [_i, _i, _l, _i, _i],
     "mig_groupnorm_stats": [_i, _p, _p, _i, _l, _i, _i, _p],
     "mig_groupnorm_apply": [_i, _p, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p],
@@ -119,7 +119,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.mig_abi_version() != 2:
+    if lib.mig_abi_version() != 3:
         raise RuntimeError("libmedimgen_b200.so ABI version mismatch")
     _lib = lib
     return lib

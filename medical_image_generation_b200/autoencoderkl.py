@@ -74,7 +74,8 @@ class ResBlock(nn.Module):
 
     def forward(self, x):
         x = _entry(x)
-        h = self.conv1(self.norm1(x, silu=True), gn_groups=self.norm2.num_groups)
+        h, x = self.norm1(x, silu=True, with_skip=True)   # the skip gradient is added inside norm1's backward kernel
+        h = self.conv1(h, gn_groups=self.norm2.num_groups)
         h._mig_sole_consumer_gn = True   # norm2 is conv1's only consumer: its backward hands conv1 the column sums of dy
         h = self.norm2(h, silu=True)
         skip = x if self.in_channels == self.out_channels else self.nin_shortcut(x)

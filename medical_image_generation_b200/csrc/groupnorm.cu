@@ -20,8 +20,8 @@ int gt_stats(const void* x, double* sums, int N, int64_t S, int C, int G, void* 
 int gt_apply(const void* x, const float* gamma, const float* beta, const double* sums, void* y, float* mean, float* rstd,
              int N, int64_t S, int C, int G, float eps, int silu, void* stream);
 int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean, const float* rstd,
-           void* dx, float* dgamma, float* dbeta, float* dx_colsum, int N, int64_t S, int C, int G, int silu, void* ws,
-           int64_t ws_bytes, void* stream);
+           void* dx, float* dgamma, float* dbeta, float* dx_colsum, const void* dx_addend, int accumulate_dparams, int N,
+           int64_t S, int C, int G, int silu, void* ws, int64_t ws_bytes, void* stream);
 
 static bool gt_use(int dtype_bytes, const void* a, const void* b, int N, int64_t S, int C, int G) {
   static int disabled = -1;   // A/B switch for profiling: MIG_GN_LEGACY=1 keeps the register-streaming kernels
@@ -384,11 +384,25 @@ static int gn_fwd(const void* x, const float* gamma, const float* beta, void* y,
 
 template <typename T>
 static int gn_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean,
-                  const float* rstd, void* dx, float* dgamma, float* dbeta, float* dx_colsum, int N, int64_t S, int C,
-                  int G, int silu, void* ws, int64_t ws_bytes, void* stream) {
+                  const float* rstd, void* dx, float* dgamma, float* dbeta, float* dx_colsum, const void* dx_addend,
+                  int accumulate_dparams, int N, int64_t S, int C, int G, int silu, void* ws, int64_t ws_bytes,
+                  void* stream) {
   if (gn_check<T>(x, N, S, C, G)) return 1;
-  if (gt_use((int)sizeof(T), x, dy, N, S, C, G) && (reinterpret_cast<uintptr_t>(dx) & 15) == 0)
-    return gt_bwd(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, N, S, C, G, silu, ws, ws_bytes, stream);
+  if (gt_use((int)sizeof(T), x, dy, N, S, C, G) && (reinterpret_cast<uintptr_t>(dx) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dx_addend) & 15) == 0)
+    return gt_bwd(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, dx_addend, accumulate_dparams, N, S, C, G,
+                  silu, ws, ws_bytes, stream);
+  // legacy kernels SET dgamma / dbeta and know no addend: go through scratch / a separate add
+  float* dg_out = dgamma;
+  float* db_out = dbeta;
+  float* scratch = nullptr;
+  if (accumulate_dparams) {
+    const int64_t base = ((int64_t)N * C * 2 + (int64_t)N * G * 2) * (int64_t)sizeof(float);
+    MIG_REQUIRE(ws_bytes >= base + 2 * (int64_t)C * (int64_t)sizeof(float), "groupnorm_bwd: workspace too small");
+    scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ws) + base);
+    dgamma = scratch;
+    dbeta = scratch + C;
+  }
   int64_t need = ((int64_t)N * C * 2 + (int64_t)N * G * 2) * (int64_t)sizeof(float);
   MIG_REQUIRE(ws_bytes >= need, "groupnorm_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -416,8 +430,15 @@ static int gn_bwd(const void* x, const void* dy, const float* gamma, const float
   if (silu) gn_bwd_apply_kernel<T, true><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsg, (T*)dx, g, inv);
   else gn_bwd_apply_kernel<T, false><<<grid, threads, 0, st>>>((const T*)x, (const T*)dy, gamma, beta, mean, rstd, wsg, (T*)dx, g, inv);
   if (int rc = check_launch("groupnorm_bwd")) return rc;
+  const int dt = sizeof(T) == 2 ? MIG_BF16 : MIG_F32;
   if (dx_colsum)   // per-(n, c) sums of dx for the producing convolution's bias / time-embedding gradient
-    return mig_chan_bias_bwd(sizeof(T) == 2 ? MIG_BF16 : MIG_F32, dx, dx_colsum, N, S, C, stream);
+    if (int rc = mig_chan_bias_bwd(dt, dx, dx_colsum, N, S, C, stream)) return rc;
+  if (dx_addend)
+    if (int rc = mig_add(dt, dx, dx_addend, dx, (int64_t)N * S * C, stream)) return rc;
+  if (accumulate_dparams) {
+    if (dg_out) if (int rc = mig_add(MIG_F32, dg_out, scratch, dg_out, C, stream)) return rc;
+    if (db_out) if (int rc = mig_add(MIG_F32, db_out, scratch + C, db_out, C, stream)) return rc;
+  }
   return 0;
 }
 
@@ -495,7 +516,7 @@ using namespace mig;
 
 extern "C" int64_t mig_groupnorm_workspace_bytes(int32_t N, int64_t S, int32_t C, int32_t G) {
   int64_t fwd = (int64_t)N * G * 2 * 8;
-  int64_t bwd = ((int64_t)N * C * 2 + (int64_t)N * G * 2) * 4;
+  int64_t bwd = ((int64_t)N * C * 2 + (int64_t)N * G * 2 + 2 * (int64_t)C) * 4;
   int64_t tma = gt_bwd_workspace_bytes(N, S, C, G);
   int64_t need = fwd > bwd ? fwd : bwd;
   return need > tma ? need : tma;
@@ -509,10 +530,12 @@ extern "C" int mig_groupnorm_fwd(int dtype, const void* x, const float* gamma, c
 }
 extern "C" int mig_groupnorm_bwd(int dtype, const void* x, const void* dy, const float* gamma, const float* beta,
                                  const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                                 float* dx_colsum, int32_t N, int64_t S, int32_t C, int32_t G, int fuse_silu,
-                                 void* workspace, int64_t workspace_bytes, void* stream) {
-  MIG_DISPATCH_DTYPE(dtype, T, return (gn_bwd<T>(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, N, S, C,
-                                                 G, fuse_silu, workspace, workspace_bytes, stream)));
+                                 float* dx_colsum, const void* dx_addend, int accumulate_dparams, int32_t N, int64_t S,
+                                 int32_t C, int32_t G, int fuse_silu, void* workspace, int64_t workspace_bytes,
+                                 void* stream) {
+  MIG_DISPATCH_DTYPE(dtype, T, return (gn_bwd<T>(x, dy, gamma, beta, mean, rstd, dx, dgamma, dbeta, dx_colsum, dx_addend,
+                                                 accumulate_dparams, N, S, C, G, fuse_silu, workspace, workspace_bytes,
+                                                 stream)));
 }
 
 // Statistics and apply as separate entry points: a convolution epilogue (mig_conv_fwd_stats) can stand in for the first.

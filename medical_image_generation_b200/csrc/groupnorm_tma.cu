@@ -370,8 +370,9 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
                                                                      const float* __restrict__ grp,
                                                                      const float* __restrict__ tot,
                                                                      __nv_bfloat16* __restrict__ dx,
+                                                                     const __nv_bfloat16* __restrict__ addend,
                                                                      float* __restrict__ dgamma,
-                                                                     float* __restrict__ dbeta, GtGeom g,
+                                                                     float* __restrict__ dbeta, int accumulate, GtGeom g,
                                                                      float inv_count) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -401,11 +402,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
         a += tot[((int64_t)nn * g.C + c0 + j) * 3];
         b += tot[((int64_t)nn * g.C + c0 + j) * 3 + 1];
       }
-      if (dgamma) dgamma[c0 + j] = a;
-      if (dbeta) dbeta[c0 + j] = b;
+      if (dgamma) dgamma[c0 + j] = accumulate ? dgamma[c0 + j] + a : a;
+      if (dbeta) dbeta[c0 + j] = accumulate ? dbeta[c0 + j] + b : b;
     }
   }
   __nv_bfloat16* obase = dx + ((int64_t)n * g.S) * g.C + c0;
+  const __nv_bfloat16* abase = addend ? addend + ((int64_t)n * g.S) * g.C + c0 : nullptr;
   gt_stream<2, 3>(&xm, &dym, g, smem, smem_u32(&bars[0]), n, slab, chunk, [&](int64_t r, uint32_t a0, uint32_t a1) {
     float x[8], d[8];
     unpack8(lds16(a0), x);
@@ -420,6 +422,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) gt_bwd_apply_kernel(const __gri
         dz *= sg * fmaf(z, 1.f - sg, 1.f);
       }
       x[j] = fmaf(k1[j], dz, -fmaf(k2[j], xh, k3[j]));
+    }
+    if (abase) {   // the gradient arriving through the block's skip path (x also feeds the residual add): one fused read
+      float ad[8];
+      unpack8(*reinterpret_cast<const uint4*>(abase + r * g.C), ad);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] += ad[j];
     }
     *reinterpret_cast<uint4*>(obase + r * g.C) = pack8(x);
   });
@@ -474,8 +482,8 @@ int gt_apply(const void* x, const float* gamma, const float* beta, const double*
 }
 
 int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* mean, const float* rstd,
-           void* dx, float* dgamma, float* dbeta, float* dx_colsum, int N, int64_t S, int C, int G, int silu, void* ws,
-           int64_t ws_bytes, void* stream) {
+           void* dx, float* dgamma, float* dbeta, float* dx_colsum, const void* dx_addend, int accumulate_dparams, int N,
+           int64_t S, int C, int G, int silu, void* ws, int64_t ws_bytes, void* stream) {
   MIG_REQUIRE(ws_bytes >= gt_bwd_workspace_bytes(N, S, C, G), "groupnorm_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
   GtGeom g = gt_geom(N, S, C, G);
@@ -505,12 +513,14 @@ int gt_bwd(const void* x, const void* dy, const float* gamma, const float* beta,
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<true>, smem, o, "groupnorm_bwd")) return rc;
     gt_bwd_apply_kernel<true><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, tot,
-                                                              (__nv_bfloat16*)dx, dgamma, dbeta, g, inv);
+                                                              (__nv_bfloat16*)dx, (const __nv_bfloat16*)dx_addend, dgamma,
+                                                              dbeta, accumulate_dparams, g, inv);
   } else {
     static SmemOptIn o;
     if (int rc = gt_optin(gt_bwd_apply_kernel<false>, smem, o, "groupnorm_bwd")) return rc;
     gt_bwd_apply_kernel<false><<<grid, GT_THREADS, smem, st>>>(xm, dym, gamma, beta, mean, rstd, grp, tot,
-                                                               (__nv_bfloat16*)dx, dgamma, dbeta, g, inv);
+                                                               (__nv_bfloat16*)dx, (const __nv_bfloat16*)dx_addend, dgamma,
+                                                               dbeta, accumulate_dparams, g, inv);
   }
   return check_launch("groupnorm_bwd");
 }

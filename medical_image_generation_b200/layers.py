@@ -118,8 +118,8 @@ class GroupNorm(nn.Module):
         self.weight = nn.Parameter(torch.ones(num_channels))
         self.bias = nn.Parameter(torch.zeros(num_channels))
 
-    def forward(self, x, silu: bool = False):
-        return ops.group_norm(x, self.weight, self.bias, self.num_groups, self.eps, silu=silu)
+    def forward(self, x, silu: bool = False, with_skip: bool = False):
+        return ops.group_norm(x, self.weight, self.bias, self.num_groups, self.eps, silu=silu, with_skip=with_skip)
 
     def extra_repr(self):
         return f"{self.num_groups}, {self.num_channels}, eps={self.eps}"
@@ -202,7 +202,7 @@ class SelfAttentionBlock(nn.Module):
     def forward(self, x):
         x = ops.to_channels_last(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
         B, Cc = x.shape[0], x.shape[1]
-        h = self.norm(x)
+        h, x = self.norm(x, with_skip=True)   # x also feeds the residual add below: its gradient joins inside norm's backward
         # channels-last memory IS the (B, L, C) token matrix in the reference's d,h,w order (unet:428-434)
         tokens = h.permute(0, *range(2, h.ndim), 1).reshape(B, -1, Cc)
         fused = self._fused_qkv()

@@ -605,60 +605,103 @@ def linear(x, weight, bias=None):
 # ----------------------------------------------------------------------------------------------
 # GroupNorm (+SiLU), LayerNorm, SiLU
 # ----------------------------------------------------------------------------------------------
+def _gn_forward(ctx, x, gamma, beta, groups, eps, silu):
+    N, Cc = x.shape[0], x.shape[1]
+    S = x.numel() // (N * Cc)
+    y = torch.empty_like(x)
+    mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    pre = getattr(x, "_mig_gn_sums", None)   # statistics accumulated by the producing convolution's epilogue
+    if pre is not None and pre[1] == groups and tuple(pre[0].shape) == (N, groups, 2) and \
+            _gn_split_ok(x.dtype, N, S, Cc, groups):
+        call("mig_groupnorm_apply", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(pre[0]), _ptr(y), _ptr(mean),
+             _ptr(rstd), N, S, Cc, groups, float(eps), int(silu), _stream())
+    else:
+        need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
+        ws = _workspace(need, x.device)
+        call("mig_groupnorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), N, S, Cc,
+             groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
+    ctx.save_for_backward(x, gamma, beta, mean, rstd)
+    ctx.cfg = (groups, silu)
+    ctx.refs = (gamma, beta)
+    ctx.want_colsum = bool(getattr(x, "_mig_sole_consumer_gn", False))
+    return y
+
+
+def _gn_backward(ctx, dy, dskip=None):
+    """dskip: the gradient that reaches x through the block's skip path (x also feeds the residual add / skip conv): it is
+    added inside the GroupNorm backward kernel instead of by a separate accumulation pass."""
+    x, gamma, beta, mean, rstd = ctx.saved_tensors
+    groups, silu = ctx.cfg
+    N, Cc = x.shape[0], x.shape[1]
+    S = x.numel() // (N * Cc)
+    if dy is None:   # the normalised branch got no gradient: only the skip path contributes
+        return (None if dskip is None else as_cl(dskip)), None, None
+    dy = as_cl(dy)
+    if dy.dtype != x.dtype:
+        dy = dy.to(x.dtype)
+    if dskip is not None:
+        dskip = as_cl(dskip)
+        if dskip.dtype != x.dtype:
+            dskip = dskip.to(x.dtype)
+    dx = torch.empty_like(x)
+    gref, bref = ctx.refs
+    g_main, b_main = getattr(gref, "main_grad", None), getattr(bref, "main_grad", None)
+    into_main = g_main is not None and b_main is not None     # accumulate straight into the flat gradient buffer
+    dgamma = g_main if into_main else torch.empty_like(gamma)
+    dbeta = b_main if into_main else torch.empty_like(beta)
+    need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
+    ws = _workspace(need, x.device)
+    colsum = torch.empty((N, Cc), dtype=torch.float32, device=x.device) if (ctx.want_colsum and dskip is None) else None
+    call("mig_groupnorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx),
+         _ptr(dgamma), _ptr(dbeta), _ptr(colsum), _ptr(dskip), int(into_main), N, S, Cc, groups, int(silu), _ptr(ws),
+         ws.numel(), _stream())
+    if colsum is not None:
+        # rides on the gradient tensor to the backward of the convolution that produced x (its bias and
+        # time-embedding gradients are these column sums); if autograd hands that node a different tensor
+        # (several consumers -> accumulated gradient) the attribute is simply absent and the conv sums dy itself
+        dx._mig_colsum = colsum
+    if into_main:
+        return dx, _deliver(gref, None), _deliver(bref, None)
+    return dx, _deliver(gref, dgamma), _deliver(bref, dbeta)
+
+
 class _GroupNormFn(Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, groups, eps, silu):
-        N, Cc = x.shape[0], x.shape[1]
-        S = x.numel() // (N * Cc)
-        y = torch.empty_like(x)
-        mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
-        rstd = torch.empty_like(mean)
-        pre = getattr(x, "_mig_gn_sums", None)   # statistics accumulated by the producing convolution's epilogue
-        if pre is not None and pre[1] == groups and tuple(pre[0].shape) == (N, groups, 2) and \
-                _gn_split_ok(x.dtype, N, S, Cc, groups):
-            call("mig_groupnorm_apply", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(pre[0]), _ptr(y), _ptr(mean),
-                 _ptr(rstd), N, S, Cc, groups, float(eps), int(silu), _stream())
-        else:
-            need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
-            ws = _workspace(need, x.device)
-            call("mig_groupnorm_fwd", _dt(x), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), N, S, Cc,
-                 groups, float(eps), int(silu), _ptr(ws), ws.numel(), _stream())
-        ctx.save_for_backward(x, gamma, beta, mean, rstd)
-        ctx.cfg = (groups, silu)
-        ctx.refs = (gamma, beta)
-        ctx.want_colsum = bool(getattr(x, "_mig_sole_consumer_gn", False))
-        return y
+        return _gn_forward(ctx, x, gamma, beta, groups, eps, silu)
 
     @staticmethod
     def backward(ctx, dy):
-        x, gamma, beta, mean, rstd = ctx.saved_tensors
-        groups, silu = ctx.cfg
-        dy = as_cl(dy)
-        if dy.dtype != x.dtype:
-            dy = dy.to(x.dtype)
-        N, Cc = x.shape[0], x.shape[1]
-        S = x.numel() // (N * Cc)
-        dx = torch.empty_like(x)
-        dgamma = torch.empty_like(gamma)
-        dbeta = torch.empty_like(beta)
-        need = _lib.load().mig_groupnorm_workspace_bytes(N, S, Cc, groups)
-        ws = _workspace(need, x.device)
-        colsum = torch.empty((N, Cc), dtype=torch.float32, device=x.device) if ctx.want_colsum else None
-        call("mig_groupnorm_bwd", _dt(x), _ptr(x), _ptr(dy), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), _ptr(dx),
-             _ptr(dgamma), _ptr(dbeta), _ptr(colsum), N, S, Cc, groups, int(silu), _ptr(ws), ws.numel(), _stream())
-        if colsum is not None:
-            # rides on the gradient tensor to the backward of the convolution that produced x (its bias and
-            # time-embedding gradients are these column sums); if autograd hands that node a different tensor
-            # (several consumers -> accumulated gradient) the attribute is simply absent and the conv sums dy itself
-            dx._mig_colsum = colsum
-        return dx, _deliver(ctx.refs[0], dgamma), _deliver(ctx.refs[1], dbeta), None, None, None
+        dx, dg, db = _gn_backward(ctx, dy)
+        return dx, dg, db, None, None, None
 
 
-def group_norm(x, gamma, beta, groups: int, eps: float, silu: bool = False):
-    """nn.GroupNorm (fp32 statistics) with optional fused SiLU (unet:628-629,648,1932-1933; ae:157,194)."""
+class _GroupNormSkipFn(Function):
+    """GroupNorm whose input ALSO feeds the block's skip path (ResnetBlock: unet:674-701, x -> norm1 and x -> skip /
+    residual add; AttentionBlock: unet:418-458). Returns (norm(x), x): the second output is x itself for the skip path,
+    so both gradients arrive at this node together and are summed inside the backward kernel."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        return _gn_forward(ctx, x, gamma, beta, groups, eps, silu), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dskip):
+        dx, dg, db = _gn_backward(ctx, dy, dskip)
+        return dx, dg, db, None, None, None
+
+
+def group_norm(x, gamma, beta, groups: int, eps: float, silu: bool = False, with_skip: bool = False):
+    """nn.GroupNorm (fp32 statistics) with optional fused SiLU (unet:628-629,648,1932-1933; ae:157,194).
+    with_skip=True returns (y, x_skip): use x_skip instead of x for the block's skip path."""
     _require_cuda(x, "group_norm")
     if not _is_cl(x):
         x = to_channels_last(x, x.dtype)
+    if with_skip:
+        if torch.is_grad_enabled() and x.requires_grad:
+            return _GroupNormSkipFn.apply(x, gamma, beta, int(groups), float(eps), bool(silu))
+        return _GroupNormFn.apply(x, gamma, beta, int(groups), float(eps), bool(silu)), x
     return _GroupNormFn.apply(x, gamma, beta, int(groups), float(eps), bool(silu))
 
 

@@ -202,7 +202,8 @@ class ResnetBlock(nn.Module):
 
     def forward(self, x, emb):
         x = _entry(x)
-        h = self.norm1(x, silu=True)
+        # x feeds norm1 AND the skip path: the skip gradient is added inside norm1's backward kernel
+        h, x = self.norm1(x, silu=True, with_skip=True)
         if self.upsample is not None:      # unet:672-679
             x, h = self.upsample(x), self.upsample(h)
         elif self.downsample is not None:

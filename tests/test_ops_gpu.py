@@ -261,7 +261,7 @@ def test_group_norm_split_and_colsum(C, G, sp):
     need = _lib.load().mig_groupnorm_workspace_bytes(N, S, C, G)
     ws = torch.empty(int(need), dtype=torch.uint8, device=DEV)
     _lib.call("mig_groupnorm_bwd", 1, ops._ptr(xd), ops._ptr(dyd), ops._ptr(gamma_d), ops._ptr(beta_d),
-              ops._ptr(mean), ops._ptr(rstd), ops._ptr(dx), ops._ptr(dgam), ops._ptr(dbet), ops._ptr(colsum), N, S, C, G, 1,
+              ops._ptr(mean), ops._ptr(rstd), ops._ptr(dx), ops._ptr(dgam), ops._ptr(dbet), ops._ptr(colsum), None, 0, N, S, C, G, 1,
               ops._ptr(ws), ws.numel(), ops._stream())
     xr = x.clone().requires_grad_(True)
     F.silu(F.group_norm(xr, G, gamma, beta, 1e-6)).backward(dy)
