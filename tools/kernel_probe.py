@@ -1,6 +1,6 @@
 """Launches each kernel family ONCE PER SHAPE at the BASELINE sizes so that `ncu --set full -k regex:...` can capture them:
 
-    python tools/kernel_probe.py [gn|adamw|flash|halo|sched|all] [reps]
+    python tools/kernel_probe.py [gn|adamw|flash|flashbwd|conv|halo|sched|all] [reps]
 
   gn     GroupNorm(+SiLU) fwd + bwd on the config-3 level-0 / level-1 tensors (8x256x24^3, 8x512x12^3, bf16)
   adamw  fused clip + AdamW over 441 M parameters (flat buffers) + the sum-of-squares pass
@@ -85,6 +85,36 @@ if which in ("flash", "all"):
         with torch.no_grad():
             timed(f"flash attention fwd B={B} L={L} d={C // heads}", lambda i: ops.flash_attention(q, k, v, heads, (C // heads) ** -0.5),
                   flops=fl)
+
+if which in ("flashbwd", "all"):
+    for (B, L, C, heads) in ((1, 8192, 128, 1), (8, 1728, 512, 1), (8, 216, 768, 1)):
+        q, k, v = (torch.randn(B, L, C, device=dev, dtype=torch.bfloat16).requires_grad_(True) for _ in range(3))
+        dO = torch.randn(B, L, C, device=dev, dtype=torch.bfloat16)
+        ops.set_flash_attention(True, training=True)
+
+        def step(i):
+            ops.sdpa(q, k, v, heads, (C // heads) ** -0.5).backward(dO)
+
+        timed(f"flash attention fwd+bwd B={B} L={L} d={C // heads}", step, flops=4.0 * B * L * L * C * 3.5)
+        ops.set_flash_attention(True, training="auto")
+
+if which in ("conv", "all"):
+    # the dominant config-3 layer: Conv3d 256 -> 256, 3x3x3, 8 x 24^3 voxels -- fwd, dgrad (MN-major filter operand), wgrad
+    xs = [cl(torch.randn(8, 256, 24, 24, 24, device=dev, dtype=torch.bfloat16)).requires_grad_(True) for _ in range(2)]
+    w = cl(torch.randn(256, 256, 3, 3, 3, device=dev) * 0.01).requires_grad_(True)
+    b = torch.zeros(256, device=dev, requires_grad=True)
+    fl = 2.0 * 8 * 24 ** 3 * 256 * 256 * 27
+    ys = {}
+
+    def cfwd(i):
+        ys[i % 2] = ops.conv_nd(xs[i % 2], w, b, 1, 1)
+
+    def cbwd(i):
+        ys[i % 2].backward(torch.ones_like(ys[i % 2]), retain_graph=True)
+
+    timed("conv fwd 256->256 3^3 8x24^3 (conv_tma_kernel)", cfwd, flops=fl)
+    timed("conv bwd (dgrad MN-major filter + wgrad) 256->256 8x24^3", cbwd, flops=2 * fl)
+    del xs, ys
 
 if which in ("halo", "all"):
     for (N, Cin, Cout, sp) in ((2, 32, 32, 96), (2, 32, 64, 96), (1, 32, 32, 128)):
