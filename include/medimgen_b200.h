@@ -185,6 +185,18 @@ int mig_softmax_fwd(int dtype_in, int dtype_out, const void* x, void* y, int64_t
 int mig_softmax_bwd(int dtype_p, int dtype_d, const void* p, const void* dp, void* ds, int64_t rows, int32_t cols,
                     float scale, void* stream);
 
+/* K6: time_emb_proj(silu(emb)) of ALL ResnetBlocks of a U-Net in one launch per pass (unet:691-695; SURVEY K6 "tiny
+ * GEMM batched over all ResnetBlocks once per forward"). x: fp32 [rows][K] (= silu(emb)); layer i has weight w[i]
+ * [channels[i]][K], bias b[i] (or NULL) and output y[i] [rows][channels[i]]; n <= MIG_TEMB_MAX layers. The pointer
+ * arrays are HOST arrays (copied into the kernel parameters). Backward (rows <= 8): dw[i] / db[i] are ACCUMULATED into
+ * (dy[i] == NULL: layer without gradient), dx (optional) receives sum_i dy[i] w[i]. */
+#define MIG_TEMB_MAX 32
+int mig_temb_proj_all_fwd(const float* x, const float* const* w, const float* const* b, float* const* y,
+                          const int32_t* channels, int32_t n, int32_t rows, int32_t K, void* stream);
+int mig_temb_proj_all_bwd(const float* x, const float* const* w, const float* const* dy, float* const* dw,
+                          float* const* db, float* dx, const int32_t* channels, int32_t n, int32_t rows, int32_t K,
+                          void* stream);
+
 /* K7: sinusoidal timestep embedding, cos first (unet:461-485). t: fp32 [B] */
 int mig_timestep_embedding(const float* t, void* out, int out_dtype, int32_t B, int32_t dim, float max_period,
                            void* stream);

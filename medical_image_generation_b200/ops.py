@@ -602,6 +602,79 @@ def linear(x, weight, bias=None):
     return y.reshape(*shp[:-1], weight.shape[0])
 
 
+class _TembProjAllFn(Function):
+    """time_emb_proj of every ResnetBlock applied to the same silu(emb) in one launch per pass (unet:691-695).
+    forward(x, w0, b0, w1, b1, ...) -> (y0, y1, ...); the layers stay separate fp32 parameters."""
+
+    @staticmethod
+    def forward(ctx, x, *params):
+        ws, bs = params[0::2], params[1::2]
+        n = len(ws)
+        rows, K = x.shape
+        outs = [torch.empty((rows, w.shape[0]), dtype=torch.float32, device=x.device) for w in ws]
+        PA, IA = C.c_void_p * n, C.c_int32 * n
+        call("mig_temb_proj_all_fwd", _ptr(x), PA(*[w.data_ptr() for w in ws]),
+             PA(*[None if b is None else b.data_ptr() for b in bs]), PA(*[o.data_ptr() for o in outs]),
+             IA(*[w.shape[0] for w in ws]), n, rows, K, _stream())
+        ctx.save_for_backward(x, *[w.detach() for w in ws])
+        ctx.refs = (ws, bs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        x, *wt = ctx.saved_tensors
+        ws, bs = ctx.refs
+        n = len(ws)
+        rows, K = x.shape
+        keep, dy_p, dw_p, db_p, dw_new, db_new = [], [], [], [], [None] * n, [None] * n
+        for i in range(n):
+            g = grads[i]
+            if g is None:        # this layer received no gradient: the kernels skip it (null dy)
+                dy_p.append(None); dw_p.append(None); db_p.append(None)
+                continue
+            g = g.float().contiguous()
+            keep.append(g)
+            dy_p.append(g.data_ptr())
+            wm = getattr(ws[i], "main_grad", None)
+            if wm is None:
+                dw_new[i] = wm = torch.zeros_like(wt[i])
+            dw_p.append(wm.data_ptr())
+            if bs[i] is None:
+                db_p.append(None)
+            else:
+                bm = getattr(bs[i], "main_grad", None)
+                if bm is None:
+                    db_new[i] = bm = torch.zeros(wt[i].shape[0], dtype=torch.float32, device=x.device)
+                db_p.append(bm.data_ptr())
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        PA, IA = C.c_void_p * n, C.c_int32 * n
+        call("mig_temb_proj_all_bwd", _ptr(x), PA(*[w.data_ptr() for w in wt]), PA(*dy_p), PA(*dw_p), PA(*db_p), _ptr(dx),
+             IA(*[w.shape[0] for w in wt]), n, rows, K, _stream())
+        out = [dx]
+        for i in range(n):
+            if dy_p[i] is None:
+                out += [None, None]
+                continue
+            out.append(dw_new[i] if dw_new[i] is not None else _deliver(ws[i], None))
+            out.append(None if bs[i] is None else (db_new[i] if db_new[i] is not None else _deliver(bs[i], None)))
+        return tuple(out)
+
+
+def temb_projections(x, linears):
+    """[Linear-like modules with fp32 .weight/.bias] applied to the same fp32 input x (rows, K) -> list of (rows, C_i)
+    tensors, or None when the batched kernels do not apply (more than 32 layers, more than 8 rows, non-fp32)."""
+    if not linears or len(linears) > 32 or x.dtype != torch.float32 or x.ndim != 2 or x.shape[0] > 8 or x.shape[1] % 4:
+        return None
+    if any(m.weight.dtype != torch.float32 or not m.weight.is_contiguous() or m.weight.shape[1] != x.shape[1]
+           for m in linears):
+        return None
+    _require_cuda(x, "temb_projections")
+    params = []
+    for m in linears:
+        params += [m.weight, m.bias]
+    return list(_TembProjAllFn.apply(x.contiguous(), *params))
+
+
 # ----------------------------------------------------------------------------------------------
 # GroupNorm (+SiLU), LayerNorm, SiLU
 # ----------------------------------------------------------------------------------------------

@@ -208,8 +208,12 @@ class ResnetBlock(nn.Module):
             x, h = self.upsample(x), self.upsample(h)
         elif self.downsample is not None:
             x, h = self.downsample(x), self.downsample(h)
-        # the (B, 4*C0) embedding path stays in fp32: it is tiny and feeds the conv epilogue as an fp32 bias
-        temb = self.time_emb_proj(self.nonlinearity(emb if emb.dtype == torch.float32 else emb.float()))
+        # the (B, 4*C0) embedding path stays in fp32: it is tiny and feeds the conv epilogue as an fp32 bias.
+        # DiffusionModelUNet.forward normally computes the projections of ALL blocks in one launch and hands each block
+        # its own (ops.temb_projections); a block called on its own computes it here
+        temb = self.__dict__.pop("_mig_temb", None)
+        if temb is None:
+            temb = self.time_emb_proj(self.nonlinearity(emb if emb.dtype == torch.float32 else emb.float()))
         # conv1's epilogue accumulates norm2's statistics; conv2's those of whichever GroupNorm reads the block output
         h = self.conv1(h, chan_bias=temb, gn_groups=self.norm2.num_groups)
         h._mig_sole_consumer_gn = True   # norm2 is conv1's only consumer: its backward hands conv1 the column sums of dy
@@ -459,6 +463,17 @@ class DiffusionModelUNet(nn.Module):
             raise ValueError("model should have with_conditioning = True if context is provided")
         if context is not None:
             context = context.to(cdt).contiguous()
+
+        # time_emb_proj(silu(emb)) of every ResnetBlock in one launch (each block picks its own up in its forward)
+        resnets = self.__dict__.get("_mig_resnets")
+        if resnets is None:
+            resnets = [m for m in self.modules() if isinstance(m, ResnetBlock)]
+            self.__dict__["_mig_resnets"] = resnets
+        emb32 = emb if emb.dtype == torch.float32 else emb.float()
+        tembs = ops.temb_projections(ops.silu(emb32), [m.time_emb_proj for m in resnets]) if emb32.is_cuda else None
+        if tembs is not None:
+            for m, t in zip(resnets, tembs):
+                m.__dict__["_mig_temb"] = t
 
         h = self.conv_in(ops.to_channels_last(x, cdt))
         skips = [h]

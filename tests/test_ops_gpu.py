@@ -270,6 +270,47 @@ def test_group_norm_split_and_colsum(C, G, sp):
     assert rel_err(colsum, xr.grad.sum(dim=tuple(range(2, x.ndim)))) < 5e-3
 
 
+def test_batched_time_embedding_projections():
+    """mig_temb_proj_all_fwd / _bwd: time_emb_proj of every ResnetBlock in one launch per pass (unet:691-695) against
+    per-layer F.linear with autograd; one layer gets no gradient (null dy), one has no bias."""
+    ops = _ops()
+    from medical_image_generation_b200 import layers
+    g = torch.Generator().manual_seed(11)
+    K, rows = 128, 3
+    chans = [32, 64, 48, 96, 8]
+    lins = [layers.Linear(K, c, bias=(i != 2)) for i, c in enumerate(chans)]
+    for m in lins:
+        with torch.no_grad():
+            for p in m.parameters():
+                p.copy_(torch.randn(p.shape, generator=g) * 0.3)
+        m.to(DEV)
+    x = torch.randn(rows, K, generator=g)
+    xd = x.to(DEV).requires_grad_(True)
+    outs = ops.temb_projections(xd, lins)
+    assert outs is not None and [tuple(o.shape) for o in outs] == [(rows, c) for c in chans]
+    xr = x.clone().requires_grad_(True)
+    refs = [F.linear(xr, m.weight.detach().cpu(), None if m.bias is None else m.bias.detach().cpu()) for m in lins]
+    wr = []
+    for m in lins:
+        wr.append((m.weight.detach().cpu().clone().requires_grad_(True),
+                   None if m.bias is None else m.bias.detach().cpu().clone().requires_grad_(True)))
+    refs = [F.linear(xr, w, b) for w, b in wr]
+    for o, r in zip(outs, refs):
+        assert rel_err(o, r) < 1e-5
+    probes = [torch.randn(rows, c, generator=g) for c in chans]
+    used = [0, 1, 2, 4]                                   # layer 3 gets no gradient
+    sum((outs[i] * probes[i].to(DEV)).sum() for i in used).backward()
+    sum((refs[i] * probes[i]).sum() for i in used).backward()
+    assert rel_err(xd.grad, xr.grad) < 1e-5
+    for i, m in enumerate(lins):
+        if i in used:
+            assert rel_err(m.weight.grad, wr[i][0].grad) < 1e-5
+            if m.bias is not None:
+                assert rel_err(m.bias.grad, wr[i][1].grad) < 1e-5
+        else:
+            assert m.weight.grad is None
+
+
 @pytest.mark.parametrize("case", [
     # (N, Cin, Cout, spatial, groups, residual + time embedding, statistics expected from the tcgen05 epilogue)
     (2, 64, 256, (16, 16, 16), 32, True, True),     # 8 channels per group
