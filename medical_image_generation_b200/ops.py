@@ -618,6 +618,7 @@ class _TembProjAllFn(Function):
              IA(*[w.shape[0] for w in ws]), n, rows, K, _stream())
         ctx.save_for_backward(x, *[w.detach() for w in ws])
         ctx.refs = (ws, bs)
+        ctx.set_materialize_grads(False)   # a layer whose output is unused gets grad None (not zeros): skipped like torch
         return tuple(outs)
 
     @staticmethod
