@@ -92,6 +92,7 @@ struct ConvTmaParams {
   // (sum y, sum y^2) of the bf16-rounded values, for the GroupNorm that consumes this convolution (unet:648,698 / ae:167)
   double* gn_sums;
   int gn_cpg, gn_G;
+  int epi_groups;   // 1 or 2 epilogue warp groups (A/B switch MIG_CONV_EPI_GROUPS; default 2)
 };
 
 // Sum eight per-thread values over the 32 lanes of a warp with 7 + 2 shuffles (recursive halving: after step k every
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + 8 * a, 1);
-      mbar_init(acc_empty + 8 * a, 256);
+      mbar_init(acc_empty + 8 * a, 128 * p.epi_groups);
     }
     fence_barrier_init();
   }
@@ -178,9 +179,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
   tcgen05_fence_after();
   const uint32_t tmem_acc = tmem_slot;
 
-  if (warp < 4 || warp >= 6) {
+  if (warp < 4 || (warp >= 6 && p.epi_groups == 2)) {
     // ===================== epilogue: two groups of four warps =====================
     const int eg = warp >= 6 ? 1 : 0;          // column group
+    const int egroups = p.epi_groups, ethreads = 128 * egroups;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read (warps 6..9 -> 2,3,0,1)
     const int row = quad * 32 + lane;
     const int etid = eg * 128 + row;
@@ -195,11 +197,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
       // while the main loop runs: bias + per-sample channel bias of this tile's columns, one row per box (a box lies
       // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
       if (!p.partial) {
-        asm volatile("bar.sync 1, 256;" ::: "memory");   // the previous tile's readers are done with add_s
+        asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");   // the previous tile's readers are done with add_s
         for (int j = 0; j < nslot; ++j) {
           int n = 0, d0, h0, w0;
           if (box0 + j < g.num_boxes) box_origin(g, box0 + j, n, d0, h0, w0);
-          for (int c = etid; c < BN; c += 256) {
+          for (int c = etid; c < BN; c += ethreads) {
             const int col = n0 + c;
             float a = 0.f;
             if (col < g.Cdst) {
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
             add_s[j][c] = a;
           }
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");
       }
       mbar_wait(acc_full + 8 * ab, (uint32_t)(ti / NACC) & 1u);
       tcgen05_fence_after();
@@ -226,8 +228,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
         const uint32_t trow = tmem_acc + ((uint32_t)(quad * 32) << 16) + ab * (MT * BN) + mt * BN;
         constexpr int LDW = BN >= 64 ? 64 : 16;   // columns per TMEM load (one round trip each)
 #pragma unroll 1
-        for (int cw = eg * LDW; cw < BN; cw += 2 * LDW) {
+        for (int cw = eg * LDW; cw < BN; cw += egroups * LDW) {
           if (n0 + cw >= g.Cdst) break;
+          // residual of this row's LDW columns: all 16-byte loads issued up front, in flight during the TMEM load
+          // (one dependent global load per 16 columns cost the forward kernels ~6 % against dgrad on the same shape)
+          uint4 rres[LDW / 8];
+          const bool pre_res = p.residual != nullptr && mok && !p.partial && (g.Cdst & 7) == 0;
+          if (pre_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + n0 + cw);
+#pragma unroll
+            for (int e = 0; e < LDW / 8; ++e)
+              if (n0 + cw + 8 * e + 8 <= g.Cdst) rres[e] = rp[e];
+          }
           float vw[LDW];
           if constexpr (LDW == 64) tmem_ld64(trow + cw, vw);
           else tmem_ld16(trow + cw, vw);
@@ -253,9 +265,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
             }
             __nv_bfloat16* dst = p.out + m * g.Cdst + col0;
             if (full16) {
-              if (p.residual && mok) {
-                const uint4* rp = reinterpret_cast<const uint4*>(p.residual + m * g.Cdst + col0);
-                uint4 r0 = rp[0], r1 = rp[1];
+              if (pre_res) {
+                const uint4 r0 = rres[(c0 - cw) >> 3], r1 = rres[((c0 - cw) >> 3) + 1];
                 const __nv_bfloat16* a0 = reinterpret_cast<const __nv_bfloat16*>(&r0);
                 const __nv_bfloat16* a1 = reinterpret_cast<const __nv_bfloat16*>(&r1);
 #pragma unroll
@@ -325,6 +336,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
       tcgen05_fence_before();
       mbar_arrive(acc_empty + 8 * ab);   // this accumulator set may be overwritten by a later tile
     }
+  } else if (warp >= 6) {
+    // second epilogue group switched off
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(TBM, BN, 0, BMN ? 1 : 0);
@@ -799,7 +812,7 @@ static void plan_box_conv(const BoxGeom& b, int bn, int num_kb, bool ws_ok, int*
       if (s_ > 1 && (!ws_ok || num_kb / s_ < 4)) continue;
       const double waves = (double)((mtiles_ * ntiles * s_ + sms - 1) / sms);
       const double kb = (double)((num_kb + s_ - 1) / s_);
-      const double t_epi = 2500.0 + m_ * (bn / 32) * (s_ > 1 ? 160.0 : 110.0);   // two epilogue groups share the columns
+      const double t_epi = 2500.0 + m_ * (bn / 16) * (s_ > 1 ? 160.0 : 110.0);
       double t = waves * (kb * t_stage + t_epi + 9000.0);
       if (s_ > 1) t += (double)M * b.Cdst * 14.0 / 3000.0 + 8000.0;   // memset + fp32 reductions + finish pass
       if (t < best) { best = t; *mt = m_; *splits = s_; }
@@ -879,6 +892,14 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     ex->stats_done = true;
   }
   p.mtiles = (int)mtiles; p.ntiles = (int)ntiles; p.splits = splits;
+  {
+    static int groups = 0;
+    if (groups == 0) {
+      const char* e = getenv("MIG_CONV_EPI_GROUPS");
+      groups = (e && e[0] == '1') ? 1 : 2;
+    }
+    p.epi_groups = groups;
+  }
   int64_t nct = mtiles * ntiles * splits;
   static int one_tile_per_cta = -1;   // A/B switch: static round-robin persistence vs. hardware CTA scheduling
   if (one_tile_per_cta < 0) {

@@ -10,6 +10,7 @@ from medical_image_generation_b200 import ops  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
 which = sys.argv[2] if len(sys.argv) > 2 else "all"
+epi = len(sys.argv) > 3 and sys.argv[3] == "epi"     # forward with the fused epilogue inputs of a ResnetBlock's conv2
 SHAPES = [  # (N, Cin, Cout, spatial) 3x3x3 stride 1 pad 1 -- the LDM-default U-Net at 3x24^3, batch 8
     (8, 256, 256, 24), (8, 512, 512, 24), (8, 768, 256, 24), (8, 512, 512, 12), (8, 1280, 512, 12),
     (8, 768, 768, 12), (8, 768, 768, 6), (8, 1536, 768, 6)]
@@ -25,7 +26,11 @@ for N, Cin, Cout, s in SHAPES:
     w = (torch.randn(Cout, Cin, 3, 3, 3, device="cuda") * 0.02).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
     b = torch.zeros(Cout, device="cuda")
     flops = 2.0 * N * s ** 3 * Cout * Cin * 27
-    y = ops.conv_nd(x, w, b, 1, 1)
+    res = cb = None
+    if epi:
+        res = torch.randn(N, Cout, s, s, s, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last_3d)
+        cb = torch.randn(N, Cout, device="cuda")
+    y = ops.conv_nd(x, w, b, 1, 1, chan_bias=cb, residual=res)
     dy = torch.randn_like(y)
     y.backward(dy)
     torch.cuda.synchronize()
@@ -33,7 +38,7 @@ for N, Cin, Cout, s in SHAPES:
     for _ in range(reps):
         x.grad = None
         w.grad = None
-        y = ops.conv_nd(x, w, b, 1, 1)
+        y = ops.conv_nd(x, w, b, 1, 1, chan_bias=cb, residual=res)
         y.backward(dy)
     torch.cuda.synchronize()
     prof = ops.profile_stop()
