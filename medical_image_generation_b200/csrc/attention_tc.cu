@@ -153,12 +153,23 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
         tcgen05_fence_before();
         mbar_arrive(s_empty + 8 * buf);                // S is in registers: Q K^T of tile j+2 may overwrite it
         const int kb = kbase + hs * 64;
+        // The scores stay UNSCALED in registers: scale > 0, so the row maximum commutes with the scaling and the
+        // exponent becomes one FFMA (v * scale - m) feeding MUFU.EX2. Per element: FMNMX + FFMA + MUFU + FADD (+ half a
+        // pack) instead of FMUL + compare + select + FMNMX + FADD + MUFU + FADD -- the softmax warps were issue-bound next
+        // to the 1024 MUFU cycles of a tile. Only a ragged last key tile takes the masked form.
+        const bool ragged = kb + 64 > p.Lk;
         float tmax = -INFINITY;
+        if (ragged) {
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
-          v[e] = (kb + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
-          tmax = fmaxf(tmax, v[e]);
+          for (int e = 0; e < 64; ++e) {
+            v[e] = (kb + e < p.Lk) ? v[e] : -INFINITY;
+            tmax = fmaxf(tmax, v[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 64; ++e) tmax = fmaxf(tmax, v[e]);
         }
+        tmax *= p.scale_log2;   // (-inf stays -inf)
         // row maximum over both key halves: exchange through shared memory (double-buffered by tile parity)
         xch[j & 1][hs][r] = tmax;
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -196,7 +207,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int k0 = c * 8 + 2 * e;
-              const float p0 = fast_ex2(v[k0] - m_run), p1 = fast_ex2(v[k0 + 1] - m_run);
+              const float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -m_run)), p1 = fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -m_run));
               sum += p0 + p1;
               __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
               o[e] = *reinterpret_cast<uint32_t*>(&q2);

@@ -271,9 +271,12 @@ class FlatAdamW:
         # every owned parameter carries the callback of ITS optimiser (several FlatAdamW instances can coexist)
         for _, p in self.params:
             p._mig_grad_ready = self._grad_ready
+        self._seen = set()          # ids of parameters that have delivered a gradient at least once
+        self._checked_unused = False
 
     # called from the backward kernels' wrappers once a parameter's gradient is complete in `main_grad`
     def _grad_ready(self, p) -> None:
+        self._seen.add(id(p))
         if self.buckets is None or not self._sync_enabled:   # accumulation: only the last micro-step reduces
             return
         i = self._index_of.get(id(p))
@@ -299,6 +302,18 @@ class FlatAdamW:
             if p.grad is not None:
                 p.main_grad.add_(p.grad)
                 p.grad = None
+                self._seen.add(id(p))
+        if not self._checked_unused:
+            # torch.optim.AdamW skips parameters whose grad is None (no weight decay, no moments). The flat kernel updates
+            # the whole used region, so a trainable parameter that never receives a gradient (a branch that is not
+            # exercised) must be named in `unused` like proj_attn; say so loudly instead of silently decaying it.
+            self._checked_unused = True
+            idle = [n for n, p in self.params if p._mig_slot[0] < self.used_numel and id(p) not in self._seen]
+            if idle:
+                import warnings
+                warnings.warn("FlatAdamW: no gradient reached " + ", ".join(idle[:6]) + (" ..." if len(idle) > 6 else "") +
+                              " in the first step; unlike torch.optim.AdamW (which skips grad=None) these parameters still "
+                              "receive decoupled weight decay here. List their name fragments in `unused=` to exclude them.")
         if self.buckets is not None:
             self.finish_grad_sync()
         self.step_count += 1          # host mirror; the kernel reads the device counter (valid under graph replay)
@@ -373,8 +388,8 @@ class FlatAdamW:
         state = {}
         for i, p in enumerate(self._torch_order):
             off, k = p._mig_slot
-            if off >= self.used_numel or self.step_count == 0:
-                continue
+            if off >= self.used_numel or self.step_count == 0 or id(p) not in self._seen:
+                continue     # (torch keeps no state for parameters that never had a gradient)
             view = lambda buf: buf[off:off + k].as_strided(p.shape, p.stride()).detach().clone()  # noqa: E731
             state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": view(self.m), "exp_avg_sq": view(self.v)}
         group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False,
