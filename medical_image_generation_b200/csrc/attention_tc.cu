@@ -158,18 +158,20 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
         // pack) instead of FMUL + compare + select + FMNMX + FADD + MUFU + FADD -- the softmax warps were issue-bound next
         // to the 1024 MUFU cycles of a tile. Only a ragged last key tile takes the masked form.
         const bool ragged = kb + 64 > p.Lk;
-        float tmax = -INFINITY;
         if (ragged) {
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            v[e] = (kb + e < p.Lk) ? v[e] : -INFINITY;
-            tmax = fmaxf(tmax, v[e]);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 64; ++e) tmax = fmaxf(tmax, v[e]);
+          for (int e = 0; e < 64; ++e) v[e] = (kb + e < p.Lk) ? v[e] : -INFINITY;
         }
-        tmax *= p.scale_log2;   // (-inf stays -inf)
+        // four independent maxima (a single running maximum is a 64-deep dependent FMNMX chain on the critical path)
+        float t0 = fmaxf(v[0], v[1]), t1 = fmaxf(v[2], v[3]), t2 = fmaxf(v[4], v[5]), t3 = fmaxf(v[6], v[7]);
+#pragma unroll
+        for (int e = 8; e < 64; e += 8) {
+          t0 = fmaxf(t0, fmaxf(v[e], v[e + 1]));
+          t1 = fmaxf(t1, fmaxf(v[e + 2], v[e + 3]));
+          t2 = fmaxf(t2, fmaxf(v[e + 4], v[e + 5]));
+          t3 = fmaxf(t3, fmaxf(v[e + 6], v[e + 7]));
+        }
+        float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;   // (-inf stays -inf)
         // row maximum over both key halves: exchange through shared memory (double-buffered by tile parity)
         xch[j & 1][hs][r] = tmax;
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
           l_run *= f;
           m_run = m_new;
         }
-        float sum = 0.f;
+        float sum = 0.f, sum_b = 0.f;
         mbar_wait(p_empty + 8 * pb, ((uint32_t)(j >> 1) & 1u) ^ 1u);   // P V of tile j-2 has consumed this P buffer
         {
           const uint32_t base = p_smem + pb * FA_P_BYTES + hs * (FA_BM * 128);   // P panel of this key half
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
             for (int e = 0; e < 4; ++e) {
               const int k0 = c * 8 + 2 * e;
               const float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -m_run)), p1 = fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -m_run));
-              sum += p0 + p1;
+              if (e & 1) sum_b += p0 + p1;
+              else sum += p0 + p1;
               __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
               o[e] = *reinterpret_cast<uint32_t*>(&q2);
             }
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
                          "r"(o[2]), "r"(o[3]) : "memory");
           }
         }
-        l_run += sum;                                  // partial sum of this key half; combined in the epilogue
+        l_run += sum + sum_b;                          // partial sum of this key half; combined in the epilogue
         tcgen05_fence_before();
         fence_proxy_async();
         mbar_arrive(p_full + 8 * pb);
