@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(192, 1) flash_bwd_kernel(const __grid_constant
   const uint32_t v_smem = t_smem + 2 * FB_T_BYTES;
   __shared__ __align__(8) uint64_t bars[19];
   __shared__ uint32_t tmem_slot;
-  __shared__ float stat_s[2][2][FB_BN];   // MODE 0: (lse, D) of the streamed query tile, double-buffered by tile parity
+  __shared__ __align__(16) float stat_s[2][2][FB_BN];   // MODE 0: (lse, D * scale) of the streamed query tile, by tile parity
   const uint32_t b0 = smem_u32(&bars[0]);
   const uint32_t qk_full = b0, qk_empty = b0 + 8 * 3, v_full = b0 + 8 * 6, v_empty = b0 + 8 * 10, g_full = b0 + 8 * 14,
                  g_empty = b0 + 8 * 15, t_full = b0 + 8 * 16, t_empty = b0 + 8 * 17, o_full = b0 + 8 * 18;
@@ -109,14 +109,14 @@ __global__ void __launch_bounds__(192, 1) flash_bwd_kernel(const __grid_constant
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float* lse_bh = p.lse + (int64_t)blockIdx.z * p.Lq;
     const float* del_bh = p.delta + (int64_t)blockIdx.z * p.Lq;
-    float lse_r = INFINITY, del_r = 0.f;
-    if (MODE == 1 && xok) { lse_r = lse_bh[xr]; del_r = del_bh[xr]; }
+    float lse_r = INFINITY, del_r = 0.f;   // del_* hold delta * scale: dS = P * (dP * scale - delta * scale)
+    if (MODE == 1 && xok) { lse_r = lse_bh[xr]; del_r = del_bh[xr] * p.scale; }
     for (int j = 0; j < ntile; ++j) {
       const int y0 = j * FB_BN;
       if (MODE == 0) {   // per-column statistics of this query tile (lse = +inf for queries past the end: P = 0)
         const int q = y0 + r;
         stat_s[j & 1][0][r] = q < p.Lq ? lse_bh[q] : INFINITY;
-        stat_s[j & 1][1][r] = q < p.Lq ? del_bh[q] : 0.f;
+        stat_s[j & 1][1][r] = q < p.Lq ? del_bh[q] * p.scale : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       mbar_wait(g_full, (uint32_t)j & 1u);
@@ -128,22 +128,32 @@ __global__ void __launch_bounds__(192, 1) flash_bwd_kernel(const __grid_constant
         tmem_ld64(tmem_base + lane_off + half * 64, g1);
         tmem_ld64(tmem_base + lane_off + 128 + half * 64, g2);
         const uint32_t t1 = t_smem + half * (FB_BM * 128), t2 = t1 + FB_T_BYTES;
+        // Rows past the end of the stationary tile need no masking: their G rows are zero-filled by TMA and whatever
+        // they produce only lands in accumulator rows the epilogue never stores. Columns past the end of the streamed
+        // tile do: MODE 0 (queries) gets P = 0 from lse = +inf, MODE 1 (keys) is masked on the ragged last tile only.
+        const bool ragged = MODE == 1 && y0 + half * 64 + 64 > p.Lk;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {   // 16-byte chunks of the 128-byte row
           uint32_t o1[4], o2[4];
+          float lc[8], dc[8];
+          if (MODE == 0) {   // per-column statistics: two 16-byte broadcast reads per 4 columns
+            const float4* ls = reinterpret_cast<const float4*>(&stat_s[j & 1][0][half * 64 + c * 8]);
+            const float4* ds = reinterpret_cast<const float4*>(&stat_s[j & 1][1][half * 64 + c * 8]);
+            const float4 l0 = ls[0], l1 = ls[1], d0 = ds[0], d1 = ds[1];
+            lc[0] = l0.x; lc[1] = l0.y; lc[2] = l0.z; lc[3] = l0.w; lc[4] = l1.x; lc[5] = l1.y; lc[6] = l1.z; lc[7] = l1.w;
+            dc[0] = d0.x; dc[1] = d0.y; dc[2] = d0.z; dc[3] = d0.w; dc[4] = d1.x; dc[5] = d1.y; dc[6] = d1.z; dc[7] = d1.w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float pv[2], dv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-              const int col = c * 8 + 2 * e + u, yc = half * 64 + col;
-              float lse_c, del_c;
-              bool ok;
-              if (MODE == 0) { lse_c = stat_s[j & 1][0][yc]; del_c = stat_s[j & 1][1][yc]; ok = xok; }
-              else { lse_c = lse_r; del_c = del_r; ok = y0 + yc < p.Lk; }
-              const float pe = ok ? fb_ex2(fmaf(g1[col], p.scale_log2, -lse_c)) : 0.f;
+              const int cc = 2 * e + u, col = c * 8 + cc;
+              const float lse_c = MODE == 0 ? lc[cc] : lse_r, del_c = MODE == 0 ? dc[cc] : del_r;
+              float pe = fb_ex2(fmaf(g1[col], p.scale_log2, -lse_c));
+              if (ragged) pe = (y0 + half * 64 + col < p.Lk) ? pe : 0.f;
               pv[u] = pe;
-              dv[u] = pe * (g2[col] - del_c) * p.scale;
+              dv[u] = pe * fmaf(g2[col], p.scale, -del_c);
             }
             __nv_bfloat162 a = __floats2bfloat162_rn(pv[0], pv[1]), d = __floats2bfloat162_rn(dv[0], dv[1]);
             o1[e] = *reinterpret_cast<uint32_t*>(&a);

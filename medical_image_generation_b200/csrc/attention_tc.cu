@@ -126,18 +126,28 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
           float v[64];
           tmem_ld64(ts + half * 64, v);
           const int kb = kbase + half * 64;
-          float tmax = -INFINITY;
+          if (kb + 64 > p.Lk) {   // ragged last key tile only
 #pragma unroll
-          for (int e = 0; e < 64; ++e) {
-            v[e] = (kb + e < p.Lk) ? v[e] * p.scale_log2 : -INFINITY;
-            tmax = fmaxf(tmax, v[e]);
+            for (int e = 0; e < 64; ++e) v[e] = (kb + e < p.Lk) ? v[e] : -INFINITY;
           }
+          float t0 = fmaxf(v[0], v[1]), t1 = fmaxf(v[2], v[3]), t2 = fmaxf(v[4], v[5]), t3 = fmaxf(v[6], v[7]);
+#pragma unroll
+          for (int e = 8; e < 64; e += 8) {
+            t0 = fmaxf(t0, fmaxf(v[e], v[e + 1]));
+            t1 = fmaxf(t1, fmaxf(v[e + 2], v[e + 3]));
+            t2 = fmaxf(t2, fmaxf(v[e + 4], v[e + 5]));
+            t3 = fmaxf(t3, fmaxf(v[e + 6], v[e + 7]));
+          }
+          const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;   // scale > 0 commutes with max
           if (tmax > -INFINITY) {   // online update per 64 keys
             const float m_new = fmaxf(m_run, tmax);
-            float sum = 0.f;
+            float sum = 0.f, sum_b = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; ++e) sum += fast_ex2(v[e] - m_new);
-            l_run = l_run * fast_ex2(m_run - m_new) + sum;
+            for (int e = 0; e < 64; e += 2) {
+              sum += fast_ex2(fmaf(v[e], p.scale_log2, -m_new));
+              sum_b += fast_ex2(fmaf(v[e + 1], p.scale_log2, -m_new));
+            }
+            l_run = l_run * fast_ex2(m_run - m_new) + (sum + sum_b);
             m_run = m_new;
           }
         }
@@ -232,14 +242,18 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
           tmem_ld64(ts + half * 64, v);
           const int kb = kbase + half * 64;
           const uint32_t base = p_smem + pb * FA_P_BYTES + half * (FA_BM * 128);   // one 64-key panel per half
+          const bool ragged1 = kb + 64 > p.Lk;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {                          // 16-byte chunks of the 128-byte row
             uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int k0 = c * 8 + 2 * e;
-              const float p0 = (kb + k0 < p.Lk) ? fast_ex2(fmaf(v[k0], p.scale_log2, -lse_r)) : 0.f;
-              const float p1 = (kb + k0 + 1 < p.Lk) ? fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -lse_r)) : 0.f;
+              float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -lse_r)), p1 = fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -lse_r));
+              if (ragged1) {
+                p0 = (kb + k0 < p.Lk) ? p0 : 0.f;
+                p1 = (kb + k0 + 1 < p.Lk) ? p1 : 0.f;
+              }
               __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
               o[e] = *reinterpret_cast<uint32_t*>(&q2);
             }
