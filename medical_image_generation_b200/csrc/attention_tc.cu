@@ -400,6 +400,268 @@ __global__ void __launch_bounds__(FA_MAX_THREADS, 1) flash_fwd_kernel(const __gr
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Head dim 64 / 128: the PAIR kernel. ncu on flash_fwd_kernel<2> at the config-4 sampling shape (L = 32768, d = 128)
+// showed the tensor pipe 40 % active with neither MUFU nor issue slots saturated: the limit was SHARED-MEMORY traffic.
+// Per 128 x 128 score tile that kernel moves 256 KB through shared memory (Q and K chunks re-streamed 32 + 32 KB, V
+// 32 KB, P written 32 KB and read back 32 KB, the UMMA operand reads of Q / K / V 96 KB) = 2048 cycles at 128 B/clk
+// against 1024 cycles of UMMA. This kernel cuts it to 128 KB per tile:
+//   * one CTA owns TWO 128-row query tiles; Q (2 x 128 x dh) is loaded once and stays resident;
+//   * every K / V tile is loaded once and used by both query tiles;
+//   * P never touches shared memory: the softmax threads write it as packed bf16 into tensor memory over the first 64
+//     columns of the S tile they have just read (tcgen05.st), and P V is issued with the A operand IN tensor memory
+//     (tcgen05.mma [d], [a_tmem], b_desc). tcgen05.mma executes in issue order, so Q K^T of tile j+1 (which overwrites
+//     S / P) is simply issued after P V of tile j.
+// The two query tiles ping-pong: while softmax group g works on S_g the tensor pipe runs the other tile's MMAs.
+// Tensor memory: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+// Roles (384 threads): warps 0-3 softmax of query tile 0 (thread = row, all 128 keys of a tile in registers: no
+// exchange between key halves), warps 4-7 of query tile 1, warp 8 UMMA issuer + TMEM allocator, warp 9 TMA issuer,
+// warps 10-11 idle (they complete the third warpgroup for setmaxnreg).
+// -----------------------------------------------------------------------------------------------------------------
+// 384 threads = three warpgroups, because setmaxnreg moves registers between WHOLE warpgroups: the softmax threads keep a
+// 128-value score row plus the packed P row in registers (the 168 registers a 384-thread CTA starts with spill half the
+// row to local memory), the issuer warpgroup (UMMA warp, TMA warp, two idle warps) needs almost none.
+constexpr int FP_THREADS = 384, FP_KV_STAGES = 2;
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 packed words -> 32 consecutive TMEM columns of this thread's lane; completion is awaited by tmem_wait_st()
+__device__ __forceinline__ void tmem_st32_nowait(uint32_t taddr, const uint32_t w[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]),
+        "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]), "r"(w[16]), "r"(w[17]),
+        "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]), "r"(w[24]), "r"(w[25]), "r"(w[26]),
+        "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// bars: q_full k_full[2] k_empty[2] v_full[2] v_empty[2] s_full[2] p_full[2] pv_done[2]
+template <int DH>
+__global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_constant__ CUtensorMap qmap,   // 128-row boxes
+                                                               const __grid_constant__ CUtensorMap kmap,   // 128-row boxes
+                                                               const __grid_constant__ CUtensorMap vmap,   // 64-row boxes
+                                                               FlashParams p) {
+  constexpr int NC = DH / 64;                       // 64-channel chunks of the head dim
+  constexpr int TILE_BYTES = NC * FA_BM * 128;      // one 128-row tile of Q / K / V
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + 2 * TILE_BYTES;
+  const uint32_t v_smem = k_smem + FP_KV_STAGES * TILE_BYTES;
+  __shared__ __align__(8) uint64_t bars[15];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t b0 = smem_u32(&bars[0]);
+  const uint32_t q_full = b0, k_full = b0 + 8 * 1, k_empty = b0 + 8 * 3, v_full = b0 + 8 * 5, v_empty = b0 + 8 * 7,
+                 s_full = b0 + 8 * 9, p_full = b0 + 8 * 11, pv_done = b0 + 8 * 13;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * FA_BM);
+  const int b = blockIdx.z / p.H, h = blockIdx.z - b * p.H;
+  const int nkv = (p.Lk + FA_BN - 1) / FA_BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
+      mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); mbar_init(pv_done + 8 * i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc<512>(smem_u32(&tmem_slot));
+  if (warp == 9 && lane == 0) { tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp < 8) {
+    // ============================ softmax / epilogue: thread = query row of tile g ============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int g = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const int q = q0 + g * FA_BM + r;
+    const bool qok = q < p.Lq;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t ts = tmem_base + lane_off + g * FA_BN;          // S_g; P_g = its first 64 columns, packed bf16
+    const uint32_t to = tmem_base + lane_off + 256 + g * 128;      // O_g
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full + 8 * g, (uint32_t)j & 1u);
+      tcgen05_fence_after();
+      float v[128];
+      tmem_ld64(ts, v);
+      tmem_ld64(ts + 64, v + 64);
+      const int kbase = j * FA_BN;
+      if (kbase + FA_BN > p.Lk) {   // ragged last key tile only
+#pragma unroll
+        for (int e = 0; e < 128; ++e) v[e] = (kbase + e < p.Lk) ? v[e] : -INFINITY;
+      }
+      // scores stay unscaled (scale > 0 commutes with the maximum); four independent maxima
+      float t0 = fmaxf(v[0], v[1]), t1 = fmaxf(v[2], v[3]), t2 = fmaxf(v[4], v[5]), t3 = fmaxf(v[6], v[7]);
+#pragma unroll
+      for (int e = 8; e < 128; e += 8) {
+        t0 = fmaxf(t0, fmaxf(v[e], v[e + 1]));
+        t1 = fmaxf(t1, fmaxf(v[e + 2], v[e + 3]));
+        t2 = fmaxf(t2, fmaxf(v[e + 4], v[e + 5]));
+        t3 = fmaxf(t3, fmaxf(v[e + 6], v[e + 7]));
+      }
+      const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3)) * p.scale_log2;
+      const float m_new = fmaxf(m_run, tmax);
+      if (j == 0) {
+        m_run = m_new;
+      } else if (__any_sync(0xffffffffu, m_new > m_run + 8.f)) {
+        // LAZY rescale (P stays <= 2^8): O_g must be stable, i.e. P V of tile j-1 complete
+        mbar_wait(pv_done + 8 * g, (uint32_t)(j - 1) & 1u);
+        tcgen05_fence_after();
+        const float f = fast_ex2(m_run - m_new);   // 1 for rows whose maximum did not move
+#pragma unroll 1
+        for (int cw = 0; cw < DH; cw += 64) {
+          float ow[64];
+          tmem_ld64(to + cw, ow);
+#pragma unroll
+          for (int e = 0; e < 64; ++e) ow[e] *= f;
+          tmem_st64(to + cw, ow);
+        }
+        l_run *= f;
+        m_run = m_new;
+      }
+      float sum = 0.f, sum_b = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t w[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int k0 = half * 64 + 2 * i;
+          const float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -m_run)), p1 = fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -m_run));
+          if (i & 1) sum_b += p0 + p1;
+          else sum += p0 + p1;
+          __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
+          w[i] = *reinterpret_cast<uint32_t*>(&q2);
+        }
+        tmem_st32_nowait(ts + half * 32, w);
+      }
+      tmem_wait_st();
+      l_run += sum + sum_b;
+      tcgen05_fence_before();
+      mbar_arrive(p_full + 8 * g);
+    }
+    // ---- epilogue ----
+    const float inv_l = 1.f / l_run;
+    if (qok) p.lse[(int64_t)blockIdx.z * p.Lq + q] = m_run + log2f(l_run);
+    mbar_wait(pv_done + 8 * g, (uint32_t)(nkv - 1) & 1u);
+    tcgen05_fence_after();
+    __nv_bfloat16* orow = p.out + ((int64_t)b * p.Lq + q) * ((int64_t)p.H * DH) + (int64_t)h * DH;
+#pragma unroll 1
+    for (int cw = 0; cw < DH; cw += 64) {
+      float vw[64];
+      tmem_ld64(to + cw, vw);
+      if (!qok) continue;
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 8) {
+        uint4 o;
+        __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hh[e] = __floats2bfloat162_rn(vw[c0 + 2 * e] * inv_l, vw[c0 + 2 * e + 1] * inv_l);
+        *reinterpret_cast<uint4*>(orow + cw + c0) = o;
+      }
+    }
+    tcgen05_fence_before();
+  } else if (warp == 8) {
+    // ============================ UMMA issuer (one elected thread) ============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc(FA_BM, FA_BN, 0, 0);
+      constexpr uint32_t idesc_o = make_idesc(FA_BM, DH, 0, 1);
+      auto issue_s = [&](int g, int j) {   // S_g = Q_g K_j^T
+        const uint32_t a = q_smem + g * TILE_BYTES, bsm = k_smem + (j % FP_KV_STAGES) * TILE_BYTES;
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + g * FA_BN, make_smem_desc(a + c * (FA_BM * 128) + kk * 32, 16, 1024),
+                      make_smem_desc(bsm + c * (FA_BN * 128) + kk * 32, 16, 1024), idesc_s, (c | kk) ? 1u : 0u);
+        umma_commit(s_full + 8 * g);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full, 0);
+      tcgen05_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(k_empty);
+      for (int j = 0; j < nkv; ++j) {
+        const int vs = j % FP_KV_STAGES;
+        const uint32_t vph = (uint32_t)(j / FP_KV_STAGES) & 1u;
+        mbar_wait(v_full + 8 * vs, vph);
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(p_full + 8 * g, (uint32_t)j & 1u);
+          tcgen05_fence_after();
+          const uint32_t bsm = v_smem + vs * TILE_BYTES;
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)   // A = P_g (tensor memory, 8 columns per 16 keys); B = 16 key rows of every 64-channel panel
+              umma_bf16_ts(tmem_base + 256 + g * 128, tmem_base + g * FA_BN + half * 32 + kk * 8,
+                           make_smem_desc(bsm + half * (NC * FA_PANEL) + kk * 2048, FA_PANEL, 1024), idesc_o,
+                           (j | half | kk) ? 1u : 0u);
+          umma_commit(pv_done + 8 * g);
+          if (g == 1) umma_commit(v_empty + 8 * vs);
+          if (j + 1 < nkv) {
+            const int ks = (j + 1) % FP_KV_STAGES;
+            if (g == 0) {
+              mbar_wait(k_full + 8 * ks, (uint32_t)((j + 1) / FP_KV_STAGES) & 1u);
+              tcgen05_fence_after();
+            }
+            issue_s(g, j + 1);
+            if (g == 1) umma_commit(k_empty + 8 * ks);
+          }
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 9 && elect_one()) {
+    // ============================ TMA issuer ============================
+    mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+    for (int g = 0; g < 2; ++g)
+      for (int c = 0; c < NC; ++c)
+        tma_load_4d(q_smem + g * TILE_BYTES + c * (FA_BM * 128), &qmap, q_full, c * 64, h, q0 + g * FA_BM, b);
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j % FP_KV_STAGES;
+      const uint32_t ph = (uint32_t)(j / FP_KV_STAGES) & 1u;
+      mbar_wait(k_empty + 8 * s, ph ^ 1u);
+      mbar_arrive_expect_tx(k_full + 8 * s, TILE_BYTES);
+      for (int c = 0; c < NC; ++c)
+        tma_load_4d(k_smem + s * TILE_BYTES + c * (FA_BN * 128), &kmap, k_full + 8 * s, c * 64, h, j * FA_BN, b);
+      mbar_wait(v_empty + 8 * s, ph ^ 1u);
+      mbar_arrive_expect_tx(v_full + 8 * s, TILE_BYTES);
+      for (int half = 0; half < 2; ++half)
+        for (int pn = 0; pn < NC; ++pn)
+          tma_load_4d(v_smem + s * TILE_BYTES + half * (NC * FA_PANEL) + pn * FA_PANEL, &vmap, v_full + 8 * s, pn * 64, h,
+                      j * FA_BN + half * 64, b);
+    }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // 4-d map over a contiguous (B, L, H*dh) bf16 tensor: dims (dh, H, L, B); box (64, 1, rows, 1)
 static int bhld_map(CUtensorMap* m, const void* base, int B, int H, int L, int dh, uint32_t box_rows) {
   const uint64_t C = (uint64_t)H * dh;
@@ -429,6 +691,25 @@ static int launch_flash(const CUtensorMap& qm, const CUtensorMap& km, const CUte
   return check_launch("flash_fwd_kernel");
 }
 
+template <int DH>
+static int launch_flash_pair(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, const FlashParams& p,
+                             cudaStream_t st) {
+  const int smem = (2 + 2 * FP_KV_STAGES) * (DH / 64) * FA_BM * 128 + 1024;
+  static SmemOptIn optin;
+  if (int rc = ensure_dynamic_smem(flash_pair_kernel<DH>, smem, optin, "flash_attention (pair)")) return rc;
+  const dim3 grid((p.Lq + 2 * FA_BM - 1) / (2 * FA_BM), 1, p.B * p.H);
+  flash_pair_kernel<DH><<<grid, FP_THREADS, smem, st>>>(qm, km, vm, p);
+  return check_launch("flash_pair_kernel");
+}
+
+static bool flash_pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MIG_FLASH_PAIR");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 }  // namespace mig
 
 using namespace mig;
@@ -453,6 +734,8 @@ extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void*
   p.out = (__nv_bfloat16*)out;
   cudaStream_t st = as_stream(stream);
   const unsigned mt = (Lq + FA_BM - 1) / FA_BM;
+  if (flash_pair_enabled() && dh == 128) return launch_flash_pair<128>(qm, km, vm, p, st);
+  if (flash_pair_enabled() && dh == 64) return launch_flash_pair<64>(qm, km, vm, p, st);
   if (dh <= 256) return launch_flash<2>(qm, km, vm, p, dim3(mt, 1, B * H), st);   // single pass, online softmax
   if (launch_flash<0>(qm, km, vm, p, dim3(mt, 1, B * H), st)) return 2;
   return launch_flash<1>(qm, km, vm, p, dim3(mt, dh / p.DV, B * H), st);
