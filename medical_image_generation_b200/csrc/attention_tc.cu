@@ -449,8 +449,46 @@ __device__ __forceinline__ void tmem_st32_nowait(uint32_t taddr, const uint32_t 
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// bars: q_full k_full[2] k_empty[2] v_full[2] v_empty[2] s_full[2] p_full[2] pv_done[2]
-template <int DH>
+// 128 consecutive columns as two 64-column loads in flight together and ONE wait (a second round trip costs ~100 cycles
+// on the softmax critical path). The empty volatile asm statements pin every use of the registers behind the wait.
+__device__ __forceinline__ void tmem_ld128(uint32_t taddr, float v[128]) {
+  uint32_t r[128];
+#pragma unroll
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    uint32_t* q = r + 64 * hlf;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]), "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15]), "=r"(q[16]), "=r"(q[17]), "=r"(q[18]), "=r"(q[19]), "=r"(q[20]), "=r"(q[21]), "=r"(q[22]), "=r"(q[23]), "=r"(q[24]), "=r"(q[25]), "=r"(q[26]), "=r"(q[27]), "=r"(q[28]), "=r"(q[29]), "=r"(q[30]), "=r"(q[31]), "=r"(q[32]), "=r"(q[33]), "=r"(q[34]), "=r"(q[35]), "=r"(q[36]), "=r"(q[37]), "=r"(q[38]), "=r"(q[39]), "=r"(q[40]), "=r"(q[41]), "=r"(q[42]), "=r"(q[43]), "=r"(q[44]), "=r"(q[45]), "=r"(q[46]), "=r"(q[47]), "=r"(q[48]), "=r"(q[49]), "=r"(q[50]), "=r"(q[51]), "=r"(q[52]), "=r"(q[53]), "=r"(q[54]), "=r"(q[55]), "=r"(q[56]), "=r"(q[57]), "=r"(q[58]), "=r"(q[59]), "=r"(q[60]), "=r"(q[61]), "=r"(q[62]), "=r"(q[63])
+        : "r"(taddr + 64 * hlf)
+        : "memory");
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 128; ++i) {
+    asm volatile("" : "+r"(r[i]));
+    v[i] = __uint_as_float(r[i]);
+  }
+}
+
+// 2^x on the FMA pipe (Cody-Waite: x = n + f, |f| <= 0.5; degree-3 minimax polynomial for 2^f, relative error 7.5e-5 --
+// far below the bf16 rounding of P). The 16 MUFU lanes of an SM need 2048 cycles for the 2 x 128 x 128 exponentials of
+// one key tile, exactly the UMMA time of that tile; one exponential in four goes through here instead.
+__device__ __forceinline__ float poly_ex2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;          // 1.5 * 2^23: round-to-nearest leaves n in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float y = fmaf(f, 0.0551716648f, 0.2426111251f);
+  y = fmaf(y, f, 0.6932609677f);
+  y = fmaf(y, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(y) + (__float_as_int(t) << 23));
+}
+
+// bars: q_full k_full[2] k_empty[2] v_full[2] v_empty[2] s_full[2] p_full[2][2] pv_done[2]
+// P is handed to the UMMA issuer in two 64-key halves: P V of the first half runs while the softmax threads still
+// exponentiate the second half (the softmax latency, not its throughput, sets the pace of a query tile's
+// S -> P -> P V -> next S chain).
+template <int DH, bool POLY>
 __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_constant__ CUtensorMap qmap,   // 128-row boxes
                                                                const __grid_constant__ CUtensorMap kmap,   // 128-row boxes
                                                                const __grid_constant__ CUtensorMap vmap,   // 64-row boxes
@@ -462,11 +500,11 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
   const uint32_t q_smem = smem_base;
   const uint32_t k_smem = q_smem + 2 * TILE_BYTES;
   const uint32_t v_smem = k_smem + FP_KV_STAGES * TILE_BYTES;
-  __shared__ __align__(8) uint64_t bars[15];
+  __shared__ __align__(8) uint64_t bars[17];
   __shared__ uint32_t tmem_slot;
   const uint32_t b0 = smem_u32(&bars[0]);
   const uint32_t q_full = b0, k_full = b0 + 8 * 1, k_empty = b0 + 8 * 3, v_full = b0 + 8 * 5, v_empty = b0 + 8 * 7,
-                 s_full = b0 + 8 * 9, p_full = b0 + 8 * 11, pv_done = b0 + 8 * 13;
+                 s_full = b0 + 8 * 9, p_full = b0 + 8 * 11 /* [g][half] */, pv_done = b0 + 8 * 15;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * FA_BM);
   const int b = blockIdx.z / p.H, h = blockIdx.z - b * p.H;
@@ -477,7 +515,8 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1);
       mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
-      mbar_init(s_full + 8 * i, 1); mbar_init(p_full + 8 * i, 128); mbar_init(pv_done + 8 * i, 1);
+      mbar_init(s_full + 8 * i, 1); mbar_init(pv_done + 8 * i, 1);
+      mbar_init(p_full + 16 * i, 128); mbar_init(p_full + 16 * i + 8, 128);
     }
     fence_barrier_init();
   }
@@ -490,7 +529,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
 
   if (warp < 8) {
     // ============================ softmax / epilogue: thread = query row of tile g ============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     const int g = warp >> 2;
     const int r = (warp & 3) * 32 + lane;
     const int q = q0 + g * FA_BM + r;
@@ -503,8 +542,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
       mbar_wait(s_full + 8 * g, (uint32_t)j & 1u);
       tcgen05_fence_after();
       float v[128];
-      tmem_ld64(ts, v);
-      tmem_ld64(ts + 64, v + 64);
+      tmem_ld128(ts, v);
       const int kbase = j * FA_BN;
       if (kbase + FA_BN > p.Lk) {   // ragged last key tile only
 #pragma unroll
@@ -546,18 +584,20 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const int k0 = half * 64 + 2 * i;
-          const float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -m_run)), p1 = fast_ex2(fmaf(v[k0 + 1], p.scale_log2, -m_run));
+          const float x1 = fmaf(v[k0 + 1], p.scale_log2, -m_run);
+          const float p0 = fast_ex2(fmaf(v[k0], p.scale_log2, -m_run));
+          const float p1 = (POLY && (i & 1)) ? poly_ex2(x1) : fast_ex2(x1);
           if (i & 1) sum_b += p0 + p1;
           else sum += p0 + p1;
           __nv_bfloat162 q2 = __floats2bfloat162_rn(p0, p1);
           w[i] = *reinterpret_cast<uint32_t*>(&q2);
         }
         tmem_st32_nowait(ts + half * 32, w);
+        tmem_wait_st();
+        tcgen05_fence_before();
+        mbar_arrive(p_full + 16 * g + 8 * half);
       }
-      tmem_wait_st();
       l_run += sum + sum_b;
-      tcgen05_fence_before();
-      mbar_arrive(p_full + 8 * g);
     }
     // ---- epilogue ----
     const float inv_l = 1.f / l_run;
@@ -582,7 +622,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
     tcgen05_fence_before();
   } else if (warp == 8) {
     // ============================ UMMA issuer (one elected thread) ============================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc(FA_BM, FA_BN, 0, 0);
       constexpr uint32_t idesc_o = make_idesc(FA_BM, DH, 0, 1);
@@ -607,16 +647,17 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
         const uint32_t vph = (uint32_t)(j / FP_KV_STAGES) & 1u;
         mbar_wait(v_full + 8 * vs, vph);
         for (int g = 0; g < 2; ++g) {
-          mbar_wait(p_full + 8 * g, (uint32_t)j & 1u);
-          tcgen05_fence_after();
           const uint32_t bsm = v_smem + vs * TILE_BYTES;
 #pragma unroll
-          for (int half = 0; half < 2; ++half)
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(p_full + 16 * g + 8 * half, (uint32_t)j & 1u);
+            tcgen05_fence_after();
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)   // A = P_g (tensor memory, 8 columns per 16 keys); B = 16 key rows of every 64-channel panel
               umma_bf16_ts(tmem_base + 256 + g * 128, tmem_base + g * FA_BN + half * 32 + kk * 8,
                            make_smem_desc(bsm + half * (NC * FA_PANEL) + kk * 2048, FA_PANEL, 1024), idesc_o,
                            (j | half | kk) ? 1u : 0u);
+          }
           umma_commit(pv_done + 8 * g);
           if (g == 1) umma_commit(v_empty + 8 * vs);
           if (j + 1 < nkv) {
@@ -632,7 +673,7 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
       }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 9 && elect_one()) {
     // ============================ TMA issuer ============================
     mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
@@ -695,10 +736,20 @@ template <int DH>
 static int launch_flash_pair(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, const FlashParams& p,
                              cudaStream_t st) {
   const int smem = (2 + 2 * FP_KV_STAGES) * (DH / 64) * FA_BM * 128 + 1024;
-  static SmemOptIn optin;
-  if (int rc = ensure_dynamic_smem(flash_pair_kernel<DH>, smem, optin, "flash_attention (pair)")) return rc;
+  static const bool poly = [] {
+    const char* e = getenv("MIG_FLASH_POLY");
+    return !(e && e[0] == '0');
+  }();
   const dim3 grid((p.Lq + 2 * FA_BM - 1) / (2 * FA_BM), 1, p.B * p.H);
-  flash_pair_kernel<DH><<<grid, FP_THREADS, smem, st>>>(qm, km, vm, p);
+  if (poly) {
+    static SmemOptIn optin;
+    if (int rc = ensure_dynamic_smem(flash_pair_kernel<DH, true>, smem, optin, "flash_attention (pair)")) return rc;
+    flash_pair_kernel<DH, true><<<grid, FP_THREADS, smem, st>>>(qm, km, vm, p);
+  } else {
+    static SmemOptIn optin;
+    if (int rc = ensure_dynamic_smem(flash_pair_kernel<DH, false>, smem, optin, "flash_attention (pair)")) return rc;
+    flash_pair_kernel<DH, false><<<grid, FP_THREADS, smem, st>>>(qm, km, vm, p);
+  }
   return check_launch("flash_pair_kernel");
 }
 
