@@ -57,6 +57,7 @@ struct BoxGeom {
   int rb, nb;            // rows per shared-memory slot (64 or 128) and valid rows per box (bd*bh*bw <= rb);
                          // wgrad: rb = 64 and nb a multiple of 16 (the box is one K stage of nb/16 UMMAs)
   int nbd, nbh, nbw;     // boxes per axis (ceil)
+  uint32_t dmul[3], dshr[3];   // division by nbw / nbh / nbd as multiply-high + shift (set_box_counts); dividends < 2^31
   int64_t num_boxes;     // N*nbd*nbh*nbw
   int ks[3];             // kernel
   int off[3];            // source coordinate = row coordinate + tap*sign + off   (fwd: +1, -pad; dgrad: -1, +pad)
@@ -71,12 +72,21 @@ struct BoxGeom {
   int os[3], oo[3], OD, OH, OW;
 };
 
+// box index -> (sample, box origin). Every tile of every role decodes several boxes; with plain 64-bit / and % (a
+// reciprocal + correction sequence each) the epilogue of a small-K tile (1x1x1 convs on 32/64 channels) spent most of its
+// ~2000 instructions per tile dividing -- ncu: 8700 cycles per tile on a layer whose main loop is four UMMAs.
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, int d, uint32_t mul, uint32_t shr) {
+  return d == 1 ? x : __umulhi(x, mul) >> shr;
+}
 __device__ __forceinline__ void box_origin(const BoxGeom& g, int64_t box, int& n, int& d0, int& h0, int& w0) {
-  int64_t r = box;
-  w0 = (int)(r % g.nbw) * g.bw; r /= g.nbw;
-  h0 = (int)(r % g.nbh) * g.bh; r /= g.nbh;
-  d0 = (int)(r % g.nbd) * g.bd;
-  n = (int)(r / g.nbd);
+  uint32_t r = (uint32_t)box;
+  uint32_t q = fast_div(r, g.nbw, g.dmul[0], g.dshr[0]);
+  w0 = (int)(r - q * (uint32_t)g.nbw) * g.bw; r = q;
+  q = fast_div(r, g.nbh, g.dmul[1], g.dshr[1]);
+  h0 = (int)(r - q * (uint32_t)g.nbh) * g.bh; r = q;
+  q = fast_div(r, g.nbd, g.dmul[2], g.dshr[2]);
+  d0 = (int)(r - q * (uint32_t)g.nbd) * g.bd;
+  n = (int)q;
 }
 
 struct ConvTmaParams {
@@ -188,15 +198,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
     const int etid = eg * 128 + row;
     const int r = row & (g.rb - 1), slot = row / g.rb;
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
-    int ti = 0;
+    int ti = 0, staged_n0 = -1;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       int64_t box0;
       int n0, kb_begin, nkb;
       decode(tile, box0, n0, kb_begin, nkb);
       const int ab = ti % NACC;
       // while the main loop runs: bias + per-sample channel bias of this tile's columns, one row per box (a box lies
-      // inside one sample), so that the epilogue adds them with broadcast shared-memory reads
-      if (!p.partial) {
+      // inside one sample), so that the epilogue adds them with broadcast shared-memory reads. Without a per-sample
+      // bias the rows only depend on the column block: staged once, not per tile.
+      if (!p.partial && (p.chan_bias != nullptr || n0 != staged_n0)) {
+        staged_n0 = n0;
         asm volatile("bar.sync 1, %0;" ::"r"(ethreads) : "memory");   // the previous tile's readers are done with add_s
         for (int j = 0; j < nslot; ++j) {
           int n = 0, d0, h0, w0;
@@ -629,6 +641,24 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tma_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
+// boxes per axis, their product, and the multiply-high constants of the divisions box_origin performs
+// (q = umulhi(x, mul) >> shr for x < 2^31: mul = ceil(2^(31 + ceil(log2 d)) / d), shr = ceil(log2 d) - 1)
+static void set_box_counts(BoxGeom& b) {
+  b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
+  b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
+  const int div[3] = {b.nbw, b.nbh, b.nbd};
+  for (int i = 0; i < 3; ++i) {
+    const uint32_t d = (uint32_t)div[i];
+    b.dmul[i] = 0; b.dshr[i] = 0;
+    if (d <= 1) continue;
+    int lg = 0;
+    while ((1u << lg) < d) ++lg;   // ceil(log2 d)
+    const int pw = 31 + lg;
+    b.dmul[i] = (uint32_t)((((uint64_t)1 << pw) + d - 1) / d);
+    b.dshr[i] = (uint32_t)(pw - 32);
+  }
+}
+
 static bool pick_box(int D, int H, int W, int* bd, int* bh, int* bw) {
   // 64 voxels per box, power-of-two factors; prefer wide W (contiguous rows in memory)
   static const int cand[][3] = {{1, 8, 8}, {2, 4, 8}, {4, 2, 8}, {8, 1, 8}, {1, 4, 16}, {2, 2, 16}, {4, 1, 16},
@@ -716,6 +746,8 @@ bool tma_conv_eligible(const mig_conv_geom* g, int which) {
   if (which == 2 ? csrc % 64 != 0 : (csrc % 8 != 0 || csrc < (strided ? 32 : 48))) return false;
   if (which == 2 && g->Cout % 8 != 0) return false;
   const int32_t* dims = which == 1 ? g->in_dims : g->out_dims;
+  // box indices are 31-bit in the kernels (fast_div); a box holds at least 16 voxels
+  if ((double)g->N * dims[0] * dims[1] * dims[2] > 16.0 * 2147483647.0) return false;
   int bd, bh, bw, rb;
   if (which != 2) return pick_box_rows(dims[0], dims[1], dims[2], &bd, &bh, &bw, &rb);
   return pick_box_k(dims[0], dims[1], dims[2], &bd, &bh, &bw);
@@ -750,8 +782,7 @@ static BoxGeom make_box_geom(const mig_conv_geom* g, int which) {
   if (which == 2) pick_box_k(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
   else pick_box_rows(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw, &b.rb);
   b.nb = b.bd * b.bh * b.bw;
-  b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
-  b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
+  set_box_counts(b);
   int taps = 1;
   for (int i = 0; i < 3; ++i) {
     b.ks[i] = g->ksize[i];
@@ -1071,8 +1102,7 @@ int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w
         b.rb = 64;
         pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw);
         b.nb = b.bd * b.bh * b.bw;
-        b.nbd = (b.D + b.bd - 1) / b.bd; b.nbh = (b.H + b.bh - 1) / b.bh; b.nbw = (b.W + b.bw - 1) / b.bw;
-        b.num_boxes = (int64_t)b.N * b.nbd * b.nbh * b.nbw;
+        set_box_counts(b);
         for (int i = 0; i < 3; ++i) {
           b.ks[i] = a[i].nu;
           b.off[i] = a[i].base;
