@@ -435,6 +435,14 @@ def conv_nd(x, weight, bias=None, stride=1, padding=0, chan_bias=None, residual=
     if not _is_cl(x):
         x = to_channels_last(x, x.dtype)
     if chan_bias is not None:
+        # (rows, C) with rows = N, or ONE row broadcast over the batch: the reference adds temb[:, :, None, None, None]
+        # (unet:691-695) and the inferers pass a single timestep for a whole batch (`torch.Tensor((t,))`). The kernels index
+        # chan_bias[n * C + c], so the broadcast is made explicit here (expand is differentiable: its backward sums).
+        if chan_bias.ndim != 2 or chan_bias.shape[1] != weight.shape[0] or chan_bias.shape[0] not in (1, x.shape[0]):
+            raise RuntimeError(f"conv_nd: chan_bias {tuple(chan_bias.shape)} does not broadcast to "
+                               f"({x.shape[0]}, {weight.shape[0]})")
+        if chan_bias.shape[0] != x.shape[0]:
+            chan_bias = chan_bias.expand(x.shape[0], -1)
         chan_bias = chan_bias.float().contiguous()
     if residual is not None and (not _is_cl(residual) or residual.dtype != x.dtype):
         residual = to_channels_last(residual, x.dtype)

@@ -176,6 +176,39 @@ def test_inferer_sampling_loop_matches_oracle(golden):
     assert rel_err(got, want) < 5e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_single_timestep_broadcasts_over_the_batch(golden, dtype):
+    """The inferers call the model with ONE timestep for the whole batch (`torch.Tensor((t,))`, train_ldm.py:356-362): the
+    reference broadcasts temb[:, :, None, None, None] (unet:691-695). Batch 2 with a (1,) timestep must equal the oracle
+    and the same samples run one by one (the fused epilogue indexes the time-embedding bias per sample)."""
+    from oracle import torch_oracle as O
+    g = golden("unet3d_aniso")
+    m, params = _build(g, dtype)
+    m.eval()
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 1, 12, 12, 6, generator=gen)
+    t = torch.Tensor((417,))
+    want = O.unet_forward(params, g["cfg"], x, t)
+    with torch.no_grad():
+        got = m(x.to(DEV), timesteps=t.to(DEV))
+        one = torch.cat([m(x[i:i + 1].to(DEV), timesteps=t.to(DEV)) for i in range(2)])
+    tol = 1e-4 if dtype == torch.float32 else BF16_TOL
+    assert rel_err(got, want) < tol
+    assert rel_err(got[1:], one[1:]) < (1e-5 if dtype == torch.float32 else BF16_TOL)   # batch-dependent reduction order
+    # and through the sampler: two volumes in one batch == the oracle loop
+    from oracle.ddpm_oracle import OracleDDPMScheduler, OracleDiffusionInferer
+    import medical_image_generation_b200 as mig
+    if dtype == torch.float32:
+        kw = dict(num_train_timesteps=1000, schedule="scaled_linear_beta", beta_start=0.0015, beta_end=0.0205)
+        s, o = mig.DDPMScheduler(**kw), OracleDDPMScheduler(**kw)
+        s.set_timesteps(4); o.set_timesteps(4)
+        zs = [torch.randn(x.shape, generator=gen) for _ in range(4)]
+        want_s = OracleDiffusionInferer(o).sample(
+            x, lambda img, timesteps, context=None: O.unet_forward(params, g["cfg"], img, timesteps), o, step_noises=zs)
+        got_s = mig.DiffusionInferer(s).sample(x.to(DEV), m, s, verbose=False, step_noises=[z.to(DEV) for z in zs])
+        assert rel_err(got_s, want_s) < 5e-4
+
+
 def test_inferer_sampling_with_cuda_graph(golden):
     """sample(cuda_graph=True) replays one captured model forward per step and must reproduce the eager loop."""
     import medical_image_generation_b200 as mig

@@ -46,9 +46,15 @@ def trainer_env():
     finally:
         compat.uninstall()
         sys.path[:] = saved_path
+        # drop what this fixture made importable (and only that: torch lazily imports sub-packages that register
+        # operator libraries once per process -- deleting and re-importing those fails)
+        scoped = ("medimgen", "generative", "monai", "matplotlib", "torchinfo")
         for k in list(sys.modules):
-            if k not in saved_mods:
+            if k not in saved_mods and k.split(".")[0] in scoped:
                 del sys.modules[k]
+        for k, v in saved_mods.items():
+            if k.split(".")[0] in scoped:
+                sys.modules[k] = v
 
 
 def test_unmodified_trainer_imports_and_binds_b200_classes(trainer_env):
@@ -142,3 +148,98 @@ def test_unmodified_train_ldm_runs_on_b200_modules(trainer_env, tmp_path):
     assert os.path.isfile(os.path.join(cfg3["results_path"], "checkpoints", "best_model.pth"))
     assert os.path.isfile(os.path.join(cfg3["results_path"], "loss_dict.pkl"))
     assert len(ldm3.loss_dict["rec_loss"]) == 1 and len(ldm3.loss_dict["val_rec_loss"]) == 1
+
+
+# ---- train_autoencoder.AutoEncoder (SURVEY.md 8f-1 second trainer, 8f-3 adversarial loss) --------------------------------
+def test_unmodified_autoencoder_trainer_imports_and_binds_b200_classes(trainer_env):
+    """CPU: `from medimgen.train_autoencoder import AutoEncoder` works; AutoencoderKL is the B200 class; the adversarial
+    pieces it imports from `generative` are real (shipped restatements), the perceptual loss is a loud placeholder."""
+    import medical_image_generation_b200 as mig
+    ta = __import__("medimgen.train_autoencoder", fromlist=["AutoEncoder"])
+    assert ta.__file__.endswith(os.path.join("medimgen", "train_autoencoder.py"))
+    assert ta.AutoencoderKL is mig.AutoencoderKL
+    disc = ta.PatchDiscriminator(spatial_dims=3, in_channels=1, out_channels=1, num_channels=8, num_layers_d=3)
+    feats = disc(torch.rand(2, 1, 32, 32, 32))
+    assert [tuple(f.shape[1:]) for f in feats] == [(8, 16, 16, 16), (16, 8, 8, 8), (32, 4, 4, 4), (64, 3, 3, 3), (1, 2, 2, 2)]
+    keys = list(disc.state_dict())
+    assert keys[:3] == ["initial_conv.conv.weight", "initial_conv.conv.bias", "0.conv.weight"] and "0.conv.bias" not in keys
+    assert "2.adn.N.running_var" in keys and keys[-2:] == ["final_conv.conv.weight", "final_conv.conv.bias"]
+    adv = ta.PatchAdversarialLoss(criterion="least_squares")
+    logits = torch.tensor([[2.0, -2.0]])
+    # least squares on LeakyReLU(0.05)(logits): ((2-1)^2 + (-0.1-1)^2) / 2 and (2^2 + 0.1^2) / 2
+    assert abs(float(adv(logits, target_is_real=True, for_discriminator=True)) - (1.0 + 1.21) / 2) < 1e-6
+    assert abs(float(adv(logits, target_is_real=False, for_discriminator=True)) - (4.0 + 0.01) / 2) < 1e-6
+    with pytest.warns(UserWarning):
+        g = adv(logits, target_is_real=False, for_discriminator=False)     # a generator target is always "real"
+    assert abs(float(g) - (1.0 + 1.21) / 2) < 1e-6
+    with pytest.raises(NotImplementedError):
+        ta.PerceptualLoss(spatial_dims=3, network_type="vgg")
+
+
+def _ae_config(tmp_path):
+    down = [[[1, 1, 1], [3, 3, 3], [1, 1, 1]], [[2, 2, 2], [3, 3, 3], [1, 1, 1]]]
+    vae = dict(spatial_dims=3, in_channels=1, out_channels=1, latent_channels=3, num_res_blocks=1,
+               with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False, use_flash_attention=False,
+               use_checkpointing=False, use_convtranspose=False, num_channels=[32, 64], attention_levels=[False, False],
+               norm_num_groups=16, downsample_parameters=down, upsample_parameters=list(reversed(down))[:-1])
+    return dict(vae_params=vae, load_model_path=None, ae_learning_rate=1e-3, d_learning_rate=1e-3, lr_scheduler=None,
+                lr_scheduler_params=None, grad_accumulate_step=2, grad_clip_max_norm=1, kl_weight=1e-6, adv_weight=0.05,
+                perc_weight=0.125, autoencoder_warm_up_epochs=2, output_mode="log", progress_bar=False,
+                results_path=str(tmp_path / "ae"), n_epochs=3, val_plot_interval=10, ae_batch_size=2,
+                ae_transformations=dict(patch_size=[16, 16, 16]),
+                discriminator_params=dict(spatial_dims=3, in_channels=1, out_channels=1, num_channels=8, num_layers_d=2))
+
+
+@pytest.mark.gpu
+def test_unmodified_train_autoencoder_runs_on_b200_modules(trainer_env, tmp_path):
+    """AutoEncoder.train_one_epoch through the reference's own code (train_autoencoder.py:331-436): generator step (B200
+    AutoencoderKL forward, L1 + KL + perceptual + -- after the warm-up epochs -- adversarial loss), discriminator step,
+    the per-step requires_grad toggling (:374-377,401-404), fp16 autocast + two GradScalers, accumulation, clipping, Adam;
+    then validate_one_epoch and save_model / load_model. The perceptual network needs downloaded weights, so the test
+    passes a weight-free stand-in callable (train_one_epoch takes it as an argument)."""
+    from torch.cuda.amp import GradScaler
+    ta = __import__("medimgen.train_autoencoder", fromlist=["AutoEncoder"])
+    torch.manual_seed(0)
+    cfg = _ae_config(tmp_path)
+    ae = ta.AutoEncoder(cfg, latent_space_type="vae", print_summary=False)
+    disc = ta.PatchDiscriminator(**cfg["discriminator_params"]).to(ae.device)
+    opt_g, opt_d, sched_g, sched_d = ae.get_optimizers_and_lr_schedules(disc)
+    assert isinstance(opt_g, torch.optim.Adam) and sched_g is None and sched_d is None
+
+    def perceptual(a, b):   # stand-in for LPIPS / MedicalNet features: gradient-carrying, weight-free
+        return torch.nn.functional.avg_pool3d(a - b, 4).abs().mean()
+
+    gen = torch.Generator().manual_seed(3)
+    base = torch.rand(2, 1, 16, 16, 16, generator=gen)
+    loader = [{"id": i, "image": (base + 0.05 * torch.rand(2, 1, 16, 16, 16, generator=gen)).clamp(0, 1)} for i in range(5)]
+    w_before = {k: v.detach().clone() for k, v in ae.autoencoder.state_dict().items()}
+    d_before = {k: v.detach().clone() for k, v in disc.state_dict().items()}
+    sg, sd = GradScaler(), GradScaler()
+    for epoch in (1, 2, 3, 4):     # epochs 1 (< warm-up 2): no adversarial terms; 2-4: generator + discriminator steps
+        ae.train_one_epoch(epoch, loader, disc, perceptual, opt_g, opt_d, sg, sd)
+    ld = ae.loss_dict
+    assert len(ld["rec_loss"]) == 4 and all(v == v and v > 0 for v in ld["rec_loss"]), ld
+    assert ld["rec_loss"][-1] < ld["rec_loss"][0], ld["rec_loss"]
+    assert ld["gen_loss"][0] == 0 and ld["disc_loss"][0] == 0                   # warm-up epoch
+    assert all(v > 0 for v in ld["gen_loss"][1:]) and all(v > 0 for v in ld["disc_loss"][1:]), ld
+    assert all(v == v and v >= 0 for v in ld["reg_loss"] + ld["perc_loss"])
+    w_after, d_after = ae.autoencoder.state_dict(), disc.state_dict()
+    assert sum(not torch.equal(w_before[k], w_after[k]) for k in w_before) >= 0.9 * len(w_before)
+    assert any(not torch.equal(d_before[k], d_after[k]) for k in d_before if k.endswith("conv.weight"))
+    assert all(p.requires_grad is False for p in ae.autoencoder.parameters())   # state the discriminator step leaves behind
+    ae.validate_one_epoch(loader[:2])
+    assert len(ld["val_rec_loss"]) == 1 and 0 < ld["val_rec_loss"][0] < 1
+    ae.save_model(4, ld["val_rec_loss"][-1], opt_g, disc, opt_d)
+    ckpt_path = os.path.join(cfg["results_path"], "checkpoints", "last_model.pth")
+    ckpt = torch.load(ckpt_path)
+    assert set(ckpt) == {"epoch", "network_state_dict", "optimizer_state_dict", "validation_loss", "discriminator_state_dict",
+                         "disc_optimizer_state_dict"}
+    ae2 = ta.AutoEncoder(cfg, latent_space_type="vae", print_summary=False)
+    disc2 = ta.PatchDiscriminator(**cfg["discriminator_params"]).to(ae2.device)
+    og2, od2, _, _ = ae2.get_optimizers_and_lr_schedules(disc2)
+    assert ae2.load_model(ckpt_path, optimizer=og2, discriminator=disc2, disc_optimizer=od2, for_training=True) == 5
+    x = loader[0]["image"].cuda()
+    with torch.no_grad():
+        mu1, _ = ae.autoencoder.eval().encode(x)
+        mu2, _ = ae2.autoencoder.eval().encode(x)
+    assert float((mu1.float() - mu2.float()).norm() / mu2.float().norm()) < 2e-2
