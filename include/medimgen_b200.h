@@ -62,7 +62,8 @@ int mig_conv_fwd_stats_in_epilogue(const mig_conv_geom* g, int dtype, int32_t gn
  * replaces nn.Conv{2,3}d inside monai Convolution: unet:510-518,557-565,630-659,664,1820,1935;
  * ae:66-129,158-179,372-381,454-463,523-532,606-615,723-749.
  * y[n,o,co] = sum_{tap,ci} x[n, o*stride - pad + tap, ci] * w[co,tap,ci] + bias[co]
- *             (+ chan_bias[n,co]  -- the time-embedding add, unet:691-695)
+ *             (+ chan_bias[n,co]  -- the time-embedding add, unet:691-695; N x Cout fp32 -- a single embedding shared by
+ *                the whole batch, as the inferers' one-timestep calls produce, must be replicated to N rows by the caller)
  *             (+ residual[n,o,co] -- the skip add, unet:701 / ae:204)
  * `engine`: 0 = auto, 1 = SIMT fp32-accumulate CUDA-core path, 2 = tcgen05 tensor-core path (bf16 only). */
 int mig_conv_fwd(const mig_conv_geom* g, int dtype, const void* x, const void* w, const float* bias,

@@ -20,6 +20,8 @@
 //                     split across CTAs, fp32 red.global.add into the gradient.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tc_host.cuh"
@@ -89,6 +91,13 @@ __device__ __forceinline__ void box_origin(const BoxGeom& g, int64_t box, int& n
   n = (int)q;
 }
 
+// Dynamic tile scheduler state of one launch. A CTA's first tile is blockIdx.x; every further tile is
+// gridDim.x + atomicAdd(next, 1). The last CTA to finish zeroes the pair again, so a slot is reusable by the next launch
+// that picks it (and by every replay of a CUDA graph that captured it) without a memset node per convolution.
+struct TileCounter {
+  unsigned int next, done;
+};
+
 struct ConvTmaParams {
   BoxGeom g;
   const float* bias;
@@ -103,6 +112,7 @@ struct ConvTmaParams {
   double* gn_sums;
   int gn_cpg, gn_G;
   int epi_groups;   // 1 or 2 epilogue warp groups (A/B switch MIG_CONV_EPI_GROUPS; default 2)
+  TileCounter* sched;   // dynamic tile counter of this launch (nullptr: static round-robin)
 };
 
 // Sum eight per-thread values over the 32 lanes of a warp with 7 + 2 shuffles (recursive halving: after step k every
@@ -132,7 +142,12 @@ __device__ __forceinline__ float warp_sum8(const float v[8], int lane) {
 
 // BN: output-channel tile; MT: number of stacked 128-row accumulators (tile = MT*128 voxels x BN channels).
 //
-// PERSISTENT: one CTA per SM walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... The shared-memory ring and its
+// PERSISTENT: one CTA per SM walks a sequence of tiles. The sequence is DYNAMIC (TileCounter): the TMA thread draws the
+// next tile index while it loads the current one and hands it to the UMMA warp and the epilogue threads through a small
+// shared-memory ring. With the static round-robin (blockIdx.x, blockIdx.x + gridDim.x, ...) a CTA that starts late does
+// its whole share late: when an NCCL kernel of the overlapped gradient exchange holds k SMs, the k CTAs that wait for
+// them double the duration of the convolution; drawn dynamically, the resident CTAs simply take those tiles
+// (SCALE_r01: dgrad 19 % slower at N = 8). The shared-memory ring and its
 // barriers run straight through tile boundaries, so the producer prefetches the next tile's operands while the
 // current tile is still in the tensor pipe; when two accumulator sets fit in tensor memory (2*MT*BN <= 512 columns)
 // the epilogue of tile i also overlaps the main loop of tile i+1. ncu on the one-tile-per-CTA version showed ~15 k
@@ -150,11 +165,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
   constexpr int TCOLS = tmem_cols(NACC * MT * BN);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  constexpr int SQ = 4;   // depth of the tile-index ring
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4 + 2 * SQ];
   __shared__ uint32_t tmem_slot;
+  __shared__ int tile_ring[SQ];   // tile index, or -1: no more tiles
   __shared__ __align__(16) float add_s[2 * MT][BN];
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[STAGES]), acc_full = smem_u32(&bars[2 * STAGES]),
-                 acc_empty = smem_u32(&bars[2 * STAGES + 2]);
+                 acc_empty = smem_u32(&bars[2 * STAGES + 2]), sq_full = smem_u32(&bars[2 * STAGES + 4]),
+                 sq_empty = smem_u32(&bars[2 * STAGES + 4 + SQ]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const BoxGeom& g = p.g;
   const int spt = TBM / g.rb;            // boxes per 128-row accumulator
@@ -171,6 +189,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
     nkb = min(p.num_kb, kb_begin + p.kb_per_split) - kb_begin;
   };
 
+  // consumer side of the tile ring: the ti-th tile of this CTA (-1 when the sequence has ended)
+  auto next_tile = [&](int ti) -> int64_t {
+    const int q = ti % SQ;
+    mbar_wait(sq_full + 8 * q, (uint32_t)(ti / SQ) & 1u);
+    const int t = tile_ring[q];
+    mbar_arrive(sq_empty + 8 * q);
+    return t;
+  };
+
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full0 + 8 * s, 1);
@@ -179,6 +206,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
     for (int a = 0; a < 2; ++a) {
       mbar_init(acc_full + 8 * a, 1);
       mbar_init(acc_empty + 8 * a, 128 * p.epi_groups);
+    }
+    for (int a = 0; a < SQ; ++a) {
+      mbar_init(sq_full + 8 * a, 1);
+      mbar_init(sq_empty + 8 * a, 32 + 128 * p.epi_groups);   // consumers: the UMMA warp and the epilogue threads
     }
     fence_barrier_init();
   }
@@ -198,8 +229,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
     const int etid = eg * 128 + row;
     const int r = row & (g.rb - 1), slot = row / g.rb;
     const int lw = r % g.bw, lh = (r / g.bw) % g.bh, ld = r / (g.bw * g.bh);
-    int ti = 0, staged_n0 = -1;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    int staged_n0 = -1;
+    for (int ti = 0;; ++ti) {
+      const int64_t tile = next_tile(ti);
+      if (tile < 0) break;
       int64_t box0;
       int n0, kb_begin, nkb;
       decode(tile, box0, n0, kb_begin, nkb);
@@ -353,9 +386,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc(TBM, BN, 0, BMN ? 1 : 0);
-    int s = 0, ti = 0;
+    int s = 0;
     uint32_t ph = 0;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int ti = 0;; ++ti) {
+      const int64_t tile = next_tile(ti);
+      if (tile < 0) break;
       int64_t box0;
       int n0, kb_begin, nkb;
       decode(tile, box0, n0, kb_begin, nkb);
@@ -394,7 +429,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
       const uint32_t slot_bytes = (uint32_t)g.rb * 128u;
       int s = 0;
       uint32_t ph = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int64_t tile = blockIdx.x;
+      for (int ti = 0;; ++ti) {
+        // publish the ti-th tile of this CTA (or the end marker) to the UMMA warp and the epilogue threads
+        const bool more = tile < total_tiles;
+        const int q = ti % SQ;
+        mbar_wait(sq_empty + 8 * q, ((uint32_t)(ti / SQ) & 1u) ^ 1u);
+        tile_ring[q] = more ? (int)tile : -1;
+        mbar_arrive(sq_full + 8 * q);
+        if (!more) break;
+        // draw the next index now: the atomic's round trip hides behind this tile's loads
+        unsigned int drawn = 0;
+        if (p.sched) drawn = atomicAdd(&p.sched->next, 1u);
         int64_t box0;
         int n0, kb_begin, nkb;
         decode(tile, box0, n0, kb_begin, nkb);
@@ -436,6 +482,15 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_tma_kernel(const __grid_
             if (++t2 == g.ks[2]) { t2 = 0; if (++t1 == g.ks[1]) { t1 = 0; ++t0; } }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        tile = p.sched ? (int64_t)gridDim.x + drawn : tile + gridDim.x;
+      }
+      if (p.sched) {   // the last CTA to get here re-arms the counter for the next launch / graph replay
+        __threadfence();
+        if (atomicAdd(&p.sched->done, 1u) == gridDim.x - 1) {
+          p.sched->next = 0;
+          p.sched->done = 0;
+          __threadfence();
         }
       }
     }
@@ -851,6 +906,41 @@ static void plan_box_conv(const BoxGeom& b, int bn, int num_kb, bool ws_ok, int*
   }
 }
 
+// One TileCounter per launch out of a per-device pool, handed out round-robin: launches in flight (and the kernel nodes
+// of a captured graph) never share a slot unless more than kTileSlots convolutions are in flight at once. The pool is
+// allocated on first use; if that first use happens inside a stream capture (no allocation allowed) the launch keeps the
+// static schedule. MIG_CONV_SCHED=static switches the dynamic schedule off (A/B measurements).
+static TileCounter* next_tile_counter(cudaStream_t st) {
+  constexpr unsigned kTileSlots = 2048;
+  static std::mutex mu;
+  static TileCounter* pool[16] = {};
+  static unsigned cursor[16] = {};
+  static int mode = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (mode < 0) {
+    const char* e = getenv("MIG_CONV_SCHED");
+    mode = (e && e[0] == 's') ? 0 : 1;
+  }
+  if (!mode) return nullptr;
+  if (!pool[dev]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    TileCounter* ptr = nullptr;
+    if (cudaMalloc(&ptr, kTileSlots * sizeof(TileCounter)) != cudaSuccess ||
+        cudaMemset(ptr, 0, kTileSlots * sizeof(TileCounter)) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    pool[dev] = ptr;
+  }
+  return pool[dev] + (cursor[dev]++ % kTileSlots);
+}
+
 // The epilogue can only deliver the statistics when it sees final values (no split-K) and whole 8-channel units of one
 // group. It is USED when it is free: with two accumulator sets in tensor memory (2*MT*BN <= 512 columns) the epilogue of
 // tile i overlaps the main loop of tile i+1. For the 256 x 256 tile the epilogue is exposed, and measured on the
@@ -937,8 +1027,10 @@ static int launch_box_conv(const BoxGeom& b, int N, const int32_t* sdims, const 
     const char* e = getenv("MIG_CONV_NONPERSISTENT");
     one_tile_per_cta = (e && e[0] == '1') ? 1 : 0;
   }
+  const int64_t all_tiles = nct;
   if (nct > sms && !one_tile_per_cta) nct = sms;
   dim3 grid((unsigned)nct);   // persistent: one CTA per SM walks the tiles
+  p.sched = all_tiles > nct ? next_tile_counter(st) : nullptr;
   int rc;
   if (bmn) {
     if (mt == 2 && bn == 256) rc = launch_conv_tma<256, 2, true>(xm, wm, p, grid, st);
