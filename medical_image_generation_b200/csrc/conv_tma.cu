@@ -142,12 +142,12 @@ __device__ __forceinline__ float warp_sum8(const float v[8], int lane) {
 
 // BN: output-channel tile; MT: number of stacked 128-row accumulators (tile = MT*128 voxels x BN channels).
 //
-// PERSISTENT: one CTA per SM walks a sequence of tiles. The sequence is DYNAMIC (TileCounter): the TMA thread draws the
-// next tile index while it loads the current one and hands it to the UMMA warp and the epilogue threads through a small
-// shared-memory ring. With the static round-robin (blockIdx.x, blockIdx.x + gridDim.x, ...) a CTA that starts late does
-// its whole share late: when an NCCL kernel of the overlapped gradient exchange holds k SMs, the k CTAs that wait for
-// them double the duration of the convolution; drawn dynamically, the resident CTAs simply take those tiles
-// (SCALE_r01: dgrad 19 % slower at N = 8). The shared-memory ring and its
+// PERSISTENT: one CTA per SM walks a sequence of tiles: blockIdx.x, blockIdx.x + gridDim.x, ... by default, or -- with a
+// TileCounter (p.sched) -- drawn dynamically: the TMA thread draws the next tile index while it loads the current one.
+// Either way the TMA thread hands the indices to the UMMA warp and the epilogue threads through a small shared-memory
+// ring. (Why dynamic: with the static round-robin a CTA that starts late does its whole share late, e.g. when an NCCL
+// kernel of the overlapped gradient exchange holds its SM. See next_tile_counter() for what was measured.)
+// The shared-memory ring and its
 // barriers run straight through tile boundaries, so the producer prefetches the next tile's operands while the
 // current tile is still in the tensor pipe; when two accumulator sets fit in tensor memory (2*MT*BN <= 512 columns)
 // the epilogue of tile i also overlaps the main loop of tile i+1. ncu on the one-tile-per-CTA version showed ~15 k
@@ -909,7 +909,12 @@ static void plan_box_conv(const BoxGeom& b, int bn, int num_kb, bool ws_ok, int*
 // One TileCounter per launch out of a per-device pool, handed out round-robin: launches in flight (and the kernel nodes
 // of a captured graph) never share a slot unless more than kTileSlots convolutions are in flight at once. The pool is
 // allocated on first use; if that first use happens inside a stream capture (no allocation allowed) the launch keeps the
-// static schedule. MIG_CONV_SCHED=static switches the dynamic schedule off (A/B measurements).
+// static schedule.
+// OFF by default (MIG_CONV_SCHED=dynamic switches it on). Measured on 2 B200s, same box, back to back
+// (bench.py --gpus 2, sharded optimiser): in the eager instrumented steps the dynamic schedule does what it was built for
+// (dgrad 1105 -> 1145 TFLOP/s while reduce-scatter kernels hold SMs, step 42.1 -> 41.7 ms), but the CUDA-graph step --
+// the one that is timed and shipped -- is 2 % SLOWER with it (39.7 / 39.8 vs 38.9 ms); at N = 1 it is neutral
+// (36.9 vs 36.8 ms). The static round-robin therefore stays the default.
 static TileCounter* next_tile_counter(cudaStream_t st) {
   constexpr unsigned kTileSlots = 2048;
   static std::mutex mu;
@@ -921,7 +926,7 @@ static TileCounter* next_tile_counter(cudaStream_t st) {
   std::lock_guard<std::mutex> lk(mu);
   if (mode < 0) {
     const char* e = getenv("MIG_CONV_SCHED");
-    mode = (e && e[0] == 's') ? 0 : 1;
+    mode = (e && e[0] == 'd') ? 1 : 0;
   }
   if (!mode) return nullptr;
   if (!pool[dev]) {
