@@ -83,22 +83,35 @@ def run_bf16(shard):
 
 master_s, shadow_s, sd_s, loss_s, nb = run_bf16(True)
 master_r, shadow_r, sd_r, loss_r, _ = run_bf16(False)
+_, _, sd_r2, loss_r2, _ = run_bf16(False)     # the replicated scheme AGAIN: its own run-to-run noise is the yardstick
 chk = shadow_s.float().clone()
 dist.broadcast(chk, src=0)
 same_shadow = bool(torch.equal(chk, shadow_s.float()))
 chk = master_s.clone()
 dist.broadcast(chk, src=0)
 same_master = bool(torch.equal(chk, master_s))
-# global (norm-weighted) difference: single tensors whose true gradient is zero (to_k.bias, ...) take sign-random Adam
-# steps of size lr in BOTH runs, so a per-tensor maximum measures noise, not the optimiser
-num = sum(float((sd_s[k].float() - sd_r[k].float()).pow(2).sum()) for k in sd_r)
-den = sum(float(sd_r[k].float().pow(2).sum()) for k in sd_r)
-worst_sd = (num / den) ** 0.5
+
+
+def global_diff(a, b):
+    # global (norm-weighted) difference: single tensors whose true gradient is zero (to_k.bias, ...) take sign-random
+    # Adam steps of size lr in BOTH runs, so a per-tensor maximum measures noise, not the optimiser
+    num = sum(float((a[k].float() - b[k].float()).pow(2).sum()) for k in b)
+    den = sum(float(b[k].float().pow(2).sum()) for k in b)
+    return (num / den) ** 0.5
+
+
+# bf16 runs are not bit-reproducible (GroupNorm / split-K partial sums are reduced with atomics, and Adam at lr 1e-3 turns
+# a flipped gradient sign into a full step), so "follows the replicated scheme" means: no further from it than two
+# replicated runs are from each other (x3 head room, floor 1e-3)
+noise = global_diff(sd_r2, sd_r)
+worst_sd = global_diff(sd_s, sd_r)
+loss_noise = max(abs(a - b) / abs(b) for a, b in zip(loss_r2, loss_r))
 loss_dev = max(abs(a - b) / abs(b) for a, b in zip(loss_s, loss_r))
-ok_shard = same_shadow and same_master and worst_sd < 2e-3 and loss_dev < 2e-3 and nb > 1
+ok_shard = same_shadow and same_master and worst_sd < max(3 * noise, 1e-3) and loss_dev < max(3 * loss_noise, 2e-3) and nb > 1
 if rank == 0:
     print(f"dp{world} bf16 sharded ({nb} buckets): bf16 weights identical on all ranks={same_shadow}; consolidated fp32 masters "
-          f"identical={same_master}; sharded vs replicated state_dict global rel diff {worst_sd:.2e}; losses {loss_s} vs {loss_r}",
+          f"identical={same_master}; sharded vs replicated state_dict global rel diff {worst_sd:.2e} (replicated vs replicated "
+          f"again: {noise:.2e}); losses {loss_s} vs {loss_r} (max dev {loss_dev:.1e}, replicated rerun {loss_noise:.1e})",
           flush=True)
 flag = torch.tensor([int(same and ok_global and ok_shard)], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)

@@ -52,8 +52,9 @@ if rank == 0:
         agg[k][1] += e.device_time
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
         print(f"   {t / 1e3:8.3f} ms x{c:<4d} {k}")
-    for e in nccl[:3] + nccl[-3:]:
-        print(f"   {e.name[:60]:60s} start {(e.time_range.start - t0) / 1e3:7.2f} ms dur {e.device_time / 1e3:6.3f} ms")
+    print(f"adamw kernels: {[(round((e.time_range.start - t0) / 1e3, 2), round(e.device_time / 1e3, 3)) for e in comp if 'adamw' in e.name]}")
+    for e in nccl:
+        print(f"   {e.name[:48]:48s} start {(e.time_range.start - t0) / 1e3:7.2f} ms dur {e.device_time / 1e3:6.3f} ms")
 dist.barrier()
 torch.cuda.synchronize()
 os._exit(0)
