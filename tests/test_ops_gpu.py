@@ -613,7 +613,11 @@ def test_errors_are_loud():
 
 @pytest.mark.parametrize("B,Lq,Lk,C,heads", [(2, 256, 256, 128, 1), (1, 200, 333, 128, 2), (2, 216, 216, 768, 1),
                                               (1, 1728, 1728, 512, 1), (1, 130, 70, 64, 1), (1, 5, 3, 256, 4),
-                                              (1, 1024, 4096, 128, 1)])
+                                              (1, 1024, 4096, 128, 1),
+                                              # head dim 128 / 64 through the two-query-tile kernel with ragged tails on both
+                                              # sides: second query tile partly / wholly past the end, last key tile ragged
+                                              (1, 300, 200, 128, 1), (2, 257, 129, 256, 2), (1, 513, 640, 192, 3),
+                                              (1, 100, 1000, 128, 1)])
 def test_flash_attention_forward(B, Lq, Lk, C, heads):
     """Fused tcgen05 flash-style attention (forward only) vs fp32 softmax attention on the CPU; includes ragged tails,
     cross-attention lengths, multi-head and the 512/768-channel single heads of the LDM default (value-dim slicing)."""
@@ -644,7 +648,7 @@ def test_flash_attention_forward(B, Lq, Lk, C, heads):
 
 @pytest.mark.parametrize("B,Lq,Lk,C,heads", [(2, 256, 256, 128, 1), (1, 200, 333, 128, 2), (2, 216, 216, 768, 1),
                                               (1, 1728, 1728, 512, 1), (1, 130, 70, 64, 1), (1, 5, 3, 256, 4),
-                                              (1, 700, 300, 256, 1), (2, 384, 384, 192, 1)])
+                                              (1, 700, 300, 256, 1), (2, 384, 384, 192, 1), (1, 300, 200, 128, 1)])
 def test_flash_attention_backward(B, Lq, Lk, C, heads):
     """Training attention through the fused kernels (no L x L tensor): dQ, dK, dV of mig_flash_attention_bwd against fp32
     autograd of softmax attention on the CPU -- ragged tails, cross-attention lengths, multi-head, and the 512 / 768-channel
