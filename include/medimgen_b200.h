@@ -28,7 +28,7 @@ extern "C" {
 #define MIG_F32 0
 #define MIG_BF16 1
 
-#define MIG_ABI_VERSION 3
+#define MIG_ABI_VERSION 4
 
 /* Geometry of one N-d convolution (1 <= nd <= 3 handled by setting leading dims to 1). */
 typedef struct {
@@ -98,6 +98,12 @@ int mig_gemm_strided(const mig_gemm_desc* d, int dtype_ab, int dtype_c, const vo
  * (receives the log2-domain log-sum-exp). dh must be a multiple of 64 (above 256: a multiple of 256). */
 int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B, int32_t H,
                             int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream);
+/* The same with q / k / v given as row-strided matrices: row pitch ldq / ldk / ldv in ELEMENTS (>= H*dh, a multiple of 8),
+ * batch stride L * ld. This is how attention reads the three column blocks of ONE fused q/k/v projection output
+ * (B, L, 3*H*dh) in place (unet:436-438 as one Linear). `out` stays contiguous (B, Lq, H*dh). */
+int mig_flash_attention_fwd_ld(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B, int32_t H,
+                               int32_t Lq, int32_t Lk, int32_t dh, int64_t ldq, int64_t ldk, int64_t ldv, float scale,
+                               void* stream);
 /* Backward of the above without any L x L tensor (training path of unet:396-416): P is recomputed per tile from q, k and
  * the forward's `lse`; o / d_o are the forward output and its gradient; `delta` is a workspace of B*H*Lq floats
  * (receives rowsum(d_o * o)). dq (B,Lq,H*dh), dk / dv (B,Lk,H*dh): bf16, fully written. dh: a multiple of 64. Heads wider

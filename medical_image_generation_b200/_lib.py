@@ -47,6 +47,7 @@ _SIGNATURES = {
     "mig_conv_workspace_bytes": [C.POINTER(ConvGeom), _i, _i, _i],
     "mig_gemm_strided": [C.POINTER(GemmDesc), _i, _i, _p, _p, _p, _i, _p],
     "mig_flash_attention_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
+    "mig_flash_attention_fwd_ld": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _l, _l, _l, _f, _p],
     "mig_flash_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p],
     "mig_groupnorm_fwd": [_i, _p, _p, _p, _p, _p, _p, _i, _l, _i, _i, _f, _i, _p, _l, _p],
     "mig_groupnorm_bwd": [_i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p],
@@ -121,7 +122,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.mig_abi_version() != 3:
+    if lib.mig_abi_version() != 4:
         raise RuntimeError("libmedimgen_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -703,11 +703,11 @@ __global__ void __launch_bounds__(FP_THREADS, 1) flash_pair_kernel(const __grid_
   }
 }
 
-// 4-d map over a contiguous (B, L, H*dh) bf16 tensor: dims (dh, H, L, B); box (64, 1, rows, 1)
-static int bhld_map(CUtensorMap* m, const void* base, int B, int H, int L, int dh, uint32_t box_rows) {
-  const uint64_t C = (uint64_t)H * dh;
+// 4-d map over a (B, L, H*dh) bf16 tensor with row pitch ld >= H*dh elements (contiguous: ld = H*dh):
+// dims (dh, H, L, B); box (64, 1, rows, 1)
+static int bhld_map(CUtensorMap* m, const void* base, int B, int H, int L, int dh, uint32_t box_rows, int64_t ld) {
   uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)L, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)dh * 2, C * 2, (uint64_t)L * C * 2};
+  uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)ld * 2, (uint64_t)L * (uint64_t)ld * 2};
   uint32_t box[4] = {64, 1, box_rows, 1};
   return make_map(m, base, 4, dims, strides, box);
 }
@@ -765,18 +765,22 @@ static bool flash_pair_enabled() {
 
 using namespace mig;
 
-extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B,
-                                       int32_t H, int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream) {
+extern "C" int mig_flash_attention_fwd_ld(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B,
+                                          int32_t H, int32_t Lq, int32_t Lk, int32_t dh, int64_t ldq, int64_t ldk,
+                                          int64_t ldv, float scale, void* stream) {
   MIG_REQUIRE(q && k && v && out && lse, "flash_attention: null argument");
   MIG_REQUIRE(mig_has_tcgen05(), "flash_attention: needs an sm_100 device");
   MIG_REQUIRE(flash_eligible(H, dh), "flash_attention: head dim %d not supported (multiple of 64; above 256 a multiple of 256)", dh);
   MIG_REQUIRE(B > 0 && Lq > 0 && Lk > 0 && (int64_t)B * H < 65536, "flash_attention: bad sizes");
   MIG_REQUIRE(((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
                 reinterpret_cast<uintptr_t>(out)) & 15) == 0, "flash_attention: tensors must be 16-byte aligned");
+  const int64_t C = (int64_t)H * dh;
+  MIG_REQUIRE(ldq >= C && ldk >= C && ldv >= C && ((ldq | ldk | ldv) & 7) == 0,
+              "flash_attention: row pitches must be >= H*dh and multiples of 8 elements");
   CUtensorMap qm, km, vm;
-  if (bhld_map(&qm, q, B, H, Lq, dh, FA_BM)) return 1;
-  if (bhld_map(&km, k, B, H, Lk, dh, FA_BN)) return 1;
-  if (bhld_map(&vm, v, B, H, Lk, dh, 64)) return 1;
+  if (bhld_map(&qm, q, B, H, Lq, dh, FA_BM, ldq)) return 1;
+  if (bhld_map(&km, k, B, H, Lk, dh, FA_BN, ldk)) return 1;
+  if (bhld_map(&vm, v, B, H, Lk, dh, 64, ldv)) return 1;
   FlashParams p{};
   p.B = B; p.H = H; p.Lq = Lq; p.Lk = Lk; p.dh = dh;
   p.DV = dh > 256 ? 256 : dh;
@@ -790,4 +794,10 @@ extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void*
   if (dh <= 256) return launch_flash<2>(qm, km, vm, p, dim3(mt, 1, B * H), st);   // single pass, online softmax
   if (launch_flash<0>(qm, km, vm, p, dim3(mt, 1, B * H), st)) return 2;
   return launch_flash<1>(qm, km, vm, p, dim3(mt, dh / p.DV, B * H), st);
+}
+
+extern "C" int mig_flash_attention_fwd(const void* q, const void* k, const void* v, void* out, float* lse, int32_t B,
+                                       int32_t H, int32_t Lq, int32_t Lk, int32_t dh, float scale, void* stream) {
+  const int64_t C = (int64_t)H * dh;
+  return mig_flash_attention_fwd_ld(q, k, v, out, lse, B, H, Lq, Lk, dh, C, C, C, scale, stream);
 }

@@ -199,6 +199,19 @@ class SelfAttentionBlock(nn.Module):
             self.__dict__["_mig_qkv"] = cache
         return cache[1]
 
+    def _eval_qkv(self):
+        """(3C, C) bf16 weight and (3C,) fp32 bias of to_q / to_k / to_v stacked, cached until one of them changes."""
+        ps = (self.to_q.weight, self.to_k.weight, self.to_v.weight, self.to_q.bias, self.to_k.bias, self.to_v.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = self.__dict__.get("_mig_qkv_eval")
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                w = torch.cat([p.detach().to(torch.bfloat16) for p in ps[:3]], 0).contiguous()
+                b = torch.cat([p.detach().float() for p in ps[3:]], 0).contiguous()
+            cache = (key, w, b)
+            self.__dict__["_mig_qkv_eval"] = cache
+        return cache[1], cache[2]
+
     def forward(self, x):
         x = ops.to_channels_last(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.float32)
         B, Cc = x.shape[0], x.shape[1]
@@ -206,7 +219,14 @@ class SelfAttentionBlock(nn.Module):
         # channels-last memory IS the (B, L, C) token matrix in the reference's d,h,w order (unet:428-434)
         tokens = h.permute(0, *range(2, h.ndim), 1).reshape(B, -1, Cc)
         fused = self._fused_qkv()
-        if fused is not None:
+        if fused is None and not torch.is_grad_enabled() and tokens.dtype == torch.bfloat16:
+            # inference without an optimiser (sampling): the same single projection on a cached concatenation of the three
+            # weight matrices; the attention kernel reads q / k / v as column blocks of its output (6 x (3 GEMMs -> 1)
+            # per reverse step of the config-4 U-Net)
+            w, b = self._eval_qkv()
+            qkv = ops.linear(tokens, w, b)
+            o = ops.sdpa_qkv(qkv, self.num_heads, self.scale)
+        elif fused is not None:
             # to_q / to_k / to_v (unet:436-438) as ONE projection GEMM: the flat optimiser keeps the three weight matrices
             # side by side; attention reads the column slices in place and returns ONE gradient tensor
             fused.refresh()

@@ -1110,9 +1110,14 @@ class _QkvSdpaFn(Function):
         q, k, v = sl["q"], sl["k"], sl["v"]
         use_flash = flash_attention_usable(qkv[:, :, :Cc], qkv[:, :, :Cc], qkv[:, :, :Cc], heads, needs_grad=bool(ctx.needs_input_grad[0]))
         if use_flash:
-            qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
-            O, lse = _flash_fwd(qc, kc, vc, heads, scale_)
-            ctx.save_for_backward(qc, kc, vc, O, lse)
+            # the forward kernel reads the three column blocks in place (row pitch 3C); contiguous copies are only made
+            # when a backward will need them
+            if ctx.needs_input_grad[0]:
+                qc, kc, vc = q.contiguous(), k.contiguous(), v.contiguous()
+                O, lse = _flash_fwd(qc, kc, vc, heads, scale_)
+                ctx.save_for_backward(qc, kc, vc, O, lse)
+            else:
+                O, lse = _flash_fwd(q, k, v, heads, scale_)
         else:
             O, P = _sdpa_fwd_unfused(q, k, v, B, L, L, Cc, heads, scale_, C3)
             ctx.save_for_backward(qkv, P)
@@ -1208,13 +1213,28 @@ def flash_attention_usable(q, k, v, heads: int, needs_grad=None) -> bool:
     return bool(_lib.load().mig_has_tcgen05())
 
 
+def _row_pitch(t):
+    """Row pitch (elements) of a (B, L, C) matrix stack the strided attention entry point can read in place: unit column
+    stride, rows `ld` apart, batches L * ld apart, 16-byte aligned -- e.g. a column block of a fused q/k/v projection
+    output. None if `t` is laid out otherwise."""
+    B, L, Cc = t.shape
+    ld = t.stride(1) if L > 1 else max(t.stride(1), Cc)
+    if t.stride(2) != 1 or ld < Cc or ld % 8 or (B > 1 and t.stride(0) != L * ld) or t.data_ptr() % 16:
+        return None
+    return ld
+
+
 def _flash_fwd(q, k, v, heads: int, scale_: float):
     B, Lq, Cc = q.shape
     Lk = k.shape[1]
-    out = torch.empty_like(q)
+    lds = [_row_pitch(t) for t in (q, k, v)]
+    if any(ld is None for ld in lds):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        lds = [Cc, Cc, Cc]
+    out = torch.empty((B, Lq, Cc), dtype=q.dtype, device=q.device)
     lse = torch.empty((B * heads, Lq), dtype=torch.float32, device=q.device)
-    call("mig_flash_attention_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, Lq, Lk, Cc // heads,
-         float(scale_), _stream())
+    call("mig_flash_attention_fwd_ld", _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(lse), B, heads, Lq, Lk, Cc // heads,
+         int(lds[0]), int(lds[1]), int(lds[2]), float(scale_), _stream())
     return out, lse
 
 

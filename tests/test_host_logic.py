@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/medimgen_b200.h but not exported"
     assert set(declared) == set(_lib._SIGNATURES), "ctypes signature table out of sync with the header"
-    assert _lib.load().mig_abi_version() == 3
+    assert _lib.load().mig_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

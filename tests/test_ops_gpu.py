@@ -677,7 +677,7 @@ def test_flash_attention_backward(B, Lq, Lk, C, heads):
     finally:
         ops.call = real
         ops.set_flash_attention(True, training="auto")
-    assert seen == ["mig_flash_attention_fwd", "mig_flash_attention_bwd"], seen
+    assert seen == ["mig_flash_attention_fwd_ld", "mig_flash_attention_bwd"], seen
     assert rel_err(got, want) < BF16_TOL
     assert rel_err(qd.grad, qr.grad) < BF16_TOL
     assert rel_err(kd.grad, kr.grad) < BF16_TOL
@@ -756,6 +756,48 @@ def test_conv_transpose_fwd_bwd(case, dtype):
     assert rel_err(xd.grad, xr.grad) < tol
     assert rel_err(wd.grad, wr.grad) < tol
     assert rel_err(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("B,L,C,heads", [(2, 300, 128, 1), (1, 200, 128, 2), (1, 1728, 512, 1), (2, 216, 768, 1)])
+def test_flash_attention_reads_fused_qkv_in_place(B, L, C, heads):
+    """mig_flash_attention_fwd_ld: q / k / v as the column blocks of ONE (B, L, 3C) projection output (row pitch 3C) must
+    give bit-identical results to contiguous copies of the same data -- same kernels, same tiles, only the tensor-map
+    strides differ. Covers the two-query-tile kernel (head dim 64 / 128) and the two-pass kernels (512 / 768)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(L + C)
+    qkv = bf16_round(torch.randn(B, L, 3 * C, generator=g)).to(DEV).bfloat16()
+    q, k, v = (qkv[:, :, i * C:(i + 1) * C] for i in range(3))
+    scale = 1 / math.sqrt(C / heads)
+    assert ops._row_pitch(q) == 3 * C and ops._row_pitch(v) == 3 * C
+    got, lse = ops._flash_fwd(q, k, v, heads, scale)
+    want, lse_w = ops._flash_fwd(q.contiguous(), k.contiguous(), v.contiguous(), heads, scale)
+    assert got.is_contiguous() and torch.equal(got, want) and torch.equal(lse, lse_w)
+    with torch.no_grad():
+        fused = ops.sdpa_qkv(qkv, heads, scale)            # no gradient needed: no copies, strided read
+    assert torch.equal(fused, want)
+
+
+@pytest.mark.parametrize("C,nhc", [(128, 128), (128, 64), (512, 512), (32, 32)])
+def test_attention_block_inference_uses_one_projection(C, nhc):
+    """SelfAttentionBlock under no_grad in bf16 (the sampling path) projects q, k, v with ONE GEMM on a cached stacked
+    weight and lets attention read the column blocks in place; it must match the three-GEMM path that runs when
+    gradients are enabled, and follow in-place weight changes (the cache is keyed by the parameters' versions)."""
+    from medical_image_generation_b200.layers import SelfAttentionBlock
+    torch.manual_seed(C + nhc)
+    blk = SelfAttentionBlock(3, C, num_head_channels=nhc, norm_num_groups=32).to(DEV)
+    x = torch.randn(2, C, 6, 6, 5, device=DEV).bfloat16()
+    with torch.enable_grad():
+        ref = blk(x.clone().requires_grad_(True)).detach()
+    with torch.no_grad():
+        got = blk(x)
+    assert "_mig_qkv_eval" in blk.__dict__
+    assert rel_err(got, ref) < 5e-3
+    with torch.no_grad():
+        blk.to_v.weight.mul_(0.5)
+        got2 = blk(x)
+    with torch.enable_grad():
+        ref2 = blk(x.clone().requires_grad_(True)).detach()
+    assert rel_err(got2, ref2) < 5e-3 and rel_err(got2, got) > 1e-3
 
 
 @pytest.mark.parametrize("C,heads", [(128, 1), (256, 2), (512, 1)])
