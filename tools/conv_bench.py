@@ -18,6 +18,8 @@ if which == "big":
     SHAPES = SHAPES[:2]
 elif which == "deep":
     SHAPES = SHAPES[3:]
+elif which == "six":   # the 6^3 level only (split-K plans)
+    SHAPES = [(8, 768, 768, 6)]
 elif which == "mid":   # 64/128-channel layers of the AE / pixel-space U-Nets
     SHAPES = [(1, 64, 64, 64), (2, 64, 64, 48), (1, 128, 128, 32), (1, 64, 32, 96)]
 print(torch.cuda.get_device_name(0))
