@@ -473,7 +473,8 @@ __device__ __forceinline__ void tmem_ld128(uint32_t taddr, float v[128]) {
 
 // 2^x on the FMA pipe (Cody-Waite: x = n + f, |f| <= 0.5; degree-3 minimax polynomial for 2^f, relative error 7.5e-5 --
 // far below the bf16 rounding of P). The 16 MUFU lanes of an SM need 2048 cycles for the 2 x 128 x 128 exponentials of
-// one key tile, exactly the UMMA time of that tile; one exponential in four goes through here instead.
+// one key tile, exactly the UMMA time of that tile; with POLY one exponential in four goes through here instead
+// (optional, off by default: see launch_flash_pair).
 __device__ __forceinline__ float poly_ex2(float x) {
   x = fmaxf(x, -125.f);
   const float t = x + 12582912.f;          // 1.5 * 2^23: round-to-nearest leaves n in the low mantissa bits
@@ -736,9 +737,11 @@ template <int DH>
 static int launch_flash_pair(const CUtensorMap& qm, const CUtensorMap& km, const CUtensorMap& vm, const FlashParams& p,
                              cudaStream_t st) {
   const int smem = (2 + 2 * FP_KV_STAGES) * (DH / 64) * FA_BM * 128 + 1024;
+  // polynomial exp2 for one exponential in four: measured no faster than MUFU alone (the kernel is not MUFU-bound), so
+  // the exact path is the default; MIG_FLASH_POLY=1 keeps the variant available for A/B runs
   static const bool poly = [] {
     const char* e = getenv("MIG_FLASH_POLY");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   const dim3 grid((p.Lq + 2 * FA_BM - 1) / (2 * FA_BM), 1, p.B * p.H);
   if (poly) {
