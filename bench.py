@@ -324,6 +324,7 @@ def hbm_block(dev, pk):
     a pool larger than L2 (cold inputs), launches captured in one CUDA graph so host launch cost is not in the number.
     bytes = ALGORITHMIC bytes. Returns the `hbm_roofline` object."""
     import ctypes as C
+    import numpy as np
     import torch
     from medical_image_generation_b200 import _lib, ops
     call, ptr = _lib.call, ops._ptr
@@ -405,6 +406,39 @@ def hbm_block(dev, pk):
     lossb = torch.empty((), device=dev)
     run("mse_fwd", lambda i: call("mig_mse_fwd", 0, ptr(a[i]), ptr(b[i]), ptr(lossb), ptr(partials), numel, 0, ops._stream()),
         2 * numel * 4, "MSE forward: read pred, target (fp32)")
+    del a, b, z
+    # data path: a config-5 batch (2 patches x 2 channels x 160x160x128 fp32) cut out of resident cases;
+    # every launch reads a different pair of cases (pool of 2R cases, 2R x 37 MB > L2)
+    from medical_image_generation_b200 import data as mdata
+    vols = mdata.ResidentVolumes(dev)
+    cshape = (2, 176, 176, 150)
+    for i in range(2 * R):
+        vols.add(f"case{i}", torch.rand(cshape, device=dev))
+    vols.finalize()
+    P = (160, 160, 128)
+    Sp = P[0] * P[1] * P[2]
+    descs = np.zeros((R, 2), dtype=mdata._DESC)
+    for i in range(R):
+        for k in range(2):
+            d = descs[i, k]
+            d["src_offset"], d["src_dims"] = vols.offsets[2 * i + k], cshape
+            d["lb"], d["flip"], d["mult"] = (5 + k, 3, 9), (0, 0, k), 1.0
+            d["mat"] = np.eye(3, dtype=np.float32).reshape(-1)
+            d["channel"][:2] = (0, 1)
+    descs_dev = torch.from_numpy(descs.view(np.uint8).reshape(-1).copy()).to(dev)
+    patches = [torch.empty(2, 2, *P, device=dev) for _ in range(R)]
+    stride = 2 * mdata._DESC.itemsize
+    run("patch_gather", lambda i: mdata.patch_gather(vols.buffer, descs_dev[i * stride:], patches[i], 2, 2, P,
+                                                     clamp=(0.0, 1.0)),
+        2 * 4 * Sp * 4, "crop + pad + mirror + clamp of a 2 x 2 x 160x160x128 batch from resident cases: read + write fp32")
+    st = torch.zeros(4, 4, device=dev)
+    ws = torch.empty(int(_lib.load().mig_patch_stats_workspace_bytes(4)), dtype=torch.uint8, device=dev)
+    run("patch_stats", lambda i: call("mig_patch_stats", ptr(patches[i]), ptr(st), None, 4, Sp, ptr(ws), ws.numel(),
+                                      ops._stream()),
+        4 * Sp * 4, "mean / std / min / max per (patch, channel): read fp32")
+    gamma_op = torch.tensor([[2.0, 0.9, 0.0, 0.0]] * 4, device=dev).reshape(-1)
+    run("patch_intensity_gamma", lambda i: mdata.patch_intensity(patches[i], patches[(i + 1) % R], gamma_op, st, st, 2, 2, Sp),
+        2 * 4 * Sp * 4, "gamma transform of the batch: read + write fp32")
     return {"bound": "hbm", "peak": pk["hbm"], "unit": "GB/s", "peak_source": pk["source"], "kernels": out,
             "method": f"{R} launches on {R} different buffers (pool > L2) in one CUDA graph, 2 replays timed with CUDA events"}
 

@@ -258,6 +258,46 @@ int mig_adamw_step_strided(float* p, const float* g, float* m, float* v, int64_t
                            const float* sumsq, float max_norm, void* bf16_shadow, const int32_t* step_device,
                            void* stream);
 
+/* ---- D1-D3: data path -- MedicalDataset.__getitem__, medimgen/data_processing.py:540-598 ------------
+ * The preprocessed cases ((C,Z,Y,X) fp32, data_processing.py:536-556) live in ONE device buffer `volumes` (the whole
+ * dataset fits 180 GB of HBM3e); a training batch is cut out of it on the device instead of by DataLoader workers.
+ * One mig_patch_desc per output patch, as a DEVICE array of B entries. */
+#define MIG_PATCH_MAX_CH 8
+typedef struct {
+  int64_t src_offset;                /* element offset of the case's (C,Z,Y,X) block inside `volumes` */
+  int32_t src_dims[4];               /* C, Z, Y, X of the case */
+  int32_t lb[3];                     /* bbox lower bound per axis (get_bbox, data_processing.py:463-527); may lie outside
+                                        the case: those voxels are `pad_value` (crop_and_pad_nd, :150-225) */
+  int32_t flip[3];                   /* MirrorTransform per axis (data_processing.py:841-846) */
+  int32_t affine;                    /* 0: plain crop; 1: trilinear resample (SpatialTransform rotation / scaling,
+                                        :766-774): source offset from the patch centre = mat * output offset (z,y,x);
+                                        corners outside the cropped box or the case contribute 0 (zeros padding) */
+  float mat[9];
+  float mult[MIG_PATCH_MAX_CH];      /* MultiplicativeBrightnessTransform per output channel (:793-800), 1 = off */
+  int32_t channel[MIG_PATCH_MAX_CH]; /* source channel per output channel (channel_ids, :565-566) */
+} mig_patch_desc;
+/* out[b][c][z][y][x] (channels_last = 0, what the reference's DataLoader delivers) or out[b][z][y][x][c], fp32 or bf16:
+ * crop + pad + channel selection + resample + mirror + brightness + clamp(lo, hi) in one pass (pass lo > hi for no clamp).
+ * 2-D datasets use patch[0] = 1. */
+int mig_patch_gather(const float* volumes, const mig_patch_desc* descs, void* out, int out_dtype, int32_t B, int32_t C,
+                     const int32_t patch[3], int channels_last, int any_affine /* 0: no desc has affine set */,
+                     float pad_value, float lo, float hi, void* stream);
+/* per (patch, channel) row of S contiguous fp32 voxels: stats[row] = {mean, unbiased std, min, max}; rows with
+ * active[row] == 0 are skipped (active may be NULL = all). Deterministic two-stage reduction, fp64 sums;
+ * workspace = mig_patch_stats_workspace_bytes(rows). ContrastTransform / GammaTransform statistics (:801-839). */
+int mig_patch_stats(const float* x, float* stats, const int32_t* active, int32_t rows, int64_t S, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+int64_t mig_patch_stats_workspace_bytes(int32_t rows);
+/* per-row intensity transform, x (fp32 rows of S voxels) -> y (fp32 / bf16; channels_last as above, C channels per
+ * patch), then clamp(lo, hi) (data_processing.py:595; lo > hi = none). op[row] = {mode, param, invert, 0} as floats:
+ *   0 copy (skipped when y == x and no clamp)
+ *   1 contrast, preserve_range: clamp((x - mean) * param + mean, min, max)               with stats0[row]
+ *   2 gamma: pow((x' - min') / max(range, 1e-7), param) * range + min', x' = -x if invert  with stats0[row]
+ *   3 retain_stats: (x - mean1) * std0 / max(std1, 1e-7) + mean0                          with stats0 / stats1 */
+int mig_patch_intensity(const float* x, void* y, int out_dtype, const float* op, const float* stats0,
+                        const float* stats1, int32_t B, int32_t C, int64_t S, int channels_last, float lo, float hi,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,9 +94,13 @@ _SIGNATURES = {
     "mig_adamw_step": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _i, _p, _f, _p, _p, _p],
     "mig_sumsq_strided": [_p, _p, _p, _l, _l, _l, _p],
     "mig_adamw_step_strided": [_p, _p, _p, _p, _l, _l, _l, _f, _f, _f, _f, _f, _i, _p, _f, _p, _p, _p],
+    "mig_patch_gather": [_p, _p, _p, _i, _i, _i, _I3, _i, _i, _f, _f, _f, _p],
+    "mig_patch_stats": [_p, _p, _p, _i, _l, _p, _l, _p],
+    "mig_patch_stats_workspace_bytes": [_i],
+    "mig_patch_intensity": [_p, _p, _i, _p, _p, _p, _i, _i, _l, _i, _f, _f, _p],
 }
 _RESTYPES = {"mig_last_error": C.c_char_p, "mig_conv_workspace_bytes": C.c_int64,
-             "mig_groupnorm_workspace_bytes": C.c_int64}
+             "mig_groupnorm_workspace_bytes": C.c_int64, "mig_patch_stats_workspace_bytes": C.c_int64}
 
 _lib = None
 
@@ -105,7 +109,7 @@ def declared_symbols() -> list[str]:
     """Every function name declared in include/medimgen_b200.h."""
     text = open(HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(mig_[a-z0-9_]+)\s*\(", text)) - {"mig_conv_geom", "mig_gemm_desc"})
+    return sorted(set(re.findall(r"\b(mig_[a-z0-9_]+)\s*\(", text)) - {"mig_conv_geom", "mig_gemm_desc", "mig_patch_desc"})
 
 
 def load():

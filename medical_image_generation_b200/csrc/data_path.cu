@@ -1,0 +1,260 @@
+// Data path on the device: what MedicalDataset.__getitem__ (medimgen/data_processing.py:540-598) does per
+// sample with numpy + DataLoader workers -- bounding-box crop with zero padding (crop_and_pad_nd, :150-225), channel
+// selection, the soft augmentations the planner switches on (configuration.py:933-945: scaling / rotation about the slice
+// axis, brightness, contrast, gamma, mirror) and the final clamp to [0, 1] -- done for a whole batch on cases that are
+// resident in HBM. All of it is byte movement plus a few flops per voxel: HBM-bound, one thread per output voxel with
+// warp-contiguous 4-byte accesses along x (a crop starts at an arbitrary x, so wider vectors would be misaligned).
+#include "common.cuh"
+
+namespace mig {
+
+static_assert(sizeof(mig_patch_desc) == 152, "mig_patch_desc layout is part of the ABI (ctypes mirror in data.py)");
+
+struct PatchDims {
+  int C, PZ, PY, PX;
+  int64_t S;   // PZ*PY*PX
+};
+
+// one source voxel of the case, or the pad value outside it (crop_and_pad_nd pads the crop with a constant)
+__device__ __forceinline__ float fetch(const float* __restrict__ src, int Z, int Y, int X, int iz, int iy, int ix,
+                                       float pad) {
+  if ((unsigned)iz < (unsigned)Z && (unsigned)iy < (unsigned)Y && (unsigned)ix < (unsigned)X)
+    return __ldg(src + ((int64_t)iz * Y + iy) * X + ix);
+  return pad;
+}
+
+// Grid: (y groups, PZ, B*C); block (TX, 256/TX): no integer division per voxel -- at 8 bytes per voxel the kernel has
+// ~40 issue slots per voxel before it stops being HBM-bound. A thread covers kRowsPerThread rows (independent loads).
+constexpr int kRowsPerThread = 4;
+
+template <typename T, bool AFFINE>
+__global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restrict__ volumes,
+                                                           const mig_patch_desc* __restrict__ descs,
+                                                           T* __restrict__ out, PatchDims p, int channels_last,
+                                                           float pad, float lo, float hi) {
+  __shared__ mig_patch_desc d;
+  const int b = blockIdx.z / p.C, c = blockIdx.z - b * p.C;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (tid < (int)(sizeof(mig_patch_desc) / 4))
+    reinterpret_cast<int32_t*>(&d)[tid] = reinterpret_cast<const int32_t*>(descs + b)[tid];
+  __syncthreads();
+  const int Z = d.src_dims[1], Y = d.src_dims[2], X = d.src_dims[3];
+  const float* src = volumes + d.src_offset + (int64_t)d.channel[c] * Z * Y * X;
+  const float mult = d.mult[c];
+  const float cz = 0.5f * (p.PZ - 1), cy = 0.5f * (p.PY - 1), cx = 0.5f * (p.PX - 1);
+  const int zo = blockIdx.y;
+  // mirror is the LAST transform of the reference's pipeline and commutes with the per-channel intensity steps:
+  // output voxel (z,y,x) shows pre-mirror voxel (P-1-z, ...)
+  const int z = d.flip[0] ? p.PZ - 1 - zo : zo;
+#pragma unroll
+  for (int u = 0; u < kRowsPerThread; ++u) {
+    const int yo = (blockIdx.x * kRowsPerThread + u) * blockDim.y + threadIdx.y;
+    if (yo >= p.PY) break;
+    const int y = d.flip[1] ? p.PY - 1 - yo : yo;
+    for (int xo = threadIdx.x; xo < p.PX; xo += blockDim.x) {
+      const int x = d.flip[2] ? p.PX - 1 - xo : xo;
+      float v;
+      if constexpr (!AFFINE) {
+        v = fetch(src, Z, Y, X, d.lb[0] + z, d.lb[1] + y, d.lb[2] + x, pad);
+      } else if (!d.affine) {
+        v = fetch(src, Z, Y, X, d.lb[0] + z, d.lb[1] + y, d.lb[2] + x, pad);
+      } else {
+        const float oz = z - cz, oy = y - cy, ox = x - cx;
+        const float fz = cz + d.mat[0] * oz + d.mat[1] * oy + d.mat[2] * ox;
+        const float fy = cy + d.mat[3] * oz + d.mat[4] * oy + d.mat[5] * ox;
+        const float fx = cx + d.mat[6] * oz + d.mat[7] * oy + d.mat[8] * ox;
+        const float z0f = floorf(fz), y0f = floorf(fy), x0f = floorf(fx);
+        const float wz = fz - z0f, wy = fy - y0f, wx = fx - x0f;
+        const int z0 = (int)z0f, y0 = (int)y0f, x0 = (int)x0f;
+        v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+          const int pz = z0 + dz, py = y0 + dy, px = x0 + dx;   // position inside the cropped patch
+          const float w = (dz ? wz : 1.f - wz) * (dy ? wy : 1.f - wy) * (dx ? wx : 1.f - wx);
+          // outside the crop: zeros padding of the resample; inside the crop but outside the case: the crop's pad value
+          if ((unsigned)pz < (unsigned)p.PZ && (unsigned)py < (unsigned)p.PY && (unsigned)px < (unsigned)p.PX)
+            v = fmaf(w, fetch(src, Z, Y, X, d.lb[0] + pz, d.lb[1] + py, d.lb[2] + px, pad), v);
+        }
+      }
+      v *= mult;
+      if (lo <= hi) v = fminf(fmaxf(v, lo), hi);
+      const int64_t idx = ((int64_t)zo * p.PY + yo) * p.PX + xo;
+      const int64_t o = channels_last ? ((int64_t)b * p.S + idx) * p.C + c : ((int64_t)b * p.C + c) * p.S + idx;
+      out[o] = from_f<T>(v);
+    }
+  }
+}
+
+// ---- per-row statistics: {mean, unbiased std, min, max} ---------------------------------------------------------
+constexpr int kStatChunks = 64;   // partials per row
+struct StatPartial {
+  double sum, sumsq;
+  float mn, mx;
+};
+
+__global__ void __launch_bounds__(256) patch_stats_partial_kernel(const float* __restrict__ x,
+                                                                  const int32_t* __restrict__ active,
+                                                                  StatPartial* __restrict__ part, int64_t S) {
+  const int row = blockIdx.y;
+  if (active && !active[row]) return;
+  const float* xr = x + (int64_t)row * S;
+  const int64_t per = (S + kStatChunks - 1) / kStatChunks;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < S ? lo + per : S;
+  double s = 0.0, q = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  // fp32 partial sums over short runs (16 values per thread), promoted to fp64: keeps the error at the fp64 level
+  for (int64_t i0 = lo + threadIdx.x; i0 < hi; i0 += (int64_t)blockDim.x * 16) {
+    float fs = 0.f, fq = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int64_t i = i0 + (int64_t)k * blockDim.x;
+      if (i < hi) {
+        const float v = __ldg(xr + i);
+        fs += v;
+        fq = fmaf(v, v, fq);
+        mn = fminf(mn, v);
+        mx = fmaxf(mx, v);
+      }
+    }
+    s += fs;
+    q += fq;
+  }
+  __shared__ double sh_s[8], sh_q[8];
+  __shared__ float sh_mn[8], sh_mx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) { sh_s[warp] = s; sh_q[warp] = q; sh_mn[warp] = mn; sh_mx[warp] = mx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      s += sh_s[w]; q += sh_q[w]; mn = fminf(mn, sh_mn[w]); mx = fmaxf(mx, sh_mx[w]);
+    }
+    part[(int64_t)row * kStatChunks + blockIdx.x] = StatPartial{s, q, mn, mx};
+  }
+}
+
+__global__ void patch_stats_final_kernel(const StatPartial* __restrict__ part, const int32_t* __restrict__ active,
+                                         float* __restrict__ stats, int rows, int64_t S) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows || (active && !active[row])) return;
+  double s = 0.0, q = 0.0;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int k = 0; k < kStatChunks; ++k) {   // fixed order: deterministic
+    const StatPartial p = part[(int64_t)row * kStatChunks + k];
+    s += p.sum; q += p.sumsq; mn = fminf(mn, p.mn); mx = fmaxf(mx, p.mx);
+  }
+  const double mean = s / (double)S;
+  double var = S > 1 ? (q - s * mean) / (double)(S - 1) : 0.0;   // torch.Tensor.std(): unbiased
+  if (var < 0.0) var = 0.0;
+  stats[row * 4 + 0] = (float)mean;
+  stats[row * 4 + 1] = (float)sqrt(var);
+  stats[row * 4 + 2] = mn;
+  stats[row * 4 + 3] = mx;
+}
+
+// ---- per-row intensity transform --------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) patch_intensity_kernel(const float* __restrict__ x, T* __restrict__ y,
+                                                              const float* __restrict__ op,
+                                                              const float* __restrict__ stats0,
+                                                              const float* __restrict__ stats1, int C, int64_t S,
+                                                              int channels_last, int in_place, float lo, float hi) {
+  const int row = blockIdx.y, b = row / C, c = row - b * C;
+  const int mode = (int)op[row * 4 + 0];
+  const float param = op[row * 4 + 1];
+  const bool invert = op[row * 4 + 2] != 0.f;
+  if (mode == 0 && in_place && lo > hi) return;
+  float mean0 = 0.f, std0 = 0.f, mn0 = 0.f, mx0 = 0.f, mean1 = 0.f, std1 = 1.f;
+  if (mode != 0) { mean0 = stats0[row * 4]; std0 = stats0[row * 4 + 1]; mn0 = stats0[row * 4 + 2]; mx0 = stats0[row * 4 + 3]; }
+  if (mode == 3) { mean1 = stats1[row * 4]; std1 = stats1[row * 4 + 1]; }
+  // gamma works on x' = -x when inverted: min' = -max, max' = -min
+  const float gmin = invert ? -mx0 : mn0;
+  const float rnge = mx0 - mn0;
+  const float inv_rnge = 1.f / fmaxf(rnge, 1e-7f);
+  const float restat = std0 / fmaxf(std1, 1e-7f);
+  const float* xr = x + (int64_t)row * S;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < S; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = xr[i];
+    if (mode == 1) {
+      v = fminf(fmaxf(fmaf(v - mean0, param, mean0), mn0), mx0);
+    } else if (mode == 2) {
+      const float xi = invert ? -v : v;
+      const float g = powf((xi - gmin) * inv_rnge, param) * rnge + gmin;
+      v = invert ? -g : g;
+    } else if (mode == 3) {
+      v = fmaf(v - mean1, restat, mean0);
+    }
+    if (lo <= hi) v = fminf(fmaxf(v, lo), hi);
+    const int64_t o = channels_last ? ((int64_t)b * S + i) * C + c : (int64_t)row * S + i;
+    y[o] = from_f<T>(v);
+  }
+}
+
+}  // namespace mig
+
+using namespace mig;
+
+extern "C" int mig_patch_gather(const float* volumes, const mig_patch_desc* descs, void* out, int out_dtype, int32_t B,
+                                int32_t C, const int32_t patch[3], int channels_last, int any_affine, float pad_value,
+                                float lo, float hi, void* stream) {
+  MIG_REQUIRE(volumes && descs && out, "patch_gather: null pointer");
+  MIG_REQUIRE(B > 0 && C > 0 && C <= MIG_PATCH_MAX_CH && (int64_t)B * C <= 65535,
+              "patch_gather: batch %d / channels %d out of range (<= %d channels, B*C <= 65535)", B, C, MIG_PATCH_MAX_CH);
+  MIG_REQUIRE(patch[0] > 0 && patch[0] <= 65535 && patch[1] > 0 && patch[2] > 0, "patch_gather: bad patch size");
+  PatchDims p{C, patch[0], patch[1], patch[2], (int64_t)patch[0] * patch[1] * patch[2]};
+  int tx = 32;
+  while (tx < 256 && tx < p.PX) tx *= 2;
+  dim3 block(tx, 256 / tx);
+  dim3 grid((p.PY + block.y * kRowsPerThread - 1) / (block.y * kRowsPerThread), p.PZ, B * C);
+  MIG_DISPATCH_DTYPE(out_dtype, T, {
+    // a batch without any resampled patch runs the plain-crop instantiation (fewer registers, no per-voxel branch)
+    if (any_affine)
+      patch_gather_kernel<T, true><<<grid, block, 0, as_stream(stream)>>>(volumes, descs, (T*)out, p, channels_last,
+                                                                         pad_value, lo, hi);
+    else
+      patch_gather_kernel<T, false><<<grid, block, 0, as_stream(stream)>>>(volumes, descs, (T*)out, p, channels_last,
+                                                                          pad_value, lo, hi);
+  });
+  return check_launch("patch_gather");
+}
+
+extern "C" int64_t mig_patch_stats_workspace_bytes(int32_t rows) {
+  return (int64_t)rows * kStatChunks * (int64_t)sizeof(StatPartial);
+}
+
+extern "C" int mig_patch_stats(const float* x, float* stats, const int32_t* active, int32_t rows, int64_t S,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  MIG_REQUIRE(x && stats && rows > 0 && rows <= 65535 && S > 0, "patch_stats: bad arguments");
+  MIG_REQUIRE(workspace && workspace_bytes >= mig_patch_stats_workspace_bytes(rows),
+              "patch_stats: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+              (long long)mig_patch_stats_workspace_bytes(rows));
+  patch_stats_partial_kernel<<<dim3(kStatChunks, rows), 256, 0, as_stream(stream)>>>(x, active, (StatPartial*)workspace, S);
+  patch_stats_final_kernel<<<(rows + 63) / 64, 64, 0, as_stream(stream)>>>((const StatPartial*)workspace, active, stats,
+                                                                          rows, S);
+  return check_launch("patch_stats");
+}
+
+extern "C" int mig_patch_intensity(const float* x, void* y, int out_dtype, const float* op, const float* stats0,
+                                   const float* stats1, int32_t B, int32_t C, int64_t S, int channels_last, float lo,
+                                   float hi, void* stream) {
+  MIG_REQUIRE(x && y && op && B > 0 && C > 0 && S > 0 && (int64_t)B * C <= 65535, "patch_intensity: bad arguments");
+  MIG_REQUIRE(stats0 && stats1, "patch_intensity: statistics pointers must be valid (unused rows are not read)");
+  const int rows = B * C;
+  const int in_place = (const void*)x == y;
+  MIG_REQUIRE(!in_place || (out_dtype == MIG_F32 && !(channels_last && C > 1)),
+              "patch_intensity: in-place needs fp32 output in the input's layout");
+  int per_row = (device_info().sm_count * 8 + rows - 1) / rows;
+  const int64_t need = (S + 255) / 256;
+  if (per_row > need) per_row = (int)need;
+  if (per_row < 1) per_row = 1;
+  MIG_DISPATCH_DTYPE(out_dtype, T, (patch_intensity_kernel<T><<<dim3(per_row, rows), 256, 0, as_stream(stream)>>>(
+                                       x, (T*)y, op, stats0, stats1, C, S, channels_last, in_place, lo, hi)));
+  return check_launch("patch_intensity");
+}

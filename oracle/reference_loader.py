@@ -65,6 +65,47 @@ def planner_functions() -> dict:
     return _cache["planner"]
 
 
+def data_functions() -> dict:
+    """`crop_and_pad_nd`, `MedicalDataset` and `CustomBatchSampler` of medimgen/data_processing.py:150-225,274-641, extracted by
+    AST and executed as written (the file itself imports zarr / blosc2 / batchgenerators(v2) at top, all absent here).
+    The names the extracted code touches are bound to the real numpy / torch objects; `zarr` / `blosc2` are empty stand-ins
+    (only used in isinstance checks and for file formats that cannot be read in this image), and
+    `define_nnunet_transformations` -- the batchgeneratorsv2 pipeline, a third-party dependency -- is the identity, so
+    `MedicalDataset.__getitem__` yields crop + pad + channel selection + clamp exactly as the reference computes them."""
+    if "data" in _cache:
+        return _cache["data"]
+    import glob
+    import pickle
+    import types
+    from functools import partial
+    from typing import List, Tuple, Union
+
+    import numpy as np
+    import torch
+    import torch.nn.functional as F
+    from torch.utils.data import Dataset, Sampler
+
+    path = os.path.join(REFERENCE_ROOT, "medimgen", "data_processing.py")
+    tree = ast.parse(open(path).read())
+    want = {"crop_and_pad_nd", "MedicalDataset", "CustomBatchSampler"}
+    body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in want]
+
+    class _Never:   # isinstance(x, _Never) is always False for arrays
+        pass
+    blosc2 = types.SimpleNamespace(ndarray=types.SimpleNamespace(NDArray=_Never), open=None)
+    zarr = types.SimpleNamespace(core=types.SimpleNamespace(Array=_Never), open_group=None)
+
+    def identity_pipeline(params, validation=False):
+        return lambda image: {"image": image}
+
+    ns = {"np": np, "torch": torch, "F": F, "os": os, "glob": glob, "pickle": pickle, "partial": partial,
+          "Dataset": Dataset, "Sampler": Sampler, "List": List, "Tuple": Tuple, "Union": Union, "blosc2": blosc2,
+          "zarr": zarr, "define_nnunet_transformations": identity_pipeline}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    _cache["data"] = {k: ns[k] for k in want}
+    return _cache["data"]
+
+
 def rerandomize_zero_init(module, seed: int = 1234, std: float = 0.05):
     """zero_module() (unet:62-69) makes a fresh U-Net output exactly 0, so parity on fresh modules is
     vacuous. Re-draw every all-zero weight/bias tensor from N(0, std) with a fixed seed."""

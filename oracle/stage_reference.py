@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.environ.get("MEDIMGEN_REFERENCE", "/root/reference")
 DST = os.path.join(ROOT, "baseline", "_ref")
 FILES = ["__init__.py", "diffusion_model_unet_with_strides.py", "autoencoderkl_with_strides.py", "train_ldm.py",
-         "train_autoencoder.py", "train_ddpm.py", "utils.py", "configuration.py"]
+         "train_autoencoder.py", "train_ddpm.py", "utils.py", "configuration.py", "data_processing.py"]
 
 
 def stage(verbose: bool = True) -> str | None:
