@@ -86,6 +86,21 @@ def install(strict: bool = False) -> List[str]:
                 _saved.append((mod, name, originals[name]))
             setattr(mod, name, repl[name])
             patched.append(f"{modname}.{name}")
+    # the data pipeline (`from medimgen.data_processing import get_data_loaders`, train_ldm.py:34): where the reference's
+    # module cannot be imported (zarr / blosc2 / batchgenerators(v2) missing) a module of the same name exposes the
+    # resident-in-HBM loaders of .data; an importable reference module is left alone (opt in with
+    # `compat.use_resident_loaders()`)
+    if "medimgen.data_processing" not in sys.modules:
+        try:
+            importlib.import_module("medimgen.data_processing")
+        except ImportError:
+            try:
+                importlib.import_module("medimgen")
+                _register_data_module()
+                patched.append("medimgen.data_processing (resident loaders)")
+            except ImportError:
+                if strict:
+                    raise
     # trainer modules imported earlier hold their own references (`from x import Y`)
     for modname in _CONSUMERS:
         mod = sys.modules.get(modname)
@@ -98,6 +113,36 @@ def install(strict: bool = False) -> List[str]:
                 setattr(mod, name, new)
                 patched.append(f"{modname}.{name}")
     return patched
+
+
+_DATA_NAMES = ("get_data_loaders", "create_split_files", "get_data_ids", "generate_crossval_split", "MedicalDataset",
+               "CustomBatchSampler", "crop_and_pad_nd")
+
+
+def _register_data_module() -> None:
+    from . import data
+    mod = types.ModuleType("medimgen.data_processing")
+    mod.__doc__ = "registered by medical_image_generation_b200.compat: resident-in-HBM data path (data.py)"
+    for name in _DATA_NAMES:
+        setattr(mod, name, getattr(data, name))
+    sys.modules["medimgen.data_processing"] = mod
+    _saved.append((sys.modules, "medimgen.data_processing", None))
+
+
+def use_resident_loaders() -> None:
+    """Rebind `get_data_loaders` (and the dataset classes) of an importable `medimgen.data_processing`, and of trainer
+    modules that already imported it, to the resident-in-HBM versions."""
+    from . import data
+    mod = importlib.import_module("medimgen.data_processing")
+    for name in _DATA_NAMES:
+        if hasattr(mod, name):
+            _saved.append((mod, name, getattr(mod, name)))
+        setattr(mod, name, getattr(data, name))
+    for modname in _CONSUMERS:
+        tm = sys.modules.get(modname)
+        if tm is not None and hasattr(tm, "get_data_loaders"):
+            _saved.append((tm, "get_data_loaders", tm.get_data_loaders))
+            tm.get_data_loaders = data.get_data_loaders
 
 
 def uninstall() -> None:

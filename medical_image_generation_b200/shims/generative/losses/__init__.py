@@ -4,7 +4,7 @@
   [upstream-memory; parity unpinned -- the package is neither installed nor under /root/reference]. `least_squares` (the
   reference's criterion) = MSE between LeakyReLU(0.05)(logits) and a constant 1 / 0 target; `bce` and `hinge` follow the
   same upstream conventions. Accepts one logits tensor or a list (multi-scale discriminators) and averages over it.
-* PerceptualLoss needs downloaded LPIPS / MedicalNet weights -> placeholder (there is no network in this image)."""
+* PerceptualLoss: LPIPS-VGG with (fake-3D) slice sampling, weights from a local file -- see .perceptual."""
 from __future__ import annotations
 
 import warnings
@@ -12,9 +12,7 @@ import warnings
 import torch
 from torch import nn
 
-from .._placeholder import placeholder
-
-PerceptualLoss = placeholder("losses.PerceptualLoss", "needs downloaded LPIPS / MedicalNet weights")
+from .perceptual import PerceptualLoss  # noqa: F401
 
 
 class PatchAdversarialLoss(nn.Module):

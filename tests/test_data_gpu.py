@@ -245,3 +245,55 @@ def test_kernel_argument_errors_are_reported():
         pkg.patch_gather(x, d, x, 1, 9, (1, 1, 1))
     with pytest.raises(RuntimeError, match="in-place"):
         pkg.patch_intensity(x, x, x, x, x, 1, 2, 4, channels_last=True)
+
+
+def test_get_data_loaders_from_files_feeds_the_autoencoder(tmp_path, monkeypatch):
+    """Files -> HBM -> batches -> B200 AutoencoderKL: zarr v2 cases written by hand (zlib chunks of (1, 1, Y, X), the
+    chunking of configuration.py:1404-1410), split file created like data_processing.py:47-101, 250 / 50 step loaders."""
+    import json
+    import pickle
+    from test_data_oracle import _write_zarr
+    import medical_image_generation_b200 as mig
+    root = tmp_path / "Task001_Synthetic"
+    images = root / "imagesTr"
+    images.mkdir(parents=True)
+    rs = np.random.RandomState(0)
+    truth = {}
+    for i in range(10):
+        arr = rs.rand(1, 20 + i, 40, 36).astype(np.float32)
+        truth[f"p{i:02d}"] = arr
+        _write_zarr(str(images / f"p{i:02d}.zarr" / "image"), arr, (1, 1, 40, 36), {"id": "zlib", "level": 1})
+        # _write_zarr leaves chunk #1 out on purpose (fill value 0)
+        truth[f"p{i:02d}"] = arr.copy()
+        truth[f"p{i:02d}"][0, 1] = 0
+        with open(images / f"p{i:02d}.pkl", "wb") as f:
+            pickle.dump({"class_locations": {1: [(5, 20, 18)]}}, f)
+    monkeypatch.setenv("medimgen_preprocessed", str(tmp_path))
+    config = {"oversample_ratio": 0.33, "input_channels": [0], "num_workers": 0}
+    tf = dict(_ON, patch_size=[16, 32, 32])
+    np.random.seed(0)
+    train, val = pkg.get_data_loaders(config, "001", "train-val-test", 2, "3d", tf)
+    split = json.loads((root / "splits_train_val_test.json").read_text())
+    assert len(split["train"]) == 7 and len(split["val"]) == 1 and len(split["test"]) == 2
+    assert len(train) == 250 and len(val) == 50
+    assert sorted(train.dataset.ids) == sorted(split["train"])
+    # the resident buffer holds the files' voxels
+    vols = train.dataset.volumes
+    for name, off, shp in zip(vols.names, vols.offsets, vols.shapes):
+        n = int(np.prod(shp))
+        assert np.array_equal(vols.buffer[off:off + n].cpu().numpy().reshape(shp), truth[name])
+    ae = mig.AutoencoderKL(spatial_dims=3, in_channels=1, out_channels=1, num_res_blocks=1, num_channels=(16, 32),
+                           attention_levels=(False, False), latent_channels=3, norm_num_groups=8,
+                           with_encoder_nonlocal_attn=False, with_decoder_nonlocal_attn=False,
+                           downsample_parameters=[[[1, 1, 1], [3, 3, 3], [1, 1, 1]], [[2, 2, 2], [3, 3, 3], [1, 1, 1]]],
+                           upsample_parameters=[[[2, 2, 2], [3, 3, 3], [1, 1, 1]]]).cuda()
+    for step, batch in enumerate(train):
+        img = batch["image"]
+        assert img.shape == (2, 1, 16, 32, 32) and img.is_cuda and len(batch["id"]) == 2
+        assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+        recon, mu, sigma = ae(img)
+        assert recon.shape == img.shape and torch.isfinite(recon.float()).all()
+        if step == 3:
+            break
+    vb = next(iter(val))
+    assert vb["image"].shape == (2, 1, 16, 32, 32)

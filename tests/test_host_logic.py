@@ -282,3 +282,86 @@ def test_compat_install_rebinds_trainer_imports():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_compat_registers_resident_data_module_when_reference_pipeline_is_not_importable(tmp_path, monkeypatch):
+    """`from medimgen.data_processing import get_data_loaders` (train_ldm.py:34) resolves to the resident loaders when the
+    reference's module cannot be imported (zarr / blosc2 / batchgenerators missing, as in this image)."""
+    import sys
+    import medical_image_generation_b200.compat as compat
+    from medical_image_generation_b200 import data
+    pkgdir = tmp_path / "medimgen"
+    pkgdir.mkdir()
+    (pkgdir / "__init__.py").write_text("")
+    (pkgdir / "data_processing.py").write_text("import zarr_is_not_installed_here\n")
+    monkeypatch.syspath_prepend(str(tmp_path))
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("medimgen", "generative")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        patched = compat.install()
+        assert any("data_processing" in p for p in patched), patched
+        from medimgen.data_processing import get_data_loaders, MedicalDataset
+        assert get_data_loaders is data.get_data_loaders and MedicalDataset is data.MedicalDataset
+    finally:
+        compat.uninstall()
+        for k in [k for k in sys.modules if k.split(".")[0] in ("medimgen", "generative")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    assert "medimgen.data_processing" not in sys.modules or "medimgen.data_processing" in saved
+
+
+def test_perceptual_loss_lpips_vgg_fake_3d(tmp_path, monkeypatch):
+    """generative.losses.PerceptualLoss as configuration.py:961-964 configures it (row f3): LPIPS-VGG, fake-3D slice
+    sampling, weights from a local file only."""
+    import sys
+    shims = os.path.join(os.path.dirname(mig.__file__), "shims")
+    monkeypatch.syspath_prepend(shims)
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] == "generative"}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        from generative.losses import PerceptualLoss
+        monkeypatch.delenv("MEDIMGEN_LPIPS_WEIGHTS", raising=False)
+        with pytest.raises(RuntimeError, match="local file"):
+            PerceptualLoss(spatial_dims=3, network_type="vgg", is_fake_3d=True, fake_3d_ratio=0.2)
+        with pytest.raises(NotImplementedError):
+            PerceptualLoss(spatial_dims=3, network_type="medicalnet_resnet10_23datasets", is_fake_3d=False, pretrained=False)
+        torch.manual_seed(0)
+        pl = PerceptualLoss(spatial_dims=3, network_type="vgg", is_fake_3d=True, fake_3d_ratio=0.25, pretrained=False)
+        assert all(not p.requires_grad for p in pl.parameters()) and not pl.perceptual_function.training
+        pl.train()
+        assert not pl.perceptual_function.training          # frozen metric network
+        a = torch.rand(2, 1, 16, 16, 16, requires_grad=True)
+        b = torch.rand(2, 1, 16, 16, 16)
+        seen = []
+        orig = pl.perceptual_function.forward
+        pl.perceptual_function.forward = lambda x, y, **k: (seen.append(tuple(x.shape)), orig(x, y, **k))[1]
+        loss = pl(a, b)
+        assert seen == [(8, 1, 16, 16)] * 3                  # int(2 * 16 * 0.25) slices along each of the three axes
+        assert loss.ndim == 0 and float(loss) > 0
+        loss.backward()
+        assert float(a.grad.abs().sum()) > 0
+        assert float(pl(b, b)) == 0.0
+        with pytest.raises(ValueError):
+            pl(a, b[:, :, :8])
+        # symmetric in its arguments (same slice draw)
+        torch.manual_seed(3); l1 = float(pl(a.detach(), b))
+        torch.manual_seed(3); l2 = float(pl(b, a.detach()))
+        assert abs(l1 - l2) < 1e-6
+        # weights from a file: the lpips package's key layout, lin layers stored twice
+        sd = dict(pl.perceptual_function.state_dict())
+        assert "net.slice1.0.weight" in sd and "net.slice5.28.bias" in sd and "lin4.model.1.weight" in sd
+        sd.update({f"lins.{k}.model.1.weight": sd[f"lin{k}.model.1.weight"] for k in range(5)})
+        path = tmp_path / "lpips_vgg.pt"
+        torch.save(sd, path)
+        monkeypatch.setenv("MEDIMGEN_LPIPS_WEIGHTS", str(path))
+        pl2 = PerceptualLoss(spatial_dims=3, network_type="vgg", is_fake_3d=True, fake_3d_ratio=0.25)
+        torch.manual_seed(3)
+        assert abs(float(pl2(a.detach(), b)) - l1) < 1e-7
+        p2d = PerceptualLoss(spatial_dims=2, network_type="vgg", pretrained=False)
+        assert float(p2d(torch.rand(2, 1, 32, 32), torch.rand(2, 1, 32, 32))) > 0
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] == "generative"]:
+            del sys.modules[k]
+        sys.modules.update(saved)

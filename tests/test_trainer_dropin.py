@@ -153,7 +153,7 @@ def test_unmodified_train_ldm_runs_on_b200_modules(trainer_env, tmp_path):
 # ---- train_autoencoder.AutoEncoder (SURVEY.md 8f-1 second trainer, 8f-3 adversarial loss) --------------------------------
 def test_unmodified_autoencoder_trainer_imports_and_binds_b200_classes(trainer_env):
     """CPU: `from medimgen.train_autoencoder import AutoEncoder` works; AutoencoderKL is the B200 class; the adversarial
-    pieces it imports from `generative` are real (shipped restatements), the perceptual loss is a loud placeholder."""
+    pieces it imports from `generative` are real (shipped restatements), the perceptual loss is the shipped LPIPS-VGG restatement and needs a local weight file."""
     import medical_image_generation_b200 as mig
     ta = __import__("medimgen.train_autoencoder", fromlist=["AutoEncoder"])
     assert ta.__file__.endswith(os.path.join("medimgen", "train_autoencoder.py"))
@@ -172,8 +172,10 @@ def test_unmodified_autoencoder_trainer_imports_and_binds_b200_classes(trainer_e
     with pytest.warns(UserWarning):
         g = adv(logits, target_is_real=False, for_discriminator=False)     # a generator target is always "real"
     assert abs(float(g) - (1.0 + 1.21) / 2) < 1e-6
-    with pytest.raises(NotImplementedError):
+    os.environ.pop("MEDIMGEN_LPIPS_WEIGHTS", None)
+    with pytest.raises(RuntimeError, match="local file"):      # published LPIPS weights cannot be downloaded here
         ta.PerceptualLoss(spatial_dims=3, network_type="vgg")
+    assert ta.PerceptualLoss(spatial_dims=3, network_type="vgg", is_fake_3d=True, fake_3d_ratio=0.2, pretrained=False)
 
 
 def _ae_config(tmp_path):
@@ -195,8 +197,9 @@ def test_unmodified_train_autoencoder_runs_on_b200_modules(trainer_env, tmp_path
     """AutoEncoder.train_one_epoch through the reference's own code (train_autoencoder.py:331-436): generator step (B200
     AutoencoderKL forward, L1 + KL + perceptual + -- after the warm-up epochs -- adversarial loss), discriminator step,
     the per-step requires_grad toggling (:374-377,401-404), fp16 autocast + two GradScalers, accumulation, clipping, Adam;
-    then validate_one_epoch and save_model / load_model. The perceptual network needs downloaded weights, so the test
-    passes a weight-free stand-in callable (train_one_epoch takes it as an argument)."""
+    then validate_one_epoch and save_model / load_model. The perceptual loss is the shipped LPIPS-VGG
+    `PerceptualLoss` with fake-3D slice sampling as configuration.py:964 configures it, randomly initialised (its published
+    weights cannot be downloaded here)."""
     from torch.cuda.amp import GradScaler
     ta = __import__("medimgen.train_autoencoder", fromlist=["AutoEncoder"])
     torch.manual_seed(0)
@@ -206,8 +209,10 @@ def test_unmodified_train_autoencoder_runs_on_b200_modules(trainer_env, tmp_path
     opt_g, opt_d, sched_g, sched_d = ae.get_optimizers_and_lr_schedules(disc)
     assert isinstance(opt_g, torch.optim.Adam) and sched_g is None and sched_d is None
 
-    def perceptual(a, b):   # stand-in for LPIPS / MedicalNet features: gradient-carrying, weight-free
-        return torch.nn.functional.avg_pool3d(a - b, 4).abs().mean()
+    # the reference builds PerceptualLoss(**config['perceptual_params']) (train_autoencoder.py:601) with downloaded LPIPS
+    # weights; there is no network here, so the same class is built with pretrained=False (random VGG-16 trunk)
+    perceptual = ta.PerceptualLoss(spatial_dims=3, network_type="vgg", is_fake_3d=True, fake_3d_ratio=0.2,
+                                   pretrained=False).to(ae.device)
 
     gen = torch.Generator().manual_seed(3)
     base = torch.rand(2, 1, 16, 16, 16, generator=gen)
