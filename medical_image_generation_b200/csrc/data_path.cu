@@ -93,14 +93,29 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(const float* __restri
           const float wz = fz - z0f, wy = fy - y0f, wx = fxx - x0f;
           const int z0 = (int)z0f, y0 = (int)y0f, x0 = (int)x0f;
           float acc = 0.f;
+          const int sz = d.lb[0] + z0, sy = d.lb[1] + y0, sx = d.lb[2] + x0;
+          // interior voxels (all eight corners inside the crop AND inside the case -- nearly all of them): eight loads off
+          // one base address, no per-corner bounds work (the checked loop below cost ~150 instructions per voxel)
+          if (z0 >= 0 && z0 + 1 < p.PZ && y0 >= 0 && y0 + 1 < p.PY && x0 >= 0 && x0 + 1 < p.PX &&
+              sz >= 0 && sz + 1 < Z && sy >= 0 && sy + 1 < Y && sx >= 0 && sx + 1 < X) {
+            const float* q0 = src + ((int64_t)sz * Y + sy) * X + sx;
+            const float* q1 = q0 + (int64_t)Y * X;
+            const float a00 = fmaf(wx, __ldg(q0 + 1) - __ldg(q0), __ldg(q0));
+            const float a01 = fmaf(wx, __ldg(q0 + X + 1) - __ldg(q0 + X), __ldg(q0 + X));
+            const float a10 = fmaf(wx, __ldg(q1 + 1) - __ldg(q1), __ldg(q1));
+            const float a11 = fmaf(wx, __ldg(q1 + X + 1) - __ldg(q1 + X), __ldg(q1 + X));
+            const float b0 = fmaf(wy, a01 - a00, a00), b1 = fmaf(wy, a11 - a10, a10);
+            acc = fmaf(wz, b1 - b0, b0);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int dz = q >> 2, dy = (q >> 1) & 1, dx = q & 1;
-            const int pz = z0 + dz, py = y0 + dy, px = x0 + dx;   // position inside the cropped patch
-            const float w = (dz ? wz : 1.f - wz) * (dy ? wy : 1.f - wy) * (dx ? wx : 1.f - wx);
-            // outside the crop: zeros padding of the resample; inside the crop but outside the case: the crop's pad value
-            if ((unsigned)pz < (unsigned)p.PZ && (unsigned)py < (unsigned)p.PY && (unsigned)px < (unsigned)p.PX)
-              acc = fmaf(w, fetch(src, Z, Y, X, d.lb[0] + pz, d.lb[1] + py, d.lb[2] + px, pad), acc);
+            for (int q = 0; q < 8; ++q) {
+              const int dz = q >> 2, dy = (q >> 1) & 1, dx = q & 1;
+              const int pz = z0 + dz, py = y0 + dy, px = x0 + dx;   // position inside the cropped patch
+              const float w = (dz ? wz : 1.f - wz) * (dy ? wy : 1.f - wy) * (dx ? wx : 1.f - wx);
+              // outside the crop: zeros padding of the resample; inside the crop, outside the case: the crop's pad value
+              if ((unsigned)pz < (unsigned)p.PZ && (unsigned)py < (unsigned)p.PY && (unsigned)px < (unsigned)p.PX)
+                acc = fmaf(w, fetch(src, Z, Y, X, d.lb[0] + pz, d.lb[1] + py, d.lb[2] + px, pad), acc);
+            }
           }
           v[k] = acc;
         }
