@@ -298,6 +298,27 @@ int mig_patch_intensity(const float* x, void* y, int out_dtype, const float* op,
                         const float* stats1, int32_t B, int32_t C, int64_t S, int channels_last, float lo, float hi,
                         void* stream);
 
+/* ---- K8: nearest upsample folded into the convolution that follows it (unet:576-584, ae:97-106) -----------------
+ * "nearest x f, then Conv k^n (stride 1, padding p)" only ever reads low-resolution voxels j + floor((r + t - p)/f) for
+ * an output voxel f*j + r: per output residue class r it IS a dense convolution of the low-resolution tensor with the
+ * taps that land on the same voxel summed (f = 2, k = 3, p = 1: 2 folded taps per axis instead of 3 -> 64/216 of the
+ * multiply-adds of a 2x isotropic upsample, and the f^n-times larger tensor never exists). The convolutions themselves
+ * are ordinary mig_conv_fwd / mig_conv_wgrad geometries on the low-resolution tensor (ksize = folded taps, pad = -base,
+ * out_dims = in_dims); these entry points are the glue. Filters bf16, k <= 4, f in {1, 2} per axis.
+ *   which = 0: folded[class r][Cout][u][Cin], classes concatenated in (r0, r1, r2) order -- forward / wgrad filters
+ *   which = 1: folded[Cin][s][Cout], s over (f + k - 1)^n -- the filter of the stride-f convolution over dy (kernel
+ *              f + k - 1, padding k - 1 - p) whose result is dx */
+int64_t mig_upconv_folded_elems(int32_t Cout, int32_t Cin, const int32_t ksize[3], const int32_t factor[3],
+                                const int32_t pad[3], int which);
+int mig_upconv_fold_filter(const void* w, void* folded, int32_t Cout, int32_t Cin, const int32_t ksize[3],
+                           const int32_t factor[3], const int32_t pad[3], int which, void* stream);
+/* dw[Cout][t][Cin] += sum over classes of dwc_r[Cout][u_r(t)][Cin]  (fp32; dwc laid out like which = 0 above) */
+int mig_upconv_unfold_wgrad(const float* dwc, float* dw, int32_t Cout, int32_t Cin, const int32_t ksize[3],
+                            const int32_t factor[3], const int32_t pad[3], void* stream);
+/* classes[r][N][low...][C] <-> full[N][f*low...][C] (to_classes = 1: full -> classes, the split of dy for the wgrads) */
+int mig_class_interleave(int dtype, const void* src, void* dst, int32_t N, const int32_t low[3], const int32_t factor[3],
+                         int32_t C, int to_classes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,9 +98,14 @@ _SIGNATURES = {
     "mig_patch_stats": [_p, _p, _p, _i, _l, _p, _l, _p],
     "mig_patch_stats_workspace_bytes": [_i],
     "mig_patch_intensity": [_p, _p, _i, _p, _p, _p, _i, _i, _l, _i, _f, _f, _p],
+    "mig_upconv_folded_elems": [_i, _i, _I3, _I3, _I3, _i],
+    "mig_upconv_fold_filter": [_p, _p, _i, _i, _I3, _I3, _I3, _i, _p],
+    "mig_upconv_unfold_wgrad": [_p, _p, _i, _i, _I3, _I3, _I3, _p],
+    "mig_class_interleave": [_i, _p, _p, _i, _I3, _I3, _i, _i, _p],
 }
 _RESTYPES = {"mig_last_error": C.c_char_p, "mig_conv_workspace_bytes": C.c_int64,
-             "mig_groupnorm_workspace_bytes": C.c_int64, "mig_patch_stats_workspace_bytes": C.c_int64}
+             "mig_groupnorm_workspace_bytes": C.c_int64, "mig_patch_stats_workspace_bytes": C.c_int64,
+             "mig_upconv_folded_elems": C.c_int64}
 
 _lib = None
 

@@ -39,8 +39,8 @@ class Upsample(nn.Module):
     def forward(self, x):
         if self.use_convtranspose:
             return self.conv(_entry(x))
-        x = ops.upsample_nearest(_entry(x), _tup(self.stride, x.ndim - 2))
-        return self.conv(x)
+        c = self.conv.conv
+        return ops.upsample_conv_nd(_entry(x), c.weight, c.bias, _tup(self.stride, x.ndim - 2), c.padding)
 
 
 class Downsample(nn.Module):

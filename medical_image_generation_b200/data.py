@@ -28,7 +28,7 @@ import json
 import math
 import os
 import pickle
-from typing import Optional, Sequence
+from typing import Optional
 
 import numpy as np
 import torch
@@ -133,7 +133,7 @@ def load_case(data_path: str, name: str):
 
 # -------------------------------------------------------------------------------------------------- resident volumes
 class ResidentVolumes:
-    """All cases of a split as ONE fp32 device buffer (a 160x160x128 case is 13 MB; thousands fit 180 GB of HBM3e)."""
+    """All cases of a split as ONE fp32 device buffer (a 160x160x128 channel is 13 MB; thousands of cases fit 180 GB of HBM3e)."""
 
     def __init__(self, device="cuda"):
         self.device = torch.device(device)
@@ -200,11 +200,24 @@ class _Scratch:
         return dev
 
 
+def _on_one_device(what: str, *tensors) -> torch.device:
+    dev = tensors[0].device
+    for t in tensors:
+        if t is not None and (not t.is_cuda or t.device != dev):
+            raise RuntimeError(f"{what}: every tensor must live on the same CUDA device (got {t.device} and {dev}); "
+                               "this package has no CPU path")
+    return dev
+
+
 def patch_gather(volumes: torch.Tensor, descs_dev: torch.Tensor, out: torch.Tensor, B: int, C_: int, patch, *,
                  channels_last: bool = False, any_affine: bool = False, pad_value: float = 0.0, clamp=NO_CLAMP):
-    _lib.call("mig_patch_gather", _ptr(volumes), _ptr(descs_dev), _ptr(out), _dtype_code(out.dtype), B, C_,
-              _I3(*[int(v) for v in patch]), int(channels_last), int(any_affine), float(pad_value), float(clamp[0]),
-              float(clamp[1]), _stream())
+    """`mig_patch_gather`: B patches of C_ channels cut out of `volumes` as `descs_dev` (B packed `mig_patch_desc`) says."""
+    if volumes.dtype != torch.float32:
+        raise RuntimeError("patch_gather: the resident cases are float32")
+    with torch.cuda.device(_on_one_device("patch_gather", volumes, descs_dev, out)):
+        _lib.call("mig_patch_gather", _ptr(volumes), _ptr(descs_dev), _ptr(out), _dtype_code(out.dtype), B, C_,
+                  _I3(*[int(v) for v in patch]), int(channels_last), int(any_affine), float(pad_value), float(clamp[0]),
+                  float(clamp[1]), _stream())
     return out
 
 
@@ -218,15 +231,20 @@ def patch_stats(x: torch.Tensor, rows: int, S: int, active: Optional[torch.Tenso
         out = torch.zeros(rows, 4, dtype=torch.float32, device=x.device)
     ws_bytes = int(lib.mig_patch_stats_workspace_bytes(rows))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    _lib.call("mig_patch_stats", _ptr(x), _ptr(out), None if active is None else _ptr(active), rows, S, _ptr(ws),
-              ws_bytes, _stream())
+    with torch.cuda.device(_on_one_device("patch_stats", x, out, active)):
+        _lib.call("mig_patch_stats", _ptr(x), _ptr(out), None if active is None else _ptr(active), rows, S, _ptr(ws),
+                  ws_bytes, _stream())
     return out
 
 
 def patch_intensity(x: torch.Tensor, y: torch.Tensor, op: torch.Tensor, stats0: torch.Tensor, stats1: torch.Tensor,
                     B: int, C_: int, S: int, *, channels_last: bool = False, clamp=NO_CLAMP):
-    _lib.call("mig_patch_intensity", _ptr(x), _ptr(y), _dtype_code(y.dtype), _ptr(op), _ptr(stats0), _ptr(stats1), B, C_,
-              S, int(channels_last), float(clamp[0]), float(clamp[1]), _stream())
+    """`mig_patch_intensity`: per-row contrast / gamma / re-standardisation (op = rows x {mode, param, invert, 0})."""
+    if x.dtype != torch.float32:
+        raise RuntimeError("patch_intensity: the staged batch is float32")
+    with torch.cuda.device(_on_one_device("patch_intensity", x, y, op, stats0, stats1)):
+        _lib.call("mig_patch_intensity", _ptr(x), _ptr(y), _dtype_code(y.dtype), _ptr(op), _ptr(stats0), _ptr(stats1), B,
+                  C_, S, int(channels_last), float(clamp[0]), float(clamp[1]), _stream())
     return y
 
 

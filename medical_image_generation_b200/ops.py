@@ -12,6 +12,8 @@ ae:N = medimgen/autoencoderkl_with_strides.py:N).
 from __future__ import annotations
 
 import ctypes as C
+import math
+import os
 from typing import Optional, Sequence
 
 import torch
@@ -1022,6 +1024,170 @@ def upsample_nearest(x, factors):
 # ----------------------------------------------------------------------------------------------
 # attention core: softmax(scale * Q K^T) V with heads inside the channel dim (unet:406-416)
 # ----------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------
+# nearest upsample folded into the convolution that follows it (K8; unet:576-584, ae:97-106)
+# ----------------------------------------------------------------------------------------------
+_UPCONV = os.environ.get("MIG_UPCONV", "auto")    # auto | always | never (A/B switch and tests)
+
+
+def set_upconv(mode: str) -> None:
+    """'auto' (fold where the cost model says it pays), 'always' (wherever the kernels can), 'never'."""
+    global _UPCONV
+    if mode not in ("auto", "always", "never"):
+        raise ValueError("set_upconv: mode must be 'auto', 'always' or 'never'")
+    _UPCONV = mode
+
+
+def _axis_fold(k: int, f: int, p: int):
+    """Per output residue class r of one axis: (base, folded tap count). An output o = f*j + r reads low-resolution voxels
+    j + floor((r + t - p) / f), t = 0..k-1: `base` is the smallest offset, the count how many distinct ones there are."""
+    out = []
+    for r in range(f):
+        d = [(r + t - p) // f for t in range(k)]
+        out.append((min(d), max(d) - min(d) + 1))
+    return out
+
+
+def upconv_usable(x, weight, factors, padding) -> bool:
+    """Can (and should) `upsample_nearest(x, factors)` + `conv_nd(weight, stride 1, padding)` run folded?"""
+    if _UPCONV == "never" or x.dtype != torch.bfloat16 or _ENGINE == _lib.ENGINE_SIMT or not x.is_cuda:
+        return False
+    nd = x.ndim - 2
+    k, f, p = tuple(weight.shape[2:]), tuple(int(v) for v in factors), tuple(int(v) for v in padding)
+    if all(v == 1 for v in f) or any(v not in (1, 2) for v in f):
+        return False
+    if any(ki != 2 * pi + 1 or ki > 3 for ki, pi in zip(k, p)):     # "same" convolutions only: output = f * input
+        return False
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    if Cin % 64 != 0 or Cout % 64 != 0:      # every piece on the TMA box kernels (wgrad panels: multiples of 64)
+        return False
+    if not _lib.load().mig_has_tcgen05():
+        return False
+    if _UPCONV == "always":
+        return True
+    # cost model: the per-class convolutions run one after the other, each over 1/f^n of the output voxels; on a small
+    # level a class no longer fills the 148 SMs with 256 x 256 tiles and the fold loses to one big launch
+    rows = x.shape[0] * math.prod(x.shape[2:])
+    tiles = -(-rows // 256) * -(-Cout // 256)
+    return tiles >= 96
+
+
+class _UpConvFn(Function):
+    """y = conv(nearest_upsample(x, f), w, b, stride 1, padding p) without the upsampled tensor (csrc/upconv.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, factors, padding):
+        N, Cin = x.shape[0], x.shape[1]
+        nd = x.ndim - 2
+        Cout = weight.shape[0]
+        if weight.shape[1] != Cin:
+            raise RuntimeError(f"conv: input has {Cin} channels but the filter expects {weight.shape[1]}")
+        low3 = _sp3(x.shape[2:])
+        k3 = _sp3(weight.shape[2:])
+        f3 = (1,) * (3 - nd) + tuple(factors)
+        p3 = (0,) * (3 - nd) + tuple(padding)
+        I3 = C.c_int32 * 3
+        kk, ff, pp = I3(*k3), I3(*f3), I3(*p3)
+        lib = _lib.load()
+        wk = _filter_for(weight, x.dtype)
+        folded = torch.empty(int(lib.mig_upconv_folded_elems(Cout, Cin, kk, ff, pp, 0)), dtype=x.dtype, device=x.device)
+        call("mig_upconv_fold_filter", _ptr(wk), _ptr(folded), Cout, Cin, kk, ff, pp, 0, _stream())
+        folds = [_axis_fold(k3[i], f3[i], p3[i]) for i in range(3)]
+        classes = [(r0, r1, r2) for r0 in range(f3[0]) for r1 in range(f3[1]) for r2 in range(f3[2])]
+        per_class = N * low3[0] * low3[1] * low3[2] * Cout
+        yc = torch.empty(len(classes) * per_class, dtype=x.dtype, device=x.device)
+        dt = _dt(x)
+        geoms, off = [], 0
+        for ci, r in enumerate(classes):
+            base = [folds[i][r[i]][0] for i in range(3)]
+            nu = [folds[i][r[i]][1] for i in range(3)]
+            geom = _lib.conv_geom(N, low3, low3, Cin, Cout, nu, (1, 1, 1), [-b for b in base])
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+            ws = _workspace(need, x.device)
+            _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), C.c_void_p(folded.data_ptr() + 2 * off),
+                       _ptr(bias), None, None, C.c_void_p(yc.data_ptr() + 2 * ci * per_class), _ENGINE, _ptr(ws),
+                       ws.numel(), _stream())
+            geoms.append((geom, off))
+            off += nu[0] * nu[1] * nu[2] * Cout * Cin
+        out_sp = tuple(low3[i] * f3[i] for i in range(3))[3 - nd:]
+        y = empty_cl((N, Cout, *out_sp), x.dtype, x.device)
+        call("mig_class_interleave", dt, _ptr(yc), _ptr(y), N, I3(*low3), ff, Cout, 0, _stream())
+        ctx.cfg = (low3, k3, f3, p3, geoms, per_class, off)
+        ctx.bias_ref, ctx.weight_ref = bias, weight
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, _ = ctx.saved_tensors
+        weight, bias = ctx.weight_ref, ctx.bias_ref
+        low3, k3, f3, p3, geoms, per_class, folded_elems = ctx.cfg
+        N, Cin, Cout = x.shape[0], x.shape[1], weight.shape[0]
+        I3 = C.c_int32 * 3
+        kk, ff, pp = I3(*k3), I3(*f3), I3(*p3)
+        lib = _lib.load()
+        dy = as_cl(dy)
+        if dy.dtype != x.dtype:
+            dy = dy.to(x.dtype)
+        dt = _dt(x)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx = a stride-f convolution of dy with the (f + k - 1)^n-tap folded filter [Cin][s][Cout]
+            wk = _filter_for(weight, x.dtype)
+            wd = torch.empty(int(lib.mig_upconv_folded_elems(Cout, Cin, kk, ff, pp, 1)), dtype=x.dtype, device=x.device)
+            call("mig_upconv_fold_filter", _ptr(wk), _ptr(wd), Cout, Cin, kk, ff, pp, 1, _stream())
+            full3 = tuple(low3[i] * f3[i] for i in range(3))
+            geom = _lib.conv_geom(N, full3, low3, Cout, Cin, [f3[i] + k3[i] - 1 for i in range(3)], f3,
+                                  [k3[i] - 1 - p3[i] for i in range(3)])
+            dx = torch.empty_like(x)
+            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+            ws = _workspace(need, x.device)
+            _conv_call("dgrad", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(dy), _ptr(wd), None, None, None, _ptr(dx),
+                       _ENGINE, _ptr(ws), ws.numel(), _stream())
+        want_w, want_b = ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]
+        if want_w or want_b:
+            w_main = getattr(weight, "main_grad", None) if want_w else None
+            b_main = getattr(bias, "main_grad", None) if want_b else None
+            dw_buf = db_buf = None
+            if want_w:
+                dw_buf = w_main if w_main is not None else empty_cl(weight.shape, torch.float32, x.device).zero_()
+            if want_b:
+                db_buf = b_main if b_main is not None else torch.zeros(Cout, dtype=torch.float32, device=x.device)
+            # dy split into its residue classes (contiguous low-resolution tensors), one wgrad per class into the folded
+            # layout, then unfolded onto the k^n taps; the bias gradient rides on the class wgrads
+            dyc = torch.empty(len(geoms) * per_class, dtype=x.dtype, device=x.device)
+            call("mig_class_interleave", dt, _ptr(dy), _ptr(dyc), N, I3(*low3), ff, Cout, 1, _stream())
+            dwc = torch.zeros(folded_elems, dtype=torch.float32, device=x.device) if want_w else None
+            for ci, (geom, off) in enumerate(geoms):
+                need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 2, _ENGINE)
+                ws = _workspace(need, x.device)
+                _conv_call("wgrad", geom, "mig_conv_wgrad", C.byref(geom), dt, _ptr(x),
+                           C.c_void_p(dyc.data_ptr() + 2 * ci * per_class),
+                           C.c_void_p(dwc.data_ptr() + 4 * off) if want_w else None, _ptr(db_buf), _ENGINE, _ptr(ws),
+                           ws.numel(), _stream())
+            if want_w:
+                call("mig_upconv_unfold_wgrad", _ptr(dwc), _ptr(dw_buf), Cout, Cin, kk, ff, pp, _stream())
+                dw = _deliver(weight, None) if w_main is not None else dw_buf
+            if want_b:
+                db = _deliver(bias, None) if b_main is not None else db_buf
+        return dx, dw, db, None, None
+
+
+def upsample_conv_nd(x, weight, bias, factors, padding):
+    """conv_nd(upsample_nearest(x, factors), weight, bias, stride 1, padding): folded into per-class convolutions of the
+    low-resolution tensor where `upconv_usable` says so, the two separate operators otherwise."""
+    _require_cuda(x, "upsample_conv_nd")
+    nd = x.ndim - 2
+    f = tuple(factors) if isinstance(factors, (list, tuple)) else (factors,) * nd
+    p = tuple(padding) if isinstance(padding, (list, tuple)) else (padding,) * nd
+    fi = tuple(int(v) for v in f)
+    if any(float(a) != float(b) for a, b in zip(f, fi)) or min(fi) < 1 or not upconv_usable(x, weight, fi, p):
+        return conv_nd(upsample_nearest(x, f), weight, bias, 1, p)
+    if not _is_cl(x):
+        x = to_channels_last(x, x.dtype)
+    return _UpConvFn.apply(x, weight, bias, fi, tuple(int(v) for v in p))
+
+
 def _gemm(A, B, Cm, M, N, K, bo, bi, a, b, c, alpha=1.0, accumulate=False):
     d = _lib.GemmDesc()
     d.M, d.N, d.K, d.batch_outer, d.batch_inner = M, N, K, bo, bi

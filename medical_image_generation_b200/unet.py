@@ -165,8 +165,11 @@ class Upsample(nn.Module):
         del emb
         if x.shape[1] != self.num_channels:
             raise ValueError("Input channels should be equal to num_channels")
-        x = ops.upsample_nearest(_entry(x), _tup(self.stride, x.ndim - 2))
-        return self.conv(x) if self.use_conv else x
+        if not self.use_conv:
+            return ops.upsample_nearest(_entry(x), _tup(self.stride, x.ndim - 2))
+        # nearest upsample + conv in one operator: folded into convolutions of the low-resolution tensor where that pays
+        c = self.conv.conv
+        return ops.upsample_conv_nd(_entry(x), c.weight, c.bias, _tup(self.stride, x.ndim - 2), c.padding)
 
 
 class ResnetBlock(nn.Module):

@@ -553,3 +553,34 @@ def test_ae_trainer_and_sampling_sharder(golden):
     # same seeds -> same volumes (up to the rounding of atomic reduction order inside GroupNorm)
     assert sorted(a) == [0, 1, 2] and all(rel_err(a[k], b[k]) < 1e-4 for k in a)
     assert not torch.equal(a[0], a[1]) and all(torch.isfinite(v).all() for v in a.values())
+
+
+def test_ldm_width_unet_with_folded_upsample_convs_matches_reference_golden(golden):
+    """BASELINE config 3 at full width with BOTH Upsample convolutions folded (ops.set_upconv('always'); in 'auto' mode
+    the 8^3 golden is too small for the fold to pay): same bf16 bar as the unfolded model."""
+    from medical_image_generation_b200 import ops, _lib
+    from oracle.golden_util import sketch
+    g = golden("unet3d_ldm_width")
+    m, _ = _build(g, torch.bfloat16)
+    inp = g["inputs"]
+    x = inp["x"].to(DEV).requires_grad_(True)
+    ops.set_upconv("always")
+    try:
+        before = _lib.launch_count
+        y = m(x, inp["timesteps"].to(DEV))
+        (y * inp["probe"].to(DEV)).sum().backward()
+        launches = _lib.launch_count - before
+    finally:
+        ops.set_upconv("auto")
+    assert rel_err(y, g["out"]) < BF16_TOL
+    assert rel_err(x.grad, g["grad_x"]) < 2.5 * BF16_TOL
+    named = dict(m.named_parameters())
+    for k in ("up_blocks.0.upsampler.conv.conv.weight", "up_blocks.1.upsampler.conv.conv.weight",
+              "up_blocks.0.upsampler.conv.conv.bias", "up_blocks.1.upsampler.conv.conv.bias"):
+        assert rel_err(sketch(named[k].grad), g["grad_sketch"][k], floor=0.1) < 8e-2, k
+    # and the fold really ran: the unfolded model needs fewer ABI calls (2 x (8 class convs + 8 class wgrads + glue))
+    before = _lib.launch_count
+    m.zero_grad(set_to_none=True)
+    y2 = m(x, inp["timesteps"].to(DEV))
+    (y2 * inp["probe"].to(DEV)).sum().backward()
+    assert launches > (_lib.launch_count - before) + 20

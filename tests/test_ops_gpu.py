@@ -825,3 +825,152 @@ def test_flash_attention_growing_logits(C, heads):
     with torch.no_grad():
         got = ops.sdpa(qd, kd, vd, heads, scale)
     assert torch.isfinite(got).all() and rel_err(got, want) < BF16_TOL
+
+
+# ---- nearest upsample folded into the convolution (ops.upsample_conv_nd, csrc/upconv.cu; unet:576-584, ae:97-106) ----
+def _upconv_ref(x, w, b, f, p):
+    xu = x
+    for i, fi in enumerate(f):
+        xu = xu.repeat_interleave(fi, dim=2 + i)          # F.interpolate(mode="nearest") for integer factors
+    conv = F.conv3d if x.ndim == 5 else F.conv2d
+    return conv(xu, w, b, stride=1, padding=p)
+
+
+# (N, Cin, Cout, low-resolution spatial, factors)
+UPCONV_CASES = [
+    (2, 64, 64, (4, 6, 8), (2, 2, 2)),
+    (1, 128, 64, (5, 7, 3), (2, 2, 1)),       # anisotropic level (config 4 strides [2, 2, 1]), odd sizes
+    (2, 64, 128, (8, 8), (2, 2)),             # 2-D
+    (1, 64, 64, (3, 4, 16), (1, 2, 2)),
+    (2, 512, 512, (6, 6, 6), (2, 2, 2)),      # LDM width
+]
+
+
+@pytest.mark.parametrize("case", UPCONV_CASES)
+def test_upsample_conv_folded_matches_reference_and_unfolded(case):
+    """Folded path vs (a) torch's interpolate + conv on the same bf16-rounded operands, (b) the two separate operators."""
+    ops = _ops()
+    N, Cin, Cout, low, f = case
+    nd = len(low)
+    k, p = (3,) * nd, (1,) * nd
+    g = torch.Generator().manual_seed(sum(low) + Cin)
+    x = bf16_round(torch.randn((N, Cin, *low), generator=g))
+    w = bf16_round(torch.randn((Cout, Cin, *k), generator=g) / math.sqrt(Cin * math.prod(k)))
+    b = torch.randn(Cout, generator=g) * 0.1
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y_ref = _upconv_ref(xr, wr, br, f, p)
+    probe = torch.randn(y_ref.shape, generator=g)
+    (y_ref * probe).sum().backward()
+    got = {}
+    for mode in ("always", "never"):
+        ops.set_upconv(mode)
+        try:
+            xd = _cl(x.to(DEV).to(torch.bfloat16)).requires_grad_(True)
+            wd = _cl(w.to(DEV)).requires_grad_(True)
+            bd = b.to(DEV).requires_grad_(True)
+            assert ops.upconv_usable(xd, wd, f, p) == (mode == "always")
+            y = ops.upsample_conv_nd(xd, wd, bd, f, p)
+            assert y.shape == y_ref.shape and y.dtype == torch.bfloat16
+            (y.float() * probe.to(DEV)).sum().backward()
+            got[mode] = (y, xd.grad, wd.grad, bd.grad)
+        finally:
+            ops.set_upconv("auto")
+        assert rel_err(y, y_ref) < BF16_TOL, mode
+        assert rel_err(xd.grad, xr.grad) < BF16_TOL, mode
+        assert rel_err(wd.grad, wr.grad) < BF16_TOL, mode
+        assert rel_err(bd.grad, br.grad) < BF16_TOL, mode
+        assert wd.grad.dtype == torch.float32
+    # the fold only changes where bf16 rounding happens (summed taps are rounded once more): close to the unfolded path
+    for a, c in zip(got["always"], got["never"]):
+        assert rel_err(a, c) < BF16_TOL
+
+
+def test_upconv_fold_tables_match_a_torch_restatement():
+    """mig_upconv_fold_filter / _unfold_wgrad / mig_class_interleave against index arithmetic written out in torch."""
+    import ctypes as C
+    import itertools
+    from medical_image_generation_b200 import _lib
+    ops = _ops()
+    I3 = C.c_int32 * 3
+    lib = _lib.load()
+    for k3, f3, p3 in [((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 1), (1, 1, 1)), ((1, 3, 3), (1, 2, 2), (0, 1, 1)),
+                       ((3, 3, 3), (1, 2, 1), (1, 1, 1))]:
+        Cout, Cin = 40, 24
+        g = torch.Generator().manual_seed(sum(f3))
+        w = bf16_round(torch.randn(Cout, math.prod(k3), Cin, generator=g))
+        wd = w.to(DEV).to(torch.bfloat16)
+        folds = [ops._axis_fold(k3[i], f3[i], p3[i]) for i in range(3)]
+        # forward fold
+        n0 = int(lib.mig_upconv_folded_elems(Cout, Cin, I3(*k3), I3(*f3), I3(*p3), 0))
+        out = torch.empty(n0, dtype=torch.bfloat16, device=DEV)
+        _lib.call("mig_upconv_fold_filter", ops._ptr(wd), ops._ptr(out), Cout, Cin, I3(*k3), I3(*f3), I3(*p3), 0, ops._stream())
+        want, dwc_parts, umaps = [], [], []
+        for r in itertools.product(*[range(v) for v in f3]):
+            base = [folds[i][r[i]][0] for i in range(3)]
+            nu = [folds[i][r[i]][1] for i in range(3)]
+            wc = torch.zeros(Cout, math.prod(nu), Cin)
+            umap = {}
+            for t in itertools.product(*[range(v) for v in k3]):
+                u = [(r[i] + t[i] - p3[i]) // f3[i] - base[i] for i in range(3)]
+                ui = (u[0] * nu[1] + u[1]) * nu[2] + u[2]
+                ti = (t[0] * k3[1] + t[1]) * k3[2] + t[2]
+                wc[:, ui] += w[:, ti]
+                umap[ti] = ui
+            want.append(wc.reshape(-1))
+            umaps.append((umap, math.prod(nu)))
+        want = torch.cat(want)
+        assert want.numel() == n0
+        assert torch.equal(out.float().cpu(), bf16_round(want))
+        # dgrad fold: [Cin][s][Cout]
+        K2 = [f3[i] + k3[i] - 1 for i in range(3)]
+        pad2 = [k3[i] - 1 - p3[i] for i in range(3)]
+        n1 = int(lib.mig_upconv_folded_elems(Cout, Cin, I3(*k3), I3(*f3), I3(*p3), 1))
+        assert n1 == Cin * math.prod(K2) * Cout
+        outd = torch.empty(n1, dtype=torch.bfloat16, device=DEV)
+        _lib.call("mig_upconv_fold_filter", ops._ptr(wd), ops._ptr(outd), Cout, Cin, I3(*k3), I3(*f3), I3(*p3), 1, ops._stream())
+        wantd = torch.zeros(Cin, math.prod(K2), Cout)
+        for s in itertools.product(*[range(v) for v in K2]):
+            si = (s[0] * K2[1] + s[1]) * K2[2] + s[2]
+            for t in itertools.product(*[range(v) for v in k3]):
+                if all(0 <= (s[i] - pad2[i]) + t[i] - p3[i] < f3[i] for i in range(3)):
+                    wantd[:, si] += w[:, (t[0] * k3[1] + t[1]) * k3[2] + t[2]].t()
+        assert torch.equal(outd.float().cpu().reshape(wantd.shape), bf16_round(wantd))
+        # wgrad unfold (accumulates)
+        dwc = torch.randn(n0, generator=g)
+        dw0 = torch.randn(Cout, math.prod(k3), Cin, generator=g)
+        dwd = dw0.clone().to(DEV)
+        _lib.call("mig_upconv_unfold_wgrad", ops._ptr(dwc.to(DEV)), ops._ptr(dwd), Cout, Cin, I3(*k3), I3(*f3), I3(*p3),
+                  ops._stream())
+        wantw, off = dw0.clone(), 0
+        for umap, U in umaps:
+            blk = dwc[off:off + Cout * U * Cin].reshape(Cout, U, Cin)
+            for ti, ui in umap.items():
+                wantw[:, ti] += blk[:, ui]
+            off += Cout * U * Cin
+        assert torch.allclose(dwd.cpu(), wantw, rtol=1e-6, atol=1e-6)
+        # interleave both ways
+        N, low, Cc = 2, (3, 2, 5), 24
+        full = torch.randn(N, low[0] * f3[0], low[1] * f3[1], low[2] * f3[2], Cc, generator=g).to(torch.bfloat16)
+        cls = torch.empty(full.numel(), dtype=torch.bfloat16, device=DEV)
+        _lib.call("mig_class_interleave", 1, ops._ptr(full.to(DEV)), ops._ptr(cls), N, I3(*low), I3(*f3), Cc, 1, ops._stream())
+        wantc = torch.cat([full[:, r[0]::f3[0], r[1]::f3[1], r[2]::f3[2]].reshape(-1)
+                           for r in itertools.product(*[range(v) for v in f3])])
+        assert torch.equal(cls.cpu(), wantc)
+        back = torch.empty_like(full, device=DEV)
+        _lib.call("mig_class_interleave", 1, ops._ptr(cls), ops._ptr(back), N, I3(*low), I3(*f3), Cc, 0, ops._stream())
+        assert torch.equal(back.cpu(), full)
+
+
+def test_upconv_cost_model_and_fallbacks():
+    ops = _ops()
+    w512 = _cl(torch.zeros(512, 512, 3, 3, 3, device=DEV))
+    x24 = _cl(torch.zeros(8, 512, 12, 12, 12, device=DEV, dtype=torch.bfloat16))
+    x12 = _cl(torch.zeros(8, 768, 6, 6, 6, device=DEV, dtype=torch.bfloat16))
+    w768 = _cl(torch.zeros(768, 768, 3, 3, 3, device=DEV))
+    assert ops.upconv_usable(x24, w512, (2, 2, 2), (1, 1, 1))            # the largest layer of the LDM U-Net: folded
+    assert not ops.upconv_usable(x12, w768, (2, 2, 2), (1, 1, 1))        # 6^3 level: one class does not fill the GPU
+    assert not ops.upconv_usable(x24.float(), w512, (2, 2, 2), (1, 1, 1))   # fp32 parity mode keeps the reference order
+    assert not ops.upconv_usable(x24, w512, (2, 2, 2), (1, 1, 0))        # the reference's level-padding defect (unet:557-565)
+    assert not ops.upconv_usable(x24, w512, (1, 1, 1), (1, 1, 1))
+    w48 = _cl(torch.zeros(48, 48, 3, 3, 3, device=DEV))
+    assert not ops.upconv_usable(_cl(torch.zeros(2, 48, 32, 32, 32, device=DEV, dtype=torch.bfloat16)), w48, (2, 2, 2), (1, 1, 1))
