@@ -312,6 +312,13 @@ int64_t mig_upconv_folded_elems(int32_t Cout, int32_t Cin, const int32_t ksize[3
                                 const int32_t pad[3], int which);
 int mig_upconv_fold_filter(const void* w, void* folded, int32_t Cout, int32_t Cin, const int32_t ksize[3],
                            const int32_t factor[3], const int32_t pad[3], int which, void* stream);
+/* The folded forward in one call, every class written straight into its positions of the full-resolution output
+ * y[N][f*low...][Cout] (no class buffers, no interleave pass): x bf16 [N][low...][Cin], folded = which-0 filters above.
+ * Needs mig_upconv_fwd_direct_ok (tcgen05 box kernel: Cin >= 48, channel counts multiples of 8, a TMA box for `low`). */
+int mig_upconv_fwd_direct_ok(int32_t N, const int32_t low[3], int32_t Cin, int32_t Cout);
+int mig_upconv_fwd(const void* x, const void* folded, const float* bias, void* y, int32_t N, const int32_t low[3],
+                   int32_t Cin, int32_t Cout, const int32_t ksize[3], const int32_t factor[3], const int32_t pad[3],
+                   void* stream);
 /* dw[Cout][t][Cin] += sum over classes of dwc_r[Cout][u_r(t)][Cin]  (fp32; dwc laid out like which = 0 above) */
 int mig_upconv_unfold_wgrad(const float* dwc, float* dw, int32_t Cout, int32_t Cin, const int32_t ksize[3],
                             const int32_t factor[3], const int32_t pad[3], void* stream);

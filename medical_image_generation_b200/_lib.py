@@ -100,6 +100,8 @@ _SIGNATURES = {
     "mig_patch_intensity": [_p, _p, _i, _p, _p, _p, _i, _i, _l, _i, _f, _f, _p],
     "mig_upconv_folded_elems": [_i, _i, _I3, _I3, _I3, _i],
     "mig_upconv_fold_filter": [_p, _p, _i, _i, _I3, _I3, _I3, _i, _p],
+    "mig_upconv_fwd_direct_ok": [_i, _I3, _i, _i],
+    "mig_upconv_fwd": [_p, _p, _p, _p, _i, _I3, _i, _i, _I3, _I3, _I3, _p],
     "mig_upconv_unfold_wgrad": [_p, _p, _i, _i, _I3, _I3, _I3, _p],
     "mig_class_interleave": [_i, _p, _p, _i, _I3, _I3, _i, _i, _p],
 }

@@ -1219,6 +1219,44 @@ int tma_conv_dgrad_strided(const mig_conv_geom* g, const void* dy, const void* w
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// folded upsample convolution, forward: one residue class written straight into the full-resolution output
+// ---------------------------------------------------------------------------------------------------
+// Class r of "nearest x f + conv" (upconv.cu) is a dense stride-1 convolution of the low-resolution tensor whose rows
+// land at f*j + r of the output: the row mapping (os, oo, OD/OH/OW) the strided dgrad above uses, with sign = +1.
+bool tma_upconv_class_eligible(int N, const int32_t low[3], int Cin, int Cout) {
+  if (Cin % 8 != 0 || Cin < 48 || Cout % 8 != 0) return false;
+  if ((double)N * low[0] * low[1] * low[2] > 16.0 * 2147483647.0) return false;
+  int bd, bh, bw;
+  return pick_box(low[0], low[1], low[2], &bd, &bh, &bw);
+}
+
+int tma_upconv_class_fwd(int N, const int32_t low[3], const int32_t factor[3], const int32_t res[3], const int32_t nu[3],
+                         const int32_t base[3], int Cin, int Cout, const void* x, const void* wc, const float* bias,
+                         void* y, void* stream) {
+  BoxGeom b{};
+  b.N = N; b.D = low[0]; b.H = low[1]; b.W = low[2];
+  b.rb = 64;
+  MIG_REQUIRE(pick_box(b.D, b.H, b.W, &b.bd, &b.bh, &b.bw), "upconv_fwd: no TMA box for this volume");
+  b.nb = b.bd * b.bh * b.bw;
+  set_box_counts(b);
+  int taps = 1;
+  for (int i = 0; i < 3; ++i) {
+    b.ks[i] = nu[i];
+    b.off[i] = base[i];
+    b.ss[i] = 1;
+    b.os[i] = factor[i];
+    b.oo[i] = res[i];
+    taps *= nu[i];
+  }
+  b.sign = 1;
+  b.Csrc = Cin; b.Cdst = Cout;
+  b.K = taps * Cin;
+  b.cchunks = (Cin + 63) / 64;
+  b.OD = low[0] * factor[0]; b.OH = low[1] * factor[1]; b.OW = low[2] * factor[2];
+  return launch_box_conv(b, N, low, x, wc, bias, nullptr, nullptr, y, nullptr, 0, stream);
+}
+
 template <int BN, int MT>
 static int launch_wgrad_tma(const CUtensorMap& dym, const CUtensorMap& xm, const WgradTmaParams& p, dim3 grid,
                             cudaStream_t st) {

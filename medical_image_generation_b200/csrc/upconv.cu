@@ -180,9 +180,41 @@ __global__ void __launch_bounds__(256) class_interleave_kernel(const uint4* __re
   }
 }
 
+bool tma_upconv_class_eligible(int N, const int32_t low[3], int Cin, int Cout);
+int tma_upconv_class_fwd(int N, const int32_t low[3], const int32_t factor[3], const int32_t res[3], const int32_t nu[3],
+                         const int32_t base[3], int Cin, int Cout, const void* x, const void* wc, const float* bias,
+                         void* y, void* stream);
+
 }  // namespace mig
 
 using namespace mig;
+
+extern "C" int mig_upconv_fwd_direct_ok(int32_t N, const int32_t low[3], int32_t Cin, int32_t Cout) {
+  return device_info().cc_major == 10 && tma_upconv_class_eligible(N, low, Cin, Cout) ? 1 : 0;
+}
+
+extern "C" int mig_upconv_fwd(const void* x, const void* folded, const float* bias, void* y, int32_t N,
+                              const int32_t low[3], int32_t Cin, int32_t Cout, const int32_t ksize[3],
+                              const int32_t factor[3], const int32_t pad[3], void* stream) {
+  MIG_REQUIRE(x && folded && y, "upconv_fwd: null argument");
+  MIG_REQUIRE(mig_upconv_fwd_direct_ok(N, low, Cin, Cout), "upconv_fwd: shape not eligible for the tcgen05 box kernel");
+  UpPlan pl;
+  if (make_plan(&pl, ksize, factor, pad, (int64_t)Cout * Cin)) return 1;
+  int c = 0;
+  for (int r0 = 0; r0 < factor[0]; ++r0)
+    for (int r1 = 0; r1 < factor[1]; ++r1)
+      for (int r2 = 0; r2 < factor[2]; ++r2, ++c) {
+        const int32_t r[3] = {r0, r1, r2};
+        int32_t nu[3], base[3];
+        for (int i = 0; i < 3; ++i) {
+          nu[i] = pl.cls[c].nu[i];
+          base[i] = floordiv(r[i] - pad[i], factor[i]);     // offset of tap 0 = the smallest one
+        }
+        const __nv_bfloat16* wc = (const __nv_bfloat16*)folded + pl.cls[c].offset;
+        if (int rc = tma_upconv_class_fwd(N, low, factor, r, nu, base, Cin, Cout, x, wc, bias, y, stream)) return rc;
+      }
+  return 0;
+}
 
 extern "C" int64_t mig_upconv_folded_elems(int32_t Cout, int32_t Cin, const int32_t ksize[3], const int32_t factor[3],
                                            const int32_t pad[3], int which) {

@@ -1028,6 +1028,8 @@ def upsample_nearest(x, factors):
 # nearest upsample folded into the convolution that follows it (K8; unet:576-584, ae:97-106)
 # ----------------------------------------------------------------------------------------------
 _UPCONV = os.environ.get("MIG_UPCONV", "auto")    # auto | always | never (A/B switch and tests)
+_UPCONV_MIN_TILES = int(os.environ.get("MIG_UPCONV_MIN_TILES", "96"))     # 256 x 256 tiles per class for 'auto'
+_UPCONV_DIRECT = os.environ.get("MIG_UPCONV_DIRECT", "1") != "0"          # forward scatters straight into y (A/B)
 
 
 def set_upconv(mode: str) -> None:
@@ -1067,9 +1069,12 @@ def upconv_usable(x, weight, factors, padding) -> bool:
         return True
     # cost model: the per-class convolutions run one after the other, each over 1/f^n of the output voxels; on a small
     # level a class no longer fills the 148 SMs with 256 x 256 tiles and the fold loses to one big launch
+    return _upconv_tiles(x, Cout) >= _UPCONV_MIN_TILES
+
+
+def _upconv_tiles(x, Cout) -> int:
     rows = x.shape[0] * math.prod(x.shape[2:])
-    tiles = -(-rows // 256) * -(-Cout // 256)
-    return tiles >= 96
+    return -(-rows // 256) * -(-Cout // 256)
 
 
 class _UpConvFn(Function):
@@ -1095,23 +1100,35 @@ class _UpConvFn(Function):
         folds = [_axis_fold(k3[i], f3[i], p3[i]) for i in range(3)]
         classes = [(r0, r1, r2) for r0 in range(f3[0]) for r1 in range(f3[1]) for r2 in range(f3[2])]
         per_class = N * low3[0] * low3[1] * low3[2] * Cout
-        yc = torch.empty(len(classes) * per_class, dtype=x.dtype, device=x.device)
         dt = _dt(x)
-        geoms, off = [], 0
-        for ci, r in enumerate(classes):
-            base = [folds[i][r[i]][0] for i in range(3)]
-            nu = [folds[i][r[i]][1] for i in range(3)]
-            geom = _lib.conv_geom(N, low3, low3, Cin, Cout, nu, (1, 1, 1), [-b for b in base])
-            need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
-            ws = _workspace(need, x.device)
-            _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x), C.c_void_p(folded.data_ptr() + 2 * off),
-                       _ptr(bias), None, None, C.c_void_p(yc.data_ptr() + 2 * ci * per_class), _ENGINE, _ptr(ws),
-                       ws.numel(), _stream())
-            geoms.append((geom, off))
-            off += nu[0] * nu[1] * nu[2] * Cout * Cin
         out_sp = tuple(low3[i] * f3[i] for i in range(3))[3 - nd:]
         y = empty_cl((N, Cout, *out_sp), x.dtype, x.device)
-        call("mig_class_interleave", dt, _ptr(yc), _ptr(y), N, I3(*low3), ff, Cout, 0, _stream())
+        geoms, off = [], 0
+        for r in classes:
+            base = [folds[i][r[i]][0] for i in range(3)]
+            nu = [folds[i][r[i]][1] for i in range(3)]
+            geoms.append((_lib.conv_geom(N, low3, low3, Cin, Cout, nu, (1, 1, 1), [-b for b in base]), off))
+            off += nu[0] * nu[1] * nu[2] * Cout * Cin
+        # Large levels: every class goes through the persistent box kernel and its epilogue writes rows j to f*j + r of y
+        # (the strided dgrad's row mapping). Small levels need split-K to fill the GPU, which wants rows 1:1 with the
+        # output: per-class convolutions into class buffers, then one interleave pass.
+        same_taps = all(tuple(g.ksize) == tuple(geoms[0][0].ksize) for g, _ in geoms)
+        direct = (_UPCONV_DIRECT and same_taps and _upconv_tiles(x, Cout) >= _UPCONV_MIN_TILES
+                  and lib.mig_upconv_fwd_direct_ok(N, I3(*low3), Cin, Cout))
+        if direct:
+            g0 = geoms[0][0]
+            total = _lib.conv_geom(N * len(classes), low3, low3, Cin, Cout, tuple(g0.ksize), (1, 1, 1), tuple(g0.pad))
+            _conv_call("fwd", total, "mig_upconv_fwd", _ptr(x), _ptr(folded), _ptr(bias), _ptr(y), N, I3(*low3), Cin, Cout,
+                       kk, ff, pp, _stream())
+        else:
+            yc = torch.empty(len(classes) * per_class, dtype=x.dtype, device=x.device)
+            for ci, (geom, goff) in enumerate(geoms):
+                need = lib.mig_conv_workspace_bytes(C.byref(geom), dt, 0, _ENGINE)
+                ws = _workspace(need, x.device)
+                _conv_call("fwd", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(x),
+                           C.c_void_p(folded.data_ptr() + 2 * goff), _ptr(bias), None, None,
+                           C.c_void_p(yc.data_ptr() + 2 * ci * per_class), _ENGINE, _ptr(ws), ws.numel(), _stream())
+            call("mig_class_interleave", dt, _ptr(yc), _ptr(y), N, I3(*low3), ff, Cout, 0, _stream())
         ctx.cfg = (low3, k3, f3, p3, geoms, per_class, off)
         ctx.bias_ref, ctx.weight_ref = bias, weight
         ctx.save_for_backward(x, weight)

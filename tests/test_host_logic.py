@@ -365,3 +365,59 @@ def test_perceptual_loss_lpips_vgg_fake_3d(tmp_path, monkeypatch):
         for k in [k for k in sys.modules if k.split(".")[0] == "generative"]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_upconv_fold_algebra_fp64():
+    """The sub-pixel decomposition behind ops.upsample_conv_nd (csrc/upconv.cu), in fp64 on the CPU with the package's own
+    fold table (ops._axis_fold): per-class convolutions of the low-resolution tensor == conv(nearest_upsample(x)); the
+    stride-f convolution of dy with the folded (f + k - 1)^n-tap filter == d/dx; class wgrads unfolded == d/dw."""
+    import itertools
+    import torch.nn.functional as F
+    from medical_image_generation_b200 import ops
+    torch.manual_seed(0)
+    for f3, k3, p3, n3 in [((2, 2, 2), (3, 3, 3), (1, 1, 1), (3, 4, 5)), ((2, 2, 1), (3, 3, 3), (1, 1, 1), (4, 3, 5)),
+                           ((1, 2, 2), (1, 3, 3), (0, 1, 1), (1, 5, 4))]:
+        x = torch.randn(2, 3, *n3, dtype=torch.float64, requires_grad=True)
+        w = torch.randn(4, 3, *k3, dtype=torch.float64, requires_grad=True)
+        b = torch.randn(4, dtype=torch.float64)
+        xu = x
+        for i in range(3):
+            xu = xu.repeat_interleave(f3[i], dim=2 + i)
+        ref = F.conv3d(xu, w, b, padding=p3)
+        dy = torch.randn_like(ref)
+        gx, gw = torch.autograd.grad(ref, (x, w), dy)
+        folds = [ops._axis_fold(k3[i], f3[i], p3[i]) for i in range(3)]
+        y = torch.zeros_like(ref)
+        dW = torch.zeros_like(w)
+        xd, wd_ = x.detach(), w.detach()
+        for r in itertools.product(*[range(v) for v in f3]):
+            base = [folds[i][r[i]][0] for i in range(3)]
+            nu = [folds[i][r[i]][1] for i in range(3)]
+            umap = {t: tuple((r[i] + t[i] - p3[i]) // f3[i] - base[i] for i in range(3))
+                    for t in itertools.product(*[range(v) for v in k3])}
+            wc = torch.zeros(4, 3, *nu, dtype=torch.float64)
+            for t, u in umap.items():
+                wc[(slice(None), slice(None)) + u] += wd_[(slice(None), slice(None)) + t]
+            pad = []
+            for i in (2, 1, 0):     # pad_before = -base, pad_after = nu - 1 + base: out_dims = in_dims
+                pad += [-base[i], nu[i] - 1 + base[i]]
+            xp = F.pad(xd, pad)
+            y[:, :, r[0]::f3[0], r[1]::f3[1], r[2]::f3[2]] = F.conv3d(xp, wc, b)
+            dyc = dy[:, :, r[0]::f3[0], r[1]::f3[1], r[2]::f3[2]]
+            dwc = torch.zeros_like(wc)
+            for u in itertools.product(*[range(v) for v in nu]):
+                xs = xp[:, :, u[0]:u[0] + n3[0], u[1]:u[1] + n3[1], u[2]:u[2] + n3[2]]
+                dwc[(slice(None), slice(None)) + u] = torch.einsum("nodhw,nidhw->oi", dyc, xs)
+            for t, u in umap.items():
+                dW[(slice(None), slice(None)) + t] += dwc[(slice(None), slice(None)) + u]
+        assert float((y - ref).abs().max()) < 1e-12
+        assert float((dW - gw).abs().max()) < 1e-11
+        K2 = [f3[i] + k3[i] - 1 for i in range(3)]
+        pad2 = [k3[i] - 1 - p3[i] for i in range(3)]
+        wd = torch.zeros(3, 4, *K2, dtype=torch.float64)
+        for s in itertools.product(*[range(v) for v in K2]):
+            for t in itertools.product(*[range(v) for v in k3]):
+                if all(0 <= (s[i] - pad2[i]) + t[i] - p3[i] < f3[i] for i in range(3)):
+                    wd[(slice(None), slice(None)) + s] += wd_[(slice(None), slice(None)) + t].t()
+        dx = F.conv3d(dy, wd, None, stride=f3, padding=pad2)
+        assert dx.shape == gx.shape and float((dx - gx).abs().max()) < 1e-11

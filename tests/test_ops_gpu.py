@@ -846,10 +846,14 @@ UPCONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("direct", [True, False])
 @pytest.mark.parametrize("case", UPCONV_CASES)
-def test_upsample_conv_folded_matches_reference_and_unfolded(case):
-    """Folded path vs (a) torch's interpolate + conv on the same bf16-rounded operands, (b) the two separate operators."""
+def test_upsample_conv_folded_matches_reference_and_unfolded(case, direct, monkeypatch):
+    """Folded path vs (a) torch's interpolate + conv on the same bf16-rounded operands, (b) the two separate operators.
+    direct: the forward classes scatter straight into the output (large levels) / go through class buffers + interleave."""
     ops = _ops()
+    monkeypatch.setattr(ops, "_UPCONV_DIRECT", direct)
+    monkeypatch.setattr(ops, "_UPCONV_MIN_TILES", 0)
     N, Cin, Cout, low, f = case
     nd = len(low)
     k, p = (3,) * nd, (1,) * nd
