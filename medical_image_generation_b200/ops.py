@@ -166,10 +166,25 @@ def from_channels_last(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
 _PROFILE = None  # list of (kind, algorithmic flops, (Cin, Cout, out_dims, ksize), start_event, end_event) or None
 
 
+def _profile_saved(kind: str, flops: float) -> None:
+    if _PROFILE is not None:
+        _PROFILE_SAVED[kind] = _PROFILE_SAVED.get(kind, 0.0) + flops
+
+
 def profile_start() -> None:
+    _PROFILE_SAVED.clear()
     """bench.py: record CUDA events (on the launching stream) around every conv implicit-GEMM launch."""
     global _PROFILE
     _PROFILE = []
+
+
+_PROFILE_SAVED = {}   # kind -> FLOPs the reference's algorithm would have spent that a folded operator did not execute
+
+
+def profile_saved_flops() -> dict:
+    """FLOPs NOT executed since profile_start() because an operator ran an algebraically reduced form (the folded
+    Upsample convolutions, ops.upsample_conv_nd): reference-algorithm FLOPs minus executed FLOPs, per kind."""
+    return dict(_PROFILE_SAVED)
 
 
 def profile_stop() -> list:
@@ -1129,6 +1144,8 @@ class _UpConvFn(Function):
                            C.c_void_p(folded.data_ptr() + 2 * goff), _ptr(bias), None, None,
                            C.c_void_p(yc.data_ptr() + 2 * ci * per_class), _ENGINE, _ptr(ws), ws.numel(), _stream())
             call("mig_class_interleave", dt, _ptr(yc), _ptr(y), N, I3(*low3), ff, Cout, 0, _stream())
+        ref = 2.0 * N * math.prod(low3) * math.prod(f3) * Cout * Cin * math.prod(k3)      # the reference's k^n taps
+        _profile_saved("fwd", ref - sum(2.0 * N * math.prod(low3) * Cout * Cin * math.prod(g.ksize) for g, _ in geoms))
         ctx.cfg = (low3, k3, f3, p3, geoms, per_class, off)
         ctx.bias_ref, ctx.weight_ref = bias, weight
         ctx.save_for_backward(x, weight)
@@ -1161,6 +1178,8 @@ class _UpConvFn(Function):
             ws = _workspace(need, x.device)
             _conv_call("dgrad", geom, "mig_conv_fwd", C.byref(geom), dt, _ptr(dy), _ptr(wd), None, None, None, _ptr(dx),
                        _ENGINE, _ptr(ws), ws.numel(), _stream())
+            ref = 2.0 * N * math.prod(full3) * Cout * Cin * math.prod(k3)
+            _profile_saved("dgrad", ref - 2.0 * N * math.prod(low3) * Cout * Cin * math.prod(geom.ksize))
         want_w, want_b = ctx.needs_input_grad[1], bias is not None and ctx.needs_input_grad[2]
         if want_w or want_b:
             w_main = getattr(weight, "main_grad", None) if want_w else None
@@ -1182,6 +1201,8 @@ class _UpConvFn(Function):
                            C.c_void_p(dyc.data_ptr() + 2 * ci * per_class),
                            C.c_void_p(dwc.data_ptr() + 4 * off) if want_w else None, _ptr(db_buf), _ENGINE, _ptr(ws),
                            ws.numel(), _stream())
+            ref = 2.0 * N * math.prod(low3) * math.prod(f3) * Cout * Cin * math.prod(k3)
+            _profile_saved("wgrad", ref - sum(2.0 * N * math.prod(low3) * Cout * Cin * math.prod(g.ksize) for g, _ in geoms))
             if want_w:
                 call("mig_upconv_unfold_wgrad", _ptr(dwc), _ptr(dw_buf), Cout, Cin, kk, ff, pp, _stream())
                 dw = _deliver(weight, None) if w_main is not None else dw_buf
