@@ -191,6 +191,9 @@ int mig_softmax_fwd(int dtype_in, int dtype_out, const void* x, void* y, int64_t
                     void* stream);
 int mig_softmax_bwd(int dtype_p, int dtype_d, const void* p, const void* dp, void* ds, int64_t rows, int32_t cols,
                     float scale, void* stream);
+/* the same with bf16 probabilities, fp32 dP and a bf16 dS written directly (no fp32 dS round trip + cast pass) */
+int mig_softmax_bwd_narrow(const void* p, const void* dp, void* ds, int64_t rows, int32_t cols, float scale,
+                           void* stream);
 
 /* K6: time_emb_proj(silu(emb)) of ALL ResnetBlocks of a U-Net in one launch per pass (unet:691-695; SURVEY K6 "tiny
  * GEMM batched over all ResnetBlocks once per forward"). x: fp32 [rows][K] (= silu(emb)); layer i has weight w[i]

@@ -79,6 +79,7 @@ _SIGNATURES = {
     "mig_chan_bias_bwd": [_i, _p, _p, _i, _l, _i, _p],
     "mig_softmax_fwd": [_i, _i, _p, _p, _l, _i, _f, _p],
     "mig_softmax_bwd": [_i, _i, _p, _p, _p, _l, _i, _f, _p],
+    "mig_softmax_bwd_narrow": [_p, _p, _p, _l, _i, _f, _p],
     "mig_temb_proj_all_fwd": [_p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mig_temb_proj_all_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _p],
     "mig_timestep_embedding": [_p, _p, _i, _i, _i, _f, _p],

@@ -679,19 +679,77 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const TI* __restrict__
   const float inv = 1.f / sum;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) yr[c] = from_f<TO>(__expf(to_f(xr[c]) * scale - mx) * inv);
 }
-// ds = scale * p * (dp - sum(dp*p))
-template <typename TP, typename TD>
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const TP* __restrict__ p, const TD* __restrict__ dp,
-                                                          TD* __restrict__ ds, int cols, float scale) {
+// Rows of up to 256 * kSoftmaxVPT columns (the LDM's L = 1728 attention rows): the row is loaded ONCE, all loads in
+// flight together, and lives in registers for the maximum, the sum and the store -- the three-pass kernel above re-read
+// it twice through L1 and evaluated every exponential twice (0.29 of HBM on the 8 x 1728 x 1728 score matrix).
+constexpr int kSoftmaxVPT = 8;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) softmax_fwd_row_kernel(const TI* __restrict__ x, TO* __restrict__ y, int cols,
+                                                              float scale) {
+  __shared__ float red[33];
+  const TI* xr = x + (int64_t)blockIdx.x * cols;
+  TO* yr = y + (int64_t)blockIdx.x * cols;
+  float v[kSoftmaxVPT];
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) {
+    const int c = threadIdx.x + k * 256;
+    v[k] = c < cols ? to_f(xr[c]) * scale : -INFINITY;
+  }
+  float mx = v[0];
+#pragma unroll
+  for (int k = 1; k < kSoftmaxVPT; ++k) mx = fmaxf(mx, v[k]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) {
+    v[k] = __expf(v[k] - mx);     // exp(-inf) = 0 for the columns past the end
+    sum += v[k];
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < cols) yr[c] = from_f<TO>(v[k] * inv);
+  }
+}
+template <typename TP, typename TD, typename TS = TD>
+__global__ void __launch_bounds__(256) softmax_bwd_row_kernel(const TP* __restrict__ p, const TD* __restrict__ dp,
+                                                              TS* __restrict__ ds, int cols, float scale) {
   __shared__ float red[33];
   const TP* pr = p + (int64_t)blockIdx.x * cols;
   const TD* dr = dp + (int64_t)blockIdx.x * cols;
-  TD* sr = ds + (int64_t)blockIdx.x * cols;
+  TS* sr = ds + (int64_t)blockIdx.x * cols;
+  float pv[kSoftmaxVPT], dv[kSoftmaxVPT];
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) {
+    const int c = threadIdx.x + k * 256;
+    pv[k] = c < cols ? to_f(pr[c]) : 0.f;
+    dv[k] = c < cols ? to_f(dr[c]) : 0.f;
+  }
+  float dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) dot = fmaf(pv[k], dv[k], dot);
+  dot = block_sum(dot, red);
+#pragma unroll
+  for (int k = 0; k < kSoftmaxVPT; ++k) {
+    const int c = threadIdx.x + k * 256;
+    if (c < cols) sr[c] = from_f<TS>(scale * pv[k] * (dv[k] - dot));
+  }
+}
+// ds = scale * p * (dp - sum(dp*p))
+template <typename TP, typename TD, typename TS = TD>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const TP* __restrict__ p, const TD* __restrict__ dp,
+                                                          TS* __restrict__ ds, int cols, float scale) {
+  __shared__ float red[33];
+  const TP* pr = p + (int64_t)blockIdx.x * cols;
+  const TD* dr = dp + (int64_t)blockIdx.x * cols;
+  TS* sr = ds + (int64_t)blockIdx.x * cols;
   float dot = 0.f;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) dot += to_f(pr[c]) * to_f(dr[c]);
   dot = block_sum(dot, red);
   for (int c = threadIdx.x; c < cols; c += blockDim.x)
-    sr[c] = from_f<TD>(scale * to_f(pr[c]) * (to_f(dr[c]) - dot));
+    sr[c] = from_f<TS>(scale * to_f(pr[c]) * (to_f(dr[c]) - dot));
 }
 }  // namespace mig
 
@@ -700,29 +758,53 @@ extern "C" int mig_softmax_fwd(int dtype_in, int dtype_out, const void* x, void*
   if (rows <= 0 || cols <= 0) return 0;
   MIG_REQUIRE(rows < (1ll << 31), "softmax: too many rows");
   cudaStream_t s = as_stream(stream);
-  if (dtype_in == MIG_F32 && dtype_out == MIG_F32)
-    softmax_fwd_kernel<float, float><<<(unsigned)rows, 256, 0, s>>>((const float*)x, (float*)y, cols, scale);
-  else if (dtype_in == MIG_F32 && dtype_out == MIG_BF16)
-    softmax_fwd_kernel<float, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)y, cols, scale);
-  else if (dtype_in == MIG_BF16 && dtype_out == MIG_BF16)
-    softmax_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, cols, scale);
+  const bool row = cols <= 256 * kSoftmaxVPT;     // the whole row fits the registers of one CTA
+#define MIG_SOFTMAX_FWD(TI, TO)                                                                               \
+  do {                                                                                                        \
+    if (row) softmax_fwd_row_kernel<TI, TO><<<(unsigned)rows, 256, 0, s>>>((const TI*)x, (TO*)y, cols, scale); \
+    else softmax_fwd_kernel<TI, TO><<<(unsigned)rows, 256, 0, s>>>((const TI*)x, (TO*)y, cols, scale);         \
+  } while (0)
+  if (dtype_in == MIG_F32 && dtype_out == MIG_F32) MIG_SOFTMAX_FWD(float, float);
+  else if (dtype_in == MIG_F32 && dtype_out == MIG_BF16) MIG_SOFTMAX_FWD(float, __nv_bfloat16);
+  else if (dtype_in == MIG_BF16 && dtype_out == MIG_BF16) MIG_SOFTMAX_FWD(__nv_bfloat16, __nv_bfloat16);
   else
     MIG_REQUIRE(false, "softmax_fwd: unsupported dtype pair %d -> %d", dtype_in, dtype_out);
+#undef MIG_SOFTMAX_FWD
   return check_launch("softmax_fwd");
 }
 extern "C" int mig_softmax_bwd(int dtype_p, int dtype_d, const void* p, const void* dp, void* ds, int64_t rows,
                                int32_t cols, float scale, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   cudaStream_t s = as_stream(stream);
-  if (dtype_p == MIG_F32 && dtype_d == MIG_F32)
-    softmax_bwd_kernel<float, float><<<(unsigned)rows, 256, 0, s>>>((const float*)p, (const float*)dp, (float*)ds, cols, scale);
-  else if (dtype_p == MIG_BF16 && dtype_d == MIG_F32)
-    softmax_bwd_kernel<__nv_bfloat16, float><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)p, (const float*)dp, (float*)ds, cols, scale);
-  else if (dtype_p == MIG_BF16 && dtype_d == MIG_BF16)
-    softmax_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>((const __nv_bfloat16*)p, (const __nv_bfloat16*)dp, (__nv_bfloat16*)ds, cols, scale);
+  const bool row = cols <= 256 * kSoftmaxVPT;
+#define MIG_SOFTMAX_BWD(TP, TD)                                                                                          \
+  do {                                                                                                                   \
+    if (row) softmax_bwd_row_kernel<TP, TD><<<(unsigned)rows, 256, 0, s>>>((const TP*)p, (const TD*)dp, (TD*)ds, cols, scale); \
+    else softmax_bwd_kernel<TP, TD><<<(unsigned)rows, 256, 0, s>>>((const TP*)p, (const TD*)dp, (TD*)ds, cols, scale);         \
+  } while (0)
+  if (dtype_p == MIG_F32 && dtype_d == MIG_F32) MIG_SOFTMAX_BWD(float, float);
+  else if (dtype_p == MIG_BF16 && dtype_d == MIG_F32) MIG_SOFTMAX_BWD(__nv_bfloat16, float);
+  else if (dtype_p == MIG_BF16 && dtype_d == MIG_BF16) MIG_SOFTMAX_BWD(__nv_bfloat16, __nv_bfloat16);
   else
     MIG_REQUIRE(false, "softmax_bwd: unsupported dtype pair %d / %d", dtype_p, dtype_d);
+#undef MIG_SOFTMAX_BWD
   return check_launch("softmax_bwd");
+}
+
+// bf16 probabilities, fp32 dP (the GEMM's accumulator precision) -> bf16 dS in ONE pass: what the bf16 training chain
+// feeds its dQ / dK GEMMs (the fp32 dS round trip + cast pass cost 190 MB of traffic per attention block)
+extern "C" int mig_softmax_bwd_narrow(const void* p, const void* dp, void* ds, int64_t rows, int32_t cols, float scale,
+                                      void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  MIG_REQUIRE(p && dp && ds && rows < (1ll << 31), "softmax_bwd_narrow: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  if (cols <= 256 * kSoftmaxVPT)
+    softmax_bwd_row_kernel<__nv_bfloat16, float, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(
+        (const __nv_bfloat16*)p, (const float*)dp, (__nv_bfloat16*)ds, cols, scale);
+  else
+    softmax_bwd_kernel<__nv_bfloat16, float, __nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(
+        (const __nv_bfloat16*)p, (const float*)dp, (__nv_bfloat16*)ds, cols, scale);
+  return check_launch("softmax_bwd_narrow");
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1267,9 +1267,8 @@ def _sdpa_bwd_unfused(q, k, v, P, dO, dQ, dK, dV, B, Lq, Lk, Cc, heads, scale_, 
     if q.dtype == torch.float32:
         call("mig_softmax_bwd", F32, F32, _ptr(P), _ptr(dP), _ptr(dS), B * heads * Lq, Lk, float(scale_), _stream())
     else:
-        dS32 = dP  # in place on the fp32 buffer, then narrowed
-        call("mig_softmax_bwd", BF16, F32, _ptr(P), _ptr(dP), _ptr(dS32), B * heads * Lq, Lk, float(scale_), _stream())
-        call("mig_cast", F32, BF16, _ptr(dS32), _ptr(dS), dS.numel(), _stream())
+        # bf16 P, fp32 dP -> bf16 dS in one pass
+        call("mig_softmax_bwd_narrow", _ptr(P), _ptr(dP), _ptr(dS), B * heads * Lq, Lk, float(scale_), _stream())
     del dP
     # dQ[q, d] = sum_key dS[q, key] K[key, d] ; dK[key, d] = sum_q dS[q, key] Q[q, d]
     _gemm(dS, k, dQ, Lq, dh, Lk, B, heads, sP, (ld, 1, Lk * ld, dh), (ldg, 1, Lq * ldg, dh))

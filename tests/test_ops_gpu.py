@@ -978,3 +978,37 @@ def test_upconv_cost_model_and_fallbacks():
     assert not ops.upconv_usable(x24, w512, (1, 1, 1), (1, 1, 1))
     w48 = _cl(torch.zeros(48, 48, 3, 3, 3, device=DEV))
     assert not ops.upconv_usable(_cl(torch.zeros(2, 48, 32, 32, 32, device=DEV, dtype=torch.bfloat16)), w48, (2, 2, 2), (1, 1, 1))
+
+
+@pytest.mark.parametrize("cols", [3, 216, 1728, 2048, 2049, 6400])
+@pytest.mark.parametrize("pair", ["f32", "f32->bf16", "bf16"])
+def test_softmax_kernels_both_row_layouts(cols, pair):
+    """mig_softmax_fwd / _bwd (the unfused training attention, unet:414): rows that fit the registers of one CTA
+    (<= 2048 columns: LDM levels) and the three-pass kernel for longer ones (config 5: L = 6400), every dtype pair the
+    attention uses (fp32 scores -> bf16 probabilities; bf16 P with fp32 dP)."""
+    from medical_image_generation_b200 import _lib
+    ops = _ops()
+    rows, scale = 37, 0.31
+    g = torch.Generator().manual_seed(cols)
+    x = torch.randn(rows, cols, generator=g) * 3
+    ti, to = {"f32": (torch.float32, torch.float32), "f32->bf16": (torch.float32, torch.bfloat16),
+              "bf16": (torch.bfloat16, torch.bfloat16)}[pair]
+    code = {torch.float32: 0, torch.bfloat16: 1}
+    xd = x.to(DEV).to(ti)
+    y = torch.empty(rows, cols, dtype=to, device=DEV)
+    _lib.call("mig_softmax_fwd", code[ti], code[to], ops._ptr(xd), ops._ptr(y), rows, cols, scale, ops._stream())
+    want = torch.softmax(xd.float().cpu() * scale, dim=-1)
+    assert rel_err(y, want) < (1e-5 if to == torch.float32 else 4e-3)
+    assert torch.allclose(y.float().sum(-1).cpu(), torch.ones(rows), atol=1e-5 if to == torch.float32 else 2e-2)
+    # backward: ds = scale * p * (dp - sum(dp * p)); P in `to`, dP / dS in fp32 unless everything is bf16
+    td = torch.float32 if pair != "bf16" else torch.bfloat16
+    dp = torch.randn(rows, cols, generator=g).to(DEV).to(td)
+    ds = torch.empty(rows, cols, dtype=td, device=DEV)
+    _lib.call("mig_softmax_bwd", code[to], code[td], ops._ptr(y), ops._ptr(dp), ops._ptr(ds), rows, cols, scale, ops._stream())
+    pf, df = y.float().cpu(), dp.float().cpu()
+    want_ds = scale * pf * (df - (df * pf).sum(-1, keepdim=True))
+    assert rel_err(ds, want_ds) < (1e-5 if td == torch.float32 else 1e-2)
+    if pair == "f32->bf16":      # the bf16 training chain: bf16 P, fp32 dP, bf16 dS in one pass
+        dsn = torch.empty(rows, cols, dtype=torch.bfloat16, device=DEV)
+        _lib.call("mig_softmax_bwd_narrow", ops._ptr(y), ops._ptr(dp), ops._ptr(dsn), rows, cols, scale, ops._stream())
+        assert torch.equal(dsn, ds.to(torch.bfloat16))
