@@ -87,7 +87,8 @@ def data_functions() -> dict:
 
     path = os.path.join(REFERENCE_ROOT, "medimgen", "data_processing.py")
     tree = ast.parse(open(path).read())
-    want = {"crop_and_pad_nd", "MedicalDataset", "CustomBatchSampler"}
+    want = {"crop_and_pad_nd", "MedicalDataset", "CustomBatchSampler", "generate_crossval_split", "create_split_files",
+            "get_data_ids"}
     body = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in want]
 
     class _Never:   # isinstance(x, _Never) is always False for arrays
@@ -98,7 +99,10 @@ def data_functions() -> dict:
     def identity_pipeline(params, validation=False):
         return lambda image: {"image": image}
 
-    ns = {"np": np, "torch": torch, "F": F, "os": os, "glob": glob, "pickle": pickle, "partial": partial,
+    import json
+    from sklearn.model_selection import KFold, train_test_split
+    ns = {"json": json, "KFold": KFold, "train_test_split": train_test_split,
+          "np": np, "torch": torch, "F": F, "os": os, "glob": glob, "pickle": pickle, "partial": partial,
           "Dataset": Dataset, "Sampler": Sampler, "List": List, "Tuple": Tuple, "Union": Union, "blosc2": blosc2,
           "zarr": zarr, "define_nnunet_transformations": identity_pipeline}
     exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)

@@ -252,3 +252,74 @@ def test_data_path_refuses_cpu():
     with pytest.raises(RuntimeError, match="CUDA"):
         pkg.ResidentVolumes("cpu")
     assert pkg._DESC.itemsize == 152
+
+
+def _fake_task(root, n=20, ext=".zarr"):
+    import os
+    images = os.path.join(root, "Task007_Fake", "imagesTr")
+    os.makedirs(images)
+    for i in range(n):
+        path = os.path.join(images, f"pat{i:03d}{ext}")
+        if ext == ".zarr":
+            os.makedirs(path)
+        else:
+            open(path, "wb").close()
+    return os.path.join(root, "Task007_Fake")
+
+
+@pytest.mark.parametrize("splitting", ["train-val-test", "5-fold"])
+def test_split_files_like_reference(tmp_path, monkeypatch, splitting):
+    """create_split_files / get_data_ids (data_processing.py:34-116): 70 / 10 / 20 split or 5 folds with seed 12345, file
+    reused when present; identical to the unmodified reference functions when they are available."""
+    import json
+    import os
+    mine_root = tmp_path / "mine"
+    mine_root.mkdir()
+    task = _fake_task(str(mine_root))
+    monkeypatch.setenv("medimgen_preprocessed", str(mine_root))
+    path = pkg.create_split_files("007", splitting, "3d")
+    assert os.path.dirname(path) == task
+    split = json.load(open(path))
+    names = sorted(f"pat{i:03d}" for i in range(20))
+    if splitting == "train-val-test":
+        assert os.path.basename(path) == "splits_train_val_test.json"
+        assert (len(split["train"]), len(split["val"]), len(split["test"])) == (14, 2, 4)
+        assert sorted(split["train"] + split["val"] + split["test"]) == names
+        ids = pkg.get_data_ids(path)
+    else:
+        assert os.path.basename(path) == "splits_final.json" and len(split) == 5
+        assert all(sorted(f["train"] + f["val"]) == names and len(f["val"]) == 4 for f in split)
+        ids = pkg.get_data_ids(path, fold=2)
+        assert ids["val"] == split[2]["val"]
+    assert set(ids) == {"train", "val"}
+    # an existing split file is reused, not regenerated
+    with open(path, "w") as f:
+        json.dump({"train": ["a"], "val": ["b"], "test": []} if splitting == "train-val-test" else [{"train": ["a"], "val": ["b"]}] * 5, f)
+    assert pkg.create_split_files("007", splitting, "3d") == path
+    assert pkg.get_data_ids(path, fold=None if splitting == "train-val-test" else 0) == {"train": ["a"], "val": ["b"]}
+    with pytest.raises(ValueError):
+        os.remove(path)
+        pkg.create_split_files("007", "leave-one-out", "3d")
+    if ref.available():
+        ref_root = tmp_path / "ref"
+        ref_root.mkdir()
+        _fake_task(str(ref_root))
+        monkeypatch.setenv("medimgen_preprocessed", str(ref_root))
+        fn = ref.data_functions()
+        want = json.load(open(fn["create_split_files"]("007", splitting, "3d")))
+        monkeypatch.setenv("medimgen_preprocessed", str(mine_root))
+        got = json.load(open(pkg.create_split_files("007", splitting, "3d")))
+        norm = (lambda s: {k: sorted(v) for k, v in s.items()}) if splitting == "train-val-test" else \
+            (lambda s: [{k: sorted(v) for k, v in f.items()} for f in s])
+        assert norm(got) == norm(want)
+
+
+def test_npz_cases_are_found_when_there_is_no_zarr(tmp_path, monkeypatch):
+    mine_root = tmp_path / "npz"
+    mine_root.mkdir()
+    _fake_task(str(mine_root), n=10, ext=".npz")
+    monkeypatch.setenv("medimgen_preprocessed", str(mine_root))
+    import json
+    split = json.load(open(pkg.create_split_files("007", "train-val-test", "3d")))
+    assert len(split["train"]) + len(split["val"]) + len(split["test"]) == 10
+    assert all(not n.endswith(".npz") for n in split["train"])
