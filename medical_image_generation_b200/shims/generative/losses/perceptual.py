@@ -4,7 +4,8 @@
 (configuration.py:961-964: 2-D `vgg`; 3-D `vgg` with is_fake_3d and fake_3d_ratio 0.2): LPIPS on a VGG-16 trunk, applied
 to a random subset of the slices along each of the three axes for volumes. Restated from the published definitions of
 monai-generative's `PerceptualLoss` and of the `lpips` package [upstream-memory; PARITY UNPINNED -- neither package is
-installed here nor under /root/reference]. Outside the north star's hot path: plain torch.nn (ATen / cuDNN), like the
+installed here nor under /root/reference; the VGG-16 trunk's layer layout IS pinned, to torchvision's definition:
+tests/test_host_logic.py::test_lpips_vgg_trunk_matches_torchvision_vgg16_layout]. Outside the north star's hot path: plain torch.nn (ATen / cuDNN), like the
 discriminator.
 
 Weights: there is no network in this image, so nothing is downloaded. `pretrained=True` (the default, as upstream) needs

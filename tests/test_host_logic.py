@@ -421,3 +421,44 @@ def test_upconv_fold_algebra_fp64():
                     wd[(slice(None), slice(None)) + s] += wd_[(slice(None), slice(None)) + t].t()
         dx = F.conv3d(dy, wd, None, stride=f3, padding=pad2)
         assert dx.shape == gx.shape and float((dx - gx).abs().max()) < 1e-11
+
+
+def test_lpips_vgg_trunk_matches_torchvision_vgg16_layout(monkeypatch):
+    """The perceptual loss's trunk (shims/generative/losses/perceptual.py) against torchvision's vgg16 definition -- the
+    network the `lpips` package slices: same conv indices / shapes (so `net.slice*.N.*` keys of a real LPIPS state dict
+    load) and, with the weights copied over, the same relu1_2 / 2_2 / 3_3 / 4_3 / 5_3 feature maps."""
+    import sys
+    torchvision = pytest.importorskip("torchvision")
+    shims = os.path.join(os.path.dirname(mig.__file__), "shims")
+    monkeypatch.syspath_prepend(shims)
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] == "generative"}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        from generative.losses.perceptual import LPIPS
+        torch.manual_seed(0)
+        tv = torchvision.models.vgg16(weights=None).features.eval()
+        lp = LPIPS(pretrained=False)
+        sd = {}
+        for k in range(1, 6):
+            for name, mod in getattr(lp.net, f"slice{k}").named_children():
+                ref_mod = tv[int(name)]
+                assert type(mod) is type(ref_mod), (k, name)
+                if isinstance(mod, torch.nn.Conv2d):
+                    assert mod.weight.shape == ref_mod.weight.shape and mod.padding == ref_mod.padding
+                    sd[f"slice{k}.{name}.weight"], sd[f"slice{k}.{name}.bias"] = ref_mod.weight, ref_mod.bias
+        lp.net.load_state_dict(sd)
+        x = torch.rand(2, 3, 32, 32)
+        feats = lp.net(x)
+        taps, h = [], x
+        for i, layer in enumerate(tv):
+            h = layer(h)
+            if i in (3, 8, 15, 22, 29):
+                taps.append(h)
+        assert len(feats) == 5
+        for a, b in zip(feats, taps):
+            assert a.shape == b.shape and torch.allclose(a, b, atol=1e-6)
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] == "generative"]:
+            del sys.modules[k]
+        sys.modules.update(saved)
